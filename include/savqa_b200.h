@@ -1,0 +1,167 @@
+/* savqa_b200 -- C ABI of the B200-native graph-guided attention encoder path of SA-VQA.
+ *
+ * The reference (Peixixiong/Structured-Alignment-VQA) is pure Python on PyTorch and has NO plugin / FFI
+ * boundary of its own; the seam this library plugs into is the nn.Module surface of models/modules.py and
+ * the two branch models of models/AttModel_x3.py.  Each entry point below names the
+ * reference code it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference
+ * side (it is what structured-alignment-vqa_b200/savqa_b200/_lib.py does).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates; the library owns nothing
+ *     except cached TMA descriptors); row-major; "ld*" are leading dimensions in ELEMENTS.
+ *   - bf16 tensors are passed as void*; fp32 as float*.
+ *   - `stream` is a cudaStream_t; kernels are only enqueued (no sync, CUDA-graph capturable).
+ *   - return value: 0 on success, a SAVQA_ERR_* code otherwise; savqa_last_error() gives the message of the
+ *     calling thread.  Never aborts, never falls back to a CPU path.
+ *   - requires an sm_100a device (B200); savqa_device_check() reports anything else as an error.
+ */
+#ifndef SAVQA_B200_H_
+#define SAVQA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAVQA_OK 0
+#define SAVQA_ERR_BAD_ARGUMENT 1
+#define SAVQA_ERR_CUDA 2
+#define SAVQA_ERR_UNSUPPORTED 3
+
+#define SAVQA_ABI_VERSION 1
+
+typedef void* savqa_stream_t; /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------------- */
+int savqa_abi_version(void);
+const char* savqa_last_error(void);
+/* 0 if the current device is sm_100 (B200); error otherwise.  *sm_count receives the SM count. */
+int savqa_device_check(int* sm_count);
+
+/* ---- a4: scene-graph mask construction (AttModel_x3.py:103-122 vis, :229-247 syb) ------------------
+ * first_mask [B,V,V], q_mask [B,Q,Q], q_graph [B,Q,Q], first_graph [B,V,V] or NULL (vis branch: top-left
+ * block of `graph` is all ones).  Inputs are int32 when in_is_float == 0 (collate_fn output), fp32 otherwise.
+ * Outputs fp32, T = V+Q: graph_diag [B,T,T] (only the Q x Q block = q_mask), graph [B,T,T]
+ * (TL = 1 | first_graph, TR = BL = 1, BR = q_graph; the reference aliases graph_cross and graph),
+ * dec_mask [B,1,T] (1 where the block-diagonal mask row has a non-zero sum; all zero if !dec_mask_on).
+ * Bit exact with the reference. */
+int savqa_build_masks(const void* first_mask, const void* q_mask, const void* q_graph, const void* first_graph,
+                      int in_is_float, int B, int V, int Q, int dec_mask_on,
+                      float* graph_diag, float* graph, float* dec_mask, savqa_stream_t stream);
+
+/* ---- a1/a2: embedding gathers (nn.Embedding at AttModel_x3.py:96,216; modules.py:32-46) ------------
+ * out[r, 0:width] = table[idx[r], 0:width] * scale   (scale == 1.0f leaves the bits untouched).
+ * out_f32 and/or out_bf16 may be NULL.  Columns [width, pad_to) of out_bf16 are zero-filled (TMA needs
+ * 16-byte row pitches: 300 -> 304).  Index out of [0,table_rows) -> the row is zero-filled and the call
+ * still succeeds (checked on the host side of the Python modules, like F.embedding). */
+int savqa_gather_rows(const float* table, int64_t table_rows, int width, const int64_t* idx, int64_t n_idx, float scale,
+                      float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, int pad_to, savqa_stream_t stream);
+/* dtable[idx[r], :] += dout[r, :] * scale, skipping rows whose index == skip_row (padding_idx semantics of
+ * F.embedding: modules.py:34-41).  dense fp32 table gradient, atomics. */
+int savqa_scatter_add_rows(float* dtable, int64_t table_rows, int width, const int64_t* idx, int64_t n_idx, const float* dout,
+                           int64_t ld_dout, float scale, int64_t skip_row, savqa_stream_t stream);
+
+/* ---- staging casts --------------------------------------------------------------------------------- */
+/* dst_bf16[r, c] = src[r, c] for c < cols, 0 for cols <= c < pad_to. */
+int savqa_cast_bf16(const float* src, int64_t ld_src, void* dst_bf16, int64_t ld_dst, int64_t rows, int cols, int pad_to,
+                    savqa_stream_t stream);
+/* dst_bf16[c, r] = src[r, c]  (weight transposes for dgrad), dst row pitch ld_dst, columns [rows, pad_to) zero. */
+int savqa_cast_transpose_bf16(const float* src, int64_t ld_src, void* dst_bf16, int64_t ld_dst, int64_t rows, int cols, int pad_to,
+                              savqa_stream_t stream);
+/* on[r] = (sum_c x[r, c] != 0) ? 1.0f : 0.0f  -- the activation-derived key / query masks
+ * sign(abs(sum(x,-1))) of modules.py:257,289.  Optionally also writes a bf16 copy of x. */
+int savqa_row_nonzero(const float* x, int64_t ld, int64_t rows, int cols, float* on, void* x_bf16, int64_t ld_bf16,
+                      savqa_stream_t stream);
+/* out_bf16[r,c] = (act_bf16[r,c] > 0) ? dy[r,c] : 0   -- ReLU backward staged as the bf16 GEMM operand.
+ * dy is fp32 when dy_is_f32 != 0, bf16 otherwise. */
+int savqa_relu_gate_bf16(const void* dy, int dy_is_f32, int64_t ld_dy, const void* act_bf16, int64_t ld_act, void* out_bf16,
+                         int64_t ld_out, int64_t rows, int cols, savqa_stream_t stream);
+/* out[c] += sum_r x_bf16[r, c]  (bias gradients). */
+int savqa_colsum_bf16(const void* x_bf16, int64_t ld, int64_t rows, int cols, float* out, savqa_stream_t stream);
+
+/* ---- a6: residual + layer_normalization (modules.py:62-65; residuals at :304, :439) ------------------
+ * pre = x (+ res);  y = gamma * (pre - mean) / (std_unbiased + eps) + beta.
+ * Optional outputs: pre (saved for backward), y_bf16, on[r] = (sum_c y[r,c] != 0). */
+int savqa_residual_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float eps,
+                                 int64_t rows, int C, float* pre, float* y, void* y_bf16, float* on, savqa_stream_t stream);
+/* dx = LN'(pre)[dy] (+ dres_in);  dgamma/dbeta are ACCUMULATED (+=).  sigma == 0 rows follow autograd:
+ * dx = (g - mean g) / eps.  dx_bf16 optional. */
+int savqa_layernorm_bwd(const float* dy, const float* pre, const float* gamma, float eps, int64_t rows, int C,
+                        const float* dres_in, float* dx, void* dx_bf16, float* dgamma, float* dbeta, savqa_stream_t stream);
+
+/* ---- a3/a5/a7: bf16 tensor-core GEMM with fused epilogue ----------------------------------------------
+ * acc[m,n] = sum_k A[m,k] * B[n,k]   (nn.Linear: A = activations [M,K], B = weight [N,K])
+ *   K-major operands (a_mn_major == 0): A is [M, lda] with k contiguous;   B is [N, ldb] with k contiguous.
+ *   MN-major operands (== 1, used by wgrad): A is stored [K, lda] with m contiguous; B is [K, ldb] with n contiguous.
+ * v = alpha*acc + bias[n] + res[m,n] + rowtab[(m % rowtab_period), n];  relu -> v = max(v,0);
+ * gate -> v = (gate_bf16[m,n] > 0) ? v : 0  (ReLU backward);
+ * out_f32 / out_bf16 receive v (either may be NULL).  accumulate: 0 store, 1 out_f32 += v, 2 atomic add
+ * (required when split_k > 1).  Replaces nn.Linear (+ReLU) at modules.py:227-229, 428-429 and
+ * AttModel_x3.py:42-44, 97-101. */
+typedef struct savqa_gemm_epilogue {
+  float alpha;
+  int relu;
+  int accumulate;
+  int rowtab_period;
+  const float* bias;
+  const float* res;
+  int64_t ld_res;
+  const float* rowtab;
+  int64_t ld_rowtab;
+  const void* gate_bf16;
+  int64_t ld_gate;
+  float* out_f32;
+  int64_t ld_out_f32;
+  void* out_bf16;
+  int64_t ld_out_bf16;
+} savqa_gemm_epilogue_t;
+
+int savqa_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, int M, int N, int K,
+                    const savqa_gemm_epilogue_t* epilogue, int split_k, savqa_stream_t stream);
+
+/* ---- a5: graph-weighted attention core (modules.py:246-301 between the projections and the residual) ---
+ * For each sample n and head h (channels [h*d,(h+1)*d) of q/k/v):
+ *   S = Q K^T / sqrt(d);  S[:, j] = -4294967296 where !key_on[n,j];  optional causal tril mask;
+ *   P = softmax(S);  renorm 0: W = P;  1: A = G*P, W = A / max(sum|A|, 1e-12);  2: W = A / (sum A + 1e-7);
+ *   att[h*N+n] = W (optional, BEFORE the query mask);  W' = W * query_on[n,i];  O = W' V.
+ * graph is fp32 [N,Tq,Tk]; graph_q_stride = Tk normally, 0 to broadcast one row over all queries ([N,1,Tk]).
+ * engine: 0 = tcgen05/TMEM kernel (TMA-staged tiles), 1 = CUDA-core fp32 verification kernel. */
+typedef struct savqa_attn_args {
+  const void* q; int64_t ldq;      /* bf16 [N*Tq, ldq] */
+  const void* k; int64_t ldk;      /* bf16 [N*Tk, ldk] */
+  const void* v; int64_t ldv;      /* bf16 [N*Tk, ldv] */
+  const float* graph; int64_t graph_n_stride; int64_t graph_q_stride;
+  const float* key_on;             /* fp32 [N,Tk] */
+  const float* query_on;           /* fp32 [N,Tq] */
+  int N, H, Tq, Tk, d;
+  int causal, renorm, engine;
+  float* out; int64_t ldo;         /* fp32 [N*Tq, ldo] */
+  float* att;                      /* fp32 [H*N,Tq,Tk] or NULL */
+  /* backward only */
+  const float* dout; int64_t ld_dout;   /* fp32 [N*Tq, ld_dout] */
+  void* dq; int64_t ld_dq;         /* bf16, ReLU-gated: dq = dQ * (q > 0) */
+  void* dk; int64_t ld_dk;
+  void* dv; int64_t ld_dv;
+  float* scratch;                  /* fp32 [2, H*N, Tq, Tk] workspace (dS and W') */
+} savqa_attn_args_t;
+
+int savqa_graph_attn_fwd(const savqa_attn_args_t* args, savqa_stream_t stream);
+int savqa_graph_attn_bwd(const savqa_attn_args_t* args, savqa_stream_t stream);
+
+/* ---- a10: label-smoothed three-head loss (main_itp_ddp_tar_super_node.py:335-345) ---------------------
+ * loss = mean_b -sum_c t[b,c] * (lsm(lv)+lsm(ls)+lsm(lc))[b,c]/3, t = (1-eps)*onehot + eps/ncls.
+ * Writes loss[0] and the three logit gradients (scaled by grad_scale; any may be NULL). */
+int savqa_answer_loss(const float* logits_concat, const float* logits_vis, const float* logits_syb, const int64_t* answer, int B,
+                      int ncls, float epsilon, float grad_scale, float* loss, float* d_concat, float* d_vis, float* d_syb,
+                      savqa_stream_t stream);
+
+/* ---- f3 (next): fused Adam over a flat fp32 parameter / gradient pair (torch.optim.Adam semantics,
+ * main_itp_ddp_tar_super_node.py:206) and its row-sparse form for the word tables. ------------------------ */
+int savqa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                    float beta2, float eps, int step, savqa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAVQA_B200_H_ */

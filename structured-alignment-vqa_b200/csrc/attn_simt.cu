@@ -1,0 +1,351 @@
+// a5: graph-weighted attention core on CUDA cores in fp32 (engine 1).
+//
+// Role: (i) the backward of the attention core (a11), (ii) the on-device cross-check of the tcgen05 forward
+// kernel (attn_tcgen05.cu), (iii) head sizes the tensor-core kernel does not take (d not in {32,64,128}).
+// Semantics follow modules.py:246-301 exactly, including the fp32 key-mask constant, softmax over ALL keys,
+// multiplicative graph after the softmax, L1 renormalisation with the 1e-12 clamp, and the query mask.
+#include "common.cuh"
+
+namespace savqa {
+namespace {
+
+constexpr int kMaxJ = 16;  // scores of one query row live in registers: Tk <= 32 * 16 = 512
+constexpr float kMaskFill = -4294967296.0f;  // fp32 value of -2**32 + 1 (modules.py:261)
+
+struct RowSoftmax {
+  float w[kMaxJ];   // W  (attention weight before the query mask)
+  float p[kMaxJ];   // P  (plain softmax)
+  float r;          // sum |G*P|
+  float sumw;       // sum W
+};
+
+// Computes P and W for one query row held across the warp (key j = jj*32 + lane).
+__device__ __forceinline__ void row_weights(const float (&s)[kMaxJ], const float* __restrict__ grow, int Tk, int renorm, int lane,
+                                            RowSoftmax& o) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int jj = 0; jj < kMaxJ; ++jj)
+    if (jj * 32 + lane < Tk) m = fmaxf(m, s[jj]);
+  m = warp_max(m);
+  float z = 0.0f;
+#pragma unroll
+  for (int jj = 0; jj < kMaxJ; ++jj) {
+    const int j = jj * 32 + lane;
+    o.p[jj] = (j < Tk) ? expf(s[jj] - m) : 0.0f;
+    z += o.p[jj];
+  }
+  z = warp_sum(z);
+  const float iz = 1.0f / z;
+  float r = 0.0f, sa = 0.0f;
+#pragma unroll
+  for (int jj = 0; jj < kMaxJ; ++jj) {
+    const int j = jj * 32 + lane;
+    o.p[jj] *= iz;
+    float a = o.p[jj];
+    if (renorm != 0) a *= (j < Tk) ? grow[j] : 0.0f;
+    o.w[jj] = a;
+    r += fabsf(a);
+    sa += a;
+  }
+  r = warp_sum(r);
+  sa = warp_sum(sa);
+  o.r = r;
+  float scale = 1.0f;
+  if (renorm == 1) scale = 1.0f / fmaxf(r, 1e-12f);
+  else if (renorm == 2) scale = 1.0f / (sa + 1e-7f);
+  float sw = 0.0f;
+#pragma unroll
+  for (int jj = 0; jj < kMaxJ; ++jj) {
+    o.w[jj] *= scale;
+    sw += o.w[jj];
+  }
+  o.sumw = warp_sum(sw);
+}
+
+// Shared-memory staging of one head's K and V ([Tk][d+2] bf16: the +2 keeps row-per-lane reads conflict free).
+__device__ __forceinline__ void stage_kv(const savqa_attn_args_t& a, int n, int h, __nv_bfloat16* sK, __nv_bfloat16* sV) {
+  const int d = a.d, dp = d + 2;
+  const __nv_bfloat16* K = static_cast<const __nv_bfloat16*>(a.k);
+  const __nv_bfloat16* V = static_cast<const __nv_bfloat16*>(a.v);
+  for (int i = threadIdx.x; i < a.Tk * (d / 2); i += blockDim.x) {
+    const int j = i / (d / 2), c = (i % (d / 2)) * 2;
+    const long row = static_cast<long>(n) * a.Tk + j;
+    *reinterpret_cast<uint32_t*>(sK + j * dp + c) = *reinterpret_cast<const uint32_t*>(K + row * a.ldk + h * d + c);
+    *reinterpret_cast<uint32_t*>(sV + j * dp + c) = *reinterpret_cast<const uint32_t*>(V + row * a.ldv + h * d + c);
+  }
+}
+
+__device__ __forceinline__ void row_scores(const savqa_attn_args_t& a, int n, int i, const float* sq, const __nv_bfloat16* sK, int lane,
+                                           float (&s)[kMaxJ]) {
+  const int d = a.d, dp = d + 2;
+  const float sqrt_d = sqrtf(static_cast<float>(d));
+#pragma unroll
+  for (int jj = 0; jj < kMaxJ; ++jj) {
+    const int j = jj * 32 + lane;
+    float acc = kMaskFill;
+    if (j < a.Tk) {
+      acc = 0.0f;
+      const __nv_bfloat16* kr = sK + j * dp;
+      for (int c = 0; c < d; c += 2) {
+        const float2 kv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(kr + c));
+        acc = fmaf(sq[c], kv.x, acc);
+        acc = fmaf(sq[c + 1], kv.y, acc);
+      }
+      acc = acc / sqrt_d;  // divide AFTER the contraction (modules.py:254)
+      if (a.key_on && a.key_on[static_cast<long>(n) * a.Tk + j] == 0.0f) acc = kMaskFill;
+      if (a.causal && j > i) acc = kMaskFill;
+    }
+    s[jj] = acc;
+  }
+}
+
+constexpr int kRowsPerCta = 32;
+
+__global__ void __launch_bounds__(256) attn_fwd_simt_kernel(const savqa_attn_args_t a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int d = a.d, dp = d + 2;
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sV = sK + a.Tk * dp;
+  float* sW = reinterpret_cast<float*>(sV + a.Tk * dp);  // [8 warps][Tk]
+  float* sQ = sW + 8 * a.Tk;                             // [8 warps][d]
+  const int hn = blockIdx.x;  // = h * N + n  (the reference's head-major batch index)
+  const int h = hn / a.N, n = hn % a.N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_kv(a, n, h, sK, sV);
+  __syncthreads();
+  const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q);
+  float* wbuf = sW + warp * a.Tk;
+  float* sq = sQ + warp * d;
+  const int i_end = min(a.Tq, (blockIdx.y + 1) * kRowsPerCta);
+  for (int i = blockIdx.y * kRowsPerCta + warp; i < i_end; i += 8) {
+    const long qrow = static_cast<long>(n) * a.Tq + i;
+    for (int c = lane; c < d; c += 32) sq[c] = __bfloat162float(Q[qrow * a.ldq + h * d + c]);
+    __syncwarp();
+    float s[kMaxJ];
+    row_scores(a, n, i, sq, sK, lane, s);
+    const float* grow = a.graph ? a.graph + static_cast<long>(n) * a.graph_n_stride + static_cast<long>(i) * a.graph_q_stride : nullptr;
+    RowSoftmax rs;
+    row_weights(s, grow, a.Tk, a.graph ? a.renorm : 0, lane, rs);
+    const float qon = a.query_on ? a.query_on[qrow] : 1.0f;
+#pragma unroll
+    for (int jj = 0; jj < kMaxJ; ++jj) {
+      const int j = jj * 32 + lane;
+      if (j < a.Tk) {
+        if (a.att) a.att[(static_cast<long>(hn) * a.Tq + i) * a.Tk + j] = rs.w[jj];
+        wbuf[j] = rs.w[jj] * qon;
+      }
+    }
+    __syncwarp();
+    for (int c = lane; c < d; c += 32) {
+      float acc = 0.0f;
+      for (int j = 0; j < a.Tk; ++j) acc = fmaf(wbuf[j], __bfloat162float(sV[j * dp + c]), acc);
+      a.out[qrow * a.ldo + h * d + c] = acc;
+    }
+    __syncwarp();
+  }
+}
+
+// Backward, pass 1 (query-row parallel): recompute P and W, dW = (dO V^T) * qm, dS, dQ; spill dS/sqrt(d) and W'.
+__global__ void __launch_bounds__(256) attn_bwd_rows_kernel(const savqa_attn_args_t a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int d = a.d, dp = d + 2;
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sV = sK + a.Tk * dp;
+  float* sW = reinterpret_cast<float*>(sV + a.Tk * dp);  // [8][Tk]
+  float* sQ = sW + 8 * a.Tk;                             // [8][d]
+  float* sG = sQ + 8 * d;                                // [8][d]  dO row
+  const int hn = blockIdx.x;
+  const int h = hn / a.N, n = hn % a.N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_kv(a, n, h, sK, sV);
+  __syncthreads();
+  const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q);
+  __nv_bfloat16* dQ = static_cast<__nv_bfloat16*>(a.dq);
+  float* wbuf = sW + warp * a.Tk;
+  float* sq = sQ + warp * d;
+  float* sg = sG + warp * d;
+  const float sqrt_d = sqrtf(static_cast<float>(d));
+  const long plane = static_cast<long>(a.H) * a.N * a.Tq * a.Tk;
+  const int renorm = a.graph ? a.renorm : 0;
+  const int i_end = min(a.Tq, (blockIdx.y + 1) * kRowsPerCta);
+  for (int i = blockIdx.y * kRowsPerCta + warp; i < i_end; i += 8) {
+    const long qrow = static_cast<long>(n) * a.Tq + i;
+    for (int c = lane; c < d; c += 32) {
+      sq[c] = __bfloat162float(Q[qrow * a.ldq + h * d + c]);
+      sg[c] = a.dout[qrow * a.ld_dout + h * d + c];
+    }
+    __syncwarp();
+    float s[kMaxJ];
+    row_scores(a, n, i, sq, sK, lane, s);
+    const float* grow = a.graph ? a.graph + static_cast<long>(n) * a.graph_n_stride + static_cast<long>(i) * a.graph_q_stride : nullptr;
+    RowSoftmax rs;
+    row_weights(s, grow, a.Tk, renorm, lane, rs);
+    const float qon = a.query_on ? a.query_on[qrow] : 1.0f;
+    // dW_j = qm * sum_c dO[c] V[j][c];  t = sum_j W_j dW_j
+    float dw[kMaxJ];
+    float t = 0.0f;
+#pragma unroll
+    for (int jj = 0; jj < kMaxJ; ++jj) {
+      const int j = jj * 32 + lane;
+      float acc = 0.0f;
+      if (j < a.Tk) {
+        const __nv_bfloat16* vr = sV + j * dp;
+        for (int c = 0; c < d; c += 2) {
+          const float2 vv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vr + c));
+          acc = fmaf(sg[c], vv.x, acc);
+          acc = fmaf(sg[c + 1], vv.y, acc);
+        }
+        acc *= qon;
+      }
+      dw[jj] = acc;
+      t += rs.w[jj] * acc;
+    }
+    t = warp_sum(t);
+    const bool clamped = (renorm == 1) && (rs.r < 1e-12f);
+    float* dS_out = a.scratch + (static_cast<long>(hn) * a.Tq + i) * a.Tk;
+    float* Wq_out = dS_out + plane;
+#pragma unroll
+    for (int jj = 0; jj < kMaxJ; ++jj) {
+      const int j = jj * 32 + lane;
+      if (j < a.Tk) {
+        float ds;
+        if (renorm == 1 && clamped) ds = rs.w[jj] * dw[jj] - rs.p[jj] * t;
+        else if (renorm == 2) ds = rs.w[jj] * (dw[jj] - t) - rs.p[jj] * t * (1.0f - rs.sumw);
+        else ds = rs.w[jj] * (dw[jj] - t);
+        // masked scores are constants: no gradient flows into them
+        if (a.key_on && a.key_on[static_cast<long>(n) * a.Tk + j] == 0.0f) ds = 0.0f;
+        if (a.causal && j > i) ds = 0.0f;
+        ds = ds / sqrt_d;
+        wbuf[j] = ds;
+        dS_out[j] = ds;
+        Wq_out[j] = rs.w[jj] * qon;
+      }
+    }
+    __syncwarp();
+    for (int c = lane; c < d; c += 32) {
+      float acc = 0.0f;
+      for (int j = 0; j < a.Tk; ++j) acc = fmaf(wbuf[j], __bfloat162float(sK[j * dp + c]), acc);
+      if (!(sq[c] > 0.0f)) acc = 0.0f;  // ReLU of the Q projection (modules.py:227)
+      dQ[qrow * a.ld_dq + h * d + c] = __float2bfloat16_rn(acc);
+    }
+    __syncwarp();
+  }
+}
+
+// Backward, pass 2 (key parallel): dK[j,:] = sum_i dS[i,j] Q[i,:],  dV[j,:] = sum_i W'[i,j] dO[i,:], ReLU-gated.
+// Thread (jj, cg): key j0+jj, columns [cg*CPT, (cg+1)*CPT) of the head.
+template <int CPT>
+__global__ void __launch_bounds__(256) attn_bwd_keys_kernel(const savqa_attn_args_t a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int d = a.d;  // == 8 * CPT
+  float* sQ = reinterpret_cast<float*>(smem);  // [Tq][d]
+  float* sG = sQ + a.Tq * d;                   // [Tq][d] dO
+  const int hn = blockIdx.x;
+  const int h = hn / a.N, n = hn % a.N;
+  const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q);
+  for (int idx = threadIdx.x; idx < a.Tq * d; idx += blockDim.x) {
+    const int i = idx / d, c = idx % d;
+    const long qrow = static_cast<long>(n) * a.Tq + i;
+    sQ[idx] = __bfloat162float(Q[qrow * a.ldq + h * d + c]);
+    sG[idx] = a.dout[qrow * a.ld_dout + h * d + c];
+  }
+  __syncthreads();
+  const int jj = threadIdx.x & 31, cg = threadIdx.x >> 5;
+  const int j = blockIdx.y * 32 + jj;
+  const long plane = static_cast<long>(a.H) * a.N * a.Tq * a.Tk;
+  const float* dS = a.scratch + static_cast<long>(hn) * a.Tq * a.Tk;
+  const float* Wq = dS + plane;
+  float accK[CPT], accV[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) accK[c] = accV[c] = 0.0f;
+  if (j < a.Tk) {
+    for (int i = 0; i < a.Tq; ++i) {
+      const float ds = dS[static_cast<long>(i) * a.Tk + j];
+      const float wq = Wq[static_cast<long>(i) * a.Tk + j];
+      const float* qi = sQ + i * d + cg * CPT;
+      const float* gi = sG + i * d + cg * CPT;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        accK[c] = fmaf(ds, qi[c], accK[c]);
+        accV[c] = fmaf(wq, gi[c], accV[c]);
+      }
+    }
+    const long krow = static_cast<long>(n) * a.Tk + j;
+    const __nv_bfloat16* K = static_cast<const __nv_bfloat16*>(a.k);
+    const __nv_bfloat16* V = static_cast<const __nv_bfloat16*>(a.v);
+    __nv_bfloat16* dK = static_cast<__nv_bfloat16*>(a.dk);
+    __nv_bfloat16* dV = static_cast<__nv_bfloat16*>(a.dv);
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int col = h * d + cg * CPT + c;
+      const float kk = __bfloat162float(K[krow * a.ldk + col]);
+      const float vv = __bfloat162float(V[krow * a.ldv + col]);
+      dK[krow * a.ld_dk + col] = __float2bfloat16_rn(kk > 0.0f ? accK[c] : 0.0f);
+      dV[krow * a.ld_dv + col] = __float2bfloat16_rn(vv > 0.0f ? accV[c] : 0.0f);
+    }
+  }
+}
+
+int check_common(const savqa_attn_args_t* a, const char* who) {
+  SAVQA_REQUIRE(a, "%s: null args", who);
+  SAVQA_REQUIRE(a->q && a->k && a->v, "%s: null q/k/v", who);
+  SAVQA_REQUIRE(a->N > 0 && a->H > 0 && a->Tq > 0 && a->Tk > 0 && a->d > 0, "%s: empty problem", who);
+  SAVQA_REQUIRE(a->d % 2 == 0, "%s: head size %d must be even", who, a->d);
+  SAVQA_REQUIRE(a->Tk <= 32 * kMaxJ, "%s: Tk=%d exceeds the single-pass limit %d", who, a->Tk, 32 * kMaxJ);
+  SAVQA_REQUIRE(a->renorm >= 0 && a->renorm <= 2, "%s: renorm mode %d", who, a->renorm);
+  SAVQA_REQUIRE(a->ldq % 2 == 0 && a->ldk % 2 == 0 && a->ldv % 2 == 0, "%s: odd leading dimension", who);
+  SAVQA_REQUIRE(static_cast<long>(a->N) * a->H <= 2147483647L, "%s: too many (sample, head) pairs", who);
+  return SAVQA_OK;
+}
+
+}  // namespace
+
+int attn_fwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
+  if (int rc = check_common(a, "savqa_graph_attn_fwd")) return rc;
+  SAVQA_REQUIRE(a->out, "savqa_graph_attn_fwd: null out");
+  const int dp = a->d + 2;
+  const size_t smem = static_cast<size_t>(2) * a->Tk * dp * 2 + static_cast<size_t>(8) * a->Tk * 4 + static_cast<size_t>(8) * a->d * 4;
+  SAVQA_REQUIRE(smem <= 200 * 1024, "savqa_graph_attn_fwd: Tk*d too large for one CTA (%zu bytes of smem)", smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  dim3 grid(a->N * a->H, (a->Tq + kRowsPerCta - 1) / kRowsPerCta);
+  attn_fwd_simt_kernel<<<grid, 256, smem, stream>>>(*a);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+int attn_bwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
+  if (int rc = check_common(a, "savqa_graph_attn_bwd")) return rc;
+  SAVQA_REQUIRE(a->dout && a->dq && a->dk && a->dv && a->scratch, "savqa_graph_attn_bwd: null gradient buffer");
+  SAVQA_REQUIRE(a->d == 16 || a->d == 32 || a->d == 64 || a->d == 128, "savqa_graph_attn_bwd: head size %d not in {16,32,64,128}", a->d);
+  const int dp = a->d + 2;
+  const size_t smem1 = static_cast<size_t>(2) * a->Tk * dp * 2 + static_cast<size_t>(8) * a->Tk * 4 + static_cast<size_t>(16) * a->d * 4;
+  const size_t smem2 = static_cast<size_t>(2) * a->Tq * a->d * 4;
+  SAVQA_REQUIRE(smem1 <= 200 * 1024 && smem2 <= 200 * 1024, "savqa_graph_attn_bwd: T*d too large for one CTA");
+  static bool configured = false;
+  if (!configured) {
+    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_keys_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_keys_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_keys_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_keys_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  dim3 grid1(a->N * a->H, (a->Tq + kRowsPerCta - 1) / kRowsPerCta);
+  attn_bwd_rows_kernel<<<grid1, 256, smem1, stream>>>(*a);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  dim3 grid2(a->N * a->H, (a->Tk + 31) / 32);
+  switch (a->d) {
+    case 16: attn_bwd_keys_kernel<2><<<grid2, 256, smem2, stream>>>(*a); break;
+    case 32: attn_bwd_keys_kernel<4><<<grid2, 256, smem2, stream>>>(*a); break;
+    case 64: attn_bwd_keys_kernel<8><<<grid2, 256, smem2, stream>>>(*a); break;
+    default: attn_bwd_keys_kernel<16><<<grid2, 256, smem2, stream>>>(*a); break;
+  }
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+}  // namespace savqa

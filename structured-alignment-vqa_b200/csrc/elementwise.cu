@@ -1,0 +1,432 @@
+// HBM-bound integer / byte / streaming kernels of the path: scene-graph mask construction, embedding gathers and
+// their scatter-add backward, bf16 staging casts, activation-derived padding masks, bias-gradient column sums.
+// All are coalesced, vectorised where the alignment allows, and sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace savqa {
+namespace {
+
+// ------------------------------------------------------------------------------------------------------
+// a4: masks.  One thread per output element of the [B,T,T] planes (two fp32 stores per thread, fully coalesced).
+// Reference: AttModel_x3.py:103-122 / :229-247.
+// ------------------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void build_masks_kernel(const TIn* __restrict__ first_mask, const TIn* __restrict__ q_mask, const TIn* __restrict__ q_graph,
+                                   const TIn* __restrict__ first_graph, int B, int V, int Q, int dec_mask_on,
+                                   float* __restrict__ graph_diag, float* __restrict__ graph, float* __restrict__ dec_mask) {
+  const int T = V + Q;
+  const long total = static_cast<long>(B) * T * T;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % T);
+    const int r = static_cast<int>((i / T) % T);
+    const long b = i / (static_cast<long>(T) * T);
+    float gd = 0.0f, g = 1.0f;  // off-diagonal blocks: 1 - block_diag(..) = 1
+    if (r >= V && c >= V) {
+      const long qi = (b * Q + (r - V)) * Q + (c - V);
+      gd = static_cast<float>(q_mask[qi]);
+      g = static_cast<float>(q_graph[qi]);
+    } else if (r < V && c < V) {
+      g = first_graph ? static_cast<float>(first_graph[(b * V + r) * V + c]) : 1.0f;
+    }
+    graph_diag[i] = gd;
+    graph[i] = g;
+  }
+  // dec_mask[b,0,j] = (sum_k mask[b,j,k] != 0); the sum is taken in fp32 like the reference (exact for 0/1 inputs)
+  const long rows = static_cast<long>(B) * T;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < rows; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(i % T);
+    const long b = i / T;
+    float on = 0.0f;
+    if (dec_mask_on) {
+      float s = 0.0f;
+      if (j < V) {
+        const TIn* row = first_mask + (b * V + j) * V;
+        for (int k = 0; k < V; ++k) s += static_cast<float>(row[k]);
+      } else {
+        const TIn* row = q_mask + (b * Q + (j - V)) * Q;
+        for (int k = 0; k < Q; ++k) s += static_cast<float>(row[k]);
+      }
+      on = (s != 0.0f) ? 1.0f : 0.0f;
+    }
+    dec_mask[i] = on;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// a1/a2: row gather.  One warp per output row; 16-byte loads when width % 4 == 0 (300 = 75 float4).
+// ------------------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const float* __restrict__ table, long table_rows, int width, const int64_t* __restrict__ idx,
+                                   long n_idx, float scale, float* __restrict__ out_f32, long ld_f32,
+                                   __nv_bfloat16* __restrict__ out_bf16, long ld_bf16, int pad_to) {
+  const int lane = threadIdx.x & 31;
+  const long warp0 = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+  const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+  const bool vec = (width % 4 == 0) && ((reinterpret_cast<uintptr_t>(table) & 15) == 0) &&
+                   (!out_f32 || (ld_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0)) &&
+                   (!out_bf16 || (ld_bf16 % 4 == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0));
+  for (long r = warp0; r < n_idx; r += nwarps) {
+    const long src = idx[r];
+    const bool ok = src >= 0 && src < table_rows;
+    const float* trow = table + (ok ? src : 0) * static_cast<long>(width);
+    if (vec) {
+      for (int c = lane * 4; c < width; c += 128) {
+        float4 v = ok ? __ldg(reinterpret_cast<const float4*>(trow + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (scale != 1.0f) { v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale; }
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + r * ld_f32 + c) = v;
+        if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + r * ld_bf16 + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      }
+    } else {
+      for (int c = lane; c < width; c += 32) {
+        float v = ok ? __ldg(trow + c) : 0.0f;
+        if (scale != 1.0f) v *= scale;
+        if (out_f32) out_f32[r * ld_f32 + c] = v;
+        if (out_bf16) out_bf16[r * ld_bf16 + c] = __float2bfloat16_rn(v);
+      }
+    }
+    if (out_bf16)
+      for (int c = width + lane; c < pad_to; c += 32) out_bf16[r * ld_bf16 + c] = __float2bfloat16_rn(0.0f);
+  }
+}
+
+__global__ void scatter_add_rows_kernel(float* __restrict__ dtable, long table_rows, int width, const int64_t* __restrict__ idx,
+                                        long n_idx, const float* __restrict__ dout, long ld_dout, float scale, long skip_row) {
+  const int lane = threadIdx.x & 31;
+  const long warp0 = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+  const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+  for (long r = warp0; r < n_idx; r += nwarps) {
+    const long dst = idx[r];
+    if (dst < 0 || dst >= table_rows || dst == skip_row) continue;
+    float* trow = dtable + dst * static_cast<long>(width);
+    const float* g = dout + r * ld_dout;
+    for (int c = lane; c < width; c += 32) atomicAdd(trow + c, g[c] * scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// staging casts
+// ------------------------------------------------------------------------------------------------------
+__global__ void cast_bf16_kernel(const float* __restrict__ src, long ld_src, __nv_bfloat16* __restrict__ dst, long ld_dst, long rows,
+                                 int cols, int pad_to) {
+  const long per_row = (pad_to + 3) / 4;
+  const long total = rows * per_row;
+  const bool vec = (ld_src % 4 == 0) && (ld_dst % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / per_row;
+    const int c = static_cast<int>(i % per_row) * 4;
+    if (vec && c + 4 <= cols) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * ld_src + c));
+      *reinterpret_cast<uint2*>(dst + r * ld_dst + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    } else {
+      for (int j = 0; j < 4 && c + j < pad_to; ++j)
+        dst[r * ld_dst + c + j] = __float2bfloat16_rn(c + j < cols ? src[r * ld_src + c + j] : 0.0f);
+    }
+  }
+}
+
+// dst[c, r] = src[r, c]; 32x32 smem tile, coalesced on both sides.
+__global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, long ld_src, __nv_bfloat16* __restrict__ dst, long ld_dst,
+                                           long rows, int cols, int pad_to) {
+  __shared__ float tile[32][33];
+  const long r0 = static_cast<long>(blockIdx.y) * 32;
+  const int c0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long r = r0 + j;
+    const int c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? src[r * ld_src + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j;             // dst row
+    const long r = r0 + threadIdx.x;  // dst col
+    if (c < cols && r < pad_to) dst[static_cast<long>(c) * ld_dst + r] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+  }
+}
+
+template <typename TDy>
+__global__ void relu_gate_kernel(const TDy* __restrict__ dy, long ld_dy, const __nv_bfloat16* __restrict__ act, long ld_act,
+                                 __nv_bfloat16* __restrict__ out, long ld_out, long rows, int cols) {
+  const long total = rows * cols;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / cols;
+    const int c = static_cast<int>(i % cols);
+    const float g = static_cast<float>(dy[r * ld_dy + c]);
+    const float a = __bfloat162float(act[r * ld_act + c]);
+    out[r * ld_out + c] = __float2bfloat16_rn(a > 0.0f ? g : 0.0f);
+  }
+}
+
+// One warp per row: fp32 row sum (the reference's sum(x,-1)), on = (sum != 0); optional bf16 copy of the row.
+__global__ void row_nonzero_kernel(const float* __restrict__ x, long ld, long rows, int cols, float* __restrict__ on,
+                                   __nv_bfloat16* __restrict__ x_bf16, long ld_bf16) {
+  const int lane = threadIdx.x & 31;
+  const long warp0 = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+  const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+  const bool vec = (cols % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                   (!x_bf16 || (ld_bf16 % 4 == 0 && (reinterpret_cast<uintptr_t>(x_bf16) & 7) == 0));
+  for (long r = warp0; r < rows; r += nwarps) {
+    const float* row = x + r * ld;
+    float s = 0.0f;
+    if (vec) {
+      for (int c = lane * 4; c < cols; c += 128) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row + c));
+        s += (v.x + v.y) + (v.z + v.w);
+        if (x_bf16) *reinterpret_cast<uint2*>(x_bf16 + r * ld_bf16 + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      }
+    } else {
+      for (int c = lane; c < cols; c += 32) {
+        const float v = row[c];
+        s += v;
+        if (x_bf16) x_bf16[r * ld_bf16 + c] = __float2bfloat16_rn(v);
+      }
+    }
+    s = warp_sum(s);
+    if (lane == 0 && on) on[r] = (s != 0.0f) ? 1.0f : 0.0f;
+  }
+}
+
+// out[c] += sum_r x[r,c].  Block = 32 x 8 threads over a 64-column strip (bf16x2 per thread), rows strided over
+// blockIdx.y; one atomicAdd per column per block.
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long ld, long rows, int cols, float* __restrict__ out) {
+  __shared__ float part[8][64];
+  const int c = blockIdx.x * 64 + threadIdx.x * 2;
+  float a0 = 0.0f, a1 = 0.0f;
+  if (c < cols) {
+    const bool pair = (c + 1 < cols) && (ld % 2 == 0);
+    for (long r = static_cast<long>(blockIdx.y) * blockDim.y + threadIdx.y; r < rows; r += static_cast<long>(gridDim.y) * blockDim.y) {
+      if (pair) {
+        const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
+        a0 += f.x;
+        a1 += f.y;
+      } else {
+        a0 += __bfloat162float(x[r * ld + c]);
+        if (c + 1 < cols) a1 += __bfloat162float(x[r * ld + c + 1]);
+      }
+    }
+  }
+  part[threadIdx.y][threadIdx.x * 2] = a0;
+  part[threadIdx.y][threadIdx.x * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    for (int k = 0; k < 2; ++k) {
+      float s = 0.0f;
+      for (int j = 0; j < 8; ++j) s += part[j][threadIdx.x * 2 + k];
+      if (c + k < cols) atomicAdd(out + c + k, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// a10: three-head label-smoothed loss and its gradient.  One block per sample.
+// ------------------------------------------------------------------------------------------------------
+__device__ float block_reduce(float v, bool is_max, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  float r = (threadIdx.x < nw) ? sh[threadIdx.x] : (is_max ? -INFINITY : 0.0f);
+  if (w == 0) {
+    r = is_max ? warp_max(r) : warp_sum(r);
+    if (lane == 0) sh[0] = r;
+  }
+  __syncthreads();
+  return sh[0];
+}
+
+__global__ void answer_loss_kernel(const float* __restrict__ lc, const float* __restrict__ lv, const float* __restrict__ ls,
+                                   const int64_t* __restrict__ answer, int B, int ncls, float eps, float grad_scale,
+                                   float* __restrict__ loss, float* __restrict__ dc, float* __restrict__ dv, float* __restrict__ ds) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  const float* L[3] = {lc + static_cast<long>(b) * ncls, lv + static_cast<long>(b) * ncls, ls + static_cast<long>(b) * ncls};
+  float* D[3] = {dc ? dc + static_cast<long>(b) * ncls : nullptr, dv ? dv + static_cast<long>(b) * ncls : nullptr,
+                 ds ? ds + static_cast<long>(b) * ncls : nullptr};
+  const int ans = static_cast<int>(answer[b]);
+  const float t_off = eps / ncls, t_on = (1.0f - eps) + eps / ncls;
+  float sample_loss = 0.0f;
+  for (int h = 0; h < 3; ++h) {
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < ncls; c += blockDim.x) m = fmaxf(m, L[h][c]);
+    m = block_reduce(m, true, sh);
+    float z = 0.0f;
+    for (int c = threadIdx.x; c < ncls; c += blockDim.x) z += expf(L[h][c] - m);
+    z = block_reduce(z, false, sh);
+    const float lse = m + logf(z);
+    float acc = 0.0f;
+    for (int c = threadIdx.x; c < ncls; c += blockDim.x) {
+      const float t = (c == ans) ? t_on : t_off;
+      const float lsm = L[h][c] - lse;
+      acc += t * lsm;
+      // d/dlogit of -(1/3B) sum_c t_c lsm_c = (softmax_c * sum_c t_c - t_c) / (3B);  sum_c t_c == 1
+      if (D[h]) D[h][c] = grad_scale * (expf(lsm) - t) / (3.0f * B);
+    }
+    acc = block_reduce(acc, false, sh);
+    sample_loss -= acc / 3.0f;
+  }
+  if (threadIdx.x == 0) atomicAdd(loss, sample_loss / B);
+}
+
+// f3: Adam (torch.optim.Adam defaults: no weight decay, no amsgrad), bias correction as in torch.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
+                            float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+inline int grid_for(long work_items, int threads, int per_sm = 8) {
+  long blocks = (work_items + threads - 1) / threads;
+  const long cap = static_cast<long>(sm_count()) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace
+}  // namespace savqa
+
+using namespace savqa;
+
+extern "C" int savqa_build_masks(const void* first_mask, const void* q_mask, const void* q_graph, const void* first_graph,
+                                 int in_is_float, int B, int V, int Q, int dec_mask_on, float* graph_diag, float* graph,
+                                 float* dec_mask, savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SAVQA_REQUIRE(B >= 0 && V >= 0 && Q >= 0, "savqa_build_masks: negative extent");
+  if (B == 0 || V + Q == 0) return SAVQA_OK;
+  SAVQA_REQUIRE(graph_diag && graph && dec_mask, "savqa_build_masks: null output");
+  SAVQA_REQUIRE((V == 0 || first_mask) && (Q == 0 || (q_mask && q_graph)), "savqa_build_masks: null input");
+  const long total = static_cast<long>(B) * (V + Q) * (V + Q);
+  const int grid = grid_for(total, 256);
+  if (in_is_float)
+    build_masks_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(first_mask), static_cast<const float*>(q_mask),
+                                                        static_cast<const float*>(q_graph), static_cast<const float*>(first_graph), B, V,
+                                                        Q, dec_mask_on, graph_diag, graph, dec_mask);
+  else
+    build_masks_kernel<int><<<grid, 256, 0, stream>>>(static_cast<const int*>(first_mask), static_cast<const int*>(q_mask),
+                                                      static_cast<const int*>(q_graph), static_cast<const int*>(first_graph), B, V, Q,
+                                                      dec_mask_on, graph_diag, graph, dec_mask);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_gather_rows(const float* table, int64_t table_rows, int width, const int64_t* idx, int64_t n_idx, float scale,
+                                 float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, int pad_to, savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_idx == 0) return SAVQA_OK;
+  SAVQA_REQUIRE(table && idx && width > 0 && n_idx > 0, "savqa_gather_rows: bad argument");
+  SAVQA_REQUIRE(out_f32 || out_bf16, "savqa_gather_rows: no output");
+  SAVQA_REQUIRE(!out_f32 || ld_f32 >= width, "savqa_gather_rows: ld_f32 < width");
+  SAVQA_REQUIRE(!out_bf16 || (ld_bf16 >= width && ld_bf16 >= pad_to), "savqa_gather_rows: ld_bf16 too small");
+  gather_rows_kernel<<<grid_for(n_idx * 32, 256), 256, 0, stream>>>(table, table_rows, width, idx, n_idx, scale, out_f32, ld_f32,
+                                                                     static_cast<__nv_bfloat16*>(out_bf16), ld_bf16, pad_to);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_scatter_add_rows(float* dtable, int64_t table_rows, int width, const int64_t* idx, int64_t n_idx, const float* dout,
+                                      int64_t ld_dout, float scale, int64_t skip_row, savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_idx == 0) return SAVQA_OK;
+  SAVQA_REQUIRE(dtable && idx && dout && width > 0 && ld_dout >= width, "savqa_scatter_add_rows: bad argument");
+  scatter_add_rows_kernel<<<grid_for(n_idx * 32, 256), 256, 0, stream>>>(dtable, table_rows, width, idx, n_idx, dout, ld_dout, scale,
+                                                                          skip_row);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_cast_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int cols, int pad_to,
+                               savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows == 0) return SAVQA_OK;
+  if (pad_to < cols) pad_to = cols;
+  SAVQA_REQUIRE(src && dst && cols > 0 && ld_src >= cols && ld_dst >= pad_to, "savqa_cast_bf16: bad argument");
+  const long work = rows * ((pad_to + 3) / 4);
+  cast_bf16_kernel<<<grid_for(work, 256), 256, 0, stream>>>(src, ld_src, static_cast<__nv_bfloat16*>(dst), ld_dst, rows, cols, pad_to);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_cast_transpose_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int cols, int pad_to,
+                                         savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows == 0 || cols == 0) return SAVQA_OK;
+  if (pad_to < rows) pad_to = static_cast<int>(rows);
+  SAVQA_REQUIRE(src && dst && ld_src >= cols && ld_dst >= pad_to, "savqa_cast_transpose_bf16: bad argument");
+  dim3 grid((cols + 31) / 32, static_cast<unsigned>((pad_to + 31) / 32));
+  SAVQA_REQUIRE(grid.y <= 65535, "savqa_cast_transpose_bf16: too many rows");
+  cast_transpose_bf16_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, ld_src, static_cast<__nv_bfloat16*>(dst), ld_dst, rows, cols, pad_to);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_row_nonzero(const float* x, int64_t ld, int64_t rows, int cols, float* on, void* x_bf16, int64_t ld_bf16,
+                                 savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows == 0) return SAVQA_OK;
+  SAVQA_REQUIRE(x && cols > 0 && ld >= cols && (on || x_bf16), "savqa_row_nonzero: bad argument");
+  row_nonzero_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(x, ld, rows, cols, on, static_cast<__nv_bfloat16*>(x_bf16), ld_bf16);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_relu_gate_bf16(const void* dy, int dy_is_f32, int64_t ld_dy, const void* act, int64_t ld_act, void* out, int64_t ld_out,
+                                    int64_t rows, int cols, savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows == 0 || cols == 0) return SAVQA_OK;
+  SAVQA_REQUIRE(dy && act && out && ld_dy >= cols && ld_act >= cols && ld_out >= cols, "savqa_relu_gate_bf16: bad argument");
+  const int grid = grid_for(rows * cols, 256);
+  if (dy_is_f32)
+    relu_gate_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(dy), ld_dy, static_cast<const __nv_bfloat16*>(act), ld_act,
+                                                      static_cast<__nv_bfloat16*>(out), ld_out, rows, cols);
+  else
+    relu_gate_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy,
+                                                              static_cast<const __nv_bfloat16*>(act), ld_act,
+                                                              static_cast<__nv_bfloat16*>(out), ld_out, rows, cols);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_colsum_bf16(const void* x, int64_t ld, int64_t rows, int cols, float* out, savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows == 0 || cols == 0) return SAVQA_OK;
+  SAVQA_REQUIRE(x && out && ld >= cols, "savqa_colsum_bf16: bad argument");
+  const int strips = (cols + 63) / 64;
+  long by = (rows + 63) / 64;
+  const long cap = (static_cast<long>(sm_count()) * 4 + strips - 1) / strips;
+  if (by > cap) by = cap;
+  if (by < 1) by = 1;
+  colsum_bf16_kernel<<<dim3(strips, static_cast<unsigned>(by)), dim3(32, 8), 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, rows,
+                                                                                           cols, out);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_answer_loss(const float* lc, const float* lv, const float* ls, const int64_t* answer, int B, int ncls, float epsilon,
+                                 float grad_scale, float* loss, float* dc, float* dv, float* ds, savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SAVQA_REQUIRE(lc && lv && ls && answer && loss && B > 0 && ncls > 0, "savqa_answer_loss: bad argument");
+  SAVQA_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
+  answer_loss_kernel<<<B, 256, 0, stream>>>(lc, lv, ls, answer, B, ncls, epsilon, grad_scale, loss, dc, dv, ds);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                               float beta2, float eps, int step, savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n == 0) return SAVQA_OK;
+  SAVQA_REQUIRE(param && grad && exp_avg && exp_avg_sq && step >= 1, "savqa_adam_step: bad argument");
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  adam_kernel<<<grid_for(n, 256, 16), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2));
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}

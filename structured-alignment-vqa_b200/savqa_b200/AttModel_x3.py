@@ -1,0 +1,303 @@
+"""Drop-in for the reference's `models/AttModel_x3.py` (`--model_v 3`): same classes, constructor arguments,
+forward signatures, output shapes and state_dict keys; the graph-guided encoder / decoder path runs on the
+sm_100a kernels (modules.py of this package).
+
+    AttModel_vis_grid  <- AttModel_x3.py:20-156      AttModel_syb <- :158-282      AttModel <- :471-542
+    MIL_NCE            <- :285-443  (OUT of the accelerated path, SURVEY.md 8(f1): restated with stock torch ops so
+                                     that a full AttModel step runs; only_obj=True only)
+    CompactBilinearPooling <- :444-469 (parameter holder only: torch.rfft no longer exists, `mcb=True` raises)
+
+Deliberate differences: no hard-coded `.cuda()` (inputs decide the device, which must be a B200); the per-sample
+Python loop with a host sync per sample that builds the masks (:110-116) is one kernel launch.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as Fn
+from . import ops
+from .functional import WeightPack
+from .modules import *  # noqa: F401,F403  (the reference does `from modules import *`)
+from .modules import embedding, feedforward, label_smoothing, multihead_attention, new_multihead_attention
+
+PAD = 400000
+UNK = 400001
+END = 400003
+INVALID = 400003
+VIS_PAD = -1
+LOC_PAD = -1
+VOCAB_ROWS = 407000  # hard-coded in the reference (AttModel_x3.py:36, 168, 293)
+
+
+class _CastBf16(torch.autograd.Function):
+    """fp32 -> bf16 staging of the region / symbolic node features (the A operand of syb_mlp2)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.cast_bf16(x.contiguous().reshape(-1, x.shape[-1])).reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy.float()
+
+
+def _word_table(glove) -> nn.Embedding:
+    table = torch.empty(VOCAB_ROWS, 300)
+    nn.init.xavier_normal_(table)
+    n = glove.vectors.shape[0]
+    table[:n, :] = glove.vectors
+    return nn.Embedding.from_pretrained(table, freeze=False)
+
+
+def _linear(x, lin: nn.Linear, pack: WeightPack, relu=False, out_bf16=False, rowtab=None, period=0):
+    return Fn.LinearFn.apply(x, lin.weight, lin.bias, rowtab, pack, relu, out_bf16, period)
+
+
+class _Branch(nn.Module):
+    """Shared forward of the two branch models (they differ in the top-left block of `graph` and in table sizes)."""
+
+    def _input_stage(self, first_ipt, q_ids, pos_table, pos_dropout_p):
+        B = first_ipt.shape[0]
+        q = Fn.EmbeddingFn.apply(q_ids, self.syb_emb.weight, 1.0, -1)                      # :96 / :216
+        qh = _linear(q, self.syb_mlp[0], self._pk["mlp"], relu=True, out_bf16=True)        # :97  [B,Q,2048] bf16
+        fb = first_ipt if first_ipt.dtype == torch.bfloat16 else _CastBf16.apply(first_ipt)
+        x_in = torch.cat([fb, qh], dim=1)                                                  # :98  [B,T,2048] bf16
+        T = x_in.shape[1]
+        if T > pos_table.shape[0]:
+            raise IndexError("index out of range in self")  # positional table too short, as F.embedding would report
+        if self.training and pos_dropout_p > 0:
+            x = _linear(x_in, self.syb_mlp2, self._pk["mlp2"])
+            x = x + F.dropout(pos_table[:T], pos_dropout_p, True).unsqueeze(0)             # :100-101 (vis only)
+        else:
+            x = _linear(x_in, self.syb_mlp2, self._pk["mlp2"], rowtab=pos_table, period=T)  # :99-101 fused
+        return self.enc_dropout(x)                                                         # :102
+
+    def _encode_decode(self, x, graph_diag, graph, dec_mask):
+        B, C = x.shape[0], x.shape[-1]
+        for i in range(self.num_blocks):
+            # blocks 0,1: graph_diag; the reference aliases graph_cross and graph, so 2.. all see `graph` (:118-139)
+            g = graph_diag if i < 2 else graph
+            x = getattr(self, 'enc_self_attention_%d' % i)(x, x, x, g)
+            x = getattr(self, 'enc_feed_forward_%d' % i)(x)
+        memory = x
+        # decoder input: class token 2 through dec_emb (scaled by sqrt C) + position 0 (:141-147); same for every sample
+        dec = self.dec_emb.lookup_table[2] * (C ** 0.5) + self.dec_positional_encoding.lookup_table[0]
+        dec = dec.reshape(1, 1, C).expand(B, 1, C).contiguous()
+        dec = self.dec_dropout(dec)
+        for i in range(self.num_blocks):
+            dec = getattr(self, 'dec_self_attention_%d' % i)(dec, dec, dec)
+            dec = getattr(self, 'dec_vanilla_attention_%d' % i)(dec, memory, memory, dec_mask)
+            dec = getattr(self, 'dec_feed_forward_%d' % i)(dec)
+        return dec
+
+    def _add_blocks(self, which, hidden_size):
+        for i in range(self.num_blocks):
+            if which == "enc":
+                setattr(self, 'enc_self_attention_%d' % i, new_multihead_attention(num_units=hidden_size, num_heads=self.num_heads,
+                                                                                    dropout_rate=0, causality=False))
+                setattr(self, 'enc_feed_forward_%d' % i, feedforward(hidden_size, [4 * hidden_size, hidden_size]))
+            else:
+                setattr(self, 'dec_self_attention_%d' % i, multihead_attention(num_units=hidden_size, num_heads=self.num_heads,
+                                                                                dropout_rate=0, causality=True))
+                setattr(self, 'dec_vanilla_attention_%d' % i, new_multihead_attention(num_units=hidden_size, num_heads=self.num_heads,
+                                                                                       dropout_rate=0, causality=False))
+                setattr(self, 'dec_feed_forward_%d' % i, feedforward(hidden_size, [4 * hidden_size, hidden_size]))
+
+
+class AttModel_vis_grid(_Branch):
+    def __init__(self, glove, hidden_size, maxlen, maxlen_q, num_blocks, num_heads, dropout_rate, maxlen_v, num_classes):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.num_blocks = num_blocks
+        self.num_heads = num_heads
+        self.maxlen_q = maxlen_q
+        self.maxlen = maxlen
+        self.dropout_rate = dropout_rate
+        self.enc_dropout = nn.Dropout(dropout_rate)
+        self.dec_dropout = nn.Dropout(dropout_rate)
+        self.syb_emb = _word_table(glove)
+        self.syb_mlp = nn.Sequential(nn.Linear(300, 2048), nn.ReLU(inplace=True))
+        self.syb_mlp2 = nn.Linear(2048, hidden_size)
+        # allocated but never used by the reference's forward; kept so that checkpoints load with strict=True
+        self.v_mlp = nn.Sequential(nn.Linear(2048, hidden_size), nn.ReLU(inplace=True), nn.Linear(hidden_size, hidden_size))
+        self.v_positional_encoding = nn.Sequential(embedding(maxlen_v, hidden_size, zeros_pad=False, scale=False), nn.Dropout(dropout_rate))
+        self.input_proj = nn.Linear(2048, hidden_size)
+        self._add_blocks("enc", hidden_size)
+        self.q_mlp = nn.Sequential(nn.Linear(300, hidden_size), nn.ReLU(inplace=True), nn.Linear(hidden_size, hidden_size))
+        self.q_positional_encoding = nn.Sequential(embedding(maxlen_q, hidden_size, zeros_pad=False, scale=False), nn.Dropout(dropout_rate))
+        self.syb_positional_encoding = nn.Sequential(embedding(maxlen, hidden_size, zeros_pad=False, scale=False), nn.Dropout(dropout_rate))
+        self.dec_emb = embedding(num_classes, hidden_size, scale=True)
+        self.dec_positional_encoding = embedding(maxlen, hidden_size, zeros_pad=False, scale=False)
+        self._add_blocks("dec", hidden_size)
+        self._pk = {"mlp": WeightPack(), "mlp2": WeightPack()}
+
+    def forward(self, vis_fea, vis_mask, q_fea, q_graph, q_mask, decMask):
+        if vis_fea.dim() == 4:  # bs x gridx x gridy x fea_size
+            vis_fea = vis_fea.reshape(-1, vis_fea.size(1) * vis_fea.size(2), vis_fea.size(3))
+        x = self._input_stage(vis_fea, q_fea, self.syb_positional_encoding[0].lookup_table, self.dropout_rate)
+        graph_diag, graph, dec_mask = ops.build_masks(vis_mask, q_mask, q_graph, None, decMask != False)  # noqa: E712
+        return self._encode_decode(x, graph_diag, graph, dec_mask)
+
+
+class AttModel_syb(_Branch):
+    def __init__(self, glove, hidden_size, maxlen, maxlen_q, num_blocks, num_heads, dropout_rate, num_classes):
+        super().__init__()
+        self.num_blocks = num_blocks
+        self.num_heads = num_heads
+        self.hidden_size = hidden_size
+        self.dropout_rate = dropout_rate
+        self.maxlen = maxlen
+        self.maxlen_q = maxlen_q
+        self.syb_emb = _word_table(glove)
+        self.syb_mlp = nn.Sequential(nn.Linear(300, 2048), nn.ReLU(inplace=True))
+        self.syb_mlp2 = nn.Linear(2048, hidden_size)
+        self.enc_dropout = nn.Dropout(dropout_rate)
+        self.syb_positional_encoding = embedding(maxlen + maxlen_q, hidden_size, zeros_pad=False, scale=False)
+        self.q_mlp = nn.Sequential(nn.Linear(300, hidden_size), nn.Linear(hidden_size, hidden_size))
+        self.q_positional_encoding = nn.Sequential(embedding(maxlen_q, hidden_size, zeros_pad=False, scale=False), nn.Dropout(dropout_rate))
+        self.dec_emb = embedding(num_classes, hidden_size, scale=True)
+        self.dec_positional_encoding = embedding(maxlen + maxlen_q, hidden_size, zeros_pad=False, scale=False)
+        self.dec_dropout = nn.Dropout(dropout_rate)
+        self._add_blocks("dec", hidden_size)
+        self._add_blocks("enc", hidden_size)
+        self._pk = {"mlp": WeightPack(), "mlp2": WeightPack()}
+
+    def forward(self, syb_ipt, syb_mask, syb_graph, q_fea, q_graph, q_mask, decMask):
+        x = self._input_stage(syb_ipt, q_fea, self.syb_positional_encoding.lookup_table, 0.0)
+        graph_diag, graph, dec_mask = ops.build_masks(syb_mask, q_mask, q_graph, syb_graph, decMask != False)  # noqa: E712
+        return self._encode_decode(x, graph_diag, graph, dec_mask)
+
+
+class MIL_NCE(nn.Module):
+    """Object-word alignment head (AttModel_x3.py:285-443), restated with stock torch ops -- NOT part of the
+    accelerated path.  Produces `new_macro_ipt` [B,M,2048] for the symbolic branch and the
+    object MIL-NCE term.  Only the production `only_obj=True` configuration is implemented."""
+
+    def __init__(self, glove, hidden_size, dropout_rate, num_relations, only_obj):
+        super().__init__()
+        self.only_obj = only_obj
+        self.dropout_rate = dropout_rate
+        self.num_relations = num_relations
+        self.hidden_size = hidden_size
+        self.R = nn.Parameter(torch.empty(num_relations, hidden_size, hidden_size))
+        nn.init.xavier_normal_(self.R)
+        self.syb_emb = _word_table(glove)
+        self.marco_mlp = nn.Sequential(nn.Linear(300, hidden_size), nn.ReLU(inplace=True))
+        self.syb_mlp = nn.Sequential(nn.Linear(300, hidden_size), nn.ReLU(inplace=True))
+        self.vis_mlp = nn.Sequential(nn.Linear(2048, hidden_size), nn.ReLU(inplace=True))
+        self.rel_mlp = nn.Sequential(nn.Linear(hidden_size, hidden_size), nn.ReLU(inplace=True), nn.Linear(hidden_size, 1))
+        self.softmax = nn.Softmax(dim=2)
+        self.softmax_bilinear = nn.Softmax(dim=0)
+        self.bilinear = nn.Bilinear(hidden_size, hidden_size, num_relations, bias=False)
+        self.ipt_mlp = nn.Sequential(nn.Linear(hidden_size, 2048), nn.ReLU(inplace=True))
+
+    def forward(self, vis_fea, macro_ipt, macro_obj_loc, micro_positive_obj, micro_negative_obj, micro_obj_mask,
+                micro_positive_rel, micro_negative_rel, micro_positive_rel_loc, micro_negative_rel_loc):
+        if not self.only_obj:
+            raise NotImplementedError("savqa_b200: the relation branch of MIL_NCE (only_obj=False) is outside the scope of this build")
+        eps = 1e-6
+        words = lambda ids: Fn.EmbeddingFn.apply(ids, self.syb_emb.weight, 1.0, -1)  # noqa: E731
+        nodes = self.marco_mlp(words(macro_ipt)).detach().clone()                 # [B,M,h]; detached at :354
+        pos = self.syb_mlp(words(micro_positive_obj))                             # [B,V,topN,h]
+        neg = self.syb_mlp(words(micro_negative_obj))
+        vis = self.vis_mlp(vis_fea).unsqueeze(3)                                  # [B,V,h,1]
+        m4 = micro_obj_mask.unsqueeze(3)
+        raw_pos = torch.matmul(pos, vis)                                          # [B,V,topN,1]
+        s_pos = (m4 * raw_pos).clamp(min=eps)
+        s_neg = (m4 * torch.matmul(neg, vis)).clamp(min=eps)
+        floor = torch.zeros_like(s_neg).clamp(min=eps)
+        mil_nce_obj = torch.mean(torch.logsumexp(torch.cat((s_pos, floor), dim=1), dim=2)
+                                 - torch.logsumexp(torch.cat((s_pos, s_neg), dim=1), dim=2))
+        refined = torch.sum(self.softmax(raw_pos) * pos, dim=2)                   # [B,V,h]
+        b_idx, v_idx = (macro_obj_loc >= 0).nonzero(as_tuple=True)
+        nodes[b_idx, macro_obj_loc[b_idx, v_idx].long(), :] = refined[b_idx, v_idx, :]
+        return self.ipt_mlp(nodes), mil_nce_obj, 0
+
+
+class CompactBilinearPooling(nn.Module):
+    """Parameter holder for state_dict compatibility (AttModel_x3.py:444-469); the reference's forward needs the
+    removed torch.rfft and is off by default (`--mcb` False)."""
+
+    def __init__(self, input_dims, output_dim):
+        super().__init__()
+        self.output_dim = output_dim
+
+        def sketch():
+            h = torch.randint(output_dim, size=(input_dims,))
+            s = (2 * torch.randint(2, size=(input_dims,)) - 1).float()
+            m = torch.zeros(input_dims, output_dim)
+            m[torch.arange(input_dims), h] = s
+            return nn.Parameter(m, requires_grad=False)
+
+        self.sketch1 = sketch()
+        self.sketch2 = sketch()
+
+    def forward(self, x1, x2):
+        raise NotImplementedError("compact bilinear pooling relies on torch.rfft, removed from PyTorch; run with mcb=False")
+
+
+def _head(cin, hidden, ncls, p):
+    return nn.Sequential(nn.Linear(cin, hidden), nn.ReLU(), nn.Dropout(p, inplace=True), nn.Linear(hidden, ncls))
+
+
+class AttModel(nn.Module):
+    def __init__(self, glove, hidden_size, hidden_size_mil, num_classes, maxlen_q, maxlen, maxlen_v, num_blocks, num_heads,
+                 dropout_rate, dropout_rate_mcb, num_relations, only_obj):
+        super().__init__()
+        self.only_obj = only_obj
+        self.att_vis_grid = AttModel_vis_grid(glove, hidden_size, maxlen, maxlen_q, num_blocks, num_heads, dropout_rate, maxlen_v, num_classes)
+        self.att_syb = AttModel_syb(glove, hidden_size, maxlen, maxlen_q, num_blocks, num_heads, dropout_rate, num_classes)
+        self.MIL_NCE = MIL_NCE(glove, hidden_size_mil, dropout_rate, num_relations, self.only_obj)
+        self.cls = _head(hidden_size * 2, hidden_size, num_classes, dropout_rate)
+        self.cls_vis = _head(hidden_size, hidden_size, num_classes, dropout_rate)
+        self.cls_syb = _head(hidden_size, hidden_size, num_classes, dropout_rate)
+        self.mcb_out = 16000
+        self.mcb = CompactBilinearPooling(hidden_size, self.mcb_out)
+        self.mcb_dropout = nn.Dropout(dropout_rate_mcb)
+        self.cls_mcb = _head(self.mcb_out, hidden_size, num_classes, dropout_rate)
+        self.label_smoothing = label_smoothing()
+        self._pk = {k: (WeightPack(), WeightPack()) for k in ("cls", "cls_vis", "cls_syb")}
+
+    def _classify(self, name, fea):
+        head = getattr(self, name)
+        p0, p3 = self._pk[name]
+        h = _linear(fea, head[0], p0, relu=True, out_bf16=True)
+        if self.training and head[2].p > 0:
+            h = F.dropout(h, head[2].p, True)
+        return _linear(h, head[3], p3)
+
+    def answer_logits(self, fea_vis_grid, fea_syb):
+        """Classifier heads of AttModel_x3.py:531-541 on the two [B,1,C] decoder outputs."""
+        logits_vis = self._classify("cls_vis", fea_vis_grid).squeeze(1)
+        logits_syb = self._classify("cls_syb", fea_syb).squeeze(1)
+        fea = torch.cat((fea_syb.squeeze(1), fea_vis_grid.squeeze(1)), 1)
+        logits_concat = self._classify("cls", fea)
+        return logits_concat, logits_vis, logits_syb
+
+    def encoder_step(self, vis_fea, vis_mask, q_ipt, q_mask, q_graph, syb_ipt, macro_mask, macro_graph, decMask=True):
+        """The accelerated path alone: both branch models + heads, with `syb_ipt` [B,M,2048] given (what MIL_NCE
+        hands to att_syb at AttModel_x3.py:530)."""
+        fea_vis_grid = self.att_vis_grid(vis_fea, vis_mask, q_ipt, q_graph, q_mask, decMask)
+        fea_syb = self.att_syb(syb_ipt, macro_mask, macro_graph, q_ipt, q_graph, q_mask, decMask)
+        return self.answer_logits(fea_vis_grid, fea_syb)
+
+    def forward(self, vis_fea, vis_mask, q_ipt, q_mask, q_graph, macro_ipt, macro_mask, macro_graph, macro_obj_loc,
+                micro_positive_obj, micro_negative_obj, micro_obj_mask, micro_positive_rel, micro_negative_rel,
+                micro_positive_rel_loc, micro_negative_rel_loc, decMask=True, mcb=False):
+        if mcb == True:  # noqa: E712
+            raise NotImplementedError("mcb=True needs torch.rfft (removed from PyTorch); the reference cannot run it either")
+        new_macro_ipt, mil_nce_obj, mil_nce_rel = self.MIL_NCE(vis_fea, macro_ipt, macro_obj_loc, micro_positive_obj,
+                                                               micro_negative_obj, micro_obj_mask, micro_positive_rel,
+                                                               micro_negative_rel, micro_positive_rel_loc, micro_negative_rel_loc)
+        logits_concat, logits_vis, logits_syb = self.encoder_step(vis_fea, vis_mask, q_ipt, q_mask, q_graph, new_macro_ipt,
+                                                                  macro_mask, macro_graph, decMask)
+        return logits_concat, logits_vis, logits_syb, mil_nce_obj, mil_nce_rel
+
+
+def answer_loss(logits_concat, logits_vis, logits_syb, answer, epsilon=0.1):
+    """The train loop's loss (main_itp_ddp_tar_super_node.py:335-345) as one fused kernel with its gradient."""
+    return Fn.AnswerLossFn.apply(logits_concat, logits_vis, logits_syb, answer, epsilon)

@@ -1,0 +1,422 @@
+"""torch.autograd.Function wrappers that sequence the sm_100a kernels for the forward AND backward of the
+reference's transformer primitives (modules.py).  Every FLOP on these paths runs in libsavqa_b200.so; torch
+only allocates buffers and threads the autograd graph.
+
+Numerics contract: residual stream, LayerNorm, softmax and all reductions in fp32; only the
+MMA operands (activations / weights / probabilities) are bf16, accumulation is fp32.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ops
+from .ops import BF16, F32, pad8
+
+Tensor = torch.Tensor
+
+#: training under CUDA-graph replay must re-stage the bf16 weights inside the graph every step
+FORCE_RESTAGE = False
+#: attention forward engine: 0 = tcgen05/TMEM kernel, 1 = CUDA-core verification kernel
+ATTN_ENGINE = 0
+
+
+class Side:
+    """bf16 copy and row mask of an activation produced by one of our kernels, handed to the next module so that
+    it does not have to re-read the fp32 tensor (valid while the fp32 tensor is not modified in place)."""
+    __slots__ = ("bf16", "on", "version", "data_ptr")
+
+    def __init__(self, t: Tensor, bf16: Optional[Tensor], on: Optional[Tensor]):
+        self.bf16, self.on, self.version, self.data_ptr = bf16, on, t._version, t.data_ptr()
+
+    @staticmethod
+    def of(t: Tensor) -> Optional["Side"]:
+        s = getattr(t, "_savqa_side", None)
+        if s is not None and s.version == t._version and s.data_ptr == t.data_ptr():
+            return s
+        return None
+
+
+class WeightPack:
+    """bf16 staging of one or more nn.Linear layers that read the same input, concatenated along the output
+    dimension: W [sum N, pad8(K)] for forward, W^T [K, pad8(sum N)] for dgrad, fp32 bias [sum N].
+    Re-staged whenever a parameter's storage or version counter changes (optimizer step, load_state_dict)."""
+
+    def __init__(self):
+        self.key = None
+        self.w: Optional[Tensor] = None
+        self.wt: Optional[Tensor] = None
+        self.bias: Optional[Tensor] = None
+
+    def refresh(self, weights: Sequence[Tensor], biases: Sequence[Tensor]) -> "WeightPack":
+        key = tuple((w.data_ptr(), w._version, b.data_ptr(), b._version) for w, b in zip(weights, biases))
+        if key == self.key and not FORCE_RESTAGE:
+            return self
+        K = weights[0].shape[1]
+        ntot = sum(w.shape[0] for w in weights)
+        dev = weights[0].device
+        if self.w is None or self.w.shape != (ntot, pad8(K)) or self.w.device != dev:
+            self.w = torch.empty(ntot, pad8(K), device=dev, dtype=BF16)
+            self.wt = torch.zeros(K, pad8(ntot), device=dev, dtype=BF16)
+            self.bias = torch.empty(ntot, device=dev, dtype=F32)
+        r = 0
+        for w, b in zip(weights, biases):
+            n = w.shape[0]
+            wd = w.detach()
+            ops.cast_bf16(wd, out=self.w[r:r + n], pad_to=pad8(K))
+            ops.cast_transpose_bf16(wd, out=self.wt[:, r:r + n])
+            self.bias[r:r + n].copy_(b.detach())
+            r += n
+        self.key = key
+        return self
+
+
+def _as_bf16_rows(x: Tensor, M: int, K: int) -> Tensor:
+    """[M, pad8(K)] bf16 staging of an activation (cast kernel for fp32, view for bf16)."""
+    if x.dtype == BF16:
+        x2 = x.reshape(M, K)
+        if x2.stride(1) != 1 or x2.stride(0) % 8 != 0 or x2.data_ptr() % 16 != 0:
+            x2 = x2.contiguous()
+        assert K % 8 == 0, "bf16 activations must have a multiple-of-8 width"
+        return x2
+    return ops.cast_bf16(x.reshape(M, K).contiguous() if not x.is_contiguous() else x.reshape(M, K))
+
+
+# ======================================================================================================
+# nn.Linear (+ReLU) (+ broadcast row table)  -- AttModel_x3.py:42-44, 97-101; classifier heads :482-500
+# ======================================================================================================
+class LinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, rowtab, pack: WeightPack, relu: bool, out_bf16: bool, period: int):
+        K = x.shape[-1]
+        N = weight.shape[0]
+        M = x.numel() // K
+        pack.refresh([weight], [bias])
+        xb = _as_bf16_rows(x, M, K)
+        yb = torch.empty(M, N, device=x.device, dtype=BF16) if (out_bf16 or relu) and N % 8 == 0 else None
+        y32 = None if out_bf16 else torch.empty(M, N, device=x.device, dtype=F32)
+        if (out_bf16 or relu) and yb is None:
+            raise ValueError("savqa_b200: bf16 / ReLU outputs need an output width that is a multiple of 8")
+        rt = rowtab.detach()[:period] if rowtab is not None else None
+        ops.gemm(xb, pack.w, M, N, K, bias=pack.bias, rowtab=rt, rowtab_period=period if rt is not None else 0, relu=relu,
+                 out_f32=y32, out_bf16=yb)
+        ctx.pack, ctx.relu, ctx.dims, ctx.period = pack, relu, (M, N, K), period
+        ctx.x_dtype, ctx.x_shape = x.dtype, x.shape
+        ctx.rowtab_shape = None if rowtab is None else rowtab.shape
+        ctx.save_for_backward(xb, yb if relu else None)
+        out = yb if out_bf16 else y32
+        return out.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        xb, act = ctx.saved_tensors
+        pack: WeightPack = ctx.pack
+        M, N, K = ctx.dims
+        dy2 = dy.reshape(M, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        if ctx.relu:
+            dyb = ops.relu_gate_bf16(dy2, act)
+        elif dy2.dtype == BF16:
+            dyb = dy2
+        else:
+            dyb = ops.cast_bf16(dy2)
+        dev = dy.device
+        dW = db = dx = drowtab = None
+        if ctx.needs_input_grad[1]:
+            dW = torch.zeros(N, K, device=dev, dtype=F32)
+            ops.wgrad(dyb, xb, N, K, dW)
+        if ctx.needs_input_grad[2]:
+            db = torch.zeros(N, device=dev, dtype=F32)
+            ops.colsum_bf16(dyb[:, :N], db)
+        if ctx.needs_input_grad[0]:
+            if ctx.x_dtype == BF16:
+                dx = torch.empty(M, K, device=dev, dtype=BF16)
+                ops.gemm(dyb, pack.wt, M, K, N, out_bf16=dx)
+            else:
+                dx = torch.empty(M, K, device=dev, dtype=F32)
+                ops.gemm(dyb, pack.wt, M, K, N, out_f32=dx)
+            dx = dx.reshape(ctx.x_shape)
+        if ctx.rowtab_shape is not None and ctx.needs_input_grad[3]:
+            # d rowtab[t] = sum_b dy[b, t]; tiny fp32 reduction over the batch (positional table, AttModel_x3.py:100)
+            drowtab = torch.zeros(ctx.rowtab_shape, device=dev, dtype=F32)
+            drowtab[:ctx.period] = dy2.float().reshape(-1, ctx.period, N).sum(0)
+        return dx, dW, db, drowtab, None, None, None, None
+
+
+# ======================================================================================================
+# embedding gather  -- nn.Embedding (AttModel_x3.py:96) and modules.embedding (modules.py:32-46)
+# ======================================================================================================
+class EmbeddingFn(Function):
+    @staticmethod
+    def forward(ctx, idx, table, scale: float, skip_row: int):
+        flat = idx.reshape(-1)
+        out, _ = ops.gather_rows(table.detach(), flat, scale=scale, want_f32=True)
+        ctx.save_for_backward(flat)
+        ctx.table_shape, ctx.scale, ctx.skip_row = table.shape, scale, skip_row
+        return out.reshape(*idx.shape, table.shape[1])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (flat,) = ctx.saved_tensors
+        dtable = torch.zeros(ctx.table_shape, device=dy.device, dtype=F32)  # dense, like the reference
+        d2 = dy.reshape(flat.numel(), -1)
+        ops.scatter_add_rows(dtable, flat, d2 if d2.is_contiguous() else d2.contiguous(), scale=ctx.scale, skip_row=ctx.skip_row)
+        return None, dtable, None, None
+
+
+# ======================================================================================================
+# layer_normalization  -- modules.py:49-65
+# ======================================================================================================
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps: float):
+        xc = x if x.is_contiguous() else x.contiguous()
+        y, _, yb, on = ops.layernorm_fwd(xc, None, gamma.detach(), beta.detach(), eps, save_pre=False, want_bf16=True, want_on=True)
+        ctx.save_for_backward(xc, gamma)
+        ctx.eps = eps
+        ctx.mark_non_differentiable(yb, on)
+        return y, yb, on
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, _dyb, _don):
+        x, gamma = ctx.saved_tensors
+        dg = torch.zeros_like(gamma)
+        db = torch.zeros_like(gamma)
+        dx, _ = ops.layernorm_bwd(dy.contiguous(), x, gamma.detach(), ctx.eps, dg, db)
+        return dx, dg, db, None
+
+
+# ======================================================================================================
+# attention modules  -- modules.py:119-207 (renorm 0), :210-311 (renorm 1), :314-403 (renorm 2)
+# ======================================================================================================
+def _same(a: Tensor, b: Tensor) -> bool:
+    return a is b or (a.data_ptr() == b.data_ptr() and a.shape == b.shape and a.stride() == b.stride() and a._version == b._version)
+
+
+class GraphAttentionFn(Function):
+    """y = LN( merge_heads( W' V ) + queries ),  W from softmax(QK^T/sqrt d) re-weighted by the graph (see ops)."""
+
+    @staticmethod
+    def forward(ctx, queries, keys, values, graph, Wq, bq, Wk, bk, Wv, bv, gamma, beta, q_bf16, q_on, k_bf16, k_on, cfg):
+        H, causal, renorm, want_att, packs, eps = cfg["heads"], cfg["causal"], cfg["renorm"], cfg["return_att"], cfg["packs"], cfg["eps"]
+        N, Tq, C = queries.shape
+        Tk = keys.shape[1]
+        d = C // H
+        Mq, Mk = N * Tq, N * Tk
+        same_qk = _same(queries, keys)
+        same_kv = _same(keys, values)
+        xq = queries if queries.is_contiguous() else queries.contiguous()
+
+        # ---- padding masks from the RAW inputs + bf16 staging (modules.py:257, 289) ----
+        if q_bf16 is None or q_on is None:
+            q_on, q_bf16 = ops.row_nonzero(xq.reshape(Mq, C))
+        q_bf16 = q_bf16.reshape(Mq, C)
+        if same_qk:
+            k_on, k_bf16 = q_on, q_bf16
+        elif k_bf16 is None or k_on is None:
+            k_on, k_bf16 = ops.row_nonzero(keys.reshape(Mk, C) if keys.is_contiguous() else keys.contiguous().reshape(Mk, C))
+        k_bf16 = k_bf16.reshape(Mk, C)
+        if same_kv:
+            v_bf16 = k_bf16
+        else:
+            v_bf16 = ops.cast_bf16(values.reshape(Mk, C) if values.is_contiguous() else values.contiguous().reshape(Mk, C))
+
+        # ---- projections: Linear + ReLU, fused along N when the inputs coincide (modules.py:241-243) ----
+        dev = queries.device
+        if same_qk and same_kv:
+            pk = packs["qkv"].refresh([Wq, Wk, Wv], [bq, bk, bv])
+            qkv = torch.empty(Mq, 3 * C, device=dev, dtype=BF16)
+            ops.gemm(q_bf16, pk.w, Mq, 3 * C, C, bias=pk.bias, relu=True, out_bf16=qkv)
+            q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+            mode = 0
+        else:
+            pq = packs["q"].refresh([Wq], [bq])
+            q = torch.empty(Mq, C, device=dev, dtype=BF16)
+            ops.gemm(q_bf16, pq.w, Mq, C, C, bias=pq.bias, relu=True, out_bf16=q)
+            if same_kv:
+                pkv = packs["kv"].refresh([Wk, Wv], [bk, bv])
+                kv = torch.empty(Mk, 2 * C, device=dev, dtype=BF16)
+                ops.gemm(k_bf16, pkv.w, Mk, 2 * C, C, bias=pkv.bias, relu=True, out_bf16=kv)
+                k, v = kv[:, :C], kv[:, C:]
+                mode = 1
+            else:
+                pk_, pv_ = packs["k"].refresh([Wk], [bk]), packs["v"].refresh([Wv], [bv])
+                k = torch.empty(Mk, C, device=dev, dtype=BF16)
+                v = torch.empty(Mk, C, device=dev, dtype=BF16)
+                ops.gemm(k_bf16, pk_.w, Mk, C, C, bias=pk_.bias, relu=True, out_bf16=k)
+                ops.gemm(v_bf16, pv_.w, Mk, C, C, bias=pv_.bias, relu=True, out_bf16=v)
+                mode = 2
+
+        # ---- attention core ----
+        g = None
+        if graph is not None and renorm != 0:
+            g = graph if graph.dtype == F32 else graph.float()
+            g = g if g.is_contiguous() else g.contiguous()
+        engine = ATTN_ENGINE if d in (64, 128) else 1
+        o, att = ops.graph_attention_fwd(q, k, v, g, k_on, q_on, N, H, Tq, Tk, d, causal, renorm if g is not None else 0, want_att, engine)
+
+        # ---- residual (RAW queries) + LayerNorm (modules.py:304-307) ----
+        y, pre, yb, y_on = ops.layernorm_fwd(o.reshape(N, Tq, C), xq, gamma.detach(), beta.detach(), eps, save_pre=True, want_bf16=True,
+                                             want_on=True)
+        ctx.cfg, ctx.mode, ctx.dims = cfg, mode, (N, Tq, Tk, C, H, d)
+        ctx.renorm_eff = renorm if g is not None else 0
+        ctx.save_for_backward(q_bf16, k_bf16, v_bf16, q, k, v, g, q_on, k_on, pre, gamma)
+        outs = (y, yb, y_on) + ((att,) if want_att else ())
+        ctx.mark_non_differentiable(yb, y_on, *((att,) if want_att else ()))
+        return outs
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, *_unused):
+        q_bf16, k_bf16, v_bf16, q, k, v, g, q_on, k_on, pre, gamma = ctx.saved_tensors
+        cfg, mode = ctx.cfg, ctx.mode
+        N, Tq, Tk, C, H, d = ctx.dims
+        Mq, Mk = N * Tq, N * Tk
+        packs = cfg["packs"]
+        dev = dy.device
+        need = ctx.needs_input_grad
+        dgamma = torch.zeros_like(gamma)
+        dbeta = torch.zeros_like(gamma)
+        dpre, _ = ops.layernorm_bwd(dy.contiguous(), pre, gamma.detach(), cfg["eps"], dgamma, dbeta)
+        dpre2 = dpre.reshape(Mq, C)
+
+        # attention core backward -> ReLU-gated dQ, dK, dV in the layout of the fused projection outputs
+        if mode == 0:
+            dqkv = torch.empty(Mq, 3 * C, device=dev, dtype=BF16)
+            dq, dk, dv = dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:]
+        elif mode == 1:
+            dq = torch.empty(Mq, C, device=dev, dtype=BF16)
+            dkv = torch.empty(Mk, 2 * C, device=dev, dtype=BF16)
+            dk, dv = dkv[:, :C], dkv[:, C:]
+        else:
+            dq = torch.empty(Mq, C, device=dev, dtype=BF16)
+            dk = torch.empty(Mk, C, device=dev, dtype=BF16)
+            dv = torch.empty(Mk, C, device=dev, dtype=BF16)
+        ops.graph_attention_bwd(q, k, v, g, k_on, q_on, N, H, Tq, Tk, d, cfg["causal"], ctx.renorm_eff, dpre2, dq, dk, dv)
+
+        def wgrad_bias(dact, xin, n_out):
+            dW = torch.zeros(n_out, C, device=dev, dtype=F32)
+            ops.wgrad(dact, xin, n_out, C, dW)
+            db = torch.zeros(n_out, device=dev, dtype=F32)
+            ops.colsum_bf16(dact, db)
+            return dW, db
+
+        dxq = dxk = dxv = None
+        if mode == 0:
+            dW, db = wgrad_bias(dqkv, q_bf16, 3 * C)
+            dWq, dWk, dWv = dW[:C], dW[C:2 * C], dW[2 * C:]
+            dbq, dbk, dbv = db[:C], db[C:2 * C], db[2 * C:]
+            if need[0] or need[1] or need[2]:
+                dxq = torch.empty(Mq, C, device=dev, dtype=F32)
+                ops.gemm(dqkv, packs["qkv"].wt, Mq, C, 3 * C, res=dpre2, out_f32=dxq)  # + residual branch
+                dxq = dxq.reshape(N, Tq, C)
+        else:
+            dWq, dbq = wgrad_bias(dq, q_bf16, C)
+            if need[0]:
+                dxq = torch.empty(Mq, C, device=dev, dtype=F32)
+                ops.gemm(dq, packs["q"].wt, Mq, C, C, res=dpre2, out_f32=dxq)
+                dxq = dxq.reshape(N, Tq, C)
+            if mode == 1:
+                dW, db = wgrad_bias(dkv, k_bf16, 2 * C)
+                dWk, dWv, dbk, dbv = dW[:C], dW[C:], db[:C], db[C:]
+                if need[1] or need[2]:
+                    dxk = torch.empty(Mk, C, device=dev, dtype=F32)
+                    ops.gemm(dkv, packs["kv"].wt, Mk, C, 2 * C, out_f32=dxk)
+                    dxk = dxk.reshape(N, Tk, C)
+            else:
+                dWk, dbk = wgrad_bias(dk, k_bf16, C)
+                dWv, dbv = wgrad_bias(dv, v_bf16, C)
+                if need[1]:
+                    dxk = torch.empty(Mk, C, device=dev, dtype=F32)
+                    ops.gemm(dk, packs["k"].wt, Mk, C, C, out_f32=dxk)
+                    dxk = dxk.reshape(N, Tk, C)
+                if need[2]:
+                    dxv = torch.empty(Mk, C, device=dev, dtype=F32)
+                    ops.gemm(dv, packs["v"].wt, Mk, C, C, out_f32=dxv)
+                    dxv = dxv.reshape(N, Tk, C)
+        # when queries/keys/values are one tensor autograd sums the three slots: hand the total to the first
+        return (dxq, dxk, dxv, None, dWq, dbq, dWk, dbk, dWv, dbv, dgamma, dbeta, None, None, None, None, None)
+
+
+# ======================================================================================================
+# feedforward  -- modules.py:405-447
+# ======================================================================================================
+class FeedForwardFn(Function):
+    """y = LN( relu(x W1^T + b1) W2^T + b2 + x )"""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2, gamma, beta, x_bf16, cfg):
+        packs, eps = cfg["packs"], cfg["eps"]
+        C = x.shape[-1]
+        Hd = W1.shape[0]
+        M = x.numel() // C
+        xc = x if x.is_contiguous() else x.contiguous()
+        xb = x_bf16.reshape(M, C) if x_bf16 is not None else ops.cast_bf16(xc.reshape(M, C))
+        p1 = packs["w1"].refresh([W1], [b1])
+        p2 = packs["w2"].refresh([W2], [b2])
+        dev = x.device
+        h = torch.empty(M, Hd, device=dev, dtype=BF16)
+        ops.gemm(xb, p1.w, M, Hd, C, bias=p1.bias, relu=True, out_bf16=h)
+        z = torch.empty(M, C, device=dev, dtype=F32)
+        ops.gemm(h, p2.w, M, C, Hd, bias=p2.bias, res=xc.reshape(M, C), out_f32=z)
+        y, _, yb, y_on = ops.layernorm_fwd(z.reshape(x.shape), None, gamma.detach(), beta.detach(), eps, save_pre=False, want_bf16=True,
+                                           want_on=True)
+        ctx.cfg, ctx.dims = cfg, (M, C, Hd)
+        ctx.save_for_backward(xb, h, z, gamma)
+        ctx.mark_non_differentiable(yb, y_on)
+        return y, yb, y_on
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, *_unused):
+        xb, h, z, gamma = ctx.saved_tensors
+        cfg = ctx.cfg
+        M, C, Hd = ctx.dims
+        packs = cfg["packs"]
+        dev = dy.device
+        dgamma = torch.zeros_like(gamma)
+        dbeta = torch.zeros_like(gamma)
+        dz, dzb = ops.layernorm_bwd(dy.contiguous().reshape(M, C), z, gamma.detach(), cfg["eps"], dgamma, dbeta, want_bf16=True)
+        # conv2: z = h W2^T + b2 + x
+        dW2 = torch.zeros(C, Hd, device=dev, dtype=F32)
+        ops.wgrad(dzb, h, C, Hd, dW2)
+        db2 = torch.zeros(C, device=dev, dtype=F32)
+        ops.colsum_bf16(dzb, db2)
+        dh = torch.empty(M, Hd, device=dev, dtype=BF16)
+        ops.gemm(dzb, packs["w2"].wt, M, Hd, C, gate=h, out_bf16=dh)  # ReLU backward fused in the epilogue
+        # conv1: h = relu(x W1^T + b1)
+        dW1 = torch.zeros(Hd, C, device=dev, dtype=F32)
+        ops.wgrad(dh, xb, Hd, C, dW1)
+        db1 = torch.zeros(Hd, device=dev, dtype=F32)
+        ops.colsum_bf16(dh, db1)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, C, device=dev, dtype=F32)
+            ops.gemm(dh, packs["w1"].wt, M, C, Hd, res=dz, out_f32=dx)  # + residual branch
+            dx = dx.reshape(dy.shape)
+        return dx, dW1, db1, dW2, db2, dgamma, dbeta, None, None
+
+
+# ======================================================================================================
+# three-head label-smoothed loss  -- main_itp_ddp_tar_super_node.py:335-345
+# ======================================================================================================
+class AnswerLossFn(Function):
+    @staticmethod
+    def forward(ctx, logits_concat, logits_vis, logits_syb, answer, epsilon: float):
+        lc, lv, ls = (t.contiguous() for t in (logits_concat, logits_vis, logits_syb))
+        loss, grads = ops.answer_loss(lc, lv, ls, answer, epsilon, 1.0, want_grads=True)
+        ctx.save_for_backward(*grads)
+        return loss.reshape(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dloss):
+        dc, dv, ds = ctx.saved_tensors
+        return dc * dloss, dv * dloss, ds * dloss, None, None

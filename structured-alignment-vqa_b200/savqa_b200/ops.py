@@ -1,0 +1,345 @@
+"""Typed Python wrappers over the C ABI (include/savqa_b200.h).  PyTorch is only the allocator / stream owner here:
+every function validates shapes and dtypes, hands raw device pointers to libsavqa_b200.so and raises on error.
+No function in this file computes anything with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AttnArgs, GemmEpilogue, call, ptr
+
+Tensor = torch.Tensor
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _rows2d(t: Tensor) -> Tuple[int, int, int]:
+    """(rows, cols, ld) of a tensor viewed as a row-major matrix over its last dim."""
+    assert t.dim() >= 1 and t.stride(-1) == 1, "last dimension must be contiguous"
+    if t.dim() == 1:
+        return 1, t.shape[0], t.shape[0]
+    if t.dim() == 2:
+        return t.shape[0], t.shape[1], t.stride(0)
+    assert t.is_contiguous(), "tensors of rank > 2 must be contiguous"
+    return t.numel() // t.shape[-1], t.shape[-1], t.shape[-1]
+
+
+def _check(t: Optional[Tensor], dtype, name: str) -> None:
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f"savqa_b200: `{name}` must be a CUDA tensor (this path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"savqa_b200: `{name}` must be {dtype}, got {t.dtype}")
+
+
+# ------------------------------------------------------------------------------------------------------
+def build_masks(first_mask: Tensor, q_mask: Tensor, q_graph: Tensor, first_graph: Optional[Tensor], dec_mask_on: bool):
+    """AttModel_x3.py:103-122 / :229-247 -> (graph_diag [B,T,T], graph [B,T,T], dec_mask [B,1,T]) fp32, bit exact."""
+    is_float = first_mask.dtype == F32
+    want = F32 if is_float else torch.int32
+    ins = []
+    for nm, t in (("first_mask", first_mask), ("q_mask", q_mask), ("q_graph", q_graph), ("first_graph", first_graph)):
+        if t is not None:
+            if not t.is_cuda:
+                raise RuntimeError(f"savqa_b200: `{nm}` must be a CUDA tensor (this path has no CPU fallback)")
+            if t.dtype != want:
+                t = t.to(want)
+            t = t.contiguous()
+        ins.append(t)
+    fm, qm, qg, fg = ins
+    B, V, Q = fm.shape[0], fm.shape[1], qm.shape[1]
+    assert fm.shape == (B, V, V) and qm.shape == (B, Q, Q) and qg.shape == (B, Q, Q), "mask shapes"
+    assert fg is None or fg.shape == (B, V, V)
+    T = V + Q
+    graph_diag = torch.empty(B, T, T, device=fm.device, dtype=F32)
+    graph = torch.empty(B, T, T, device=fm.device, dtype=F32)
+    dec_mask = torch.empty(B, 1, T, device=fm.device, dtype=F32)
+    call("savqa_build_masks", ptr(fm), ptr(qm), ptr(qg), ptr(fg), int(is_float), B, V, Q, int(bool(dec_mask_on)),
+         ptr(graph_diag), ptr(graph), ptr(dec_mask))
+    return graph_diag, graph, dec_mask
+
+
+def gather_rows(table: Tensor, idx: Tensor, scale: float = 1.0, want_f32: bool = True, want_bf16: bool = False):
+    """out[r] = table[idx[r]] * scale.  Returns (fp32 [n, width] | None, bf16 [n, pad8(width)] | None)."""
+    _check(table, F32, "table")
+    _check(idx, torch.int64, "idx")
+    assert table.dim() == 2 and table.is_contiguous()
+    idx = idx.contiguous()
+    n, width = idx.numel(), table.shape[1]
+    out32 = torch.empty(n, width, device=table.device, dtype=F32) if want_f32 else None
+    ldb = pad8(width)
+    out16 = torch.empty(n, ldb, device=table.device, dtype=BF16) if want_bf16 else None
+    call("savqa_gather_rows", ptr(table), table.shape[0], width, ptr(idx), n, float(scale), ptr(out32), width, ptr(out16), ldb, ldb)
+    return out32, out16
+
+
+def scatter_add_rows(dtable: Tensor, idx: Tensor, dout: Tensor, scale: float = 1.0, skip_row: int = -1) -> None:
+    _check(dtable, F32, "dtable")
+    _check(idx, torch.int64, "idx")
+    _check(dout, F32, "dout")
+    idx = idx.contiguous()
+    rows, width, ld = _rows2d(dout)
+    assert rows == idx.numel() and width == dtable.shape[1] and dtable.is_contiguous()
+    call("savqa_scatter_add_rows", ptr(dtable), dtable.shape[0], width, ptr(idx), rows, ptr(dout), ld, float(scale), int(skip_row))
+
+
+def cast_bf16(src: Tensor, out: Optional[Tensor] = None, pad_to: Optional[int] = None) -> Tensor:
+    """fp32 [rows, cols] -> bf16 [rows, pad8(cols)] (pad columns zero)."""
+    _check(src, F32, "src")
+    rows, cols, ld = _rows2d(src)
+    if out is None:
+        pad_to = pad8(cols) if pad_to is None else pad_to
+        out = torch.empty(rows, pad_to, device=src.device, dtype=BF16)
+    else:
+        _check(out, BF16, "out")
+        pad_to = cols if pad_to is None else pad_to
+    orows, ocols, old = _rows2d(out)
+    assert orows == rows and ocols >= pad_to
+    call("savqa_cast_bf16", ptr(src), ld, ptr(out), old, rows, cols, pad_to)
+    return out
+
+
+def cast_transpose_bf16(src: Tensor, out: Tensor, pad_to: Optional[int] = None) -> Tensor:
+    """out[c, r] = src[r, c];  out is a (possibly strided) bf16 matrix [cols, >= rows]."""
+    _check(src, F32, "src")
+    _check(out, BF16, "out")
+    rows, cols, ld = _rows2d(src)
+    orows, ocols, old = _rows2d(out)
+    pad_to = rows if pad_to is None else pad_to
+    assert orows == cols and ocols >= pad_to >= rows
+    call("savqa_cast_transpose_bf16", ptr(src), ld, ptr(out), old, rows, cols, pad_to)
+    return out
+
+
+def row_nonzero(x: Tensor, want_bf16: bool = True):
+    """on[r] = (sum_c x[r,c] != 0) -- the key/query masks of modules.py:257,289 -- plus a bf16 copy of x."""
+    _check(x, F32, "x")
+    rows, cols, ld = _rows2d(x)
+    on = torch.empty(rows, device=x.device, dtype=F32)
+    xb = torch.empty(rows, pad8(cols), device=x.device, dtype=BF16) if want_bf16 else None
+    if xb is not None and pad8(cols) != cols:
+        xb.zero_()
+    call("savqa_row_nonzero", ptr(x), ld, rows, cols, ptr(on), ptr(xb), pad8(cols))
+    return on, xb
+
+
+def relu_gate_bf16(dy: Tensor, act: Tensor) -> Tensor:
+    """bf16 (act > 0 ? dy : 0); dy fp32 or bf16, act bf16 -- the staged A operand of dgrad / wgrad behind a ReLU."""
+    _check(act, BF16, "act")
+    if dy.dtype not in (F32, BF16) or not dy.is_cuda:
+        raise TypeError("savqa_b200: `dy` must be a CUDA fp32 or bf16 tensor")
+    rows, cols, ld = _rows2d(dy)
+    arows, acols, ald = _rows2d(act)
+    assert arows == rows and acols >= cols
+    out = torch.empty(rows, pad8(cols), device=dy.device, dtype=BF16)
+    if pad8(cols) != cols:
+        out.zero_()
+    call("savqa_relu_gate_bf16", ptr(dy), int(dy.dtype == F32), ld, ptr(act), ald, ptr(out), out.stride(0), rows, cols)
+    return out
+
+
+def colsum_bf16(x: Tensor, out: Tensor) -> None:
+    """out[c] += sum_r x[r, c]"""
+    _check(x, BF16, "x")
+    _check(out, F32, "out")
+    rows, cols, ld = _rows2d(x)
+    assert out.numel() == cols and out.is_contiguous()
+    call("savqa_colsum_bf16", ptr(x), ld, rows, cols, ptr(out))
+
+
+def layernorm_fwd(x: Tensor, res: Optional[Tensor], gamma: Tensor, beta: Tensor, eps: float, save_pre: bool, want_bf16: bool,
+                  want_on: bool):
+    """y = LN(x + res) (modules.py:62-65).  Returns (y, pre | None, y_bf16 | None, on | None)."""
+    for nm, t in (("x", x), ("res", res), ("gamma", gamma), ("beta", beta)):
+        _check(t, F32, nm)
+    assert x.is_contiguous() and (res is None or (res.is_contiguous() and res.shape == x.shape))
+    C_ = x.shape[-1]
+    rows = x.numel() // C_
+    y = torch.empty_like(x)
+    pre = torch.empty_like(x) if save_pre else None
+    yb = torch.empty(x.shape, device=x.device, dtype=BF16) if want_bf16 else None
+    on = torch.empty(rows, device=x.device, dtype=F32) if want_on else None
+    call("savqa_residual_layernorm_fwd", ptr(x), ptr(res), ptr(gamma), ptr(beta), float(eps), rows, C_, ptr(pre), ptr(y), ptr(yb), ptr(on))
+    return y, pre, yb, on
+
+
+def layernorm_bwd(dy: Tensor, pre: Tensor, gamma: Tensor, eps: float, dgamma: Optional[Tensor], dbeta: Optional[Tensor],
+                  dres_in: Optional[Tensor] = None, want_bf16: bool = False):
+    """Returns (dx fp32, dx_bf16 | None); dgamma / dbeta are accumulated in place."""
+    for nm, t in (("dy", dy), ("pre", pre), ("gamma", gamma), ("dgamma", dgamma), ("dbeta", dbeta), ("dres_in", dres_in)):
+        _check(t, F32, nm)
+    assert dy.is_contiguous() and pre.is_contiguous() and dy.shape == pre.shape
+    C_ = pre.shape[-1]
+    rows = pre.numel() // C_
+    dx = torch.empty_like(pre)
+    dxb = torch.empty(pre.shape, device=pre.device, dtype=BF16) if want_bf16 else None
+    call("savqa_layernorm_bwd", ptr(dy), ptr(pre), ptr(gamma), float(eps), rows, C_, ptr(dres_in), ptr(dx), ptr(dxb), ptr(dgamma), ptr(dbeta))
+    return dx, dxb
+
+
+# ------------------------------------------------------------------------------------------------------
+_DEBUG_GEMM = os.environ.get("SAVQA_DEBUG_GEMM", "")  # "torch": bring-up aid ONLY (never set in tests/bench)
+
+
+def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False, bias: Optional[Tensor] = None,
+         res: Optional[Tensor] = None, rowtab: Optional[Tensor] = None, rowtab_period: int = 0, gate: Optional[Tensor] = None,
+         relu: bool = False, alpha: float = 1.0, out_f32: Optional[Tensor] = None, out_bf16: Optional[Tensor] = None,
+         accumulate: int = 0, split_k: int = 1) -> None:
+    """acc[m,n] = sum_k A[m,k] B[n,k] with the fused epilogue of savqa_gemm_bf16 (tcgen05 / TMEM / TMA kernel).
+
+    K-major operands are [rows, >=K] matrices; MN-major operands ([K, >=rows]) are used by wgrad."""
+    _check(a, BF16, "A")
+    _check(b, BF16, "B")
+    for nm, t in (("bias", bias), ("res", res), ("rowtab", rowtab), ("out_f32", out_f32)):
+        _check(t, F32, nm)
+    _check(gate, BF16, "gate")
+    _check(out_bf16, BF16, "out_bf16")
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    if a_mn:
+        assert a.shape[0] >= K and a.shape[1] >= M, (a.shape, M, K)
+    else:
+        assert a.shape[0] >= M and a.shape[1] >= K, (a.shape, M, K)
+    if b_mn:
+        assert b.shape[0] >= K and b.shape[1] >= N, (b.shape, N, K)
+    else:
+        assert b.shape[0] >= N and b.shape[1] >= K, (b.shape, N, K)
+    e = GemmEpilogue()
+    e.alpha, e.relu, e.accumulate, e.rowtab_period = float(alpha), int(relu), int(accumulate), int(rowtab_period)
+    e.bias = ptr(bias)
+    if bias is not None:
+        assert bias.numel() >= N and bias.is_contiguous()
+    if res is not None:
+        assert res.dim() == 2 and res.stride(1) == 1 and res.shape[0] >= M and res.shape[1] >= N
+        e.res, e.ld_res = ptr(res), res.stride(0)
+    if rowtab is not None:
+        assert rowtab.dim() == 2 and rowtab.stride(1) == 1 and rowtab.shape[0] >= rowtab_period > 0 and rowtab.shape[1] >= N
+        e.rowtab, e.ld_rowtab = ptr(rowtab), rowtab.stride(0)
+    if gate is not None:
+        assert gate.dim() == 2 and gate.stride(1) == 1 and gate.shape[0] >= M and gate.shape[1] >= N
+        e.gate_bf16, e.ld_gate = ptr(gate), gate.stride(0)
+    if out_f32 is not None:
+        assert out_f32.dim() == 2 and out_f32.stride(1) == 1 and out_f32.shape[0] >= M and out_f32.shape[1] >= N
+        e.out_f32, e.ld_out_f32 = ptr(out_f32), out_f32.stride(0)
+    if out_bf16 is not None:
+        assert out_bf16.dim() == 2 and out_bf16.stride(1) == 1 and out_bf16.shape[0] >= M and out_bf16.shape[1] >= N
+        e.out_bf16, e.ld_out_bf16 = ptr(out_bf16), out_bf16.stride(0)
+    if _DEBUG_GEMM == "torch":
+        _gemm_debug_torch(a, b, M, N, K, a_mn, b_mn, bias, res, rowtab, rowtab_period, gate, relu, alpha, out_f32, out_bf16, accumulate)
+        return
+    call("savqa_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), M, N, K, C.byref(e), int(split_k))
+
+
+def _gemm_debug_torch(a, b, M, N, K, a_mn, b_mn, bias, res, rowtab, period, gate, relu, alpha, out_f32, out_bf16, accumulate):
+    """Bring-up aid for the GPU box (SAVQA_DEBUG_GEMM=torch): same contract through torch.matmul, to bisect a kernel bug."""
+    A = a[:K, :M].float().t() if a_mn else a[:M, :K].float()
+    Bm = b[:K, :N].float() if b_mn else b[:N, :K].float().t()
+    v = alpha * (A @ Bm)
+    if bias is not None:
+        v = v + bias[:N]
+    if res is not None:
+        v = v + res[:M, :N]
+    if rowtab is not None:
+        v = v + rowtab[:period, :N].repeat((M + period - 1) // period, 1)[:M]
+    if relu:
+        v = torch.relu(v)
+    if gate is not None:
+        v = v * (gate[:M, :N].float() > 0)
+    if out_f32 is not None:
+        if accumulate:
+            out_f32[:M, :N] += v
+        else:
+            out_f32[:M, :N] = v
+    if out_bf16 is not None:
+        out_bf16[:M, :N] = v.to(BF16)
+
+
+def split_k_for(tiles: int, k_blocks: int) -> int:
+    """Enough K-splits to put ~2 work units on every SM, at least 4 k-blocks each."""
+    if tiles >= 2 * 148:
+        return 1
+    want = (2 * 148 + tiles - 1) // tiles
+    return max(1, min(want, k_blocks // 4 if k_blocks >= 8 else 1))
+
+
+def wgrad(dy: Tensor, x: Tensor, n_out: int, k_in: int, out: Tensor) -> None:
+    """out[n_out, k_in] += dy[M, n_out]^T x[M, k_in]  (both operands read MN-major straight from the activations)."""
+    M = dy.shape[0]
+    assert x.shape[0] == M
+    tiles = ((n_out + 127) // 128) * ((k_in + 127) // 128)
+    gemm(dy, x, n_out, k_in, M, a_mn=True, b_mn=True, out_f32=out, accumulate=2, split_k=split_k_for(tiles, (M + 63) // 64))
+
+
+# ------------------------------------------------------------------------------------------------------
+def graph_attention_fwd(q: Tensor, k: Tensor, v: Tensor, graph: Optional[Tensor], key_on: Tensor, query_on: Tensor, N: int, H: int,
+                        Tq: int, Tk: int, d: int, causal: bool, renorm: int, want_att: bool, engine: int):
+    """Attention core of modules.py:246-301.  q/k/v: bf16 2-D views [N*T, >= H*d].  Returns (out fp32 [N*Tq, H*d], att | None)."""
+    for nm, t in (("q", q), ("k", k), ("v", v)):
+        _check(t, BF16, nm)
+        assert t.dim() == 2 and t.stride(1) == 1
+    _check(graph, F32, "graph")
+    a = AttnArgs()
+    a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0)
+    if graph is not None:
+        assert graph.dim() == 3 and graph.shape[0] == N and graph.shape[2] == Tk and graph.shape[1] in (Tq, 1) and graph.is_contiguous()
+        a.graph, a.graph_n_stride = ptr(graph), graph.shape[1] * Tk
+        a.graph_q_stride = Tk if graph.shape[1] == Tq else 0
+    a.key_on, a.query_on = ptr(key_on), ptr(query_on)
+    a.N, a.H, a.Tq, a.Tk, a.d = N, H, Tq, Tk, d
+    a.causal, a.renorm, a.engine = int(causal), int(renorm), int(engine)
+    out = torch.empty(N * Tq, H * d, device=q.device, dtype=F32)
+    att = torch.empty(H * N, Tq, Tk, device=q.device, dtype=F32) if want_att else None
+    a.out, a.ldo, a.att = ptr(out), H * d, ptr(att)
+    call("savqa_graph_attn_fwd", C.byref(a))
+    return out, att
+
+
+def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout: Tensor, dq: Tensor, dk: Tensor,
+                        dv: Tensor) -> None:
+    """Gradient of the attention core; dq/dk/dv are bf16 2-D views and come back ReLU-gated by q/k/v > 0."""
+    a = AttnArgs()
+    a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0)
+    if graph is not None:
+        a.graph, a.graph_n_stride = ptr(graph), graph.shape[1] * Tk
+        a.graph_q_stride = Tk if graph.shape[1] == Tq else 0
+    a.key_on, a.query_on = ptr(key_on), ptr(query_on)
+    a.N, a.H, a.Tq, a.Tk, a.d = N, H, Tq, Tk, d
+    a.causal, a.renorm, a.engine = int(causal), int(renorm), 1
+    _check(dout, F32, "dout")
+    assert dout.dim() == 2 and dout.stride(1) == 1
+    a.dout, a.ld_dout = ptr(dout), dout.stride(0)
+    a.dq, a.ld_dq, a.dk, a.ld_dk, a.dv, a.ld_dv = ptr(dq), dq.stride(0), ptr(dk), dk.stride(0), ptr(dv), dv.stride(0)
+    scratch = torch.empty(2, H * N, Tq, Tk, device=q.device, dtype=F32)
+    a.scratch = ptr(scratch)
+    call("savqa_graph_attn_bwd", C.byref(a))
+
+
+def answer_loss(lc: Tensor, lv: Tensor, ls: Tensor, answer: Tensor, epsilon: float, grad_scale: float, want_grads: bool):
+    """main_itp_ddp_tar_super_node.py:335-345.  Returns (loss [1], (d_concat, d_vis, d_syb) | None)."""
+    for nm, t in (("logits_concat", lc), ("logits_vis", lv), ("logits_syb", ls)):
+        _check(t, F32, nm)
+        assert t.is_contiguous() and t.shape == lc.shape
+    _check(answer, torch.int64, "answer")
+    B, ncls = lc.shape
+    loss = torch.empty(1, device=lc.device, dtype=F32)
+    grads = tuple(torch.empty_like(lc) for _ in range(3)) if want_grads else (None, None, None)
+    call("savqa_answer_loss", ptr(lc), ptr(lv), ptr(ls), ptr(answer.contiguous()), B, ncls, float(epsilon), float(grad_scale), ptr(loss),
+         ptr(grads[0]), ptr(grads[1]), ptr(grads[2]))
+    return loss, (grads if want_grads else None)
+
+
+def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr: float, beta1: float, beta2: float, eps: float,
+              step: int) -> None:
+    for nm, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        _check(t, F32, nm)
+        assert t.is_contiguous() and t.numel() == param.numel()
+    call("savqa_adam_step", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2, eps, int(step))

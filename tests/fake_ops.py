@@ -1,0 +1,238 @@
+"""CPU stand-ins for savqa_b200.ops, used ONLY by the `not gpu` host-logic tests (tests/test_host_logic.py).
+
+The product never imports this file.  Each function restates, with torch CPU ops, the contract of the matching
+C-ABI kernel (including the explicit backward formulas the CUDA kernels implement -- NOT autograd), so that the
+autograd wiring in savqa_b200/functional.py and the module composition can be checked against the oracle on a box
+without a GPU.  The kernels themselves are checked on the B200 by the `gpu` tests.
+"""
+from __future__ import annotations
+
+import torch
+
+BF16, F32 = torch.bfloat16, torch.float32
+MASK_FILL = -4294967296.0
+
+
+def pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def build_masks(first_mask, q_mask, q_graph, first_graph, dec_mask_on):
+    B, V, Q = first_mask.shape[0], first_mask.shape[1], q_mask.shape[1]
+    T = V + Q
+    gd = torch.zeros(B, T, T)
+    gd[:, V:, V:] = q_mask.float()
+    g = torch.ones(B, T, T)
+    if first_graph is not None:
+        g[:, :V, :V] = first_graph.float()
+    g[:, V:, V:] = q_graph.float()
+    dm = torch.zeros(B, 1, T)
+    if dec_mask_on:
+        dm[:, 0, :V] = (first_mask.float().sum(-1) != 0).float()
+        dm[:, 0, V:] = (q_mask.float().sum(-1) != 0).float()
+    return gd, g, dm
+
+
+def gather_rows(table, idx, scale=1.0, want_f32=True, want_bf16=False):
+    out = table[idx.reshape(-1)]
+    if scale != 1.0:
+        out = out * scale
+    o16 = None
+    if want_bf16:
+        o16 = torch.zeros(out.shape[0], pad8(out.shape[1]), dtype=BF16)
+        o16[:, :out.shape[1]] = out.to(BF16)
+    return (out if want_f32 else None), o16
+
+
+def scatter_add_rows(dtable, idx, dout, scale=1.0, skip_row=-1):
+    idx = idx.reshape(-1)
+    keep = idx != skip_row
+    dtable.index_add_(0, idx[keep], dout.reshape(idx.numel(), -1)[keep] * scale)
+
+
+def cast_bf16(src, out=None, pad_to=None):
+    rows, cols = src.reshape(-1, src.shape[-1]).shape
+    if out is None:
+        pad_to = pad8(cols) if pad_to is None else pad_to
+        out = torch.zeros(rows, pad_to, dtype=BF16)
+    out[:, :cols] = src.reshape(rows, cols).to(BF16)
+    if pad_to is not None and pad_to > cols:
+        out[:, cols:pad_to] = 0
+    return out
+
+
+def cast_transpose_bf16(src, out, pad_to=None):
+    rows, cols = src.shape
+    out[:, :rows] = src.t().to(BF16)
+    return out
+
+
+def row_nonzero(x, want_bf16=True):
+    x2 = x.reshape(-1, x.shape[-1])
+    on = (x2.sum(-1) != 0).float()
+    xb = None
+    if want_bf16:
+        xb = torch.zeros(x2.shape[0], pad8(x2.shape[1]), dtype=BF16)
+        xb[:, :x2.shape[1]] = x2.to(BF16)
+    return on, xb
+
+
+def relu_gate_bf16(dy, act):
+    rows, cols = dy.shape
+    out = torch.zeros(rows, pad8(cols), dtype=BF16)
+    out[:, :cols] = torch.where(act[:, :cols].float() > 0, dy.float(), torch.zeros(())).to(BF16)
+    return out
+
+
+def colsum_bf16(x, out):
+    out += x.float().sum(0)[: out.numel()]
+
+
+def layernorm_fwd(x, res, gamma, beta, eps, save_pre, want_bf16, want_on):
+    pre = x if res is None else x + res
+    C = pre.shape[-1]
+    mean = pre.mean(-1, keepdim=True)
+    c = pre - mean
+    sigma = torch.sqrt((c * c).sum(-1, keepdim=True) / (C - 1))
+    y = gamma * c / (sigma + eps) + beta
+    return y, (pre.clone() if save_pre else None), (y.to(BF16) if want_bf16 else None), ((y.reshape(-1, C).sum(-1) != 0).float() if want_on else None)
+
+
+def layernorm_bwd(dy, pre, gamma, eps, dgamma, dbeta, dres_in=None, want_bf16=False):
+    # the explicit formula of csrc/layernorm.cu
+    C = pre.shape[-1]
+    mean = pre.mean(-1, keepdim=True)
+    c = pre - mean
+    sigma = torch.sqrt((c * c).sum(-1, keepdim=True) / (C - 1))
+    s = sigma + eps
+    g = dy * gamma
+    mg = g.mean(-1, keepdim=True)
+    dot = (g * c).sum(-1, keepdim=True)
+    k2 = torch.where(sigma > 0, dot / ((C - 1) * sigma * s * s), torch.zeros(()))
+    dx = (g - mg) / s - c * k2
+    if dres_in is not None:
+        dx = dx + dres_in
+    if dgamma is not None:
+        dgamma += (dy * c / s).reshape(-1, C).sum(0)
+    if dbeta is not None:
+        dbeta += dy.reshape(-1, C).sum(0)
+    return dx, (dx.to(BF16) if want_bf16 else None)
+
+
+def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, bias=None, res=None, rowtab=None, rowtab_period=0, gate=None, relu=False,
+         alpha=1.0, out_f32=None, out_bf16=None, accumulate=0, split_k=1):
+    assert a.dtype == BF16 and b.dtype == BF16
+    A = a[:K, :M].float().t() if a_mn else a[:M, :K].float()
+    Bm = b[:K, :N].float() if b_mn else b[:N, :K].float().t()
+    v = alpha * (A @ Bm)
+    if bias is not None:
+        v = v + bias[:N]
+    if res is not None:
+        v = v + res[:M, :N]
+    if rowtab is not None:
+        v = v + rowtab[:rowtab_period, :N].repeat((M + rowtab_period - 1) // rowtab_period, 1)[:M]
+    if relu:
+        v = torch.relu(v)
+    if gate is not None:
+        v = v * (gate[:M, :N].float() > 0)
+    if out_f32 is not None:
+        if accumulate:
+            out_f32[:M, :N] += v
+        else:
+            out_f32[:M, :N] = v
+    if out_bf16 is not None:
+        out_bf16[:M, :N] = v.to(BF16)
+
+
+def split_k_for(tiles, k_blocks):
+    return 1
+
+
+def wgrad(dy, x, n_out, k_in, out):
+    gemm(dy, x, n_out, k_in, dy.shape[0], a_mn=True, b_mn=True, out_f32=out, accumulate=2)
+
+
+def _heads(t, N, T, H, d):
+    return t[:, : H * d].float().reshape(N, T, H, d).permute(2, 0, 1, 3)  # [H,N,T,d]
+
+
+def _weights(q, k, graph, key_on, N, H, Tq, Tk, d, causal, renorm):
+    Q, K = _heads(q, N, Tq, H, d), _heads(k, N, Tk, H, d)
+    S = torch.matmul(Q, K.transpose(-1, -2)) / (d ** 0.5)  # [H,N,Tq,Tk]
+    fixed = (key_on.reshape(1, N, 1, Tk) == 0).expand_as(S).clone()
+    if causal:
+        fixed |= ~torch.ones(Tq, Tk, dtype=torch.bool).tril().reshape(1, 1, Tq, Tk)
+    S = torch.where(fixed, torch.full((), MASK_FILL), S)
+    P = torch.softmax(S, -1)
+    if renorm == 0:
+        return P, P, fixed, None, None
+    G = graph.reshape(1, N, graph.shape[1], Tk).expand(H, N, Tq, Tk)
+    A = G * P
+    r = A.abs().sum(-1, keepdim=True)
+    if renorm == 1:
+        W = A / r.clamp_min(1e-12)
+    else:
+        W = A / (A.sum(-1, keepdim=True) + 1e-7)
+    return P, W, fixed, r, G
+
+
+def graph_attention_fwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, want_att, engine):
+    P, W, _, _, _ = _weights(q, k, graph, key_on, N, H, Tq, Tk, d, causal, renorm)
+    V = _heads(v, N, Tk, H, d)
+    Wq = W * query_on.reshape(1, N, Tq, 1)
+    O = torch.matmul(Wq, V)  # [H,N,Tq,d]
+    out = O.permute(1, 2, 0, 3).reshape(N * Tq, H * d).contiguous()
+    att = W.reshape(H * N, Tq, Tk).contiguous() if want_att else None
+    return out, att
+
+
+def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout, dq, dk, dv):
+    # the explicit formulas of csrc/attn_simt.cu (attn_bwd_rows_kernel / attn_bwd_keys_kernel)
+    P, W, fixed, r, G = _weights(q, k, graph, key_on, N, H, Tq, Tk, d, causal, renorm)
+    Q, K, V = _heads(q, N, Tq, H, d), _heads(k, N, Tk, H, d), _heads(v, N, Tk, H, d)
+    dO = dout[:, : H * d].reshape(N, Tq, H, d).permute(2, 0, 1, 3)
+    qon = query_on.reshape(1, N, Tq, 1)
+    dW = torch.matmul(dO, V.transpose(-1, -2)) * qon
+    t = (W * dW).sum(-1, keepdim=True)
+    if renorm == 1:
+        clamped = r < 1e-12
+        dS = torch.where(clamped, W * dW - P * t, W * (dW - t))
+    elif renorm == 2:
+        dS = W * (dW - t) - P * t * (1 - W.sum(-1, keepdim=True))
+    else:
+        dS = W * (dW - t)
+    dS = torch.where(fixed, torch.zeros(()), dS) / (d ** 0.5)
+    dQ = torch.matmul(dS, K) * (Q > 0)
+    dK = torch.matmul(dS.transpose(-1, -2), Q) * (K > 0)
+    dV = torch.matmul((W * qon).transpose(-1, -2), dO) * (V > 0)
+    dq[:, : H * d] = dQ.permute(1, 2, 0, 3).reshape(N * Tq, H * d).to(BF16)
+    dk[:, : H * d] = dK.permute(1, 2, 0, 3).reshape(N * Tk, H * d).to(BF16)
+    dv[:, : H * d] = dV.permute(1, 2, 0, 3).reshape(N * Tk, H * d).to(BF16)
+
+
+def answer_loss(lc, lv, ls, answer, epsilon, grad_scale, want_grads):
+    B, ncls = lc.shape
+    t = torch.full((B, ncls), epsilon / ncls)
+    t[torch.arange(B), answer] += 1 - epsilon
+    loss = torch.zeros(1)
+    grads = []
+    for L in (lc, lv, ls):
+        lsm = torch.log_softmax(L, -1)
+        loss -= (t * lsm).sum() / (3 * B)
+        grads.append(grad_scale * (lsm.exp() - t) / (3 * B))
+    return loss, (tuple(grads) if want_grads else None)
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step):
+    exp_avg.mul_(beta1).add_(grad, alpha=1 - beta1)
+    exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    param.sub_((lr / bc1) * exp_avg / (exp_avg_sq.sqrt() / (bc2 ** 0.5) + eps))
+
+
+def install(monkeypatch):
+    """Route savqa_b200.ops through these stand-ins for the duration of a test."""
+    import savqa_b200.ops as real
+    for name, fn in list(globals().items()):
+        if callable(fn) and hasattr(real, name) and not name.startswith("_") and name not in ("install",):
+            monkeypatch.setattr(real, name, fn)

@@ -1,0 +1,204 @@
+"""Parity cases shared by the CPU host-logic tests (kernels replaced by tests/fake_ops.py) and the GPU parity tests
+(real kernels through the C ABI).  Each case builds the seeded inputs of oracle/golden_spec.py, runs OUR module on
+`device`, and checks outputs and gradients against (i) the golden vectors produced by the live reference and
+(ii) the oracle, with per-tensor tolerances calibrated by the oracle's bf16-operand emulation (parity_util.check).
+"""
+import types
+
+import torch
+
+from oracle import golden_spec as GS
+from oracle import savqa_oracle as O
+from parity_util import check, grads_of, load, set_params, t
+
+BF = torch.bfloat16
+
+
+def _oracle_attention(P0, q, k, graph, H, dy, operand_dtype, self_att, **kw):
+    P = {k_: v.clone().requires_grad_(True) for k_, v in P0.items()}
+    qq = q.clone().requires_grad_(True)
+    kk = qq if self_att else k.clone().requires_grad_(True)
+    y, att = O.attention(qq, kk, kk, graph, P, H, operand_dtype=operand_dtype, **kw)
+    (y * dy).sum().backward()
+    out = {"y": y.detach(), "att": att.detach(), "dq": qq.grad, "dk": kk.grad}
+    out.update({k_: (v.grad if v.grad is not None else torch.zeros_like(v)) for k_, v in P.items()})
+    return out
+
+
+def attention_case(M, golden_dir, device, case, C, H, N, Tq, Tk, self_att, kind="new"):
+    """kind: "new" = new_multihead_attention, "mha" = multihead_attention(causal), "gm" = ..._with_graph_mask."""
+    g = load(golden_dir, case)
+    P0 = GS.make_params(case, GS.attention_shapes(C))
+    q, k, graph = GS.attention_case(case, C, N, Tq, Tk, self_att=self_att)
+    dy = GS.randn(f"{case}/dy", N, Tq, C)
+    kw = {"new": {}, "mha": dict(causality=True, renorm="none"), "gm": dict(renorm="addeps")}[kind]
+    ref = _oracle_attention(P0, q, k, None if kind == "mha" else graph, H, dy, None, self_att, **kw)
+    emu = _oracle_attention(P0, q, k, None if kind == "mha" else graph, H, dy, BF, self_att, **kw)
+    # the oracle itself is pinned to the live reference's golden output
+    assert O.rel_err(ref["y"], t(g["y"])) < 2e-6
+
+    if kind == "new":
+        m = M.new_multihead_attention(C, H, return_att=True)
+    elif kind == "mha":
+        m = M.multihead_attention(C, H, causality=True)
+    else:
+        m = M.new_multihead_attention_with_graph_mask(C, H, return_att=True)
+    set_params(m, P0)
+    m = m.to(device)
+    qq = q.clone().to(device).requires_grad_(True)
+    kk = qq if self_att else k.clone().to(device).requires_grad_(True)
+    gd = graph.to(device)
+    if kind == "new":
+        y, att = m(qq, kk, kk, gd)
+    elif kind == "mha":
+        y, att = m(qq, kk, kk), None
+    else:
+        y, att = m(qq, kk, kk, None, gd)
+    assert y.shape == (N, Tq, C)
+    errs = {"y": check(f"{case}: output", y, t(g["y"]), emu["y"])}
+    if att is not None:
+        assert att.shape == (H * N, Tq, Tk)
+        errs["att"] = check(f"{case}: attention probabilities", att, t(g["att"]), emu["att"])
+        if Tq >= 3 and Tk >= 4 and kind == "new":
+            a4 = att.detach().cpu().view(H, N, Tq, Tk)
+            # a query row without any graph edge, and one whose only edge is key-masked: exactly zero rows
+            assert float(a4[:, 0, 1].abs().sum()) == 0.0 and float(a4[:, 0, 2].abs().sum()) == 0.0
+    (y * dy.to(device)).sum().backward()
+    # rows whose LayerNorm input is constant (zero query row) carry a 1/eps = 1e8 scaled gradient: compare apart
+    zero_q = (q.abs().sum(-1) == 0)
+    errs["dq"] = check(f"{case}: d queries", qq.grad, ref["dq"], emu["dq"], mask=zero_q)
+    if not self_att:
+        errs["dk"] = check(f"{case}: d keys", kk.grad, ref["dk"], emu["dk"])
+    ours = grads_of(m, P0.keys())
+    for k_ in P0:
+        errs[k_] = check(f"{case}: grad {k_}", ours[k_], ref[k_], emu[k_])
+    return errs
+
+
+def feedforward_case(M, golden_dir, device, case, C, N, T):
+    g = load(golden_dir, case)
+    P0 = GS.make_params(case, GS.feedforward_shapes(C))
+    xin = GS.randn(f"{case}/x", N, T, C)
+    dy = GS.randn(f"{case}/dy", N, T, C)
+
+    def run(od):
+        P = {k_: v.clone().requires_grad_(True) for k_, v in P0.items()}
+        x = xin.clone().requires_grad_(True)
+        y = O.feedforward(x, P, od)
+        (y * dy).sum().backward()
+        return dict(y=y.detach(), dx=x.grad, **{k_: v.grad for k_, v in P.items()})
+
+    ref, emu = run(None), run(BF)
+    assert O.rel_err(ref["y"], t(g["y"])) < 2e-6
+    m = M.feedforward(C, [4 * C, C])
+    set_params(m, P0)
+    m = m.to(device)
+    x = xin.clone().to(device).requires_grad_(True)
+    y = m(x)
+    errs = {"y": check(f"{case}: output", y, t(g["y"]), emu["y"])}
+    (y * dy.to(device)).sum().backward()
+    errs["dx"] = check(f"{case}: dx", x.grad, ref["dx"], emu["dx"])
+    ours = grads_of(m, P0.keys())
+    for k_ in P0:
+        errs[k_] = check(f"{case}: grad {k_}", ours[k_], ref[k_], emu[k_])
+    return errs
+
+
+def layernorm_case(M, golden_dir, device):
+    g = load(golden_dir, "layernorm")
+    C = 512
+    xin = GS.randn("layernorm/x", 5, 7, C, scale=2.0)
+    xin[0, 0, :] = 1.25
+    m = M.layer_normalization(C)
+    set_params(m, {"gamma": GS.rand("layernorm/gamma", C, lo=0.8, hi=1.2), "beta": GS.randn("layernorm/beta", C, scale=0.1)})
+    m = m.to(device)
+    x = xin.clone().to(device).requires_grad_(True)
+    y = m(x)
+    check("layernorm: y", y, t(g["y"]), floor=2e-6)  # fp32 kernel
+    assert torch.equal(y[0, 0].detach().cpu(), m.beta.detach().cpu())  # sigma == 0 row -> exactly beta
+    (y * GS.randn("layernorm/dy", *y.shape).to(device)).sum().backward()
+    dx, dxr = x.grad.detach().cpu(), t(g["dx"])
+    check("layernorm: dx", dx[1:], dxr[1:], floor=1e-5)
+    check("layernorm: dx (row 0, regular)", dx[0, 1:], dxr[0, 1:], floor=1e-5)
+    check("layernorm: dx (sigma == 0 row)", dx[0, 0], dxr[0, 0], floor=1e-4)
+    check("layernorm: dgamma", m.gamma.grad, t(g["dgamma"]), floor=1e-4)
+    check("layernorm: dbeta", m.beta.grad, t(g["dbeta"]), floor=1e-5)
+
+
+def embedding_cases(M, golden_dir, device):
+    for zp in (True, False):
+        for sc in (True, False):
+            case = f"embedding_zp{int(zp)}_sc{int(sc)}"
+            g = load(golden_dir, case)
+            table = GS.randn(f"{case}/table", 11, 64, scale=0.3)
+            idx = GS.randint(f"{case}/idx", 0, 11, 4, 6)
+            idx[0, 0], idx[0, 1] = 0, 10
+            e = M.embedding(11, 64, zeros_pad=zp, scale=sc)
+            with torch.no_grad():
+                e.lookup_table.copy_(table)
+            e = e.to(device)
+            y = e(idx.to(device))
+            assert torch.equal(y.detach().cpu(), t(g["y"])), case  # gather: bit exact
+            (y * GS.randn(f"{case}/dy", *y.shape).to(device)).sum().backward()
+            check(f"{case}: dtable", e.lookup_table.grad, t(g["dtable"]), floor=1e-6)
+            hole = 0 if zp else 10
+            assert float(e.lookup_table.grad[hole].abs().sum()) == 0.0  # padding_idx gradient hole (modules.py:34-41)
+
+
+def make_branch(A, kind, S, vocab_rows=None):
+    glove = types.SimpleNamespace(vectors=torch.zeros(4, 300))
+    saved = A.VOCAB_ROWS
+    if vocab_rows is not None:
+        A.VOCAB_ROWS = vocab_rows
+    try:
+        if kind == "vis":
+            return A.AttModel_vis_grid(glove, S["C"], S["maxlen"], S["maxlen_q"], S["blocks"], S["heads"], 0.0, S["maxlen_v"], S["ncls"])
+        return A.AttModel_syb(glove, S["C"], S["maxlen"], S["maxlen_q"], S["blocks"], S["heads"], 0.0, S["ncls"])
+    finally:
+        A.VOCAB_ROWS = saved
+
+
+def branch_case(A, golden_dir, device, kind):
+    S = GS.SMALL
+    case = f"branch_{kind}_c64"
+    g = load(golden_dir, case)
+    shapes = GS.branch_shapes(kind, S["C"], S["maxlen"], S["maxlen_q"], S["maxlen_v"], S["blocks"], S["ncls"])
+    P0 = GS.make_params(case, shapes)
+    nfirst = S["V"] if kind == "vis" else S["M"]
+    b = GS.branch_case(case, kind, S["B"], nfirst, S["Q"])
+    ddec = GS.randn(f"{case}/ddec", S["B"], 1, S["C"])
+
+    def run(od):
+        P = {k_: v.clone().requires_grad_(True) for k_, v in P0.items()}
+        first = b["first"].clone().requires_grad_(True)
+        taps = {}
+        dec = O.branch_forward(P, kind, first, b["first_mask"], b["first_graph"], b["q_ipt"], b["q_graph"], b["q_mask"], True,
+                               S["blocks"], S["heads"], operand_dtype=od, taps=taps)
+        (dec * ddec).sum().backward()
+        out = dict(dec=dec.detach(), dfirst=first.grad, taps=taps)
+        out.update({k_: (v.grad if v.grad is not None else torch.zeros_like(v)) for k_, v in P.items()})
+        return out
+
+    ref, emu = run(None), run(BF)
+    assert O.rel_err(ref["dec"], t(g["dec"])) < 1e-5
+    m = make_branch(A, kind, S, vocab_rows=GS.SMALL_VOCAB)
+    set_params(m, P0)  # strict=True: the key set equals the reference's
+    m = m.to(device)
+    first = b["first"].clone().to(device).requires_grad_(True)
+    dv = lambda x: None if x is None else x.to(device)  # noqa: E731
+    if kind == "vis":
+        dec = m(first, dv(b["first_mask"]), dv(b["q_ipt"]), dv(b["q_graph"]), dv(b["q_mask"]), True)
+    else:
+        dec = m(first, dv(b["first_mask"]), dv(b["first_graph"]), dv(b["q_ipt"]), dv(b["q_graph"]), dv(b["q_mask"]), True)
+    assert dec.shape == (S["B"], 1, S["C"])
+    errs = {"dec": check(f"{case}: decoder output", dec, t(g["dec"]), emu["dec"])}
+    (dec * ddec.to(device)).sum().backward()
+    errs["dfirst"] = check(f"{case}: d first_ipt", first.grad, ref["dfirst"], emu["dfirst"], floor=2e-2, factor=6.0)
+    ours = grads_of(m, P0.keys())
+    for k_ in P0:
+        if float(ref[k_].abs().sum()) == 0.0:  # parameters the reference's forward never uses
+            assert float(ours[k_].abs().sum()) == 0.0, k_
+            continue
+        # 12 stacked bf16-operand blocks: the emulation itself sits at 1e-2..5e-2 on the K/Q projection gradients
+        errs[k_] = check(f"{case}: grad {k_}", ours[k_], ref[k_], emu[k_], floor=2e-2, factor=6.0)
+    return errs

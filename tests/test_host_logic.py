@@ -1,0 +1,154 @@
+"""Host-side logic on CPU: autograd wiring of savqa_b200.functional and the module composition, with the C-ABI
+kernels replaced by the torch stand-ins of tests/fake_ops.py (which restate the kernels' contracts, including their
+explicit backward formulas).  Compared against the oracle at the bf16-operand tolerance.  Also: the drop-in
+contract (state_dict keys, signatures) and the "fail loudly without the extension / a GPU" rule."""
+import inspect
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import fake_ops
+from oracle import golden_spec as GS
+from oracle import savqa_oracle as O
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    fake_ops.install(monkeypatch)
+    import savqa_b200.functional as Fn
+    return Fn
+
+
+import parity_cases as PC  # noqa: E402
+from parity_util import check, grads_of, load, set_params, t  # noqa: E402,F401
+
+
+@pytest.mark.parametrize("tag,C,H,N,T", [("c64", 64, 4, 3, 10), ("c512", 512, 8, 2, 24)])
+def test_attention_self_wiring(fake, golden_dir, tag, C, H, N, T):
+    from savqa_b200 import modules as M
+    PC.attention_case(M, golden_dir, "cpu", f"attn_self_{tag}", C, H, N, T, T, True)
+
+
+@pytest.mark.parametrize("tq", [1, 3])
+def test_attention_cross_wiring(fake, golden_dir, tq):
+    from savqa_b200 import modules as M
+    PC.attention_case(M, golden_dir, "cpu", f"attn_cross{tq}_c64", 64, 4, 3, tq, 10, False)
+
+
+def test_mha_causal_and_graphmask_wiring(fake, golden_dir):
+    from savqa_b200 import modules as M
+    PC.attention_case(M, golden_dir, "cpu", "mha_causal_c64", 64, 4, 3, 6, 6, True, kind="mha")
+    PC.attention_case(M, golden_dir, "cpu", "attn_graphmask_c64", 64, 4, 3, 10, 10, True, kind="gm")
+    m = M.new_multihead_attention_with_graph_mask(64, 4)
+    q = torch.randn(2, 3, 64)
+    with pytest.raises(AttributeError):
+        m(q, q, q, None, None)  # the reference fails the same way (modules.py:375)
+
+
+@pytest.mark.parametrize("tag,C,N,T", [("c64", 64, 3, 10), ("c512", 512, 2, 24)])
+def test_feedforward_wiring(fake, golden_dir, tag, C, N, T):
+    from savqa_b200 import modules as M
+    PC.feedforward_case(M, golden_dir, "cpu", f"ffn_{tag}", C, N, T)
+
+
+def test_layernorm_and_embedding_wiring(fake, golden_dir):
+    from savqa_b200 import modules as M
+    PC.layernorm_case(M, golden_dir, "cpu")
+    PC.embedding_cases(M, golden_dir, "cpu")
+
+
+@pytest.mark.parametrize("kind", ["vis", "syb"])
+def test_branch_wiring(fake, golden_dir, kind):
+    from savqa_b200 import AttModel_x3 as A
+    PC.branch_case(A, golden_dir, "cpu", kind)
+
+
+def test_heads_and_loss_wiring(fake, golden_dir):
+    from savqa_b200 import AttModel_x3 as A
+    S = GS.SMALL
+    g = load(golden_dir, "full_c64")
+    Ph = GS.make_params("full_c64", GS.head_shapes(S["C"], S["ncls"]))
+    heads = torch.nn.Module()
+    model = A.AttModel.__new__(A.AttModel)
+    torch.nn.Module.__init__(model)
+    model.cls = A._head(2 * S["C"], S["C"], S["ncls"], 0.0)
+    model.cls_vis = A._head(S["C"], S["C"], S["ncls"], 0.0)
+    model.cls_syb = A._head(S["C"], S["C"], S["ncls"], 0.0)
+    model._pk = {k: (A.WeightPack(), A.WeightPack()) for k in ("cls", "cls_vis", "cls_syb")}
+    model.load_state_dict(Ph, strict=True)
+    # decoder outputs from the oracle, logits through our heads
+    Pv = GS.make_params("branch_vis_c64", GS.branch_shapes("vis", S["C"], S["maxlen"], S["maxlen_q"], S["maxlen_v"], S["blocks"], S["ncls"]))
+    Ps = GS.make_params("branch_syb_c64", GS.branch_shapes("syb", S["C"], S["maxlen"], S["maxlen_q"], S["maxlen_v"], S["blocks"], S["ncls"]))
+    bv = GS.branch_case("branch_vis_c64", "vis", S["B"], S["V"], S["Q"])
+    bs = GS.branch_case("branch_syb_c64", "syb", S["B"], S["M"], S["Q"])
+    fv = O.branch_forward(Pv, "vis", bv["first"], bv["first_mask"], None, bv["q_ipt"], bv["q_graph"], bv["q_mask"], True, S["blocks"], S["heads"])
+    fs = O.branch_forward(Ps, "syb", t(g["syb_ipt"]), bs["first_mask"], bs["first_graph"], bv["q_ipt"], bv["q_graph"], bv["q_mask"], True,
+                          S["blocks"], S["heads"])
+    lc, lv, ls = model.answer_logits(fv, fs)
+    assert O.rel_err(lc, t(g["logits_concat"])) < 1e-2
+    assert O.rel_err(lv, t(g["logits_vis"])) < 1e-2
+    answer = GS.randint("full_c64/answer", 0, S["ncls"], S["B"])
+    loss = A.answer_loss(t(g["logits_concat"]).clone().requires_grad_(True), t(g["logits_vis"]), t(g["logits_syb"]), answer)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    # gradient of the fused loss vs autograd through the oracle
+    L = [t(g[k]).clone().requires_grad_(True) for k in ("logits_concat", "logits_vis", "logits_syb")]
+    O.answer_loss(*L, answer).backward()
+    L2 = [t(g[k]).clone().requires_grad_(True) for k in ("logits_concat", "logits_vis", "logits_syb")]
+    A.answer_loss(*L2, answer).backward()
+    for a, b_ in zip(L, L2):
+        assert O.rel_err(b_.grad, a.grad) < 1e-5
+
+
+def test_signatures_match_reference():
+    """Constructor / forward argument names of the drop-in classes."""
+    from savqa_b200 import modules as M, AttModel_x3 as A
+
+    def args(f):
+        return list(inspect.signature(f).parameters)[1:]
+
+    assert args(M.new_multihead_attention.__init__) == ["num_units", "num_heads", "dropout_rate", "causality", "return_att"]
+    assert args(M.new_multihead_attention.forward) == ["queries", "keys", "values", "graph"]
+    assert args(M.multihead_attention.__init__) == ["num_units", "num_heads", "dropout_rate", "causality"]
+    assert args(M.multihead_attention.forward) == ["queries", "keys", "values"]
+    assert args(M.new_multihead_attention_with_graph_mask.forward) == ["queries", "keys", "values", "key_mask_ipt", "graph"]
+    assert args(M.feedforward.__init__) == ["in_channels", "num_units"]
+    assert args(M.layer_normalization.__init__) == ["features", "epsilon"]
+    assert args(M.embedding.__init__) == ["vocab_size", "num_units", "zeros_pad", "scale"]
+    assert args(A.AttModel_vis_grid.__init__) == ["glove", "hidden_size", "maxlen", "maxlen_q", "num_blocks", "num_heads", "dropout_rate",
+                                                  "maxlen_v", "num_classes"]
+    assert args(A.AttModel_vis_grid.forward) == ["vis_fea", "vis_mask", "q_fea", "q_graph", "q_mask", "decMask"]
+    assert args(A.AttModel_syb.__init__) == ["glove", "hidden_size", "maxlen", "maxlen_q", "num_blocks", "num_heads", "dropout_rate", "num_classes"]
+    assert args(A.AttModel_syb.forward) == ["syb_ipt", "syb_mask", "syb_graph", "q_fea", "q_graph", "q_mask", "decMask"]
+    assert args(A.AttModel.__init__) == ["glove", "hidden_size", "hidden_size_mil", "num_classes", "maxlen_q", "maxlen", "maxlen_v", "num_blocks",
+                                         "num_heads", "dropout_rate", "dropout_rate_mcb", "num_relations", "only_obj"]
+    assert args(A.AttModel.forward)[:5] == ["vis_fea", "vis_mask", "q_ipt", "q_mask", "q_graph"]
+    assert args(A.AttModel.forward)[-2:] == ["decMask", "mcb"]
+
+
+def test_full_state_dict_contract(golden_dir):
+    """Every key/shape of the reference AttModel state_dict (dumped from the live reference) exists in ours."""
+    import types
+    from savqa_b200 import AttModel_x3 as A
+    S = GS.SMALL
+    keys = {k: tuple(s) for k, s in json.load(open(os.path.join(golden_dir, "state_dict_keys_c64.json")))}
+    glove = types.SimpleNamespace(vectors=torch.zeros(4, 300))
+    m = A.AttModel(glove, S["C"], 16, S["ncls"], S["maxlen_q"], S["maxlen"], S["maxlen_v"], S["blocks"], S["heads"], 0.0, 0.1, 5, True)
+    ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert ours == keys, (sorted(set(ours) ^ set(keys))[:8], [k for k in keys if k in ours and ours[k] != keys[k]][:8])
+
+
+def test_product_fails_loudly_without_gpu():
+    """No CPU fallback: on a box without CUDA every op of the product path raises (never computes on the host)."""
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    from savqa_b200 import modules as M
+    m = M.feedforward(64, [256, 64])
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        m(torch.randn(2, 3, 64))
+    a = M.new_multihead_attention(64, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        x = torch.randn(2, 3, 64)
+        a(x, x, x, torch.ones(2, 3, 3))
