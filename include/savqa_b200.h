@@ -158,8 +158,18 @@ int savqa_answer_loss(const float* logits_concat, const float* logits_vis, const
 
 /* ---- f3 (next): fused Adam over a flat fp32 parameter / gradient pair (torch.optim.Adam semantics,
  * main_itp_ddp_tar_super_node.py:206) and its row-sparse form for the word tables. ------------------------ */
+/* dyn (device, may be NULL) = {lr / (1 - beta1^step), sqrt(1 - beta2^step), step}: read at run time instead of the host
+ * scalars, so that a captured CUDA graph follows the step counter. */
 int savqa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-                    float beta2, float eps, int step, savqa_stream_t stream);
+                    float beta2, float eps, int step, const float* dyn, savqa_stream_t stream);
+
+/* Row-sparse ("lazy") Adam for the 407000 x 300 word tables: only rows named in idx[0..n_idx) are updated, each exactly
+ * once per call even if it occurs several times (row_stamp[row] is set to `step` by the first claimant).  grad is the
+ * dense fp32 gradient table that savqa_scatter_add_rows accumulated into; consumed rows are zeroed again, so the table
+ * never needs a 488 MB memset. */
+int savqa_adam_rows(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int32_t* row_stamp, int64_t table_rows, int width,
+                    const int64_t* idx, int64_t n_idx, float lr, float beta1, float beta2, float eps, int step, const float* dyn,
+                    savqa_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -269,8 +269,15 @@ __global__ void answer_loss_kernel(const float* __restrict__ lc, const float* __
 }
 
 // f3: Adam (torch.optim.Adam defaults: no weight decay, no amsgrad), bias correction as in torch.
+// `dyn` (device, optional) = {lr / bias_correction1, sqrt(bias_correction2), step}: lets a captured CUDA graph see the
+// per-step scalars without re-capture.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
-                            float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt) {
+                            float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, const float* __restrict__ dyn) {
+  float step_size = lr / bc1;
+  if (dyn) {
+    step_size = dyn[0];
+    bc2_sqrt = dyn[1];
+  }
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const float gi = g[i];
     const float mi = b1 * m[i] + (1.0f - b1) * gi;
@@ -278,7 +285,39 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] -= (lr / bc1) * (mi / denom);
+    p[i] -= step_size * (mi / denom);
+  }
+}
+
+__global__ void adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                 int* __restrict__ stamp, long table_rows, int width, const int64_t* __restrict__ idx, long n_idx, float lr,
+                                 float b1, float b2, float eps, float bc1, float bc2_sqrt, int step, const float* __restrict__ dyn) {
+  float step_size = lr / bc1;
+  if (dyn) {
+    step_size = dyn[0];
+    bc2_sqrt = dyn[1];
+    step = static_cast<int>(dyn[2]);
+  }
+  const int lane = threadIdx.x & 31;
+  const long warp0 = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+  const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+  for (long r = warp0; r < n_idx; r += nwarps) {
+    const long row = idx[r];
+    if (row < 0 || row >= table_rows) continue;
+    int first = 0;
+    if (lane == 0) first = (atomicExch(stamp + row, step) != step) ? 1 : 0;
+    first = __shfl_sync(0xffffffffu, first, 0);
+    if (!first) continue;  // another occurrence of this row already took it
+    const long base = row * static_cast<long>(width);
+    for (int c = lane; c < width; c += 32) {
+      const float gi = g[base + c];
+      const float mi = b1 * m[base + c] + (1.0f - b1) * gi;
+      const float vi = b2 * v[base + c] + (1.0f - b2) * gi * gi;
+      m[base + c] = mi;
+      v[base + c] = vi;
+      p[base + c] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+      g[base + c] = 0.0f;
+    }
   }
 }
 
@@ -420,13 +459,27 @@ extern "C" int savqa_answer_loss(const float* lc, const float* lv, const float* 
 }
 
 extern "C" int savqa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-                               float beta2, float eps, int step, savqa_stream_t stream_) {
+                               float beta2, float eps, int step, const float* dyn, savqa_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n == 0) return SAVQA_OK;
   SAVQA_REQUIRE(param && grad && exp_avg && exp_avg_sq && step >= 1, "savqa_adam_step: bad argument");
   const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
-  adam_kernel<<<grid_for(n, 256, 16), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2));
+  adam_kernel<<<grid_for(n, 256, 16), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), dyn);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_adam_rows(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int32_t* row_stamp, int64_t table_rows,
+                               int width, const int64_t* idx, int64_t n_idx, float lr, float beta1, float beta2, float eps, int step,
+                               const float* dyn, savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_idx == 0) return SAVQA_OK;
+  SAVQA_REQUIRE(param && grad && exp_avg && exp_avg_sq && row_stamp && idx && width > 0 && step >= 1, "savqa_adam_rows: bad argument");
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  adam_rows_kernel<<<grid_for(n_idx * 32, 256), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, row_stamp, table_rows, width, idx, n_idx,
+                                                                   lr, beta1, beta2, eps, bc1, sqrtf(bc2), step, dyn);
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;
 }

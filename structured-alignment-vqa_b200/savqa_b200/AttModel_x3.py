@@ -62,7 +62,7 @@ class _Branch(nn.Module):
 
     def _input_stage(self, first_ipt, q_ids, pos_table, pos_dropout_p):
         B = first_ipt.shape[0]
-        q = Fn.EmbeddingFn.apply(q_ids, self.syb_emb.weight, 1.0, -1)                      # :96 / :216
+        q = Fn.EmbeddingFn.apply(q_ids, self.syb_emb.weight, 1.0, -1, getattr(self.syb_emb, "_savqa_rowlog", None))  # :96 / :216
         qh = _linear(q, self.syb_mlp[0], self._pk["mlp"], relu=True, out_bf16=True)        # :97  [B,Q,2048] bf16
         fb = first_ipt if first_ipt.dtype == torch.bfloat16 else _CastBf16.apply(first_ipt)
         x_in = torch.cat([fb, qh], dim=1)                                                  # :98  [B,T,2048] bf16

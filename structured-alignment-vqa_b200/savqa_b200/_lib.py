@@ -56,7 +56,8 @@ SIGNATURES = {
     "savqa_graph_attn_fwd": [C.POINTER(AttnArgs), vp],
     "savqa_graph_attn_bwd": [C.POINTER(AttnArgs), vp],
     "savqa_answer_loss": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp, vp],
-    "savqa_adam_step": [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp],
+    "savqa_adam_rows": [vp, vp, vp, vp, vp, i64, C.c_int, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp],
+    "savqa_adam_step": [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp],
 }
 
 _lib: Optional[C.CDLL] = None

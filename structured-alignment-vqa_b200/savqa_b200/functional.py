@@ -20,6 +20,8 @@ Tensor = torch.Tensor
 
 #: training under CUDA-graph replay must re-stage the bf16 weights inside the graph every step
 FORCE_RESTAGE = False
+#: bumped by the trainer after it updates parameters with its own kernels (which do not touch torch's version counters)
+WEIGHT_EPOCH = 0
 #: attention forward engine: 0 = tcgen05/TMEM kernel, 1 = CUDA-core verification kernel
 ATTN_ENGINE = 0
 
@@ -52,7 +54,7 @@ class WeightPack:
         self.bias: Optional[Tensor] = None
 
     def refresh(self, weights: Sequence[Tensor], biases: Sequence[Tensor]) -> "WeightPack":
-        key = tuple((w.data_ptr(), w._version, b.data_ptr(), b._version) for w, b in zip(weights, biases))
+        key = (WEIGHT_EPOCH,) + tuple((w.data_ptr(), w._version, b.data_ptr(), b._version) for w, b in zip(weights, biases))
         if key == self.key and not FORCE_RESTAGE:
             return self
         K = weights[0].shape[1]
@@ -151,23 +153,39 @@ class LinearFn(Function):
 # ======================================================================================================
 # embedding gather  -- nn.Embedding (AttModel_x3.py:96) and modules.embedding (modules.py:32-46)
 # ======================================================================================================
+class RowGradLog:
+    """Row-sparse gradient hand-off for the 407000 x 300 word tables (train.py): instead of materialising a dense
+    488 MB gradient per step, EmbeddingFn.backward records (row ids, row gradients) here and returns no table gradient;
+    the trainer exchanges / scatters / applies them (savqa_scatter_add_rows + savqa_adam_rows)."""
+
+    def __init__(self):
+        self.pending = []  # list of (flat_idx int64 [n], rows fp32 [n, width], scale)
+
+    def clear(self):
+        self.pending.clear()
+
+
 class EmbeddingFn(Function):
     @staticmethod
-    def forward(ctx, idx, table, scale: float, skip_row: int):
+    def forward(ctx, idx, table, scale: float, skip_row: int, rowlog: Optional[RowGradLog] = None):
         flat = idx.reshape(-1)
         out, _ = ops.gather_rows(table.detach(), flat, scale=scale, want_f32=True)
         ctx.save_for_backward(flat)
-        ctx.table_shape, ctx.scale, ctx.skip_row = table.shape, scale, skip_row
+        ctx.table_shape, ctx.scale, ctx.skip_row, ctx.rowlog = table.shape, scale, skip_row, rowlog
         return out.reshape(*idx.shape, table.shape[1])
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
         (flat,) = ctx.saved_tensors
-        dtable = torch.zeros(ctx.table_shape, device=dy.device, dtype=F32)  # dense, like the reference
         d2 = dy.reshape(flat.numel(), -1)
-        ops.scatter_add_rows(dtable, flat, d2 if d2.is_contiguous() else d2.contiguous(), scale=ctx.scale, skip_row=ctx.skip_row)
-        return None, dtable, None, None
+        d2 = d2 if d2.is_contiguous() else d2.contiguous()
+        if ctx.rowlog is not None:
+            ctx.rowlog.pending.append((flat, d2, ctx.scale, ctx.skip_row))
+            return None, None, None, None, None
+        dtable = torch.zeros(ctx.table_shape, device=dy.device, dtype=F32)  # dense, like the reference
+        ops.scatter_add_rows(dtable, flat, d2, scale=ctx.scale, skip_row=ctx.skip_row)
+        return None, dtable, None, None, None
 
 
 # ======================================================================================================

@@ -338,8 +338,21 @@ def answer_loss(lc: Tensor, lv: Tensor, ls: Tensor, answer: Tensor, epsilon: flo
 
 
 def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr: float, beta1: float, beta2: float, eps: float,
-              step: int) -> None:
+              step: int, dyn: Optional[Tensor] = None) -> None:
     for nm, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
         _check(t, F32, nm)
         assert t.is_contiguous() and t.numel() == param.numel()
-    call("savqa_adam_step", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2, eps, int(step))
+    call("savqa_adam_step", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2, eps, int(step), ptr(dyn))
+
+
+def adam_rows(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, row_stamp: Tensor, idx: Tensor, lr: float, beta1: float,
+              beta2: float, eps: float, step: int, dyn: Optional[Tensor] = None) -> None:
+    """Row-sparse Adam over the rows named in idx (each once); consumed gradient rows are zeroed."""
+    for nm, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        _check(t, F32, nm)
+        assert t.is_contiguous() and t.shape == param.shape
+    _check(row_stamp, torch.int32, "row_stamp")
+    _check(idx, torch.int64, "idx")
+    idx = idx.contiguous()
+    call("savqa_adam_rows", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(row_stamp), param.shape[0], param.shape[1], ptr(idx),
+         idx.numel(), lr, beta1, beta2, eps, int(step), ptr(dyn))

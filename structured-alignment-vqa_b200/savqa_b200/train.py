@@ -1,0 +1,178 @@
+"""Data-parallel training step of the graph-guided encoder path: one process per GPU.
+
+Replaces, for this path, the reference's `DistributedDataParallel(find_unused_parameters=True)` + dense
+`torch.optim.Adam` over 470 M parameters (main_itp_ddp_tar_super_node.py:203-206, 363-366):
+
+  * the dense parameters that the step actually uses live in ONE flat fp32 buffer (parameter views), their gradients
+    in another: one NCCL all-reduce (AVG) over NVLink and one fused Adam kernel per step;
+  * the two 407000 x 300 word tables exchange row-sparse gradients: all-gather of (row id, row gradient) lists, local
+    scatter-add, row-wise Adam on the touched rows (savqa_adam_rows).  `rowsparse=False` restores the reference's dense
+    table gradients (and dense Adam) for comparison.  Lazy row-wise Adam differs from dense Adam for rows that are
+    absent from a batch (their moments do not decay); documented in DESIGN.md;
+  * the whole step (bf16 weight staging, forward, backward, all-reduce, optimizer) can be captured into one CUDA graph
+    and replayed, which removes the Python / launch overhead of ~1500 kernel launches per step.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import AttModel_x3 as A
+from . import functional as Fn
+from . import ops
+
+STEP_KEYS = ("vis_fea", "vis_fea_mask", "q_ipt", "q_ipt_mask", "q_ipt_graph", "syb_ipt", "macro_node_mask", "macro_graph_ipt", "answer")
+
+
+class EncoderTrainer:
+    def __init__(self, model: A.AttModel, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, rowsparse: bool = True,
+                 process_group=None, dec_mask: bool = True):
+        self.model = model
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.rowsparse = rowsparse
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.dec_mask = dec_mask
+        self.step_count = 0
+        self.tables = [model.att_vis_grid.syb_emb, model.att_syb.syb_emb]
+        self.flat_param: Optional[torch.Tensor] = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.static: Optional[Dict[str, torch.Tensor]] = None
+        self.static_loss: Optional[torch.Tensor] = None
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------------------------------------
+    def _forward_backward(self, b: Dict[str, torch.Tensor]) -> torch.Tensor:
+        logits = self.model.encoder_step(b["vis_fea"], b["vis_fea_mask"], b["q_ipt"], b["q_ipt_mask"], b["q_ipt_graph"], b["syb_ipt"],
+                                         b["macro_node_mask"], b["macro_graph_ipt"], self.dec_mask)
+        loss = A.answer_loss(*logits, b["answer"])
+        loss.backward()
+        return loss.detach()
+
+    def prepare(self, batch: Dict[str, torch.Tensor]) -> None:
+        """Discovers (one dry run) which parameters the step gives gradients to, then moves them and their gradients
+        into flat buffers.  The reference needs find_unused_parameters=True for the same reason."""
+        model = self.model
+        dev = batch["vis_fea"].device
+        for t in self.tables:
+            t._savqa_rowlog = Fn.RowGradLog() if self.rowsparse else None
+        model.zero_grad(set_to_none=True)
+        self._forward_backward(batch)
+        for t in self.tables:
+            if t._savqa_rowlog is not None:
+                t._savqa_rowlog.clear()
+        table_ids = {id(t.weight) for t in self.tables}
+        self.dense: List[torch.nn.Parameter] = [p for p in model.parameters() if p.grad is not None and id(p) not in table_ids]
+        if not self.rowsparse:
+            self.dense += [t.weight for t in self.tables]
+        n = sum(p.numel() for p in self.dense)
+        pad = (-n) % 4
+        self.flat_param = torch.zeros(n + pad, device=dev)
+        self.flat_grad = torch.zeros(n + pad, device=dev)
+        self.exp_avg = torch.zeros(n + pad, device=dev)
+        self.exp_avg_sq = torch.zeros(n + pad, device=dev)
+        o = 0
+        with torch.no_grad():
+            for p in self.dense:
+                k = p.numel()
+                self.flat_param[o:o + k].copy_(p.reshape(-1))
+                p.data = self.flat_param[o:o + k].view(p.shape)
+                p.grad = self.flat_grad[o:o + k].view(p.shape)
+                o += k
+        self.n_dense = n
+        if self.rowsparse:
+            self.row_state = []
+            for t in self.tables:
+                w = t.weight
+                w.grad = None
+                self.row_state.append(dict(grad=torch.zeros_like(w), m=torch.zeros_like(w), v=torch.zeros_like(w),
+                                           stamp=torch.zeros(w.shape[0], dtype=torch.int32, device=dev)))
+        self.dyn = torch.zeros(3, device=dev)
+        self.dyn_host = torch.zeros(3).pin_memory() if dev.type == "cuda" else torch.zeros(3)
+        Fn.WEIGHT_EPOCH += 1
+
+    # ------------------------------------------------------------------------------------------------
+    def _set_dyn(self) -> None:
+        b1, b2 = self.betas
+        s = self.step_count
+        self.dyn_host[0] = self.lr / (1.0 - b1 ** s)
+        self.dyn_host[1] = (1.0 - b2 ** s) ** 0.5
+        self.dyn_host[2] = float(s)
+        self.dyn.copy_(self.dyn_host, non_blocking=True)
+
+    def _exchange_and_apply(self) -> None:
+        b1, b2 = self.betas
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=self.pg)
+        ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, b1, b2, self.eps, max(self.step_count, 1),
+                      dyn=self.dyn)
+        if self.rowsparse:
+            for t, st in zip(self.tables, self.row_state):
+                log = t._savqa_rowlog
+                for idx, rows, scale, skip in log.pending:
+                    if self.world > 1:
+                        idx_all = torch.empty(self.world * idx.numel(), dtype=idx.dtype, device=idx.device)
+                        rows_all = torch.empty(self.world * rows.shape[0], rows.shape[1], dtype=rows.dtype, device=rows.device)
+                        dist.all_gather_into_tensor(idx_all, idx, group=self.pg)
+                        dist.all_gather_into_tensor(rows_all, rows, group=self.pg)
+                        idx, rows, scale = idx_all, rows_all, scale / self.world
+                    ops.scatter_add_rows(st["grad"], idx, rows, scale=scale, skip_row=skip)
+                    ops.adam_rows(t.weight.data, st["grad"], st["m"], st["v"], st["stamp"], idx, self.lr, b1, b2, self.eps,
+                                  max(self.step_count, 1), dyn=self.dyn)
+                log.clear()
+
+    def _step_impl(self, b: Dict[str, torch.Tensor]) -> torch.Tensor:
+        self.flat_grad.zero_()
+        loss = self._forward_backward(b)
+        self._exchange_and_apply()
+        return loss
+
+    def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """One eager training step on device-resident inputs; returns the (device) loss."""
+        if self.flat_param is None:
+            self.prepare(batch)
+        self.step_count += 1
+        self._set_dyn()
+        from . import _lib
+        n0 = _lib.launch_count
+        loss = self._step_impl(batch)
+        self.launches_per_step = _lib.launch_count - n0
+        Fn.WEIGHT_EPOCH += 1
+        return loss
+
+    # ------------------------------------------------------------------------------------------------
+    def capture(self, batch: Dict[str, torch.Tensor], warmup: int = 3) -> None:
+        """Captures the whole step into a CUDA graph over static input buffers."""
+        if self.flat_param is None:
+            self.prepare(batch)
+        self.static = {k: batch[k].clone() for k in STEP_KEYS}
+        Fn.FORCE_RESTAGE = True  # the bf16 weight staging must be part of the replayed graph
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.step(self.static)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        self.step_count += 1
+        self._set_dyn()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._step_impl(self.static)
+        Fn.WEIGHT_EPOCH += 1
+
+    def load_static(self, batch: Dict[str, torch.Tensor], stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Copies a (pinned host or device) batch into the graph's static input buffers."""
+        ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream())
+        with ctx:
+            for k in STEP_KEYS:
+                self.static[k].copy_(batch[k], non_blocking=True)
+
+    def replay(self) -> torch.Tensor:
+        self.step_count += 1
+        self._set_dyn()
+        self.graph.replay()
+        return self.static_loss

@@ -223,11 +223,22 @@ def answer_loss(lc, lv, ls, answer, epsilon, grad_scale, want_grads):
     return loss, (tuple(grads) if want_grads else None)
 
 
-def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step):
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, dyn=None):
     exp_avg.mul_(beta1).add_(grad, alpha=1 - beta1)
     exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
     bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
     param.sub_((lr / bc1) * exp_avg / (exp_avg_sq.sqrt() / (bc2 ** 0.5) + eps))
+
+
+def adam_rows(param, grad, exp_avg, exp_avg_sq, row_stamp, idx, lr, beta1, beta2, eps, step, dyn=None):
+    rows = torch.unique(idx.reshape(-1))
+    g = grad[rows]
+    exp_avg[rows] = beta1 * exp_avg[rows] + (1 - beta1) * g
+    exp_avg_sq[rows] = beta2 * exp_avg_sq[rows] + (1 - beta2) * g * g
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    param[rows] -= (lr / bc1) * exp_avg[rows] / (exp_avg_sq[rows].sqrt() / (bc2 ** 0.5) + eps)
+    grad[rows] = 0
+    row_stamp[rows] = step
 
 
 def install(monkeypatch):

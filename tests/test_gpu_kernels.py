@@ -1,0 +1,287 @@
+"""GPU parity tests, kernel level: every C-ABI entry point against the oracle / a plain fp32 restatement on the same
+seeded inputs.  Integer / index / mask work is compared bit-exactly; floating point with the tolerance written
+next to each assert.  Run on the B200 box with `-m gpu`."""
+import math
+
+import pytest
+import torch
+
+from oracle import golden_spec as GS
+from oracle import savqa_oracle as O
+
+pytestmark = pytest.mark.gpu
+BF, F32 = torch.bfloat16, torch.float32
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from savqa_b200 import _lib, ops as o
+    _lib.require_device()
+    return o
+
+
+def dev(x):
+    return x.cuda() if x is not None else None
+
+
+def rel(a, b):
+    return O.rel_err(a.float().cpu(), b.float().cpu())
+
+
+# ------------------------------------------------------------------------------------------------ masks
+@pytest.mark.parametrize("B,V,Q,with_first_graph,as_float", [(3, 5, 4, False, False), (4, 36, 20, True, False), (2, 100, 20, True, True),
+                                                            (2, 1, 1, True, False), (128, 36, 20, False, False)])
+def test_build_masks_bit_exact(ops, B, V, Q, with_first_graph, as_float):
+    b = GS.branch_case(f"masks/{B}/{V}/{Q}", "syb" if with_first_graph else "vis", B, V, Q)
+    cast = (lambda x: x.float()) if as_float else (lambda x: x)
+    fm, qm, qg = cast(b["first_mask"]), cast(b["q_mask"]), cast(b["q_graph"])
+    fg = cast(b["first_graph"]) if with_first_graph else None
+    for dec_on in (True, False):
+        ref = O.build_masks(fm, qm, qg, fg, dec_on)
+        got = ops.build_masks(dev(fm), dev(qm), dev(qg), dev(fg), dec_on)
+        for r, g_ in zip(ref, got):
+            assert torch.equal(r, g_.cpu())
+
+
+# ------------------------------------------------------------------------------------------------ gather / scatter
+def test_gather_scatter(ops):
+    table = GS.randn("gk/table", 1000, 300)
+    idx = GS.randint("gk/idx", 0, 1000, 7, 20)
+    idx[0, :3] = torch.tensor([0, 999, 999])
+    o32, o16 = ops.gather_rows(dev(table), dev(idx), want_f32=True, want_bf16=True)
+    assert torch.equal(o32.cpu(), table[idx.reshape(-1)])  # bit exact
+    assert o16.shape == (140, 304)
+    assert torch.equal(o16.cpu()[:, :300], table[idx.reshape(-1)].to(BF))
+    assert float(o16[:, 300:].float().abs().sum()) == 0.0
+    o32s, _ = ops.gather_rows(dev(table), dev(idx), scale=math.sqrt(300.0))
+    assert torch.equal(o32s.cpu(), table[idx.reshape(-1)] * torch.tensor(math.sqrt(300.0), dtype=F32))
+    # scatter-add with a padding row that must not receive gradient
+    dout = GS.randn("gk/dout", 140, 300)
+    dt = torch.zeros(1000, 300, device="cuda")
+    ops.scatter_add_rows(dt, dev(idx), dev(dout), scale=1.0, skip_row=999)
+    ref = torch.zeros(1000, 300)
+    flat = idx.reshape(-1)
+    keep = flat != 999
+    ref.index_add_(0, flat[keep], dout[keep])
+    assert rel(dt, ref) < 1e-6
+    assert float(dt[999].abs().sum()) == 0.0
+    # empty input is a no-op
+    ops.gather_rows(dev(table), torch.zeros(0, dtype=torch.int64, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------------ casts / masks / sums
+def test_casts_rowmask_colsum(ops):
+    x = GS.randn("ck/x", 77, 300)
+    x[5] = 0
+    xb = ops.cast_bf16(dev(x))
+    assert xb.shape == (77, 304) and torch.equal(xb.cpu()[:, :300], x.to(BF)) and float(xb[:, 300:].float().abs().sum()) == 0
+    w = GS.randn("ck/w", 130, 70)
+    wt = torch.zeros(70, 136, dtype=BF, device="cuda")
+    ops.cast_transpose_bf16(dev(w), wt)
+    assert torch.equal(wt.cpu()[:, :130], w.t().to(BF))
+    on, xb2 = ops.row_nonzero(dev(x))
+    assert torch.equal(on.cpu(), (x.sum(-1) != 0).float()) and on[5] == 0
+    assert torch.equal(xb2.cpu()[:, :300], x.to(BF))
+    y = GS.randn("ck/y", 1000, 200).to(BF)
+    out = torch.zeros(200, device="cuda")
+    ops.colsum_bf16(dev(y), out)
+    assert rel(out, y.float().sum(0)) < 1e-5
+    act = GS.randn("ck/act", 77, 304).to(BF)
+    gated = ops.relu_gate_bf16(dev(x), dev(act))
+    assert torch.equal(gated.cpu()[:, :300], torch.where(act[:, :300].float() > 0, x, torch.zeros(())).to(BF))
+
+
+# ------------------------------------------------------------------------------------------------ layer norm
+@pytest.mark.parametrize("rows,C", [(35, 512), (1000, 512), (33, 64), (17, 1024), (9, 300)])
+def test_layernorm_kernels(ops, rows, C):
+    x = GS.randn(f"ln/{rows}/{C}/x", rows, C, scale=2.0)
+    r = GS.randn(f"ln/{rows}/{C}/r", rows, C)
+    x[0] = 0.75
+    r[0] = 0.5  # constant row: sigma == 0
+    gamma = GS.rand(f"ln/{C}/g", C, lo=0.8, hi=1.2)
+    beta = GS.randn(f"ln/{C}/b", C, scale=0.1)
+    dy = GS.randn(f"ln/{rows}/{C}/dy", rows, C)
+    pre = (x + r).clone().requires_grad_(True)
+    gg, bb = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y_ref = O.layer_norm(pre, gg, bb)
+    (y_ref * dy).sum().backward()
+    y, pre_k, yb, on = ops.layernorm_fwd(dev(x), dev(r), dev(gamma), dev(beta), 1e-8, True, True, True)
+    assert rel(y, y_ref) < 2e-6  # fp32 arithmetic, different reduction order only
+    assert torch.equal(pre_k.cpu(), x + r)
+    assert torch.equal(yb.cpu(), y.cpu().to(BF))
+    assert torch.equal(on.cpu(), (y.cpu().sum(-1) != 0).float())
+    dg = torch.zeros(C, device="cuda")
+    db = torch.zeros(C, device="cuda")
+    dx, dxb = ops.layernorm_bwd(dev(dy), pre_k, dev(gamma), 1e-8, dg, db, want_bf16=True)
+    assert rel(dx[1:], pre.grad[1:]) < 1e-5
+    assert rel(dx[0], pre.grad[0]) < 1e-4  # sigma == 0 row: (g - mean g) / eps, as autograd
+    assert rel(dg, gg.grad) < 1e-4 and rel(db, bb.grad) < 1e-5
+    assert torch.equal(dxb.cpu(), dx.cpu().to(BF))
+
+
+# ------------------------------------------------------------------------------------------------ GEMM (tcgen05)
+def _gemm_ref(a, b, bias=None, res=None, rowtab=None, period=0, relu=False, gate=None, alpha=1.0):
+    v = alpha * (a.float() @ b.float().t())
+    if bias is not None:
+        v = v + bias
+    if res is not None:
+        v = v + res
+    if rowtab is not None:
+        v = v + rowtab[:period].repeat((v.shape[0] + period - 1) // period, 1)[: v.shape[0]]
+    if relu:
+        v = torch.relu(v)
+    if gate is not None:
+        v = v * (gate.float() > 0)
+    return v
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 512), (200, 136, 304), (56 * 8, 1536, 512), (7168, 2048, 512),
+                                   (7168, 512, 2048), (130, 48, 512), (128, 1845, 512), (1, 512, 512), (4096, 6144, 512)])
+def test_gemm_kmajor(ops, M, N, K):
+    a = GS.randn(f"gemm/{M}/{N}/{K}/a", M, K).to(BF)
+    b = (GS.randn(f"gemm/{M}/{N}/{K}/b", N, K) / math.sqrt(K)).to(BF)
+    bias = GS.randn(f"gemm/{N}/bias", N)
+    ref = _gemm_ref(a, b, bias=bias, relu=True)
+    o32 = torch.empty(M, N, device="cuda")
+    o16 = torch.empty(M, N, device="cuda", dtype=BF) if N % 8 == 0 else None
+    ops.gemm(dev(a), dev(b), M, N, K, bias=dev(bias), relu=True, out_f32=o32, out_bf16=o16)
+    torch.cuda.synchronize()
+    assert rel(o32, ref) < 2e-5  # identical bf16 operands, fp32 accumulation: summation order only
+    if o16 is not None:
+        assert rel(o16, ref) < 4e-3  # + one bf16 rounding of the output
+
+
+def test_gemm_epilogues(ops):
+    M, N, K, T = 300, 512, 2048, 60
+    a = GS.randn("gemm/e/a", M, K).to(BF)
+    b = (GS.randn("gemm/e/b", N, K) / math.sqrt(K)).to(BF)
+    bias, res = GS.randn("gemm/e/bias", N), GS.randn("gemm/e/res", M, N)
+    rowtab = GS.randn("gemm/e/rt", 64, N)
+    gate = GS.randn("gemm/e/gate", M, N).to(BF)
+    ref = _gemm_ref(a, b, bias=bias, res=res, rowtab=rowtab, period=T, gate=gate, alpha=0.5)
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(dev(a), dev(b), M, N, K, bias=dev(bias), res=dev(res), rowtab=dev(rowtab), rowtab_period=T, gate=dev(gate), alpha=0.5, out_f32=out)
+    assert rel(out, ref) < 2e-5
+    # accumulate modes
+    base = GS.randn("gemm/e/base", M, N)
+    acc = dev(base.clone())
+    ops.gemm(dev(a), dev(b), M, N, K, out_f32=acc, accumulate=1)
+    assert rel(acc, base + _gemm_ref(a, b)) < 2e-5
+    acc = dev(base.clone())
+    ops.gemm(dev(a), dev(b), M, N, K, out_f32=acc, accumulate=2, split_k=4)
+    assert rel(acc, base + _gemm_ref(a, b)) < 2e-5
+    # strided views (fused QKV layout): B operand and output are column slices
+    big = torch.zeros(M, 3 * N, device="cuda", dtype=BF)
+    ops.gemm(dev(a), dev(b), M, N, K, out_bf16=big[:, N:2 * N])
+    assert rel(big[:, N:2 * N], _gemm_ref(a, b)) < 4e-3 and float(big[:, :N].float().abs().sum()) == 0
+
+
+@pytest.mark.parametrize("Mtok,Nout,Kin", [(256, 128, 128), (448, 1536, 512), (7168, 2048, 512), (7168, 512, 2048), (140, 2048, 300),
+                                           (128, 1845, 512)])
+def test_gemm_wgrad_mn_major(ops, Mtok, Nout, Kin):
+    """dW[Nout,Kin] = dY[Mtok,Nout]^T X[Mtok,Kin]: both operands MN-major, split-K with fp32 atomics."""
+    ldy, ldx = ops.pad8(Nout), ops.pad8(Kin)
+    dy = torch.zeros(Mtok, ldy, dtype=BF)
+    x = torch.zeros(Mtok, ldx, dtype=BF)
+    dy[:, :Nout] = GS.randn(f"wg/{Mtok}/{Nout}/dy", Mtok, Nout).to(BF)
+    x[:, :Kin] = GS.randn(f"wg/{Mtok}/{Kin}/x", Mtok, Kin).to(BF)
+    ref = dy[:, :Nout].float().t() @ x[:, :Kin].float()
+    out = torch.zeros(Nout, Kin, device="cuda")
+    ops.wgrad(dev(dy), dev(x), Nout, Kin, out)
+    assert rel(out, ref) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ attention core
+def _attn_inputs(tag, N, H, Tq, Tk, d, self_att):
+    C = H * d
+    q = torch.relu(GS.randn(f"{tag}/q", N * Tq, C)).to(BF)
+    k = q if self_att else torch.relu(GS.randn(f"{tag}/k", N * Tk, C)).to(BF)
+    v = torch.relu(GS.randn(f"{tag}/v", N * Tk, C)).to(BF)
+    graph = GS.bernoulli(f"{tag}/g", 0.3, N, Tq, Tk).float()
+    key_on = torch.ones(N, Tk)
+    query_on = torch.ones(N, Tq)
+    if Tk > 3:
+        key_on[0, Tk - 1] = 0
+        key_on[N - 1, 1] = 0
+    if Tq > 3:
+        graph[0, 1] = 0
+        graph[0, 2] = 0
+        graph[0, 2, Tk - 1] = 1
+        query_on[N - 1, 0] = 0
+    return q, k, v, graph, key_on, query_on
+
+
+def _attn_ref(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm):
+    import fake_ops
+    return fake_ops.graph_attention_fwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, True, 1)
+
+
+@pytest.mark.parametrize("engine", [1, 0])
+@pytest.mark.parametrize("N,H,Tq,Tk,d,renorm,causal", [
+    (3, 8, 56, 56, 64, 1, False), (2, 8, 120, 120, 64, 1, False), (2, 8, 299, 299, 64, 1, False), (2, 4, 130, 130, 128, 1, False),
+    (4, 8, 1, 56, 64, 1, False), (2, 8, 36, 36, 64, 0, True), (2, 8, 40, 72, 64, 2, False), (2, 8, 256, 256, 64, 1, False),
+    (1, 8, 500, 500, 64, 1, False), (2, 16, 50, 50, 32, 1, False), (3, 4, 10, 10, 16, 1, False)])
+def test_attention_forward(ops, engine, N, H, Tq, Tk, d, renorm, causal):
+    if engine == 0 and (d not in (64, 128) or Tk > 384):
+        pytest.skip("tcgen05 engine takes d in {64,128} and Tk*d that fits one CTA's shared memory; others run on engine 1")
+    q, k, v, graph, key_on, query_on = _attn_inputs(f"att/{N}/{H}/{Tq}/{Tk}/{d}", N, H, Tq, Tk, d, Tq == Tk)
+    g_in = None if renorm == 0 else graph
+    ref_out, ref_att = _attn_ref(q, k, v, g_in, key_on, query_on, N, H, Tq, Tk, d, causal, renorm)
+    out, att = ops.graph_attention_fwd(dev(q), dev(k), dev(v), dev(g_in), dev(key_on), dev(query_on), N, H, Tq, Tk, d, causal, renorm, True, engine)
+    torch.cuda.synchronize()
+    # engine 1 is fp32 on the same bf16 inputs: summation order only.  engine 0 additionally rounds the un-normalised
+    # probabilities to bf16 before P.V (one 2^-9 rounding) and uses ex2-based exp.
+    assert rel(att, ref_att) < (1e-5 if engine == 1 else 2e-5), "attention probabilities"
+    assert rel(out, ref_out) < (1e-5 if engine == 1 else 3e-3), "attention output"
+    if Tq > 3 and renorm == 1:
+        a4 = att.cpu().view(H, N, Tq, Tk)
+        assert float(a4[:, 0, 1].abs().sum()) == 0.0 and float(a4[:, 0, 2].abs().sum()) == 0.0  # zero-edge rows stay exactly zero
+    # broadcast graph [N,1,Tk] (decoder mask) must equal the expanded one
+    if renorm == 1 and Tq > 1:
+        g1 = graph[:, :1].contiguous()
+        o1, _ = ops.graph_attention_fwd(dev(q), dev(k), dev(v), dev(g1), dev(key_on), dev(query_on), N, H, Tq, Tk, d, causal, 1, False, engine)
+        o2, _ = ops.graph_attention_fwd(dev(q), dev(k), dev(v), dev(g1.expand(N, Tq, Tk).contiguous()), dev(key_on), dev(query_on), N, H, Tq,
+                                        Tk, d, causal, 1, False, engine)
+        assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("N,H,Tq,Tk,d,renorm,causal", [(3, 8, 56, 56, 64, 1, False), (2, 8, 1, 56, 64, 1, False), (2, 4, 36, 36, 16, 0, True),
+                                                       (2, 8, 40, 72, 64, 2, False), (2, 4, 130, 130, 128, 1, False), (2, 16, 50, 50, 32, 1, False)])
+def test_attention_backward(ops, N, H, Tq, Tk, d, renorm, causal):
+    import fake_ops
+    q, k, v, graph, key_on, query_on = _attn_inputs(f"attb/{N}/{H}/{Tq}/{Tk}/{d}", N, H, Tq, Tk, d, False)
+    g_in = None if renorm == 0 else graph
+    C = H * d
+    dout = GS.randn(f"attb/{N}/{Tq}/{C}/dout", N * Tq, C)
+    rq, rk, rv = torch.zeros(N * Tq, C, dtype=BF), torch.zeros(N * Tk, C, dtype=BF), torch.zeros(N * Tk, C, dtype=BF)
+    fake_ops.graph_attention_bwd(q, k, v, g_in, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout, rq, rk, rv)
+    dq = torch.zeros(N * Tq, C, dtype=BF, device="cuda")
+    dk = torch.zeros(N * Tk, C, dtype=BF, device="cuda")
+    dv = torch.zeros(N * Tk, C, dtype=BF, device="cuda")
+    ops.graph_attention_bwd(dev(q), dev(k), dev(v), dev(g_in), dev(key_on), dev(query_on), N, H, Tq, Tk, d, causal, renorm, dev(dout), dq, dk, dv)
+    # both sides round the fp32 gradients to bf16 once: 2^-9 on elements where the roundings differ
+    assert rel(dq, rq) < 2e-3 and rel(dk, rk) < 2e-3 and rel(dv, rv) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ loss / adam
+def test_answer_loss_and_adam(ops):
+    B, ncls = 37, 1845
+    L = [GS.randn(f"loss/{i}", B, ncls) for i in range(3)]
+    ans = GS.randint("loss/ans", 0, ncls, B)
+    Lr = [x.clone().requires_grad_(True) for x in L]
+    ref = O.answer_loss(*Lr, ans)
+    ref.backward()
+    loss, grads = ops.answer_loss(dev(L[0]), dev(L[1]), dev(L[2]), dev(ans), 0.1, 1.0, True)
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    for g_, r_ in zip(grads, Lr):
+        assert rel(g_, r_.grad) < 1e-5
+    p = GS.randn("adam/p", 10000)
+    g = GS.randn("adam/g", 10000)
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=1e-3)
+    pd, m, v = dev(p.clone()), torch.zeros(10000, device="cuda"), torch.zeros(10000, device="cuda")
+    for step in (1, 2, 3):
+        pr.grad = g.clone() * step
+        opt.step()
+        ops.adam_step(pd, dev(g * step), m, v, 1e-3, 0.9, 0.999, 1e-8, step)
+    assert rel(pd, pr.detach()) < 1e-6

@@ -1,0 +1,144 @@
+"""GPU parity tests, module level, THROUGH the C ABI: our drop-in modules on cuda:0 against the golden vectors of the
+live reference and the oracle (tolerances: tests/parity_util.py), plus size-independent properties at the
+BASELINE.json sizes where the oracle would take too long."""
+import pytest
+import torch
+
+import parity_cases as PC
+from oracle import golden_spec as GS
+from oracle import savqa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    from savqa_b200 import _lib, modules
+    _lib.require_device()
+    return modules
+
+
+@pytest.fixture(scope="module")
+def A():
+    from savqa_b200 import AttModel_x3
+    return AttModel_x3
+
+
+@pytest.mark.parametrize("tag,C,H,N,T", [("c64", 64, 4, 3, 10), ("c512", 512, 8, 2, 24)])
+def test_attention_self(M, golden_dir, tag, C, H, N, T):
+    errs = PC.attention_case(M, golden_dir, "cuda", f"attn_self_{tag}", C, H, N, T, T, True)
+    print(tag, {k: f"{v:.2e}" for k, v in errs.items()})
+
+
+@pytest.mark.parametrize("tag,C,H,N,T", [("c64", 64, 4, 3, 10), ("c512", 512, 8, 2, 24)])
+@pytest.mark.parametrize("tq", [1, 3])
+def test_attention_cross(M, golden_dir, tag, C, H, N, T, tq):
+    PC.attention_case(M, golden_dir, "cuda", f"attn_cross{tq}_{tag}", C, H, N, tq, T, False)
+
+
+@pytest.mark.parametrize("tag,C,H,N", [("c64", 64, 4, 3), ("c512", 512, 8, 2)])
+def test_mha_causal(M, golden_dir, tag, C, H, N):
+    PC.attention_case(M, golden_dir, "cuda", f"mha_causal_{tag}", C, H, N, 6, 6, True, kind="mha")
+
+
+@pytest.mark.parametrize("tag,C,H,N,T", [("c64", 64, 4, 3, 10), ("c512", 512, 8, 2, 24)])
+def test_attention_graphmask(M, golden_dir, tag, C, H, N, T):
+    PC.attention_case(M, golden_dir, "cuda", f"attn_graphmask_{tag}", C, H, N, T, T, True, kind="gm")
+
+
+@pytest.mark.parametrize("tag,C,N,T", [("c64", 64, 3, 10), ("c512", 512, 2, 24)])
+def test_feedforward(M, golden_dir, tag, C, N, T):
+    PC.feedforward_case(M, golden_dir, "cuda", f"ffn_{tag}", C, N, T)
+
+
+def test_layernorm_embedding(M, golden_dir):
+    PC.layernorm_case(M, golden_dir, "cuda")
+    PC.embedding_cases(M, golden_dir, "cuda")
+
+
+@pytest.mark.parametrize("kind", ["vis", "syb"])
+def test_branch_vs_golden(A, golden_dir, kind):
+    errs = PC.branch_case(A, golden_dir, "cuda", kind)
+    print(kind, "dec", f"{errs['dec']:.2e}")
+
+
+def test_engines_agree_on_module(M):
+    """The tcgen05 attention kernel and the CUDA-core verification kernel give the same module output."""
+    import savqa_b200.functional as Fn
+    C, H, N, T = 512, 8, 4, 56
+    P = GS.make_params("eng", GS.attention_shapes(C))
+    m = M.new_multihead_attention(C, H, return_att=True)
+    PC.set_params(m, P)
+    m = m.cuda()
+    x = GS.randn("eng/x", N, T, C).cuda()
+    graph = GS.bernoulli("eng/g", 0.3, N, T, T).float().cuda()
+    outs = {}
+    for eng in (0, 1):
+        Fn.ATTN_ENGINE = eng
+        try:
+            y, att = m(x, x, x, graph)
+        finally:
+            Fn.ATTN_ENGINE = 0
+        outs[eng] = (y.detach().cpu(), att.detach().cpu())
+    assert O.rel_err(outs[0][1], outs[1][1]) < 2e-5   # probabilities: fp32 on both engines
+    assert O.rel_err(outs[0][0], outs[1][0]) < 2e-3   # output: engine 0 rounds P to bf16 before P.V
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE-size properties (cfg2: B=256, V=100, Q=20 -> T=120; cfg3: B=128, T=56 / 128)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,T", [(256, 120), (128, 56), (128, 128)])
+def test_full_size_attention_properties(M, N, T):
+    C, H = 512, 8
+    P = GS.make_params("prop", GS.attention_shapes(C))
+    m = M.new_multihead_attention(C, H, return_att=True)
+    PC.set_params(m, P)
+    m = m.cuda()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(N, T, C, device="cuda", generator=g)
+    x[:, T - 3:] = 0  # padded tokens: key- and query-masked
+    graph = (torch.rand(N, T, T, device="cuda", generator=g) < 0.2).float()
+    graph[:, 5] = 0  # a node without edges
+    y, att = m(x, x, x, graph)
+    torch.cuda.synchronize()
+    a4 = att.view(H, N, T, T)
+    rows = a4.sum(-1)
+    has_edge = ((graph[:, :, : T - 3].sum(-1) > 0).unsqueeze(0).expand(H, N, T))
+    # every row with at least one allowed, unmasked key is a probability distribution; the others are exactly zero
+    assert torch.allclose(rows[has_edge], torch.ones_like(rows[has_edge]), atol=1e-5)
+    assert float(rows[~has_edge].abs().max()) == 0.0
+    assert float(a4[:, :, :, T - 3:].abs().max()) == 0.0      # key-masked columns carry no weight
+    assert float((a4 * (1 - graph).unsqueeze(0)).abs().max()) == 0.0  # no weight outside the graph
+    assert torch.isfinite(y).all()
+    # LayerNorm property with gamma, beta: (y - beta)/gamma has zero mean and unit unbiased std on every row
+    z = (y - m.normalization.beta) / m.normalization.gamma
+    assert float(z.mean(-1).abs().max()) < 1e-4
+    assert float((z.std(-1) - 1).abs().max()) < 1e-3
+    # permutation equivariance over samples (no cross-sample leakage), bit exact
+    perm = torch.randperm(N, device="cuda", generator=g)
+    y2, _ = m(x[perm].contiguous(), x[perm].contiguous(), x[perm].contiguous(), graph[perm].contiguous())
+    assert torch.equal(y2, y[perm])
+
+
+def test_full_size_step_runs_and_is_deterministic(A):
+    """cfg3-shaped full step (both branches + heads + loss + backward) twice: identical loss, finite gradients."""
+    from savqa_b200 import synthetic
+    torch.manual_seed(0)
+    cfg = synthetic.GQA_SHAPED
+    model = synthetic.build_model(cfg, vocab_rows=5000).cuda()
+    batch = synthetic.make_batch(cfg, batch_size=32, seed=1, vocab_rows=5000, device="cuda")
+    losses = []
+    for _ in range(2):
+        model.zero_grad(set_to_none=True)
+        logits = model.encoder_step(batch["vis_fea"], batch["vis_fea_mask"], batch["q_ipt"], batch["q_ipt_mask"], batch["q_ipt_graph"],
+                                    batch["syb_ipt"], batch["macro_node_mask"], batch["macro_graph_ipt"], True)
+        loss = A.answer_loss(*logits, batch["answer"])
+        loss.backward()
+        losses.append(float(loss))
+    assert abs(losses[0] - losses[1]) < 1e-4 * abs(losses[0])
+    n_grad = 0
+    for name, p in model.named_parameters():
+        if p.grad is not None:
+            assert torch.isfinite(p.grad).all(), name
+            n_grad += 1
+    assert n_grad > 300
