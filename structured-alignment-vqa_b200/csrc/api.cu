@@ -22,7 +22,27 @@ void set_error(const char* fmt, ...) {
 
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  (void)cudaGetLastError();  // do not let a reported (non-sticky) error leak into the next call's cudaGetLastError()
   return SAVQA_ERR_CUDA;
+}
+
+int ensure_dynamic_smem(const void* kernel, size_t bytes, const char* what) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, size_t> granted;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = granted.find(kernel);
+  if (it != granted.end() && it->second >= bytes) return SAVQA_OK;
+  cudaFuncAttributes fa;
+  SAVQA_CHECK_CUDA(cudaFuncGetAttributes(&fa, kernel));
+  const size_t limit = 227 * 1024;
+  if (bytes + fa.sharedSizeBytes > limit) {
+    set_error("%s needs %zu bytes of dynamic + %zu bytes of static shared memory; the sm_100 limit is %zu per CTA", what, bytes,
+              static_cast<size_t>(fa.sharedSizeBytes), limit);
+    return SAVQA_ERR_UNSUPPORTED;
+  }
+  if (bytes > 48 * 1024) SAVQA_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  granted[kernel] = bytes;
+  return SAVQA_OK;
 }
 
 int sm_count() {

@@ -305,12 +305,7 @@ int attn_fwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
   SAVQA_REQUIRE(a->out, "savqa_graph_attn_fwd: null out");
   const int dp = a->d + 2;
   const size_t smem = static_cast<size_t>(2) * a->Tk * dp * 2 + static_cast<size_t>(8) * a->Tk * 4 + static_cast<size_t>(8) * a->d * 4;
-  SAVQA_REQUIRE(smem <= 200 * 1024, "savqa_graph_attn_fwd: Tk*d too large for one CTA (%zu bytes of smem)", smem);
-  static size_t configured = 0;
-  if (smem > configured) {
-    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_fwd_simt_kernel), smem, "savqa_graph_attn_fwd (engine 1)")) return rc;
   dim3 grid(a->N * a->H, (a->Tq + kRowsPerCta - 1) / kRowsPerCta);
   attn_fwd_simt_kernel<<<grid, 256, smem, stream>>>(*a);
   SAVQA_CHECK_CUDA(cudaGetLastError());
@@ -324,16 +319,12 @@ int attn_bwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
   const int dp = a->d + 2;
   const size_t smem1 = static_cast<size_t>(2) * a->Tk * dp * 2 + static_cast<size_t>(8) * a->Tk * 4 + static_cast<size_t>(16) * a->d * 4;
   const size_t smem2 = static_cast<size_t>(2) * a->Tq * a->d * 4;
-  SAVQA_REQUIRE(smem1 <= 200 * 1024 && smem2 <= 200 * 1024, "savqa_graph_attn_bwd: T*d too large for one CTA");
-  static bool configured = false;
-  if (!configured) {
-    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_keys_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_keys_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_keys_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_keys_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_bwd_rows_kernel), smem1, "savqa_graph_attn_bwd")) return rc;
+  const void* keys_kernel = a->d == 16   ? reinterpret_cast<const void*>(attn_bwd_keys_kernel<2>)
+                            : a->d == 32 ? reinterpret_cast<const void*>(attn_bwd_keys_kernel<4>)
+                            : a->d == 64 ? reinterpret_cast<const void*>(attn_bwd_keys_kernel<8>)
+                                         : reinterpret_cast<const void*>(attn_bwd_keys_kernel<16>);
+  if (int rc = ensure_dynamic_smem(keys_kernel, smem2, "savqa_graph_attn_bwd")) return rc;
   dim3 grid1(a->N * a->H, (a->Tq + kRowsPerCta - 1) / kRowsPerCta);
   attn_bwd_rows_kernel<<<grid1, 256, smem1, stream>>>(*a);
   SAVQA_CHECK_CUDA(cudaGetLastError());

@@ -291,20 +291,18 @@ int attn_fwd_tc(const savqa_attn_args_t* a, cudaStream_t stream) {
   const int dch = a->d / 64;
   const size_t smem = 1024 + static_cast<size_t>(dch) * 16384 + static_cast<size_t>(2) * dch * p.kv_rows * 128 +
                       static_cast<size_t>(p.tk_chunks) * 16384 + static_cast<size_t>(a->Tk) * 4 + 16;
-  SAVQA_REQUIRE(smem <= 227 * 1024, "savqa_graph_attn_fwd: Tk=%d d=%d needs %zu bytes of smem", a->Tk, a->d, smem);
   alignas(64) CUtensorMap tmQ, tmK, tmV;
   if (int rc = make_map3(&tmQ, a->q, a->ldq, a->Tq, a->N, 128)) return rc;
   if (int rc = make_map3(&tmK, a->k, a->ldk, a->Tk, a->N, p.kv_box)) return rc;
   if (int rc = make_map3(&tmV, a->v, a->ldv, a->Tk, a->N, p.kv_box)) return rc;
   dim3 grid(a->N * a->H, (a->Tq + 127) / 128);
-  static bool configured = false;
-  if (!configured) {
-    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+  if (a->d == 64) {
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_fwd_tc_kernel<64>), smem, "savqa_graph_attn_fwd (tcgen05 engine)")) return rc;
+    attn_fwd_tc_kernel<64><<<grid, 128, smem, stream>>>(tmQ, tmK, tmV, p);
+  } else {
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_fwd_tc_kernel<128>), smem, "savqa_graph_attn_fwd (tcgen05 engine)")) return rc;
+    attn_fwd_tc_kernel<128><<<grid, 128, smem, stream>>>(tmQ, tmK, tmV, p);
   }
-  if (a->d == 64) attn_fwd_tc_kernel<64><<<grid, 128, smem, stream>>>(tmQ, tmK, tmV, p);
-  else attn_fwd_tc_kernel<128><<<grid, 128, smem, stream>>>(tmQ, tmK, tmV, p);
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;
 }

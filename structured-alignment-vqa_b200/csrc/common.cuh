@@ -34,6 +34,10 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int sm_count();
 
+// Opts a kernel into `bytes` of dynamic shared memory (monotonic, cached per kernel); fails with a message when
+// bytes + the kernel's static shared memory exceed the 227 KB per-CTA limit of sm_100.
+int ensure_dynamic_smem(const void* kernel, size_t bytes, const char* what);
+
 // Creates (and caches) a CUtensorMap for a row-major bf16 tensor of rank 2 or 3.
 //   dims[0] is the innermost (contiguous) extent; strides_bytes[i] is the byte stride of dims[i+1].
 // box[] is the TMA box, 128-byte swizzle when swizzle128 is set.

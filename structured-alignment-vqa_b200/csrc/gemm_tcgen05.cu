@@ -291,11 +291,7 @@ template <int BN, bool A_MN, bool B_MN>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using C = Cfg<BN>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SAVQA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_done = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "savqa_gemm_bf16")) return rc;
   const int tiles = p.num_m * p.num_n * p.split_k;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);

@@ -26,6 +26,20 @@ WEIGHT_EPOCH = 0
 ATTN_ENGINE = 0
 
 
+def tc_attention_fits(d: int, Tk: int) -> bool:
+    """Whether the tcgen05 attention kernel (csrc/attn_tcgen05.cu) takes this shape: head size 64 / 128 and Q, K, V
+    and the bf16 probability tile of one (sample, head) inside one CTA's 227 KB of shared memory, scores in 512 TMEM
+    columns.  Other shapes run on the CUDA-core kernel (engine 1)."""
+    if d not in (64, 128) or Tk > 512:
+        return False
+    dch = d // 64
+    tk16 = (Tk + 15) // 16 * 16
+    box = min(tk16, 256)
+    kv_rows = (tk16 + box - 1) // box * box
+    smem = 1024 + dch * 16384 + 2 * dch * kv_rows * 128 + ((Tk + 63) // 64) * 16384 + Tk * 4 + 16
+    return smem + 64 <= 227 * 1024
+
+
 class Side:
     """bf16 copy and row mask of an activation produced by one of our kernels, handed to the next module so that
     it does not have to re-read the fp32 tensor (valid while the fp32 tensor is not modified in place)."""
@@ -277,7 +291,7 @@ class GraphAttentionFn(Function):
         if graph is not None and renorm != 0:
             g = graph if graph.dtype == F32 else graph.float()
             g = g if g.is_contiguous() else g.contiguous()
-        engine = ATTN_ENGINE if d in (64, 128) else 1
+        engine = ATTN_ENGINE if tc_attention_fits(d, Tk) else 1
         o, att = ops.graph_attention_fwd(q, k, v, g, k_on, q_on, N, H, Tq, Tk, d, causal, renorm if g is not None else 0, want_att, engine)
 
         # ---- residual (RAW queries) + LayerNorm (modules.py:304-307) ----
