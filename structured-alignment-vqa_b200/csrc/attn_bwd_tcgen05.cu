@@ -1,0 +1,438 @@
+// a11: backward of the graph-weighted attention core on the 5th-gen tensor cores (engine 0).
+//
+// One CTA (128 threads) per (sample n, head h); Tq <= 128 query rows, Tk <= 256 keys.
+//   stage     Q, K, V by TMA (3-D maps, zero fill past the sample's rows); dO (fp32 in HBM) is converted to a bf16,
+//             128B-swizzled tile by the CTA's threads
+//   S  = Q K^T      tcgen05.mma -> TMEM [0, Tk)           } one commit
+//   dWr = dO V^T    tcgen05.mma -> TMEM [dw_off, dw_off+Tk) }
+//   rows      thread t owns query row t: recompute the forward's softmax statistics and W = G*e*scale (same arithmetic
+//             as attn_tcgen05.cu), t = sum_j W dW, dS; bf16 dS and W' = W*qmask go to two swizzled smem tiles
+//   dQ = dS K       A = dS  (K-major),            B = K  (MN-major)
+//   dK = dS^T Q     A = dS  (MN-major, same tile), B = Q  (MN-major)     accumulators overlay the consumed S / dW columns
+//   dV = W'^T dO    A = W'  (MN-major),           B = dO (MN-major)
+//   epilogue  ReLU gates of the Q/K/V projections (modules.py:227-229) applied from q/k/v, bf16 stores into the
+//             fused [.., 3C] gradient layout.
+// Formulas: SURVEY.md Appendix A (verified against autograd); attn_simt.cu is the fp32 restatement of the same maths.
+#include "common.cuh"
+
+namespace savqa {
+
+int attn_bwd_tc(const savqa_attn_args_t* a, cudaStream_t stream);
+bool attn_bwd_tc_fits(const savqa_attn_args_t* a);
+
+namespace {
+
+constexpr float kMaskFill = -4294967296.0f;
+
+struct BwdParams {
+  savqa_attn_args_t a;
+  int tk_pad16;  // Tk rounded up to 16
+  int kt;        // 128-key output tiles (1 or 2)
+  int kv_rows;   // rows of the K / V smem tiles (= TMA box rows)
+  int dw_off;    // TMEM column of the raw dW accumulator
+  int tmem_cols;
+  int gvec;      // graph rows readable as float4
+  int dvec;      // dout rows readable as float4
+};
+
+__device__ __forceinline__ void tmem_alloc_rt(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_rt(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// bf16 row-gradient store with the ReLU gate of the projection output `act` (same layout as the gradient).
+__device__ __forceinline__ void store_gated_row32(const uint32_t (&r)[32], const __nv_bfloat16* act, __nv_bfloat16* dst) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint4 av = __ldg(reinterpret_cast<const uint4*>(act) + u);
+    const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 f = unpack_bf16x2(aw[q]);
+      const float lo = f.x > 0.0f ? __uint_as_float(r[8 * u + 2 * q]) : 0.0f;
+      const float hi = f.y > 0.0f ? __uint_as_float(r[8 * u + 2 * q + 1]) : 0.0f;
+      o[q] = pack_bf16x2(lo, hi);
+    }
+    reinterpret_cast<uint4*>(dst)[u] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// g[j] = graph weight of column c0 + j of this thread's query row (1 when there is no graph, 0 past Tk)
+__device__ __forceinline__ void load_graph32(const float* grow, bool use, int c0, int Tk, int gvec, float (&g)[32]) {
+  if (use && grow) {
+    if (gvec && c0 + 32 <= Tk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(grow + c0) + j);
+        g[4 * j] = v.x; g[4 * j + 1] = v.y; g[4 * j + 2] = v.z; g[4 * j + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) g[j] = (c0 + j < Tk) ? __ldg(grow + c0 + j) : 0.0f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) g[j] = 1.0f;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                         const __grid_constant__ CUtensorMap tmV, const BwdParams p) {
+  constexpr int DCH = D / 64;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_tma, bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+  const savqa_attn_args_t& a = p.a;
+  const int t = threadIdx.x, warp = t >> 5;
+  const int hn = blockIdx.x;
+  const int h = hn / a.N, n = hn % a.N;
+  const int kc2 = 2 * p.kt;  // 64-key chunks of the dS / W' tiles (whole 128-key tiles)
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                            // DCH x [128][128 B]
+  uint8_t* sdO = sQ + DCH * 16384;               // DCH x [128][128 B]
+  uint8_t* sK = sdO + DCH * 16384;               // DCH x [kv_rows][128 B]
+  uint8_t* sV = sK + DCH * p.kv_rows * 128;      // DCH x [kv_rows][128 B]
+  uint8_t* sP = sV + DCH * p.kv_rows * 128;      // kc2 x [128][128 B]   dS
+  uint8_t* sW = sP + kc2 * 16384;                // kc2 x [128][128 B]   W'
+  float* sKeyOn = reinterpret_cast<float*>(sW + kc2 * 16384);  // [Tk]
+
+  if (t == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(&bar_tma, 1);
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_o, 1);
+    fence_barrier_init();
+    // Q / K / V travel while the CTA converts dO
+    const uint32_t bytes = static_cast<uint32_t>(DCH) * (16384u + 2u * static_cast<uint32_t>(p.kv_rows) * 128u);
+    mbar_arrive_expect_tx(&bar_tma, bytes);
+    for (int c = 0; c < DCH; ++c) {
+      tma_load_3d(sQ + c * 16384, &tmQ, &bar_tma, h * D + c * 64, 0, n);
+      tma_load_3d(sK + c * p.kv_rows * 128, &tmK, &bar_tma, h * D + c * 64, 0, n);
+      tma_load_3d(sV + c * p.kv_rows * 128, &tmV, &bar_tma, h * D + c * 64, 0, n);
+    }
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc_rt(&tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+  for (int j = t; j < a.Tk; j += 128) sKeyOn[j] = a.key_on ? a.key_on[static_cast<long>(n) * a.Tk + j] : 1.0f;
+
+  // ---- dO: fp32 [Tq, D] head slice -> bf16 K-major swizzled tile (rows >= Tq are zero) ----
+  {
+    constexpr int V4 = D / 4;  // float4 per row
+    for (int idx = t; idx < 128 * V4; idx += 128) {
+      const int row = idx / V4, col = (idx % V4) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < a.Tq) {
+        const float* src = a.dout + (static_cast<long>(n) * a.Tq + row) * a.ld_dout + h * D + col;
+        if (p.dvec) v = __ldg(reinterpret_cast<const float4*>(src));
+        else v = make_float4(src[0], src[1], src[2], src[3]);
+      }
+      const int cc = col & 63;
+      uint8_t* dst = sdO + (col >> 6) * 16384 + row * 128 + ((((cc >> 3) ^ (row & 7))) << 4) + (cc & 7) * 2;
+      *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (t == 0) {
+    mbar_wait(&bar_tma, 0);
+    tc_fence_after();
+    // S = Q K^T and raw dW = dO V^T (N up to 256 per instruction)
+    for (int n0 = 0; n0 < p.tk_pad16; n0 += 256) {
+      const int nn = min(256, p.tk_pad16 - n0);
+      const uint32_t idesc = umma_idesc_bf16(128, nn, false, false);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) {
+        const int c = k / 4, kk = k % 4;
+        const uint64_t adesc = umma_smem_desc(smem_u32(sQ + c * 16384) + kk * 32, 16, 1024);
+        const uint64_t bdesc = umma_smem_desc(smem_u32(sK + (c * p.kv_rows + n0) * 128) + kk * 32, 16, 1024);
+        umma_bf16_ss(tmem + n0, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
+      }
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) {
+        const int c = k / 4, kk = k % 4;
+        const uint64_t adesc = umma_smem_desc(smem_u32(sdO + c * 16384) + kk * 32, 16, 1024);
+        const uint64_t bdesc = umma_smem_desc(smem_u32(sV + (c * p.kv_rows + n0) * 128) + kk * 32, 16, 1024);
+        umma_bf16_ss(tmem + p.dw_off + n0, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
+      }
+    }
+    umma_commit(&bar_s);
+  }
+  __syncwarp();
+
+  // ---- row pass: thread t <-> query row t <-> TMEM lane t ----
+  mbar_wait(&bar_s, 0);
+  tc_fence_after();
+  const int i = t;
+  const bool row_ok = i < a.Tq;
+  const long qrow = static_cast<long>(n) * a.Tq + (row_ok ? i : 0);
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
+  const int renorm = a.graph ? a.renorm : 0;
+  const float* grow = (a.graph && row_ok) ? a.graph + static_cast<long>(n) * a.graph_n_stride + static_cast<long>(i) * a.graph_q_stride : nullptr;
+  const float qon = (a.query_on && row_ok) ? a.query_on[qrow] : 1.0f;
+
+  float m = -INFINITY;
+  for (int c0 = 0; c0 < a.Tk; c0 += 32) {
+    uint32_t r[32];
+    __syncwarp();
+    tmem_ld_32x32(t_lane + c0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c0 + j;
+      if (col < a.Tk) {
+        float s = __uint_as_float(r[j]) * inv_sqrt_d;
+        if (sKeyOn[col] == 0.0f) s = kMaskFill;
+        if (a.causal && col > i) s = kMaskFill;
+        m = fmaxf(m, s);
+      }
+    }
+  }
+  // statistics: Z = sum e, R = sum |g e|, SA = sum g e, U = sum g e * raw dW
+  float Z = 0.0f, R = 0.0f, SA = 0.0f, U = 0.0f;
+  for (int c0 = 0; c0 < a.Tk; c0 += 32) {
+    uint32_t r[32], w[32];
+    __syncwarp();
+    tmem_ld_32x32(t_lane + c0, r);
+    tmem_ld_32x32(t_lane + p.dw_off + c0, w);
+    tmem_ld_wait();
+    float g[32];
+    load_graph32(grow, renorm != 0, c0, a.Tk, p.gvec, g);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c0 + j;
+      if (col < a.Tk) {
+        float s = __uint_as_float(r[j]) * inv_sqrt_d;
+        if (sKeyOn[col] == 0.0f) s = kMaskFill;
+        if (a.causal && col > i) s = kMaskFill;
+        const float e = __expf(s - m);
+        const float ge = g[j] * e;
+        Z += e;
+        R += fabsf(ge);
+        SA += ge;
+        U = fmaf(ge, __uint_as_float(w[j]), U);
+      }
+    }
+  }
+  float scale;
+  bool clamped = false;
+  if (renorm == 1) {
+    clamped = !(R / Z >= 1e-12f);
+    scale = clamped ? 1.0f / (Z * 1e-12f) : 1.0f / R;
+  } else if (renorm == 2) {
+    scale = 1.0f / (SA + 1e-7f * Z);
+  } else {
+    scale = 1.0f / Z;
+  }
+  const float tsum = scale * qon * U;  // sum_j W_j dW_j
+  // dS_j = W_j (dW_j - alpha t) - beta P_j t
+  const float alpha = clamped ? 0.0f : 1.0f;
+  const float beta = clamped ? 1.0f : (renorm == 2 ? 1.0f - scale * SA : 0.0f);
+  const float inv_z = 1.0f / Z;
+
+  for (int c0 = 0; c0 < kc2 * 64; c0 += 32) {
+    float ds[32], wq[32];
+    if (c0 < a.Tk) {  // warp-uniform: the TMEM loads are .sync.aligned
+      uint32_t r[32], w[32];
+      __syncwarp();
+      tmem_ld_32x32(t_lane + c0, r);
+      tmem_ld_32x32(t_lane + p.dw_off + c0, w);
+      tmem_ld_wait();
+      float g[32];
+      load_graph32(grow, renorm != 0, c0, a.Tk, p.gvec, g);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = c0 + j;
+        float dsv = 0.0f, wv = 0.0f;
+        if (col < a.Tk && row_ok) {
+          float s = __uint_as_float(r[j]) * inv_sqrt_d;
+          bool masked = false;
+          if (sKeyOn[col] == 0.0f) { s = kMaskFill; masked = true; }
+          if (a.causal && col > i) { s = kMaskFill; masked = true; }
+          const float e = __expf(s - m);
+          const float W = g[j] * e * scale;
+          const float dW = __uint_as_float(w[j]) * qon;
+          dsv = W * (dW - alpha * tsum) - beta * (e * inv_z) * tsum;
+          if (masked) dsv = 0.0f;  // masked scores are constants
+          dsv *= inv_sqrt_d;
+          wv = W * qon;
+        }
+        ds[j] = dsv;
+        wq[j] = wv;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ds[j] = wq[j] = 0.0f;
+    }
+    const int off = (c0 >> 6) * 16384 + t * 128;
+    const int u0 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int sw = ((u0 + u) ^ (t & 7)) << 4;
+      *reinterpret_cast<uint4*>(sP + off + sw) = make_uint4(pack_bf16x2(ds[8 * u], ds[8 * u + 1]), pack_bf16x2(ds[8 * u + 2], ds[8 * u + 3]),
+                                                           pack_bf16x2(ds[8 * u + 4], ds[8 * u + 5]), pack_bf16x2(ds[8 * u + 6], ds[8 * u + 7]));
+      *reinterpret_cast<uint4*>(sW + off + sw) = make_uint4(pack_bf16x2(wq[8 * u], wq[8 * u + 1]), pack_bf16x2(wq[8 * u + 2], wq[8 * u + 3]),
+                                                           pack_bf16x2(wq[8 * u + 4], wq[8 * u + 5]), pack_bf16x2(wq[8 * u + 6], wq[8 * u + 7]));
+    }
+  }
+
+  // ---- dQ, dK, dV ----
+  const int dq_off = 0, dk_off = D, dv_off = D + p.kt * D;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (t == 0) {
+    tc_fence_after();
+    const uint32_t idesc_q = umma_idesc_bf16(128, 64, false, true);
+    const uint32_t idesc_k = umma_idesc_bf16(128, 64, true, true);
+    const int ksteps_keys = p.tk_pad16 / 16;
+    const int ksteps_rows = (a.Tq + 15) / 16;
+    for (int c = 0; c < DCH; ++c) {
+      for (int k = 0; k < ksteps_keys; ++k) {
+        const uint64_t adesc = umma_smem_desc(smem_u32(sP + (k >> 2) * 16384) + (k & 3) * 32, 16, 1024);
+        const uint64_t bdesc = umma_smem_desc(smem_u32(sK + c * p.kv_rows * 128) + k * 2048, 8192, 1024);
+        umma_bf16_ss(tmem + dq_off + c * 64, adesc, bdesc, idesc_q, k > 0 ? 1u : 0u);
+      }
+    }
+    for (int kt = 0; kt < p.kt; ++kt) {
+      for (int c = 0; c < DCH; ++c) {
+        for (int k = 0; k < ksteps_rows; ++k) {
+          const uint64_t a_ds = umma_smem_desc(smem_u32(sP + 2 * kt * 16384) + k * 2048, 16384, 1024);
+          const uint64_t b_q = umma_smem_desc(smem_u32(sQ + c * 16384) + k * 2048, 8192, 1024);
+          umma_bf16_ss(tmem + dk_off + kt * D + c * 64, a_ds, b_q, idesc_k, k > 0 ? 1u : 0u);
+        }
+        for (int k = 0; k < ksteps_rows; ++k) {
+          const uint64_t a_w = umma_smem_desc(smem_u32(sW + 2 * kt * 16384) + k * 2048, 16384, 1024);
+          const uint64_t b_do = umma_smem_desc(smem_u32(sdO + c * 16384) + k * 2048, 8192, 1024);
+          umma_bf16_ss(tmem + dv_off + kt * D + c * 64, a_w, b_do, idesc_k, k > 0 ? 1u : 0u);
+        }
+      }
+    }
+    umma_commit(&bar_o);
+  }
+  __syncwarp();
+  mbar_wait(&bar_o, 0);
+  tc_fence_after();
+
+  // ---- epilogue: ReLU gates + bf16 stores ----
+  const __nv_bfloat16* Qg = static_cast<const __nv_bfloat16*>(a.q) + qrow * a.ldq + h * D;
+  __nv_bfloat16* dQg = static_cast<__nv_bfloat16*>(a.dq) + qrow * a.ld_dq + h * D;
+#pragma unroll 1
+  for (int c0 = 0; c0 < D; c0 += 32) {
+    uint32_t r[32];
+    __syncwarp();
+    tmem_ld_32x32(t_lane + dq_off + c0, r);
+    tmem_ld_wait();
+    if (row_ok) store_gated_row32(r, Qg + c0, dQg + c0);
+  }
+#pragma unroll 1
+  for (int kt = 0; kt < p.kt; ++kt) {
+    const int j = kt * 128 + t;
+    const bool key_ok = j < a.Tk;
+    const long krow = static_cast<long>(n) * a.Tk + (key_ok ? j : 0);
+    const __nv_bfloat16* Kg = static_cast<const __nv_bfloat16*>(a.k) + krow * a.ldk + h * D;
+    const __nv_bfloat16* Vg = static_cast<const __nv_bfloat16*>(a.v) + krow * a.ldv + h * D;
+    __nv_bfloat16* dKg = static_cast<__nv_bfloat16*>(a.dk) + krow * a.ld_dk + h * D;
+    __nv_bfloat16* dVg = static_cast<__nv_bfloat16*>(a.dv) + krow * a.ld_dv + h * D;
+#pragma unroll 1
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld_32x32(t_lane + dk_off + kt * D + c0, r);
+      tmem_ld_wait();
+      if (key_ok) store_gated_row32(r, Kg + c0, dKg + c0);
+      __syncwarp();
+      tmem_ld_32x32(t_lane + dv_off + kt * D + c0, r);
+      tmem_ld_wait();
+      if (key_ok) store_gated_row32(r, Vg + c0, dVg + c0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    __syncwarp();
+    tmem_dealloc_rt(tmem, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+int make_map3(CUtensorMap* m, const void* base, int64_t ld, int T, int N, int box_rows) {
+  const uint64_t dims[3] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(T), static_cast<uint64_t>(N)};
+  const uint64_t str[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * static_cast<uint64_t>(T)};
+  const uint32_t box[3] = {64, static_cast<uint32_t>(box_rows), 1};
+  return make_tensor_map_bf16(m, base, 3, dims, str, box, true);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+void fill_params(const savqa_attn_args_t* a, BwdParams& p, size_t& smem) {
+  p.a = *a;
+  p.tk_pad16 = (a->Tk + 15) / 16 * 16;
+  p.kt = (a->Tk + 127) / 128;
+  p.kv_rows = p.tk_pad16;
+  p.dw_off = (p.tk_pad16 + 31) / 32 * 32;
+  const int need = max(p.dw_off + p.tk_pad16, (1 + 2 * p.kt) * a->d);
+  int cols = 32;
+  while (cols < need) cols *= 2;
+  p.tmem_cols = cols;
+  p.gvec = (a->graph && a->Tk % 4 == 0 && a->graph_n_stride % 4 == 0 && a->graph_q_stride % 4 == 0 && aligned16(a->graph)) ? 1 : 0;
+  p.dvec = (a->ld_dout % 4 == 0 && aligned16(a->dout) && a->d % 4 == 0) ? 1 : 0;
+  const int dch = a->d / 64;
+  smem = 1024 + static_cast<size_t>(2) * dch * 16384 + static_cast<size_t>(2) * dch * p.kv_rows * 128 +
+         static_cast<size_t>(2) * (2 * p.kt) * 16384 + static_cast<size_t>(a->Tk) * 4 + 16;
+}
+
+}  // namespace
+
+bool attn_bwd_tc_fits(const savqa_attn_args_t* a) {
+  if (!(a->d == 64 || a->d == 128)) return false;
+  if (a->Tq > 128 || a->Tk > 256 || a->Tq < 1 || a->Tk < 1) return false;
+  if (a->ldq % 8 || a->ldk % 8 || a->ldv % 8 || a->ld_dq % 8 || a->ld_dk % 8 || a->ld_dv % 8) return false;
+  if (!aligned16(a->q) || !aligned16(a->k) || !aligned16(a->v) || !aligned16(a->dq) || !aligned16(a->dk) || !aligned16(a->dv)) return false;
+  BwdParams p;
+  size_t smem;
+  fill_params(a, p, smem);
+  if (p.tmem_cols > 512) return false;
+  return smem + 64 <= 227 * 1024;
+}
+
+int attn_bwd_tc(const savqa_attn_args_t* a, cudaStream_t stream) {
+  SAVQA_REQUIRE(a->q && a->k && a->v && a->dout && a->dq && a->dk && a->dv, "savqa_graph_attn_bwd: null tensor");
+  SAVQA_REQUIRE(a->N > 0 && a->H > 0, "savqa_graph_attn_bwd: empty problem");
+  SAVQA_REQUIRE(a->renorm >= 0 && a->renorm <= 2, "savqa_graph_attn_bwd: renorm mode %d", a->renorm);
+  SAVQA_REQUIRE(attn_bwd_tc_fits(a),
+                "savqa_graph_attn_bwd: the tcgen05 engine takes d in {64,128}, Tq <= 128, Tk <= 256 and 16-byte aligned rows "
+                "(got d=%d Tq=%d Tk=%d); use engine 1",
+                a->d, a->Tq, a->Tk);
+  BwdParams p;
+  size_t smem;
+  fill_params(a, p, smem);
+  alignas(64) CUtensorMap tmQ, tmK, tmV;
+  if (int rc = make_map3(&tmQ, a->q, a->ldq, a->Tq, a->N, 128)) return rc;
+  if (int rc = make_map3(&tmK, a->k, a->ldk, a->Tk, a->N, p.kv_rows)) return rc;
+  if (int rc = make_map3(&tmV, a->v, a->ldv, a->Tk, a->N, p.kv_rows)) return rc;
+  dim3 grid(a->N * a->H);
+  if (a->d == 64) {
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_bwd_tc_kernel<64>), smem, "savqa_graph_attn_bwd (tcgen05 engine)")) return rc;
+    attn_bwd_tc_kernel<64><<<grid, 128, smem, stream>>>(tmQ, tmK, tmV, p);
+  } else {
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_bwd_tc_kernel<128>), smem, "savqa_graph_attn_bwd (tcgen05 engine)")) return rc;
+    attn_bwd_tc_kernel<128><<<grid, 128, smem, stream>>>(tmQ, tmK, tmV, p);
+  }
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+}  // namespace savqa

@@ -16,6 +16,7 @@ namespace savqa {
 
 int attn_fwd_simt(const savqa_attn_args_t* a, cudaStream_t stream);
 int attn_bwd_simt(const savqa_attn_args_t* a, cudaStream_t stream);
+int attn_bwd_tc(const savqa_attn_args_t* a, cudaStream_t stream);
 
 namespace {
 
@@ -328,5 +329,8 @@ extern "C" int savqa_graph_attn_fwd(const savqa_attn_args_t* a, savqa_stream_t s
 }
 
 extern "C" int savqa_graph_attn_bwd(const savqa_attn_args_t* a, savqa_stream_t stream_) {
-  return attn_bwd_simt(a, static_cast<cudaStream_t>(stream_));
+  SAVQA_REQUIRE(a, "savqa_graph_attn_bwd: null args");
+  if (a->engine == 1) return attn_bwd_simt(a, static_cast<cudaStream_t>(stream_));
+  SAVQA_REQUIRE(a->engine == 0, "savqa_graph_attn_bwd: unknown engine %d", a->engine);
+  return attn_bwd_tc(a, static_cast<cudaStream_t>(stream_));
 }

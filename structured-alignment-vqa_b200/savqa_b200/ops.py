@@ -303,9 +303,28 @@ def graph_attention_fwd(q: Tensor, k: Tensor, v: Tensor, graph: Optional[Tensor]
     return out, att
 
 
+def tc_attention_bwd_fits(d: int, Tq: int, Tk: int) -> bool:
+    """Shapes the tcgen05 attention backward (csrc/attn_bwd_tcgen05.cu) takes: one CTA holds the whole (sample, head)
+    problem -- Q, dO, K, V and the two bf16 [128, Tk] tiles in shared memory, S / dW / dQ / dK / dV in 512 TMEM columns."""
+    if d not in (64, 128) or Tq > 128 or Tk > 256:
+        return False
+    kt = (Tk + 127) // 128
+    tk16 = (Tk + 15) // 16 * 16
+    dw_off = (tk16 + 31) // 32 * 32
+    if max(dw_off + tk16, (1 + 2 * kt) * d) > 512:
+        return False
+    dch = d // 64
+    smem = 1024 + 2 * dch * 16384 + 2 * dch * tk16 * 128 + 2 * (2 * kt) * 16384 + Tk * 4 + 16
+    return smem + 64 <= 227 * 1024
+
+
 def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout: Tensor, dq: Tensor, dk: Tensor,
-                        dv: Tensor) -> None:
-    """Gradient of the attention core; dq/dk/dv are bf16 2-D views and come back ReLU-gated by q/k/v > 0."""
+                        dv: Tensor, engine: Optional[int] = None) -> None:
+    """Gradient of the attention core; dq/dk/dv are bf16 2-D views and come back ReLU-gated by q/k/v > 0.
+    engine None: tcgen05 kernel when the shape fits, CUDA-core kernel otherwise."""
+    if engine is None:
+        strides_ok = all(t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0 for t in (q, k, v, dq, dk, dv))
+        engine = 0 if (tc_attention_bwd_fits(d, Tq, Tk) and strides_ok and Tq > 1) else 1
     a = AttnArgs()
     a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0)
     if graph is not None:
@@ -313,13 +332,14 @@ def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causa
         a.graph_q_stride = Tk if graph.shape[1] == Tq else 0
     a.key_on, a.query_on = ptr(key_on), ptr(query_on)
     a.N, a.H, a.Tq, a.Tk, a.d = N, H, Tq, Tk, d
-    a.causal, a.renorm, a.engine = int(causal), int(renorm), 1
+    a.causal, a.renorm, a.engine = int(causal), int(renorm), int(engine)
     _check(dout, F32, "dout")
     assert dout.dim() == 2 and dout.stride(1) == 1
     a.dout, a.ld_dout = ptr(dout), dout.stride(0)
     a.dq, a.ld_dq, a.dk, a.ld_dk, a.dv, a.ld_dv = ptr(dq), dq.stride(0), ptr(dk), dk.stride(0), ptr(dv), dv.stride(0)
-    scratch = torch.empty(2, H * N, Tq, Tk, device=q.device, dtype=F32)
-    a.scratch = ptr(scratch)
+    if engine == 1:
+        scratch = torch.empty(2, H * N, Tq, Tk, device=q.device, dtype=F32)
+        a.scratch = ptr(scratch)
     call("savqa_graph_attn_bwd", C.byref(a))
 
 

@@ -186,7 +186,7 @@ def graph_attention_fwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causa
     return out, att
 
 
-def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout, dq, dk, dv):
+def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout, dq, dk, dv, engine=None):
     # the explicit formulas of csrc/attn_simt.cu (attn_bwd_rows_kernel / attn_bwd_keys_kernel)
     P, W, fixed, r, G = _weights(q, k, graph, key_on, N, H, Tq, Tk, d, causal, renorm)
     Q, K, V = _heads(q, N, Tq, H, d), _heads(k, N, Tk, H, d), _heads(v, N, Tk, H, d)
