@@ -29,7 +29,7 @@ extern "C" {
 #define SAVQA_ERR_CUDA 2
 #define SAVQA_ERR_UNSUPPORTED 3
 
-#define SAVQA_ABI_VERSION 1
+#define SAVQA_ABI_VERSION 2
 
 typedef void* savqa_stream_t; /* cudaStream_t */
 
@@ -86,9 +86,11 @@ int savqa_colsum_bf16(const void* x_bf16, int64_t ld, int64_t rows, int cols, fl
 int savqa_residual_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float eps,
                                  int64_t rows, int C, float* pre, float* y, void* y_bf16, float* on, savqa_stream_t stream);
 /* dx = LN'(pre)[dy] (+ dres_in);  dgamma/dbeta are ACCUMULATED (+=).  sigma == 0 rows follow autograd:
- * dx = (g - mean g) / eps.  dx_bf16 optional. */
+ * dx = (g - mean g) / eps.  dx_bf16 optional.  dxsum (optional, fp32 [C]) += sum_rows dx: the bias gradient of the
+ * Linear whose output fed this LayerNorm (feedforward.conv2, modules.py:429, 439). */
 int savqa_layernorm_bwd(const float* dy, const float* pre, const float* gamma, float eps, int64_t rows, int C,
-                        const float* dres_in, float* dx, void* dx_bf16, float* dgamma, float* dbeta, savqa_stream_t stream);
+                        const float* dres_in, float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum,
+                        savqa_stream_t stream);
 
 /* ---- a3/a5/a7: bf16 tensor-core GEMM with fused epilogue ----------------------------------------------
  * acc[m,n] = sum_k A[m,k] * B[n,k]   (nn.Linear: A = activations [M,K], B = weight [N,K])
@@ -115,6 +117,7 @@ typedef struct savqa_gemm_epilogue {
   int64_t ld_out_f32;
   void* out_bf16;
   int64_t ld_out_bf16;
+  float* colsum; /* optional fp32 [N]: colsum[n] += sum_m v[m,n] (bias gradient of the layer that produced A; atomics) */
 } savqa_gemm_epilogue_t;
 
 int savqa_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, int M, int N, int K,
@@ -126,7 +129,8 @@ int savqa_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, i
  *   P = softmax(S);  renorm 0: W = P;  1: A = G*P, W = A / max(sum|A|, 1e-12);  2: W = A / (sum A + 1e-7);
  *   att[h*N+n] = W (optional, BEFORE the query mask);  W' = W * query_on[n,i];  O = W' V.
  * graph is fp32 [N,Tq,Tk]; graph_q_stride = Tk normally, 0 to broadcast one row over all queries ([N,1,Tk]).
- * engine: 0 = tcgen05/TMEM kernel (TMA-staged tiles), 1 = CUDA-core fp32 verification kernel. */
+ * engine: 0 = tcgen05/TMEM kernel (TMA-staged tiles), 1 = CUDA-core fp32 kernels: the verification kernel for Tq > 1
+ * and the one-warp-per-(sample, head) row kernel for Tq == 1 (the decoder's single query, AttModel_x3.py:141-154). */
 typedef struct savqa_attn_args {
   const void* q; int64_t ldq;      /* bf16 [N*Tq, ldq] */
   const void* k; int64_t ldk;      /* bf16 [N*Tk, ldk] */
@@ -143,7 +147,9 @@ typedef struct savqa_attn_args {
   void* dq; int64_t ld_dq;         /* bf16, ReLU-gated: dq = dQ * (q > 0) */
   void* dk; int64_t ld_dk;
   void* dv; int64_t ld_dv;
-  float* scratch;                  /* fp32 [2, H*N, Tq, Tk] workspace (dS and W') */
+  float* scratch;                  /* fp32 [2, H*N, Tq, Tk] workspace (dS and W'); engine 1 with Tq > 1 only */
+  /* optional bias gradients of the Q/K/V projections: db*[c] += sum_rows gated d*[row, c]  (fp32 [H*d], atomics) */
+  float* dbq; float* dbk; float* dbv;
 } savqa_attn_args_t;
 
 int savqa_graph_attn_fwd(const savqa_attn_args_t* args, savqa_stream_t stream);
@@ -160,8 +166,10 @@ int savqa_answer_loss(const float* logits_concat, const float* logits_vis, const
  * main_itp_ddp_tar_super_node.py:206) and its row-sparse form for the word tables. ------------------------ */
 /* dyn (device, may be NULL) = {lr / (1 - beta1^step), sqrt(1 - beta2^step), step}: read at run time instead of the host
  * scalars, so that a captured CUDA graph follows the step counter. */
+/* param_bf16 (optional, same length): receives the bf16 copy of the updated parameters -- the MMA-operand mirror the
+ * GEMMs read, so no per-step staging casts are needed. */
 int savqa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-                    float beta2, float eps, int step, const float* dyn, savqa_stream_t stream);
+                    float beta2, float eps, int step, const float* dyn, void* param_bf16, savqa_stream_t stream);
 
 /* Row-sparse ("lazy") Adam for the 407000 x 300 word tables: only rows named in idx[0..n_idx) are updated, each exactly
  * once per call even if it occurs several times (row_stamp[row] is set to `step` by the first claimant).  grad is the

@@ -43,21 +43,35 @@ __device__ __forceinline__ void tmem_dealloc_rt(uint32_t taddr, uint32_t ncols) 
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-// bf16 row-gradient store with the ReLU gate of the projection output `act` (same layout as the gradient).
-__device__ __forceinline__ void store_gated_row32(const uint32_t (&r)[32], const __nv_bfloat16* act, __nv_bfloat16* dst) {
+// bf16 row-gradient store with the ReLU gate of the projection output `act` (same layout as the gradient); rows that do
+// not exist (!ok) store nothing.  When `dbias` is given the warp also adds the column sums of its 32 gated rows to it
+// (the bias gradient of the projection, modules.py:227-229) -- warp-uniform call, 31 shuffles + one atomic per lane.
+__device__ __forceinline__ void store_gated_row32(const uint32_t (&r)[32], const __nv_bfloat16* act, __nv_bfloat16* dst, bool ok,
+                                                  float* dbias, int lane) {
+  float gv[32];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const uint4 av = __ldg(reinterpret_cast<const uint4*>(act) + u);
-    const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
-    uint32_t o[4];
+  for (int j = 0; j < 32; ++j) gv[j] = 0.0f;
+  if (ok) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float2 f = unpack_bf16x2(aw[q]);
-      const float lo = f.x > 0.0f ? __uint_as_float(r[8 * u + 2 * q]) : 0.0f;
-      const float hi = f.y > 0.0f ? __uint_as_float(r[8 * u + 2 * q + 1]) : 0.0f;
-      o[q] = pack_bf16x2(lo, hi);
+    for (int u = 0; u < 4; ++u) {
+      const uint4 av = __ldg(reinterpret_cast<const uint4*>(act) + u);
+      const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = unpack_bf16x2(aw[q]);
+        const float lo = f.x > 0.0f ? __uint_as_float(r[8 * u + 2 * q]) : 0.0f;
+        const float hi = f.y > 0.0f ? __uint_as_float(r[8 * u + 2 * q + 1]) : 0.0f;
+        gv[8 * u + 2 * q] = lo;
+        gv[8 * u + 2 * q + 1] = hi;
+        o[q] = pack_bf16x2(lo, hi);
+      }
+      reinterpret_cast<uint4*>(dst)[u] = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    reinterpret_cast<uint4*>(dst)[u] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  if (dbias) {
+    const float cs = warp_colsum32(gv, lane);
+    atomicAdd(dbias + lane, cs);
   }
 }
 
@@ -335,7 +349,7 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
     __syncwarp();
     tmem_ld_32x32(t_lane + dq_off + c0, r);
     tmem_ld_wait();
-    if (row_ok) store_gated_row32(r, Qg + c0, dQg + c0);
+    store_gated_row32(r, Qg + c0, dQg + c0, row_ok, a.dbq ? a.dbq + h * D + c0 : nullptr, t & 31);
   }
 #pragma unroll 1
   for (int kt = 0; kt < p.kt; ++kt) {
@@ -352,11 +366,11 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
       __syncwarp();
       tmem_ld_32x32(t_lane + dk_off + kt * D + c0, r);
       tmem_ld_wait();
-      if (key_ok) store_gated_row32(r, Kg + c0, dKg + c0);
+      store_gated_row32(r, Kg + c0, dKg + c0, key_ok, a.dbk ? a.dbk + h * D + c0 : nullptr, t & 31);
       __syncwarp();
       tmem_ld_32x32(t_lane + dv_off + kt * D + c0, r);
       tmem_ld_wait();
-      if (key_ok) store_gated_row32(r, Vg + c0, dVg + c0);
+      store_gated_row32(r, Vg + c0, dVg + c0, key_ok, a.dbv ? a.dbv + h * D + c0 : nullptr, t & 31);
     }
   }
   tc_fence_before();

@@ -7,6 +7,9 @@
 #include "common.cuh"
 
 namespace savqa {
+
+int colsum_bf16(const void* x, int64_t ld, int64_t rows, int cols, float* out, cudaStream_t stream);  // elementwise.cu
+
 namespace {
 
 constexpr int kMaxJ = 16;  // scores of one query row live in registers: Tk <= 32 * 16 = 512
@@ -286,6 +289,181 @@ __global__ void __launch_bounds__(256) attn_bwd_keys_kernel(const savqa_attn_arg
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Tq == 1 (the decoder: one class-token query per sample, AttModel_x3.py:141-154): one warp per (sample, head).
+// K and V rows are read straight from HBM/L2 (each is one 128-byte line at d = 64): once key-per-lane for the
+// scores / dW, once channel-per-lane for the weighted sums.  No scratch, no second kernel.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kRowWarps = 8;
+
+__device__ __forceinline__ float dot_row_bf16(const float* __restrict__ x, const __nv_bfloat16* __restrict__ row, int d, bool vec) {
+  float acc = 0.0f;
+  if (vec) {
+    for (int c = 0; c < d; c += 8) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + c));
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), e = unpack_bf16x2(u.z), f = unpack_bf16x2(u.w);
+      acc = fmaf(x[c], a.x, acc); acc = fmaf(x[c + 1], a.y, acc);
+      acc = fmaf(x[c + 2], b.x, acc); acc = fmaf(x[c + 3], b.y, acc);
+      acc = fmaf(x[c + 4], e.x, acc); acc = fmaf(x[c + 5], e.y, acc);
+      acc = fmaf(x[c + 6], f.x, acc); acc = fmaf(x[c + 7], f.y, acc);
+    }
+  } else {
+    for (int c = 0; c < d; c += 2) {
+      const float2 kv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + c));
+      acc = fmaf(x[c], kv.x, acc);
+      acc = fmaf(x[c + 1], kv.y, acc);
+    }
+  }
+  return acc;
+}
+
+// scores of the single query against every key (key j = jj*32 + lane), same arithmetic as row_scores()
+__device__ __forceinline__ void row1_scores(const savqa_attn_args_t& a, int n, int h, const float* sq, int lane, bool vec, float (&s)[kMaxJ]) {
+  const int d = a.d;
+  const float sqrt_d = sqrtf(static_cast<float>(d));
+  const __nv_bfloat16* K = static_cast<const __nv_bfloat16*>(a.k);
+#pragma unroll
+  for (int jj = 0; jj < kMaxJ; ++jj) {
+    const int j = jj * 32 + lane;
+    float acc = kMaskFill;
+    if (j < a.Tk) {
+      acc = dot_row_bf16(sq, K + (static_cast<long>(n) * a.Tk + j) * a.ldk + h * d, d, vec) / sqrt_d;
+      if (a.key_on && a.key_on[static_cast<long>(n) * a.Tk + j] == 0.0f) acc = kMaskFill;
+      if (a.causal && j > 0) acc = kMaskFill;
+    }
+    s[jj] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32) attn_row1_fwd_kernel(const savqa_attn_args_t a, int vec) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int d = a.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* wbuf = reinterpret_cast<float*>(smem) + warp * (a.Tk + d);  // [Tk] W', then [d] q
+  float* sq = wbuf + a.Tk;
+  const long hn = static_cast<long>(blockIdx.x) * kRowWarps + warp;
+  if (hn >= static_cast<long>(a.N) * a.H) return;
+  const int h = static_cast<int>(hn / a.N), n = static_cast<int>(hn % a.N);
+  const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q) + static_cast<long>(n) * a.ldq + h * d;
+  for (int c = lane; c < d; c += 32) sq[c] = __bfloat162float(Q[c]);
+  __syncwarp();
+  float s[kMaxJ];
+  row1_scores(a, n, h, sq, lane, vec != 0, s);
+  const float* grow = a.graph ? a.graph + static_cast<long>(n) * a.graph_n_stride : nullptr;
+  RowSoftmax rs;
+  row_weights(s, grow, a.Tk, a.graph ? a.renorm : 0, lane, rs);
+  const float qon = a.query_on ? a.query_on[n] : 1.0f;
+#pragma unroll
+  for (int jj = 0; jj < kMaxJ; ++jj) {
+    const int j = jj * 32 + lane;
+    if (j < a.Tk) {
+      if (a.att) a.att[hn * a.Tk + j] = rs.w[jj];
+      wbuf[j] = rs.w[jj] * qon;
+    }
+  }
+  __syncwarp();
+  const __nv_bfloat16* V = static_cast<const __nv_bfloat16*>(a.v) + static_cast<long>(n) * a.Tk * a.ldv + h * d;
+  for (int c = 2 * lane; c < d; c += 64) {
+    float a0 = 0.0f, a1 = 0.0f;
+    for (int j = 0; j < a.Tk; ++j) {
+      const float2 vv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(V + static_cast<long>(j) * a.ldv + c)));
+      a0 = fmaf(wbuf[j], vv.x, a0);
+      a1 = fmaf(wbuf[j], vv.y, a1);
+    }
+    float* o = a.out + static_cast<long>(n) * a.ldo + h * d + c;
+    o[0] = a0;
+    o[1] = a1;
+  }
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32) attn_row1_bwd_kernel(const savqa_attn_args_t a, int vec) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int d = a.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* dsbuf = reinterpret_cast<float*>(smem) + warp * (2 * a.Tk + 2 * d);  // [Tk] dS/sqrt(d), [Tk] W', [d] q, [d] dO
+  float* wbuf = dsbuf + a.Tk;
+  float* sq = wbuf + a.Tk;
+  float* sg = sq + d;
+  const long hn = static_cast<long>(blockIdx.x) * kRowWarps + warp;
+  if (hn >= static_cast<long>(a.N) * a.H) return;
+  const int h = static_cast<int>(hn / a.N), n = static_cast<int>(hn % a.N);
+  const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q) + static_cast<long>(n) * a.ldq + h * d;
+  const float* dO = a.dout + static_cast<long>(n) * a.ld_dout + h * d;
+  for (int c = lane; c < d; c += 32) {
+    sq[c] = __bfloat162float(Q[c]);
+    sg[c] = dO[c];
+  }
+  __syncwarp();
+  float s[kMaxJ];
+  row1_scores(a, n, h, sq, lane, vec != 0, s);
+  const int renorm = a.graph ? a.renorm : 0;
+  const float* grow = a.graph ? a.graph + static_cast<long>(n) * a.graph_n_stride : nullptr;
+  RowSoftmax rs;
+  row_weights(s, grow, a.Tk, renorm, lane, rs);
+  const float qon = a.query_on ? a.query_on[n] : 1.0f;
+  const __nv_bfloat16* Kb = static_cast<const __nv_bfloat16*>(a.k) + static_cast<long>(n) * a.Tk * a.ldk + h * d;
+  const __nv_bfloat16* Vb = static_cast<const __nv_bfloat16*>(a.v) + static_cast<long>(n) * a.Tk * a.ldv + h * d;
+  float dw[kMaxJ];
+  float t = 0.0f;
+#pragma unroll
+  for (int jj = 0; jj < kMaxJ; ++jj) {
+    const int j = jj * 32 + lane;
+    float acc = 0.0f;
+    if (j < a.Tk) acc = dot_row_bf16(sg, Vb + static_cast<long>(j) * a.ldv, d, vec != 0) * qon;
+    dw[jj] = acc;
+    t += rs.w[jj] * acc;
+  }
+  t = warp_sum(t);
+  const bool clamped = (renorm == 1) && (rs.r < 1e-12f);
+  const float sqrt_d = sqrtf(static_cast<float>(d));
+#pragma unroll
+  for (int jj = 0; jj < kMaxJ; ++jj) {
+    const int j = jj * 32 + lane;
+    if (j < a.Tk) {
+      float ds;
+      if (renorm == 1 && clamped) ds = rs.w[jj] * dw[jj] - rs.p[jj] * t;
+      else if (renorm == 2) ds = rs.w[jj] * (dw[jj] - t) - rs.p[jj] * t * (1.0f - rs.sumw);
+      else ds = rs.w[jj] * (dw[jj] - t);
+      if (a.key_on && a.key_on[static_cast<long>(n) * a.Tk + j] == 0.0f) ds = 0.0f;
+      if (a.causal && j > 0) ds = 0.0f;
+      dsbuf[j] = ds / sqrt_d;
+      wbuf[j] = rs.w[jj] * qon;
+    }
+  }
+  __syncwarp();
+  // channel-parallel: lane owns channels c, c+1 of the head
+  __nv_bfloat16* dQ = static_cast<__nv_bfloat16*>(a.dq) + static_cast<long>(n) * a.ld_dq + h * d;
+  __nv_bfloat16* dK = static_cast<__nv_bfloat16*>(a.dk) + static_cast<long>(n) * a.Tk * a.ld_dk + h * d;
+  __nv_bfloat16* dV = static_cast<__nv_bfloat16*>(a.dv) + static_cast<long>(n) * a.Tk * a.ld_dv + h * d;
+  for (int c = 2 * lane; c < d; c += 64) {
+    const float q0 = sq[c], q1 = sq[c + 1], g0 = sg[c], g1 = sg[c + 1];
+    float dq0 = 0.0f, dq1 = 0.0f, bk0 = 0.0f, bk1 = 0.0f, bv0 = 0.0f, bv1 = 0.0f;
+    for (int j = 0; j < a.Tk; ++j) {
+      const float2 kk = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(Kb + static_cast<long>(j) * a.ldk + c)));
+      const float2 vv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(Vb + static_cast<long>(j) * a.ldv + c)));
+      const float ds = dsbuf[j], w = wbuf[j];
+      dq0 = fmaf(ds, kk.x, dq0);
+      dq1 = fmaf(ds, kk.y, dq1);
+      const float k0 = kk.x > 0.0f ? ds * q0 : 0.0f, k1 = kk.y > 0.0f ? ds * q1 : 0.0f;  // ReLU of the K projection
+      const float v0 = vv.x > 0.0f ? w * g0 : 0.0f, v1 = vv.y > 0.0f ? w * g1 : 0.0f;    // ReLU of the V projection
+      *reinterpret_cast<uint32_t*>(dK + static_cast<long>(j) * a.ld_dk + c) = pack_bf16x2(k0, k1);
+      *reinterpret_cast<uint32_t*>(dV + static_cast<long>(j) * a.ld_dv + c) = pack_bf16x2(v0, v1);
+      bk0 += k0; bk1 += k1; bv0 += v0; bv1 += v1;
+    }
+    if (!(q0 > 0.0f)) dq0 = 0.0f;  // ReLU of the Q projection
+    if (!(q1 > 0.0f)) dq1 = 0.0f;
+    *reinterpret_cast<uint32_t*>(dQ + c) = pack_bf16x2(dq0, dq1);
+    if (a.dbq) { atomicAdd(a.dbq + h * d + c, dq0); atomicAdd(a.dbq + h * d + c + 1, dq1); }
+    if (a.dbk) { atomicAdd(a.dbk + h * d + c, bk0); atomicAdd(a.dbk + h * d + c + 1, bk1); }
+    if (a.dbv) { atomicAdd(a.dbv + h * d + c, bv0); atomicAdd(a.dbv + h * d + c + 1, bv1); }
+  }
+}
+
+bool row1_vec_ok(const savqa_attn_args_t* a) {
+  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return a->d % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a16(a->k) && a16(a->v);
+}
+
 int check_common(const savqa_attn_args_t* a, const char* who) {
   SAVQA_REQUIRE(a, "%s: null args", who);
   SAVQA_REQUIRE(a->q && a->k && a->v, "%s: null q/k/v", who);
@@ -303,6 +481,14 @@ int check_common(const savqa_attn_args_t* a, const char* who) {
 int attn_fwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
   if (int rc = check_common(a, "savqa_graph_attn_fwd")) return rc;
   SAVQA_REQUIRE(a->out, "savqa_graph_attn_fwd: null out");
+  if (a->Tq == 1) {
+    const size_t smem1 = static_cast<size_t>(kRowWarps) * (a->Tk + a->d) * 4;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_row1_fwd_kernel), smem1, "savqa_graph_attn_fwd (row kernel)")) return rc;
+    const long warps = static_cast<long>(a->N) * a->H;
+    attn_row1_fwd_kernel<<<static_cast<unsigned>((warps + kRowWarps - 1) / kRowWarps), kRowWarps * 32, smem1, stream>>>(*a, row1_vec_ok(a) ? 1 : 0);
+    SAVQA_CHECK_CUDA(cudaGetLastError());
+    return SAVQA_OK;
+  }
   const int dp = a->d + 2;
   const size_t smem = static_cast<size_t>(2) * a->Tk * dp * 2 + static_cast<size_t>(8) * a->Tk * 4 + static_cast<size_t>(8) * a->d * 4;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_fwd_simt_kernel), smem, "savqa_graph_attn_fwd (engine 1)")) return rc;
@@ -314,7 +500,17 @@ int attn_fwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
 
 int attn_bwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
   if (int rc = check_common(a, "savqa_graph_attn_bwd")) return rc;
-  SAVQA_REQUIRE(a->dout && a->dq && a->dk && a->dv && a->scratch, "savqa_graph_attn_bwd: null gradient buffer");
+  SAVQA_REQUIRE(a->dout && a->dq && a->dk && a->dv, "savqa_graph_attn_bwd: null gradient buffer");
+  SAVQA_REQUIRE(a->ld_dq % 2 == 0 && a->ld_dk % 2 == 0 && a->ld_dv % 2 == 0, "savqa_graph_attn_bwd: odd leading dimension");
+  if (a->Tq == 1) {
+    const size_t smem1 = static_cast<size_t>(kRowWarps) * (2 * a->Tk + 2 * a->d) * 4;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_row1_bwd_kernel), smem1, "savqa_graph_attn_bwd (row kernel)")) return rc;
+    const long warps = static_cast<long>(a->N) * a->H;
+    attn_row1_bwd_kernel<<<static_cast<unsigned>((warps + kRowWarps - 1) / kRowWarps), kRowWarps * 32, smem1, stream>>>(*a, row1_vec_ok(a) ? 1 : 0);
+    SAVQA_CHECK_CUDA(cudaGetLastError());
+    return SAVQA_OK;
+  }
+  SAVQA_REQUIRE(a->scratch, "savqa_graph_attn_bwd: engine 1 with Tq > 1 needs the scratch buffer");
   SAVQA_REQUIRE(a->d == 16 || a->d == 32 || a->d == 64 || a->d == 128, "savqa_graph_attn_bwd: head size %d not in {16,32,64,128}", a->d);
   const int dp = a->d + 2;
   const size_t smem1 = static_cast<size_t>(2) * a->Tk * dp * 2 + static_cast<size_t>(8) * a->Tk * 4 + static_cast<size_t>(16) * a->d * 4;
@@ -336,6 +532,10 @@ int attn_bwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
     default: attn_bwd_keys_kernel<16><<<grid2, 256, smem2, stream>>>(*a); break;
   }
   SAVQA_CHECK_CUDA(cudaGetLastError());
+  const int Ch = a->H * a->d;
+  if (a->dbq) if (int rc = colsum_bf16(a->dq, a->ld_dq, static_cast<long>(a->N) * a->Tq, Ch, a->dbq, stream)) return rc;
+  if (a->dbk) if (int rc = colsum_bf16(a->dk, a->ld_dk, static_cast<long>(a->N) * a->Tk, Ch, a->dbk, stream)) return rc;
+  if (a->dbv) if (int rc = colsum_bf16(a->dv, a->ld_dv, static_cast<long>(a->N) * a->Tk, Ch, a->dbv, stream)) return rc;
   return SAVQA_OK;
 }
 

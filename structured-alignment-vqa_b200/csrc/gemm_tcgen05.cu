@@ -171,8 +171,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_32x32(t_row + c0, r);
         tmem_ld_wait();
         const int gcol = n_blk * BN + c0;
-        if (row_ok && gcol < p.N) {
         float v[32];
+        if (row_ok && gcol < p.N) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * e.alpha;
         const bool full = p.vec_ok && (gcol + 32 <= p.N);
@@ -250,7 +250,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = gcol + j;
-            if (col >= p.N) continue;
+            if (col >= p.N) {
+              v[j] = 0.0f;
+              continue;
+            }
             float x = v[j];
             if (e.bias) x += e.bias[col];
             if (e.res) x += e.res[grow * e.ld_res + col];
@@ -267,9 +270,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               else *o = x;
             }
             if (e.out_bf16) reinterpret_cast<__nv_bfloat16*>(e.out_bf16)[grow * e.ld_out_bf16 + col] = __float2bfloat16_rn(x);
+            v[j] = x;
           }
         }
         }  // row_ok
+        if (e.colsum && gcol < p.N) {  // warp-uniform: bias gradient = column sums of the tile's valid rows
+          if (!row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+          }
+          const float cs = warp_colsum32(v, lane);
+          if (gcol + lane < p.N) atomicAdd(e.colsum + gcol + lane, cs);
+        }
       }
       // all TMEM reads of this accumulator buffer are done -> hand it back to the MMA warp
       tc_fence_before();

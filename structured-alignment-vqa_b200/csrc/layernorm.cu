@@ -106,19 +106,20 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
                                                          const float* __restrict__ gamma, float eps, long rows,
                                                          const float* __restrict__ dres_in, float* __restrict__ dx,
                                                          __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-                                                         float* __restrict__ dbeta) {
+                                                         float* __restrict__ dbeta, float* __restrict__ dxsum) {
   constexpr int C = NV * 128;
-  __shared__ float red[2][8][NV * 128 + 4];  // per-warp partials of dgamma / dbeta
+  __shared__ __align__(16) float red[8][NV * 128 + 4];  // per-warp partials of one parameter gradient at a time
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
   const long warp0 = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
   const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
-  float4 gm[NV], ag[NV], ab[NV];
+  float4 gm[NV], ag[NV], ab[NV], ax[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     gm[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
     ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ax[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (long r = warp0; r < rows; r += nwarps) {
     float4 c[NV], d[NV];
@@ -165,31 +166,35 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
       }
       *(reinterpret_cast<float4*>(dx + r * C) + lane + 32 * i) = o;
       if (dx_bf16) *(reinterpret_cast<uint2*>(dx_bf16 + r * C) + lane + 32 * i) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      ax[i].x += o.x; ax[i].y += o.y; ax[i].z += o.z; ax[i].w += o.w;
     }
   }
-  // block reduction of the parameter gradients, then one atomic per column per block
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int col = (lane + 32 * i) * 4;
-    red[0][w][col] = ag[i].x; red[0][w][col + 1] = ag[i].y; red[0][w][col + 2] = ag[i].z; red[0][w][col + 3] = ag[i].w;
-    red[1][w][col] = ab[i].x; red[1][w][col + 1] = ab[i].y; red[1][w][col + 2] = ab[i].z; red[1][w][col + 3] = ab[i].w;
-  }
-  __syncthreads();
+  // block reduction of the parameter gradients (one after the other through the same buffer), then one atomic per
+  // column per block
   const int nw = blockDim.x >> 5;
-  for (int col = threadIdx.x; col < C; col += blockDim.x) {
-    float a = 0.0f, b = 0.0f;
-    for (int j = 0; j < nw; ++j) {
-      a += red[0][j][col];
-      b += red[1][j][col];
+#pragma unroll 1
+  for (int which = 0; which < 3; ++which) {
+    float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dxsum);
+    if (!dst) continue;  // uniform over the block
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 a = which == 0 ? ag[i] : (which == 1 ? ab[i] : ax[i]);
+      *reinterpret_cast<float4*>(&red[w][(lane + 32 * i) * 4]) = a;
     }
-    if (dgamma) atomicAdd(dgamma + col, a);
-    if (dbeta) atomicAdd(dbeta + col, b);
+    __syncthreads();
+    for (int col = threadIdx.x; col < C; col += blockDim.x) {
+      float a = 0.0f;
+      for (int j = 0; j < nw; ++j) a += red[j][col];
+      atomicAdd(dst + col, a);
+    }
   }
 }
 
 __global__ void ln_bwd_generic_kernel(const float* __restrict__ dy, const float* __restrict__ pre, const float* __restrict__ gamma,
                                       float eps, long rows, int C, const float* __restrict__ dres_in, float* __restrict__ dx,
-                                      __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                      __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                      float* __restrict__ dxsum) {
   const int lane = threadIdx.x & 31;
   const long warp0 = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
   const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
@@ -219,6 +224,7 @@ __global__ void ln_bwd_generic_kernel(const float* __restrict__ dy, const float*
       if (dx_bf16) dx_bf16[r * C + c] = __float2bfloat16_rn(o);
       if (dgamma) atomicAdd(dgamma + c, d * cc * inv);
       if (dbeta) atomicAdd(dbeta + c, d);
+      if (dxsum) atomicAdd(dxsum + c, o);
     }
   }
 }
@@ -260,7 +266,8 @@ extern "C" int savqa_residual_layernorm_fwd(const float* x, const float* res, co
 }
 
 extern "C" int savqa_layernorm_bwd(const float* dy, const float* pre, const float* gamma, float eps, int64_t rows, int C,
-                                   const float* dres_in, float* dx, void* dx_bf16, float* dgamma, float* dbeta, savqa_stream_t stream_) {
+                                   const float* dres_in, float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum,
+                                   savqa_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (rows == 0) return SAVQA_OK;
   SAVQA_REQUIRE(dy && pre && gamma && dx && C >= 2, "savqa_layernorm_bwd: bad argument");
@@ -270,12 +277,12 @@ extern "C" int savqa_layernorm_bwd(const float* dy, const float* pre, const floa
   if (vec) {
     const int grid = ln_grid(rows, 2);  // few, fat blocks: each ends with C atomics per parameter
     switch (C / 128) {
-#define LN_CASE(NV) case NV: ln_bwd_vec_kernel<NV><<<grid, 256, 0, stream>>>(dy, pre, gamma, eps, rows, dres_in, dx, db, dgamma, dbeta); break;
+#define LN_CASE(NV) case NV: ln_bwd_vec_kernel<NV><<<grid, 256, 0, stream>>>(dy, pre, gamma, eps, rows, dres_in, dx, db, dgamma, dbeta, dxsum); break;
       LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4)
 #undef LN_CASE
     }
   } else {
-    ln_bwd_generic_kernel<<<ln_grid(rows, 8), 256, 0, stream>>>(dy, pre, gamma, eps, rows, C, dres_in, dx, db, dgamma, dbeta);
+    ln_bwd_generic_kernel<<<ln_grid(rows, 8), 256, 0, stream>>>(dy, pre, gamma, eps, rows, C, dres_in, dx, db, dgamma, dbeta, dxsum);
   }
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;

@@ -60,6 +60,10 @@ def _linear(x, lin: nn.Linear, pack: WeightPack, relu=False, out_bf16=False, row
 class _Branch(nn.Module):
     """Shared forward of the two branch models (they differ in the top-left block of `graph` and in table sizes)."""
 
+    def _savqa_bind(self, fv):
+        Fn.bind_linear(self._pk["mlp"], self.syb_mlp[0], fv)    # K = 300: stays on the per-step staging path
+        Fn.bind_linear(self._pk["mlp2"], self.syb_mlp2, fv)
+
     def _input_stage(self, first_ipt, q_ids, pos_table, pos_dropout_p):
         B = first_ipt.shape[0]
         q = Fn.EmbeddingFn.apply(q_ids, self.syb_emb.weight, 1.0, -1, getattr(self.syb_emb, "_savqa_rowlog", None))  # :96 / :216
@@ -261,6 +265,12 @@ class AttModel(nn.Module):
         self.cls_mcb = _head(self.mcb_out, hidden_size, num_classes, dropout_rate)
         self.label_smoothing = label_smoothing()
         self._pk = {k: (WeightPack(), WeightPack()) for k in ("cls", "cls_vis", "cls_syb")}
+
+    def _savqa_bind(self, fv):
+        for name, (p0, p3) in self._pk.items():
+            head = getattr(self, name)
+            Fn.bind_linear(p0, head[0], fv)
+            Fn.bind_linear(p3, head[3], fv)
 
     def _classify(self, name, fea):
         head = getattr(self, name)

@@ -22,7 +22,7 @@ class GemmEpilogue(C.Structure):
     _fields_ = [("alpha", C.c_float), ("relu", C.c_int), ("accumulate", C.c_int), ("rowtab_period", C.c_int),
                 ("bias", vp), ("res", vp), ("ld_res", i64), ("rowtab", vp), ("ld_rowtab", i64),
                 ("gate_bf16", vp), ("ld_gate", i64), ("out_f32", vp), ("ld_out_f32", i64),
-                ("out_bf16", vp), ("ld_out_bf16", i64)]
+                ("out_bf16", vp), ("ld_out_bf16", i64), ("colsum", vp)]
 
 
 class AttnArgs(C.Structure):
@@ -34,7 +34,7 @@ class AttnArgs(C.Structure):
                 ("causal", C.c_int), ("renorm", C.c_int), ("engine", C.c_int),
                 ("out", vp), ("ldo", i64), ("att", vp),
                 ("dout", vp), ("ld_dout", i64), ("dq", vp), ("ld_dq", i64), ("dk", vp), ("ld_dk", i64),
-                ("dv", vp), ("ld_dv", i64), ("scratch", vp)]
+                ("dv", vp), ("ld_dv", i64), ("scratch", vp), ("dbq", vp), ("dbk", vp), ("dbv", vp)]
 
 
 #: every symbol include/savqa_b200.h declares: name -> argtypes (restype is int unless noted)
@@ -51,13 +51,13 @@ SIGNATURES = {
     "savqa_relu_gate_bf16": [vp, C.c_int, i64, vp, i64, vp, i64, i64, C.c_int, vp],
     "savqa_colsum_bf16": [vp, i64, i64, C.c_int, vp, vp],
     "savqa_residual_layernorm_fwd": [vp, vp, vp, vp, C.c_float, i64, C.c_int, vp, vp, vp, vp, vp],
-    "savqa_layernorm_bwd": [vp, vp, vp, C.c_float, i64, C.c_int, vp, vp, vp, vp, vp, vp],
+    "savqa_layernorm_bwd": [vp, vp, vp, C.c_float, i64, C.c_int, vp, vp, vp, vp, vp, vp, vp],
     "savqa_gemm_bf16": [vp, i64, C.c_int, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(GemmEpilogue), C.c_int, vp],
     "savqa_graph_attn_fwd": [C.POINTER(AttnArgs), vp],
     "savqa_graph_attn_bwd": [C.POINTER(AttnArgs), vp],
     "savqa_answer_loss": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp, vp],
     "savqa_adam_rows": [vp, vp, vp, vp, vp, i64, C.c_int, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp],
-    "savqa_adam_step": [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp],
+    "savqa_adam_step": [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, vp],
 }
 
 _lib: Optional[C.CDLL] = None

@@ -57,17 +57,37 @@ class Side:
 
 
 class WeightPack:
-    """bf16 staging of one or more nn.Linear layers that read the same input, concatenated along the output
-    dimension: W [sum N, pad8(K)] for forward, W^T [K, pad8(sum N)] for dgrad, fp32 bias [sum N].
-    Re-staged whenever a parameter's storage or version counter changes (optimizer step, load_state_dict)."""
+    """bf16 MMA-operand staging of one or more nn.Linear layers that read the same input, concatenated along the
+    output dimension: W [sum N, pad8(K)] (forward reads it K-major, dgrad reads the same bytes MN-major), fp32 bias [sum N].
+
+    Two modes:
+      * unbound (plain autograd use, tests): re-staged by cast kernels whenever a parameter's storage or version
+        counter changes; backward returns the parameter gradients to autograd;
+      * bound (train.EncoderTrainer): `w` / `bias` are views of the trainer's flat bf16 mirror / flat fp32 parameter
+        buffer (the optimizer kernel keeps the mirror current, so nothing is staged per step) and `gw` / `gb` are views
+        of the flat gradient buffer that the backward kernels accumulate into directly (autograd gets None)."""
 
     def __init__(self):
         self.key = None
         self.w: Optional[Tensor] = None
-        self.wt: Optional[Tensor] = None
         self.bias: Optional[Tensor] = None
+        self.gw: Optional[Tensor] = None
+        self.gb: Optional[Tensor] = None
+        self.bound = False
+
+    def bind(self, w_bf16: Tensor, bias_f32: Tensor, gw: Tensor, gb: Tensor) -> "WeightPack":
+        assert w_bf16.dtype == BF16 and w_bf16.dim() == 2 and w_bf16.shape[1] % 8 == 0 and w_bf16.data_ptr() % 16 == 0
+        assert gw.shape == w_bf16.shape and gb.shape == bias_f32.shape == (w_bf16.shape[0],)
+        self.w, self.bias, self.gw, self.gb, self.bound = w_bf16, bias_f32, gw, gb, True
+        return self
+
+    def unbind(self) -> None:
+        self.w = self.bias = self.gw = self.gb = self.key = None
+        self.bound = False
 
     def refresh(self, weights: Sequence[Tensor], biases: Sequence[Tensor]) -> "WeightPack":
+        if self.bound:
+            return self
         key = (WEIGHT_EPOCH,) + tuple((w.data_ptr(), w._version, b.data_ptr(), b._version) for w, b in zip(weights, biases))
         if key == self.key and not FORCE_RESTAGE:
             return self
@@ -76,18 +96,113 @@ class WeightPack:
         dev = weights[0].device
         if self.w is None or self.w.shape != (ntot, pad8(K)) or self.w.device != dev:
             self.w = torch.empty(ntot, pad8(K), device=dev, dtype=BF16)
-            self.wt = torch.zeros(K, pad8(ntot), device=dev, dtype=BF16)
             self.bias = torch.empty(ntot, device=dev, dtype=F32)
         r = 0
         for w, b in zip(weights, biases):
             n = w.shape[0]
-            wd = w.detach()
-            ops.cast_bf16(wd, out=self.w[r:r + n], pad_to=pad8(K))
-            ops.cast_transpose_bf16(wd, out=self.wt[:, r:r + n])
+            ops.cast_bf16(w.detach(), out=self.w[r:r + n], pad_to=pad8(K))
             self.bias[r:r + n].copy_(b.detach())
             r += n
         self.key = key
         return self
+
+    # ---- backward helpers -------------------------------------------------------------------------------
+    def bias_grad_buffer(self, n: int, dev) -> Tensor:
+        """fp32 [n] that the producer of dY accumulates the bias gradient into (the flat-gradient view when bound)."""
+        return self.gb if self.bound else torch.zeros(n, device=dev, dtype=F32)
+
+    def weight_grad(self, dyb: Tensor, xb: Tensor, n_out: int, k_in: int) -> Tensor:
+        """dW[n_out, k_in] (+)= dY^T X on the tensor cores, into the flat-gradient view when bound."""
+        if self.bound:
+            dW = self.gw if self.gw.shape[1] == k_in else self.gw[:, :k_in]
+        else:
+            dW = torch.zeros(n_out, k_in, device=dyb.device, dtype=F32)
+        ops.wgrad(dyb, xb, n_out, k_in, dW)
+        return dW
+
+    def out(self, t: Optional[Tensor]) -> Optional[Tensor]:
+        """What backward hands to autograd for a parameter gradient: nothing when it already sits in the flat buffer."""
+        return None if self.bound else t
+
+
+def dgrad(dyb: Tensor, pack: WeightPack, M: int, k_in: int, n_out: int, **epilogue) -> None:
+    """dX[M, k_in] = dY[M, n_out] W[n_out, k_in]: the weight staging is read MN-major (no transposed copy exists)."""
+    ops.gemm(dyb, pack.w, M, k_in, n_out, b_mn=True, **epilogue)
+
+
+def bind_linear(pack: WeightPack, lin, fv) -> None:
+    """Binds the pack of one nn.Linear to the trainer's flat buffers (fv) when the layer is in them and its input width is
+    a multiple of 8 (16-byte TMA row pitch in the bf16 mirror); fv None unbinds."""
+    if fv is None:
+        pack.unbind()
+        return
+    n, k = lin.weight.shape
+    if k % 8 or not fv.has([lin.weight, lin.bias]):
+        return
+    pack.bind(fv.bf16([lin.weight]).view(n, k), fv.param([lin.bias]), fv.grad([lin.weight]).view(n, k), fv.grad([lin.bias]))
+
+
+class FlatViews:
+    """Index of the trainer's flat buffers: parameter -> slice.  `param` / `grad` are fp32 [n], `mirror` is the bf16 copy
+    of `param` that the optimizer kernel maintains."""
+
+    def __init__(self, param: Tensor, grad: Tensor, mirror: Tensor, offsets: dict):
+        self._param, self._grad, self._mirror, self._off = param, grad, mirror, offsets  # offsets: id(p) -> (start, numel)
+
+    def has(self, params) -> bool:
+        if not all(id(p) in self._off for p in params):
+            return False
+        o = self._off[id(params[0])][0]
+        for p in params:  # the group must be contiguous, in this order
+            if self._off[id(p)][0] != o:
+                return False
+            o += self._off[id(p)][1]
+        return True
+
+    def _span(self, params):
+        assert self.has(params), "parameters are not contiguous in the flat buffers"
+        lo = self._off[id(params[0])][0]
+        return lo, lo + sum(self._off[id(p)][1] for p in params)
+
+    def param(self, params) -> Tensor:
+        lo, hi = self._span(params)
+        return self._param[lo:hi]
+
+    def grad(self, params) -> Tensor:
+        lo, hi = self._span(params)
+        return self._grad[lo:hi]
+
+    def bf16(self, params) -> Tensor:
+        lo, hi = self._span(params)
+        assert lo % 8 == 0
+        return self._mirror[lo:hi]
+
+
+class NormSink:
+    """Gradient sinks of one layer_normalization (gamma, beta): views of the trainer's flat gradient buffer when bound."""
+
+    def __init__(self):
+        self.dgamma: Optional[Tensor] = None
+        self.dbeta: Optional[Tensor] = None
+        self.bound = False
+
+    def bind(self, dgamma: Tensor, dbeta: Tensor) -> None:
+        self.dgamma, self.dbeta, self.bound = dgamma, dbeta, True
+
+    def unbind(self) -> None:
+        self.dgamma = self.dbeta = None
+        self.bound = False
+
+    def buffers(self, gamma: Tensor):
+        if self.bound:
+            return self.dgamma, self.dbeta
+        return torch.zeros_like(gamma), torch.zeros_like(gamma)
+
+    def out(self, t: Optional[Tensor]) -> Optional[Tensor]:
+        return None if self.bound else t
+
+
+_NO_SINK = NormSink()
 
 
 def _as_bf16_rows(x: Tensor, M: int, K: int) -> Tensor:
@@ -144,18 +259,18 @@ class LinearFn(Function):
         dev = dy.device
         dW = db = dx = drowtab = None
         if ctx.needs_input_grad[1]:
-            dW = torch.zeros(N, K, device=dev, dtype=F32)
-            ops.wgrad(dyb, xb, N, K, dW)
+            dW = pack.out(pack.weight_grad(dyb, xb, N, K))
         if ctx.needs_input_grad[2]:
-            db = torch.zeros(N, device=dev, dtype=F32)
+            db = pack.bias_grad_buffer(N, dev)
             ops.colsum_bf16(dyb[:, :N], db)
+            db = pack.out(db)
         if ctx.needs_input_grad[0]:
             if ctx.x_dtype == BF16:
                 dx = torch.empty(M, K, device=dev, dtype=BF16)
-                ops.gemm(dyb, pack.wt, M, K, N, out_bf16=dx)
+                dgrad(dyb, pack, M, K, N, out_bf16=dx)
             else:
                 dx = torch.empty(M, K, device=dev, dtype=F32)
-                ops.gemm(dyb, pack.wt, M, K, N, out_f32=dx)
+                dgrad(dyb, pack, M, K, N, out_f32=dx)
             dx = dx.reshape(ctx.x_shape)
         if ctx.rowtab_shape is not None and ctx.needs_input_grad[3]:
             # d rowtab[t] = sum_b dy[b, t]; tiny fp32 reduction over the batch (positional table, AttModel_x3.py:100)
@@ -207,11 +322,12 @@ class EmbeddingFn(Function):
 # ======================================================================================================
 class LayerNormFn(Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps: float):
+    def forward(ctx, x, gamma, beta, eps: float, sink: Optional[NormSink] = None):
         xc = x if x.is_contiguous() else x.contiguous()
         y, _, yb, on = ops.layernorm_fwd(xc, None, gamma.detach(), beta.detach(), eps, save_pre=False, want_bf16=True, want_on=True)
         ctx.save_for_backward(xc, gamma)
         ctx.eps = eps
+        ctx.sink = sink or _NO_SINK
         ctx.mark_non_differentiable(yb, on)
         return y, yb, on
 
@@ -219,10 +335,9 @@ class LayerNormFn(Function):
     @once_differentiable
     def backward(ctx, dy, _dyb, _don):
         x, gamma = ctx.saved_tensors
-        dg = torch.zeros_like(gamma)
-        db = torch.zeros_like(gamma)
+        dg, db = ctx.sink.buffers(gamma)
         dx, _ = ops.layernorm_bwd(dy.contiguous(), x, gamma.detach(), ctx.eps, dg, db)
-        return dx, dg, db, None
+        return dx, ctx.sink.out(dg), ctx.sink.out(db), None, None
 
 
 # ======================================================================================================
@@ -291,7 +406,7 @@ class GraphAttentionFn(Function):
         if graph is not None and renorm != 0:
             g = graph if graph.dtype == F32 else graph.float()
             g = g if g.is_contiguous() else g.contiguous()
-        engine = ATTN_ENGINE if tc_attention_fits(d, Tk) else 1
+        engine = ATTN_ENGINE if (tc_attention_fits(d, Tk) and Tq > 1) else 1  # Tq == 1: one-warp row kernel
         o, att = ops.graph_attention_fwd(q, k, v, g, k_on, q_on, N, H, Tq, Tk, d, causal, renorm if g is not None else 0, want_att, engine)
 
         # ---- residual (RAW queries) + LayerNorm (modules.py:304-307) ----
@@ -312,69 +427,76 @@ class GraphAttentionFn(Function):
         N, Tq, Tk, C, H, d = ctx.dims
         Mq, Mk = N * Tq, N * Tk
         packs = cfg["packs"]
+        sink: NormSink = cfg.get("norm_sink") or _NO_SINK
         dev = dy.device
         need = ctx.needs_input_grad
-        dgamma = torch.zeros_like(gamma)
-        dbeta = torch.zeros_like(gamma)
+        dgamma, dbeta = sink.buffers(gamma)
         dpre, _ = ops.layernorm_bwd(dy.contiguous(), pre, gamma.detach(), cfg["eps"], dgamma, dbeta)
         dpre2 = dpre.reshape(Mq, C)
 
-        # attention core backward -> ReLU-gated dQ, dK, dV in the layout of the fused projection outputs
+        # attention core backward -> ReLU-gated dQ, dK, dV in the layout of the fused projection outputs, and the
+        # projections' bias gradients (column sums of the gated gradients) from the same kernel
         if mode == 0:
+            pqkv = packs["qkv"]
             dqkv = torch.empty(Mq, 3 * C, device=dev, dtype=BF16)
             dq, dk, dv = dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:]
+            db = pqkv.bias_grad_buffer(3 * C, dev)
+            dbq, dbk, dbv = db[:C], db[C:2 * C], db[2 * C:]
         elif mode == 1:
+            pq, pkv = packs["q"], packs["kv"]
             dq = torch.empty(Mq, C, device=dev, dtype=BF16)
             dkv = torch.empty(Mk, 2 * C, device=dev, dtype=BF16)
             dk, dv = dkv[:, :C], dkv[:, C:]
+            dbq = pq.bias_grad_buffer(C, dev)
+            dbkv = pkv.bias_grad_buffer(2 * C, dev)
+            dbk, dbv = dbkv[:C], dbkv[C:]
         else:
+            pq, pk_, pv_ = packs["q"], packs["k"], packs["v"]
             dq = torch.empty(Mq, C, device=dev, dtype=BF16)
             dk = torch.empty(Mk, C, device=dev, dtype=BF16)
             dv = torch.empty(Mk, C, device=dev, dtype=BF16)
-        ops.graph_attention_bwd(q, k, v, g, k_on, q_on, N, H, Tq, Tk, d, cfg["causal"], ctx.renorm_eff, dpre2, dq, dk, dv)
-
-        def wgrad_bias(dact, xin, n_out):
-            dW = torch.zeros(n_out, C, device=dev, dtype=F32)
-            ops.wgrad(dact, xin, n_out, C, dW)
-            db = torch.zeros(n_out, device=dev, dtype=F32)
-            ops.colsum_bf16(dact, db)
-            return dW, db
+            dbq, dbk, dbv = pq.bias_grad_buffer(C, dev), pk_.bias_grad_buffer(C, dev), pv_.bias_grad_buffer(C, dev)
+        ops.graph_attention_bwd(q, k, v, g, k_on, q_on, N, H, Tq, Tk, d, cfg["causal"], ctx.renorm_eff, dpre2, dq, dk, dv,
+                                dbq=dbq, dbk=dbk, dbv=dbv)
 
         dxq = dxk = dxv = None
         if mode == 0:
-            dW, db = wgrad_bias(dqkv, q_bf16, 3 * C)
+            dW = pqkv.weight_grad(dqkv, q_bf16, 3 * C, C)
             dWq, dWk, dWv = dW[:C], dW[C:2 * C], dW[2 * C:]
-            dbq, dbk, dbv = db[:C], db[C:2 * C], db[2 * C:]
             if need[0] or need[1] or need[2]:
                 dxq = torch.empty(Mq, C, device=dev, dtype=F32)
-                ops.gemm(dqkv, packs["qkv"].wt, Mq, C, 3 * C, res=dpre2, out_f32=dxq)  # + residual branch
+                dgrad(dqkv, pqkv, Mq, C, 3 * C, res=dpre2, out_f32=dxq)  # + residual branch
                 dxq = dxq.reshape(N, Tq, C)
+            po = pqkv
         else:
-            dWq, dbq = wgrad_bias(dq, q_bf16, C)
+            dWq = pq.weight_grad(dq, q_bf16, C, C)
             if need[0]:
                 dxq = torch.empty(Mq, C, device=dev, dtype=F32)
-                ops.gemm(dq, packs["q"].wt, Mq, C, C, res=dpre2, out_f32=dxq)
+                dgrad(dq, pq, Mq, C, C, res=dpre2, out_f32=dxq)
                 dxq = dxq.reshape(N, Tq, C)
             if mode == 1:
-                dW, db = wgrad_bias(dkv, k_bf16, 2 * C)
-                dWk, dWv, dbk, dbv = dW[:C], dW[C:], db[:C], db[C:]
+                dW = pkv.weight_grad(dkv, k_bf16, 2 * C, C)
+                dWk, dWv = dW[:C], dW[C:]
                 if need[1] or need[2]:
                     dxk = torch.empty(Mk, C, device=dev, dtype=F32)
-                    ops.gemm(dkv, packs["kv"].wt, Mk, C, 2 * C, out_f32=dxk)
+                    dgrad(dkv, pkv, Mk, C, 2 * C, out_f32=dxk)
                     dxk = dxk.reshape(N, Tk, C)
             else:
-                dWk, dbk = wgrad_bias(dk, k_bf16, C)
-                dWv, dbv = wgrad_bias(dv, v_bf16, C)
+                dWk = pk_.weight_grad(dk, k_bf16, C, C)
+                dWv = pv_.weight_grad(dv, v_bf16, C, C)
                 if need[1]:
                     dxk = torch.empty(Mk, C, device=dev, dtype=F32)
-                    ops.gemm(dk, packs["k"].wt, Mk, C, C, out_f32=dxk)
+                    dgrad(dk, pk_, Mk, C, C, out_f32=dxk)
                     dxk = dxk.reshape(N, Tk, C)
                 if need[2]:
                     dxv = torch.empty(Mk, C, device=dev, dtype=F32)
-                    ops.gemm(dv, packs["v"].wt, Mk, C, C, out_f32=dxv)
+                    dgrad(dv, pv_, Mk, C, C, out_f32=dxv)
                     dxv = dxv.reshape(N, Tk, C)
+            po = pq
+        o = po.out  # all packs of one module are bound together
         # when queries/keys/values are one tensor autograd sums the three slots: hand the total to the first
-        return (dxq, dxk, dxv, None, dWq, dbq, dWk, dbk, dWv, dbv, dgamma, dbeta, None, None, None, None, None)
+        return (dxq, dxk, dxv, None, o(dWq), o(dbq), o(dWk), o(dbk), o(dWv), o(dbv), sink.out(dgamma), sink.out(dbeta),
+                None, None, None, None, None)
 
 
 # ======================================================================================================
@@ -411,29 +533,25 @@ class FeedForwardFn(Function):
         xb, h, z, gamma = ctx.saved_tensors
         cfg = ctx.cfg
         M, C, Hd = ctx.dims
-        packs = cfg["packs"]
+        p1, p2 = cfg["packs"]["w1"], cfg["packs"]["w2"]
+        sink: NormSink = cfg.get("norm_sink") or _NO_SINK
         dev = dy.device
-        dgamma = torch.zeros_like(gamma)
-        dbeta = torch.zeros_like(gamma)
-        dz, dzb = ops.layernorm_bwd(dy.contiguous().reshape(M, C), z, gamma.detach(), cfg["eps"], dgamma, dbeta, want_bf16=True)
-        # conv2: z = h W2^T + b2 + x
-        dW2 = torch.zeros(C, Hd, device=dev, dtype=F32)
-        ops.wgrad(dzb, h, C, Hd, dW2)
-        db2 = torch.zeros(C, device=dev, dtype=F32)
-        ops.colsum_bf16(dzb, db2)
+        dgamma, dbeta = sink.buffers(gamma)
+        # conv2: z = h W2^T + b2 + x.  db2 = column sums of dz come out of the LayerNorm backward kernel
+        db2 = p2.bias_grad_buffer(C, dev)
+        dz, dzb = ops.layernorm_bwd(dy.contiguous().reshape(M, C), z, gamma.detach(), cfg["eps"], dgamma, dbeta, want_bf16=True, dxsum=db2)
+        dW2 = p2.weight_grad(dzb, h, C, Hd)
+        # conv1: h = relu(x W1^T + b1).  ReLU backward and db1 = column sums of dh fused in the dgrad epilogue
+        db1 = p1.bias_grad_buffer(Hd, dev)
         dh = torch.empty(M, Hd, device=dev, dtype=BF16)
-        ops.gemm(dzb, packs["w2"].wt, M, Hd, C, gate=h, out_bf16=dh)  # ReLU backward fused in the epilogue
-        # conv1: h = relu(x W1^T + b1)
-        dW1 = torch.zeros(Hd, C, device=dev, dtype=F32)
-        ops.wgrad(dh, xb, Hd, C, dW1)
-        db1 = torch.zeros(Hd, device=dev, dtype=F32)
-        ops.colsum_bf16(dh, db1)
+        dgrad(dzb, p2, M, Hd, C, gate=h, out_bf16=dh, colsum=db1)
+        dW1 = p1.weight_grad(dh, xb, Hd, C)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, C, device=dev, dtype=F32)
-            ops.gemm(dh, packs["w1"].wt, M, C, Hd, res=dz, out_f32=dx)  # + residual branch
+            dgrad(dh, p1, M, C, Hd, res=dz, out_f32=dx)  # + residual branch
             dx = dx.reshape(dy.shape)
-        return dx, dW1, db1, dW2, db2, dgamma, dbeta, None, None
+        return dx, p1.out(dW1), p1.out(db1), p2.out(dW2), p2.out(db2), sink.out(dgamma), sink.out(dbeta), None, None
 
 
 # ======================================================================================================

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as Fn
-from .functional import Side, WeightPack
+from .functional import NormSink, Side, WeightPack
 
 __all__ = ["embedding", "layer_normalization", "positional_encoding", "multihead_attention", "new_multihead_attention",
            "new_multihead_attention_with_graph_mask", "feedforward", "label_smoothing"]
@@ -67,10 +67,21 @@ class layer_normalization(nn.Module):
         self.epsilon = epsilon
         self.gamma = nn.Parameter(torch.ones(features))
         self.beta = nn.Parameter(torch.zeros(features))
+        self._sink = NormSink()
 
     def forward(self, x):
-        y, yb, on = Fn.LayerNormFn.apply(x, self.gamma, self.beta, self.epsilon)
+        y, yb, on = Fn.LayerNormFn.apply(x, self.gamma, self.beta, self.epsilon, self._sink)
         return _attach(y, yb, on)
+
+    # trainer hooks (train.EncoderTrainer): which parameters must be contiguous in the flat buffers, and the binding
+    def _savqa_groups(self):
+        return [[self.gamma], [self.beta]]
+
+    def _savqa_bind(self, fv):
+        if fv is None:
+            self._sink.unbind()
+        elif fv.has([self.gamma, self.beta]):
+            self._sink.bind(fv.grad([self.gamma]), fv.grad([self.beta]))
 
 
 class positional_encoding(nn.Module):
@@ -116,12 +127,31 @@ class _attention_base(nn.Module):
         self.normalization = layer_normalization(num_units)
         self._packs = {k: WeightPack() for k in ("qkv", "q", "kv", "k", "v")}
 
+    def _savqa_groups(self):
+        q, k, v = self.Q_proj[0], self.K_proj[0], self.V_proj[0]
+        return [[q.weight, k.weight, v.weight], [q.bias, k.bias, v.bias]]
+
+    def _savqa_bind(self, fv):
+        """Points the five weight packs at slices of the trainer's flat buffers ([Wq; Wk; Wv] is one [3C, C] block there)."""
+        if fv is None:
+            for pk in self._packs.values():
+                pk.unbind()
+            return
+        gw, gb = self._savqa_groups()
+        C = self.num_units
+        if not fv.has(gw + gb) or C % 8:
+            return
+        w, b = fv.bf16(gw).view(3 * C, C), fv.param(gb)
+        dw, db = fv.grad(gw).view(3 * C, C), fv.grad(gb)
+        for name, lo, hi in (("qkv", 0, 3 * C), ("q", 0, C), ("kv", C, 3 * C), ("k", C, 2 * C), ("v", 2 * C, 3 * C)):
+            self._packs[name].bind(w[lo:hi], b[lo:hi], dw[lo:hi], db[lo:hi])
+
     def _run(self, queries, keys, values, graph):
         if self.training and self.dropout_rate:
             raise NotImplementedError("savqa_b200: attention-probability dropout is not implemented in the fused kernel "
                                       "(AttModel_x3 constructs every attention with dropout_rate=0)")
         cfg = dict(heads=self.num_heads, causal=bool(self.causality), renorm=self._renorm, return_att=bool(self.return_att),
-                   packs=self._packs, eps=self.normalization.epsilon)
+                   packs=self._packs, eps=self.normalization.epsilon, norm_sink=self.normalization._sink)
         sq, sk = Side.of(queries), Side.of(keys)
         outs = Fn.GraphAttentionFn.apply(
             queries, keys, values, graph,
@@ -177,8 +207,12 @@ class feedforward(nn.Module):
         self.normalization = layer_normalization(in_channels)
         self._packs = {k: WeightPack() for k in ("w1", "w2")}
 
+    def _savqa_bind(self, fv):
+        for name, lin in (("w1", self.conv1[0]), ("w2", self.conv2)):
+            Fn.bind_linear(self._packs[name], lin, fv)
+
     def forward(self, inputs):
-        cfg = dict(packs=self._packs, eps=self.normalization.epsilon)
+        cfg = dict(packs=self._packs, eps=self.normalization.epsilon, norm_sink=self.normalization._sink)
         s = Side.of(inputs)
         y, yb, on = Fn.FeedForwardFn.apply(inputs, self.conv1[0].weight, self.conv1[0].bias, self.conv2.weight, self.conv2.bias,
                                            self.normalization.gamma, self.normalization.beta, s.bf16 if s else None, cfg)

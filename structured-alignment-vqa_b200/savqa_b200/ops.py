@@ -174,16 +174,19 @@ def layernorm_fwd(x: Tensor, res: Optional[Tensor], gamma: Tensor, beta: Tensor,
 
 
 def layernorm_bwd(dy: Tensor, pre: Tensor, gamma: Tensor, eps: float, dgamma: Optional[Tensor], dbeta: Optional[Tensor],
-                  dres_in: Optional[Tensor] = None, want_bf16: bool = False):
-    """Returns (dx fp32, dx_bf16 | None); dgamma / dbeta are accumulated in place."""
-    for nm, t in (("dy", dy), ("pre", pre), ("gamma", gamma), ("dgamma", dgamma), ("dbeta", dbeta), ("dres_in", dres_in)):
+                  dres_in: Optional[Tensor] = None, want_bf16: bool = False, dxsum: Optional[Tensor] = None):
+    """Returns (dx fp32, dx_bf16 | None); dgamma / dbeta / dxsum (column sums of dx) are accumulated in place."""
+    for nm, t in (("dy", dy), ("pre", pre), ("gamma", gamma), ("dgamma", dgamma), ("dbeta", dbeta), ("dres_in", dres_in), ("dxsum", dxsum)):
         _check(t, F32, nm)
     assert dy.is_contiguous() and pre.is_contiguous() and dy.shape == pre.shape
     C_ = pre.shape[-1]
     rows = pre.numel() // C_
     dx = torch.empty_like(pre)
     dxb = torch.empty(pre.shape, device=pre.device, dtype=BF16) if want_bf16 else None
-    call("savqa_layernorm_bwd", ptr(dy), ptr(pre), ptr(gamma), float(eps), rows, C_, ptr(dres_in), ptr(dx), ptr(dxb), ptr(dgamma), ptr(dbeta))
+    for t in (dgamma, dbeta, dxsum):
+        assert t is None or (t.is_contiguous() and t.numel() == C_)
+    call("savqa_layernorm_bwd", ptr(dy), ptr(pre), ptr(gamma), float(eps), rows, C_, ptr(dres_in), ptr(dx), ptr(dxb), ptr(dgamma), ptr(dbeta),
+         ptr(dxsum))
     return dx, dxb
 
 
@@ -194,13 +197,13 @@ _DEBUG_GEMM = os.environ.get("SAVQA_DEBUG_GEMM", "")  # "torch": bring-up aid ON
 def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False, bias: Optional[Tensor] = None,
          res: Optional[Tensor] = None, rowtab: Optional[Tensor] = None, rowtab_period: int = 0, gate: Optional[Tensor] = None,
          relu: bool = False, alpha: float = 1.0, out_f32: Optional[Tensor] = None, out_bf16: Optional[Tensor] = None,
-         accumulate: int = 0, split_k: int = 1) -> None:
+         accumulate: int = 0, split_k: int = 1, colsum: Optional[Tensor] = None) -> None:
     """acc[m,n] = sum_k A[m,k] B[n,k] with the fused epilogue of savqa_gemm_bf16 (tcgen05 / TMEM / TMA kernel).
 
     K-major operands are [rows, >=K] matrices; MN-major operands ([K, >=rows]) are used by wgrad."""
     _check(a, BF16, "A")
     _check(b, BF16, "B")
-    for nm, t in (("bias", bias), ("res", res), ("rowtab", rowtab), ("out_f32", out_f32)):
+    for nm, t in (("bias", bias), ("res", res), ("rowtab", rowtab), ("out_f32", out_f32), ("colsum", colsum)):
         _check(t, F32, nm)
     _check(gate, BF16, "gate")
     _check(out_bf16, BF16, "out_bf16")
@@ -233,7 +236,11 @@ def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_
     if out_bf16 is not None:
         assert out_bf16.dim() == 2 and out_bf16.stride(1) == 1 and out_bf16.shape[0] >= M and out_bf16.shape[1] >= N
         e.out_bf16, e.ld_out_bf16 = ptr(out_bf16), out_bf16.stride(0)
+    if colsum is not None:
+        assert colsum.is_contiguous() and colsum.numel() >= N and split_k == 1
+        e.colsum = ptr(colsum)
     if _DEBUG_GEMM == "torch":
+        assert colsum is None
         _gemm_debug_torch(a, b, M, N, K, a_mn, b_mn, bias, res, rowtab, rowtab_period, gate, relu, alpha, out_f32, out_bf16, accumulate)
         return
     call("savqa_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), M, N, K, C.byref(e), int(split_k))
@@ -319,9 +326,11 @@ def tc_attention_bwd_fits(d: int, Tq: int, Tk: int) -> bool:
 
 
 def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout: Tensor, dq: Tensor, dk: Tensor,
-                        dv: Tensor, engine: Optional[int] = None) -> None:
+                        dv: Tensor, engine: Optional[int] = None, dbq: Optional[Tensor] = None, dbk: Optional[Tensor] = None,
+                        dbv: Optional[Tensor] = None) -> None:
     """Gradient of the attention core; dq/dk/dv are bf16 2-D views and come back ReLU-gated by q/k/v > 0.
-    engine None: tcgen05 kernel when the shape fits, CUDA-core kernel otherwise."""
+    dbq/dbk/dbv (fp32 [H*d], optional) accumulate the column sums of dq/dk/dv: the projections' bias gradients.
+    engine None: tcgen05 kernel when the shape fits, CUDA-core kernels otherwise (Tq == 1: the one-warp row kernel)."""
     if engine is None:
         strides_ok = all(t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0 for t in (q, k, v, dq, dk, dv))
         engine = 0 if (tc_attention_bwd_fits(d, Tq, Tk) and strides_ok and Tq > 1) else 1
@@ -337,7 +346,11 @@ def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causa
     assert dout.dim() == 2 and dout.stride(1) == 1
     a.dout, a.ld_dout = ptr(dout), dout.stride(0)
     a.dq, a.ld_dq, a.dk, a.ld_dk, a.dv, a.ld_dv = ptr(dq), dq.stride(0), ptr(dk), dk.stride(0), ptr(dv), dv.stride(0)
-    if engine == 1:
+    for nm, t in (("dbq", dbq), ("dbk", dbk), ("dbv", dbv)):
+        _check(t, F32, nm)
+        assert t is None or (t.is_contiguous() and t.numel() == H * d)
+    a.dbq, a.dbk, a.dbv = ptr(dbq), ptr(dbk), ptr(dbv)
+    if engine == 1 and Tq > 1:
         scratch = torch.empty(2, H * N, Tq, Tk, device=q.device, dtype=F32)
         a.scratch = ptr(scratch)
     call("savqa_graph_attn_bwd", C.byref(a))
@@ -358,11 +371,15 @@ def answer_loss(lc: Tensor, lv: Tensor, ls: Tensor, answer: Tensor, epsilon: flo
 
 
 def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr: float, beta1: float, beta2: float, eps: float,
-              step: int, dyn: Optional[Tensor] = None) -> None:
+              step: int, dyn: Optional[Tensor] = None, param_bf16: Optional[Tensor] = None) -> None:
+    """Fused Adam over flat buffers; param_bf16 (optional) receives the bf16 mirror of the updated parameters."""
     for nm, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
         _check(t, F32, nm)
         assert t.is_contiguous() and t.numel() == param.numel()
-    call("savqa_adam_step", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2, eps, int(step), ptr(dyn))
+    _check(param_bf16, BF16, "param_bf16")
+    assert param_bf16 is None or (param_bf16.is_contiguous() and param_bf16.numel() == param.numel())
+    call("savqa_adam_step", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2, eps, int(step), ptr(dyn),
+         ptr(param_bf16))
 
 
 def adam_rows(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, row_stamp: Tensor, idx: Tensor, lr: float, beta1: float,

@@ -64,23 +64,48 @@ class EncoderTrainer:
             if t._savqa_rowlog is not None:
                 t._savqa_rowlog.clear()
         table_ids = {id(t.weight) for t in self.tables}
-        self.dense: List[torch.nn.Parameter] = [p for p in model.parameters() if p.grad is not None and id(p) not in table_ids]
+        used = [p for p in model.parameters() if p.grad is not None and id(p) not in table_ids]
         if not self.rowsparse:
-            self.dense += [t.weight for t in self.tables]
-        n = sum(p.numel() for p in self.dense)
-        pad = (-n) % 4
-        self.flat_param = torch.zeros(n + pad, device=dev)
-        self.flat_grad = torch.zeros(n + pad, device=dev)
-        self.exp_avg = torch.zeros(n + pad, device=dev)
-        self.exp_avg_sq = torch.zeros(n + pad, device=dev)
-        o = 0
+            used += [t.weight for t in self.tables]
+        used_ids = {id(p) for p in used}
+        # layout: the groups the modules ask for ([Wq; Wk; Wv] of one attention as one [3C, C] block, ...) first, then the rest;
+        # every group starts on a multiple of 8 elements (16-byte aligned rows in the bf16 mirror for TMA)
+        order, placed = [], set()
+        for mod in model.modules():
+            groups = mod._savqa_groups() if hasattr(mod, "_savqa_groups") else []
+            for g in groups:
+                ids = [id(p) for p in g]
+                if all(i in used_ids for i in ids) and not any(i in placed for i in ids):
+                    if len(g) > 1 and any(p.numel() % 8 for p in g[:-1]):
+                        continue  # members would lose their alignment; leave them separate
+                    order.append(list(g))
+                    placed.update(ids)
+        order += [[p] for p in used if id(p) not in placed]
+        offsets, n = {}, 0
+        for g in order:
+            n = (n + 7) // 8 * 8
+            for p in g:
+                offsets[id(p)] = (n, p.numel())
+                n += p.numel()
+        n_pad = (n + 7) // 8 * 8
+        self.dense: List[torch.nn.Parameter] = [p for g in order for p in g]
+        self.flat_param = torch.zeros(n_pad, device=dev)
+        self.flat_grad = torch.zeros(n_pad, device=dev)
+        self.exp_avg = torch.zeros(n_pad, device=dev)
+        self.exp_avg_sq = torch.zeros(n_pad, device=dev)
+        self.flat_bf16 = torch.zeros(n_pad, device=dev, dtype=torch.bfloat16)
         with torch.no_grad():
             for p in self.dense:
-                k = p.numel()
+                o, k = offsets[id(p)]
                 self.flat_param[o:o + k].copy_(p.reshape(-1))
                 p.data = self.flat_param[o:o + k].view(p.shape)
                 p.grad = self.flat_grad[o:o + k].view(p.shape)
-                o += k
+        self.sync_mirror()
+        # the modules' weight packs / LayerNorm sinks now read the mirror and write their gradients straight into flat_grad
+        self.views = Fn.FlatViews(self.flat_param, self.flat_grad, self.flat_bf16, offsets)
+        for mod in model.modules():
+            if hasattr(mod, "_savqa_bind"):
+                mod._savqa_bind(self.views)
         self.n_dense = n
         if self.rowsparse:
             self.row_state = []
@@ -92,6 +117,16 @@ class EncoderTrainer:
         self.dyn = torch.zeros(3, device=dev)
         self.dyn_host = torch.zeros(3).pin_memory() if dev.type == "cuda" else torch.zeros(3)
         Fn.WEIGHT_EPOCH += 1
+
+    def sync_mirror(self) -> None:
+        """Re-derives the bf16 mirror from the fp32 parameters (after prepare(), or after load_state_dict wrote into them)."""
+        ops.cast_bf16(self.flat_param.view(-1, 8), out=self.flat_bf16.view(-1, 8))
+
+    def release(self) -> None:
+        """Detaches the modules from the flat buffers (they go back to per-call weight staging and autograd gradients)."""
+        for mod in self.model.modules():
+            if hasattr(mod, "_savqa_bind"):
+                mod._savqa_bind(None)
 
     # ------------------------------------------------------------------------------------------------
     def _set_dyn(self) -> None:
@@ -107,7 +142,7 @@ class EncoderTrainer:
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=self.pg)
         ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, b1, b2, self.eps, max(self.step_count, 1),
-                      dyn=self.dyn)
+                      dyn=self.dyn, param_bf16=self.flat_bf16)
         if self.rowsparse:
             for t, st in zip(self.tables, self.row_state):
                 log = t._savqa_rowlog
@@ -157,10 +192,8 @@ class EncoderTrainer:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        self.step_count += 1
-        self._set_dyn()
         torch.cuda.synchronize()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph):  # records only: the step counter moves when the graph is replayed
             self.static_loss = self._step_impl(self.static)
         Fn.WEIGHT_EPOCH += 1
 

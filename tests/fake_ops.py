@@ -98,7 +98,7 @@ def layernorm_fwd(x, res, gamma, beta, eps, save_pre, want_bf16, want_on):
     return y, (pre.clone() if save_pre else None), (y.to(BF16) if want_bf16 else None), ((y.reshape(-1, C).sum(-1) != 0).float() if want_on else None)
 
 
-def layernorm_bwd(dy, pre, gamma, eps, dgamma, dbeta, dres_in=None, want_bf16=False):
+def layernorm_bwd(dy, pre, gamma, eps, dgamma, dbeta, dres_in=None, want_bf16=False, dxsum=None):
     # the explicit formula of csrc/layernorm.cu
     C = pre.shape[-1]
     mean = pre.mean(-1, keepdim=True)
@@ -116,11 +116,13 @@ def layernorm_bwd(dy, pre, gamma, eps, dgamma, dbeta, dres_in=None, want_bf16=Fa
         dgamma += (dy * c / s).reshape(-1, C).sum(0)
     if dbeta is not None:
         dbeta += dy.reshape(-1, C).sum(0)
+    if dxsum is not None:
+        dxsum += dx.reshape(-1, C).sum(0)
     return dx, (dx.to(BF16) if want_bf16 else None)
 
 
 def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, bias=None, res=None, rowtab=None, rowtab_period=0, gate=None, relu=False,
-         alpha=1.0, out_f32=None, out_bf16=None, accumulate=0, split_k=1):
+         alpha=1.0, out_f32=None, out_bf16=None, accumulate=0, split_k=1, colsum=None):
     assert a.dtype == BF16 and b.dtype == BF16
     A = a[:K, :M].float().t() if a_mn else a[:M, :K].float()
     Bm = b[:K, :N].float() if b_mn else b[:N, :K].float().t()
@@ -142,6 +144,8 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, bias=None, res=None, rowtab=N
             out_f32[:M, :N] = v
     if out_bf16 is not None:
         out_bf16[:M, :N] = v.to(BF16)
+    if colsum is not None:
+        colsum[:N] += v.sum(0)
 
 
 def split_k_for(tiles, k_blocks):
@@ -186,7 +190,8 @@ def graph_attention_fwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causa
     return out, att
 
 
-def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout, dq, dk, dv, engine=None):
+def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout, dq, dk, dv, engine=None, dbq=None,
+                        dbk=None, dbv=None):
     # the explicit formulas of csrc/attn_simt.cu (attn_bwd_rows_kernel / attn_bwd_keys_kernel)
     P, W, fixed, r, G = _weights(q, k, graph, key_on, N, H, Tq, Tk, d, causal, renorm)
     Q, K, V = _heads(q, N, Tq, H, d), _heads(k, N, Tk, H, d), _heads(v, N, Tk, H, d)
@@ -208,6 +213,9 @@ def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causa
     dq[:, : H * d] = dQ.permute(1, 2, 0, 3).reshape(N * Tq, H * d).to(BF16)
     dk[:, : H * d] = dK.permute(1, 2, 0, 3).reshape(N * Tk, H * d).to(BF16)
     dv[:, : H * d] = dV.permute(1, 2, 0, 3).reshape(N * Tk, H * d).to(BF16)
+    for db, g, T in ((dbq, dQ, Tq), (dbk, dK, Tk), (dbv, dV, Tk)):
+        if db is not None:
+            db += g.permute(1, 2, 0, 3).reshape(N * T, H * d).sum(0)
 
 
 def answer_loss(lc, lv, ls, answer, epsilon, grad_scale, want_grads):
@@ -223,11 +231,13 @@ def answer_loss(lc, lv, ls, answer, epsilon, grad_scale, want_grads):
     return loss, (tuple(grads) if want_grads else None)
 
 
-def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, dyn=None):
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, dyn=None, param_bf16=None):
     exp_avg.mul_(beta1).add_(grad, alpha=1 - beta1)
     exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
     bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
     param.sub_((lr / bc1) * exp_avg / (exp_avg_sq.sqrt() / (bc2 ** 0.5) + eps))
+    if param_bf16 is not None:
+        param_bf16.copy_(param.to(BF16))
 
 
 def adam_rows(param, grad, exp_avg, exp_avg_sq, row_stamp, idx, lr, beta1, beta2, eps, step, dyn=None):

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} declared in include/savqa_b200.h but not exported by {lib_path}"
     lib.savqa_abi_version.restype = ctypes.c_int
-    assert lib.savqa_abi_version() == 1
+    assert lib.savqa_abi_version() == 2
 
 
 def test_python_binding_covers_the_header(lib_path):
@@ -48,5 +48,5 @@ def test_python_binding_covers_the_header(lib_path):
 def test_struct_layouts_match_header():
     """ctypes mirrors of the two argument structs have the C sizes (LP64: 8-byte pointers / int64, 4-byte int / float)."""
     from savqa_b200 import _lib
-    assert ctypes.sizeof(_lib.GemmEpilogue) == 16 + 11 * 8
-    assert ctypes.sizeof(_lib.AttnArgs) == 11 * 8 + 8 * 4 + 12 * 8
+    assert ctypes.sizeof(_lib.GemmEpilogue) == 16 + 12 * 8
+    assert ctypes.sizeof(_lib.AttnArgs) == 11 * 8 + 8 * 4 + 15 * 8

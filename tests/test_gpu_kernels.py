@@ -112,7 +112,9 @@ def test_layernorm_kernels(ops, rows, C):
     assert torch.equal(on.cpu(), (y.cpu().sum(-1) != 0).float())
     dg = torch.zeros(C, device="cuda")
     db = torch.zeros(C, device="cuda")
-    dx, dxb = ops.layernorm_bwd(dev(dy), pre_k, dev(gamma), 1e-8, dg, db, want_bf16=True)
+    dsum = torch.zeros(C, device="cuda")
+    dx, dxb = ops.layernorm_bwd(dev(dy), pre_k, dev(gamma), 1e-8, dg, db, want_bf16=True, dxsum=dsum)
+    assert float((dsum - dx.sum(0)).abs().max()) <= 1e-5 * float(dx.abs().max()) * rows  # column sums of dx (bias gradient)
     assert rel(dx[1:], pre.grad[1:]) < 1e-5
     assert rel(dx[0], pre.grad[0]) < 1e-4  # sigma == 0 row: (g - mean g) / eps, as autograd
     assert rel(dg, gg.grad) < 1e-4 and rel(db, bb.grad) < 1e-5
@@ -174,6 +176,27 @@ def test_gemm_epilogues(ops):
     big = torch.zeros(M, 3 * N, device="cuda", dtype=BF)
     ops.gemm(dev(a), dev(b), M, N, K, out_bf16=big[:, N:2 * N])
     assert rel(big[:, N:2 * N], _gemm_ref(a, b)) < 4e-3 and float(big[:, :N].float().abs().sum()) == 0
+
+
+@pytest.mark.parametrize("M,Nout,Kin", [(300, 512, 2048), (7168, 2048, 512), (128, 1845, 512), (140, 2048, 300), (130, 1536, 512)])
+def test_gemm_dgrad_mn_major_b_and_colsum(ops, M, Nout, Kin):
+    """dX[M,Kin] = dY[M,Nout] W[Nout,Kin] with W read MN-major from its forward staging [Nout, pad8(Kin)] (no transposed copy),
+    ReLU gate and the bias-gradient column sums fused in the epilogue (functional.dgrad)."""
+    ldw = ops.pad8(Kin)
+    w = torch.zeros(Nout, ldw, dtype=BF)
+    w[:, :Kin] = (GS.randn(f"dg/{Nout}/{Kin}/w", Nout, Kin) / math.sqrt(Nout)).to(BF)
+    dy = torch.zeros(M, ops.pad8(Nout), dtype=BF)
+    dy[:, :Nout] = GS.randn(f"dg/{M}/{Nout}/dy", M, Nout).to(BF)
+    gate = GS.randn(f"dg/{M}/{Kin}/gate", M, ldw).to(BF)
+    ref = (dy[:, :Nout].float() @ w[:, :Kin].float()) * (gate[:, :Kin].float() > 0)
+    out = torch.empty(M, Kin, device="cuda")
+    outb = torch.empty(M, ldw, device="cuda", dtype=BF)
+    cs = torch.zeros(Kin, device="cuda")
+    ops.gemm(dev(dy), dev(w), M, Kin, Nout, b_mn=True, gate=dev(gate), out_f32=out, out_bf16=outb, colsum=cs)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 2e-5
+    assert rel(outb[:, :Kin], ref) < 4e-3
+    assert rel(cs, ref.sum(0)) < 1e-4  # fp32 atomics over the row tiles: order only
 
 
 @pytest.mark.parametrize("Mtok,Nout,Kin", [(256, 128, 128), (448, 1536, 512), (7168, 2048, 512), (7168, 512, 2048), (140, 2048, 300),
@@ -264,9 +287,15 @@ def test_attention_backward(ops, engine, N, H, Tq, Tk, d, renorm, causal):
     # gradients land in column slices of the fused [.., 3C] projection-gradient layout, as in functional.py
     dqkv = torch.zeros(N * max(Tq, Tk), 3 * C, dtype=BF, device="cuda")
     dq, dk, dv = dqkv[:N * Tq, :C], dqkv[:N * Tk, C:2 * C], dqkv[:N * Tk, 2 * C:]
+    db = torch.zeros(3, C, device="cuda")
     ops.graph_attention_bwd(dev(q), dev(k), dev(v), dev(g_in), dev(key_on), dev(query_on), N, H, Tq, Tk, d, causal, renorm, dev(dout), dq, dk, dv,
-                            engine=engine)
+                            engine=engine, dbq=db[0], dbk=db[1], dbv=db[2])
     torch.cuda.synchronize()
+    # bias gradients of the projections = column sums of the gated gradients the same kernel stored (fp32 sums of the
+    # un-rounded values vs sums of the bf16-rounded stores: 2^-9 per element, averaged down over the rows)
+    for b_, g_ in zip(db, (dq, dk, dv)):
+        ref_b = g_.float().sum(0)
+        assert float((b_ - ref_b).abs().max()) <= 1e-2 * float(ref_b.abs().max()) + 1e-6
     # engine 1: both sides round the fp32 gradients to bf16 once (2^-9 where the roundings differ).  engine 0 additionally
     # feeds bf16 dO, dS and W' to the tensor cores (three more 2^-9 roundings, fp32 accumulation).
     tol = 2e-3 if engine == 1 else 6e-3
@@ -290,8 +319,18 @@ def test_answer_loss_and_adam(ops):
     pr = p.clone().requires_grad_(True)
     opt = torch.optim.Adam([pr], lr=1e-3)
     pd, m, v = dev(p.clone()), torch.zeros(10000, device="cuda"), torch.zeros(10000, device="cuda")
+    mirror = torch.zeros(10000, device="cuda", dtype=BF)
     for step in (1, 2, 3):
         pr.grad = g.clone() * step
         opt.step()
-        ops.adam_step(pd, dev(g * step), m, v, 1e-3, 0.9, 0.999, 1e-8, step)
+        ops.adam_step(pd, dev(g * step), m, v, 1e-3, 0.9, 0.999, 1e-8, step, param_bf16=mirror)
     assert rel(pd, pr.detach()) < 1e-6
+    assert torch.equal(mirror, pd.to(BF))  # the bf16 mirror the GEMMs read
+    # unaligned views take the scalar path
+    pd2, m2, v2 = dev(p.clone())[1:9998], torch.zeros(9999, device="cuda")[1:9998], torch.zeros(9999, device="cuda")[1:9998]
+    pr2 = p[1:9998].clone().requires_grad_(True)
+    opt2 = torch.optim.Adam([pr2], lr=1e-3)
+    pr2.grad = g[1:9998].clone()
+    opt2.step()
+    ops.adam_step(pd2, dev(g)[1:9998], m2, v2, 1e-3, 0.9, 0.999, 1e-8, 1)
+    assert rel(pd2, pr2.detach()) < 1e-6

@@ -144,3 +144,54 @@ def test_full_size_step_runs_and_is_deterministic(A):
             assert torch.isfinite(p.grad).all(), name
             n_grad += 1
     assert n_grad > 300
+
+
+def test_trainer_bound_gradients_match_autograd_and_graph_replay(A):
+    """train.EncoderTrainer: the backward kernels that accumulate straight into the flat gradient buffer (bound weight
+    packs, fused bias-gradient column sums, MN-major dgrad) give the gradients plain autograd gives through the unbound
+    modules; the captured CUDA graph replays to the eager loss; the bf16 mirror tracks the fp32 parameters."""
+    import copy
+    from savqa_b200 import synthetic, train
+    cfg = dict(synthetic.GQA_SHAPED, V=12, Q=8, M=20, ncls=64)
+    model = synthetic.build_model(cfg, vocab_rows=3000).cuda()
+    ref = copy.deepcopy(model)
+    batch = synthetic.make_batch(cfg, batch_size=8, seed=2, vocab_rows=3000, device="cuda")
+    logits = ref.encoder_step(batch["vis_fea"], batch["vis_fea_mask"], batch["q_ipt"], batch["q_ipt_mask"], batch["q_ipt_graph"],
+                              batch["syb_ipt"], batch["macro_node_mask"], batch["macro_graph_ipt"], True)
+    ref_loss = A.answer_loss(*logits, batch["answer"])
+    ref_loss.backward()
+    ref_grads = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+
+    tr = train.EncoderTrainer(model, lr=1e-4, rowsparse=True)
+    tr.prepare(batch)
+    assert model.att_syb.enc_self_attention_3._packs["qkv"].bound and model.att_vis_grid.dec_feed_forward_5._packs["w2"].bound
+    tr.flat_grad.zero_()
+    loss = tr._forward_backward(batch)
+    for t_ in tr.tables:
+        t_._savqa_rowlog.clear()
+    assert abs(float(loss) - float(ref_loss)) < 1e-5 * abs(float(ref_loss))
+    names = {id(p): k for k, p in model.named_parameters()}
+    worst = ("", 0.0)
+    for p in tr.dense:
+        k = names[id(p)]
+        scale = float(ref_grads[k].abs().max())
+        err = float((p.grad - ref_grads[k]).abs().max()) / (scale + 1e-12)
+        if err > worst[1]:
+            worst = (k, err)
+    # same kernels on the same operands: only the fp32 accumulation order differs (atomics; bias sums taken from the fp32
+    # values instead of the bf16-rounded stores: 2^-9 per element before averaging over the rows)
+    assert worst[1] < 5e-3, worst
+
+    # eager step == replayed graph step (same static batch), and the mirror follows the parameters
+    tr2_model = copy.deepcopy(ref)
+    tr2_model.zero_grad(set_to_none=True)
+    tr2 = train.EncoderTrainer(tr2_model, lr=1e-4, rowsparse=True)
+    tr3_model = copy.deepcopy(ref)
+    tr3_model.zero_grad(set_to_none=True)
+    tr3 = train.EncoderTrainer(tr3_model, lr=1e-4, rowsparse=True)
+    eager = [float(tr2.step(batch)) for _ in range(5)]
+    tr3.capture(batch, warmup=3)
+    replayed = [float(tr3.replay()) for _ in range(2)]  # capture() ran 3 eager warm-up steps: these are steps 4 and 5
+    assert abs(replayed[0] - eager[3]) < 2e-3 * abs(eager[3]) and abs(replayed[1] - eager[4]) < 2e-3 * abs(eager[4]), (eager, replayed)
+    assert eager[4] < eager[0]  # the optimizer is actually descending on the repeated batch
+    assert torch.equal(tr3.flat_bf16, tr3.flat_param.to(torch.bfloat16))

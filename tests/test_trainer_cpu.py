@@ -1,0 +1,121 @@
+"""Host logic of savqa_b200.train.EncoderTrainer on CPU (kernels replaced by tests/fake_ops.py): the flat-buffer layout,
+the binding of the modules' weight packs / gradient sinks to it, the bf16 mirror kept by the optimizer, and the
+data-parallel exchange (world size 2 over gloo).  Reference: the same model stepped by plain autograd + torch.optim.Adam
+(what main_itp_ddp_tar_super_node.py:203-206, 363-366 does)."""
+import copy
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import fake_ops
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _setup(seed=0, batch=4):
+    from savqa_b200 import synthetic
+    cfg = synthetic.TINY
+    model = synthetic.build_model(cfg, vocab_rows=1200, seed=seed)
+    b = synthetic.make_batch(cfg, batch, seed=5, vocab_rows=1200)
+    return cfg, model, b
+
+
+def _reference_steps(model, batches, lr, dec_mask=True):
+    """Plain autograd through the (unbound) modules + dense torch.optim.Adam over every parameter that gets a gradient."""
+    from savqa_b200 import AttModel_x3 as A
+    opt = None
+    losses = []
+    for b in batches:
+        model.zero_grad(set_to_none=True)
+        logits = model.encoder_step(b["vis_fea"], b["vis_fea_mask"], b["q_ipt"], b["q_ipt_mask"], b["q_ipt_graph"], b["syb_ipt"],
+                                    b["macro_node_mask"], b["macro_graph_ipt"], dec_mask)
+        loss = A.answer_loss(*logits, b["answer"])
+        loss.backward()
+        if opt is None:
+            opt = torch.optim.Adam([p for p in model.parameters() if p.grad is not None], lr=lr)
+        opt.step()
+        losses.append(float(loss))
+    return losses
+
+
+def _max_param_diff(m1, m2):
+    worst = 0.0
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        if a.dtype.is_floating_point:
+            worst = max(worst, float((a - b).abs().max()))
+    return worst
+
+
+@pytest.mark.parametrize("rowsparse,steps", [(True, 1), (False, 2)])
+def test_bound_trainer_matches_autograd_adam(monkeypatch, rowsparse, steps):
+    fake_ops.install(monkeypatch)
+    from savqa_b200 import train
+    cfg, model, b = _setup()
+    ref = copy.deepcopy(model)
+    lr = 1e-3
+    ref_losses = _reference_steps(ref, [b] * steps, lr)
+    tr = train.EncoderTrainer(model, lr=lr, rowsparse=rowsparse)
+    losses = [float(tr.step(b)) for _ in range(steps)]
+    # every attention / feed-forward / head pack that can be bound is bound, and its views alias the flat buffers
+    att = model.att_vis_grid.enc_self_attention_0
+    assert att._packs["qkv"].bound and att._packs["kv"].bound and att.normalization._sink.bound
+    assert att._packs["qkv"].gw.data_ptr() == att.Q_proj[0].weight.grad.data_ptr()
+    assert att._packs["kv"].w.data_ptr() == att._packs["qkv"].w[att.num_units:].data_ptr()
+    assert model.att_vis_grid.enc_feed_forward_0._packs["w1"].bound
+    assert not model.att_vis_grid._pk["mlp"].bound  # K = 300 is not a multiple of 8: stays on the staging path
+    assert model.att_syb._pk["mlp2"].bound and model._pk["cls"][0].bound
+    assert losses == pytest.approx(ref_losses, rel=1e-5)
+    # bf16 operands make the two runs differ only through rounding noise inside identical arithmetic: same stand-in kernels
+    assert _max_param_diff(model, ref) < 2e-5
+    # the mirror the GEMMs read is the bf16 image of the updated parameters
+    assert torch.equal(tr.flat_bf16, tr.flat_param.to(torch.bfloat16))
+    tr.release()
+    assert not att._packs["qkv"].bound and not att.normalization._sink.bound
+
+
+def _dp_worker(rank, world, port, out):
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fake_ops as F
+    import savqa_b200.ops as real
+    for name in dir(F):
+        fn = getattr(F, name)
+        if callable(fn) and hasattr(real, name) and not name.startswith("_") and name != "install":
+            setattr(real, name, fn)
+    from savqa_b200 import train
+    torch.set_num_threads(2)  # same BLAS threading (= summation order) as the single-rank run it is compared with
+    cfg, model, b = _setup(batch=4)
+    shard = {k: v[rank::world].contiguous() for k, v in b.items()}
+    tr = train.EncoderTrainer(model, lr=1e-3, eps=1e-2, rowsparse=True)
+    tr.step(shard)
+    if rank == 0:
+        torch.save({k: v.clone() for k, v in model.state_dict().items()}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_world2_gloo(monkeypatch, tmp_path):
+    """Two ranks on half batches each == one rank on the whole batch (mean loss => averaged gradients; row-sparse word-table
+    gradients exchanged by all-gather)."""
+    out = str(tmp_path / "dp.pt")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+    fake_ops.install(monkeypatch)
+    from savqa_b200 import train
+    nthreads = torch.get_num_threads()
+    torch.set_num_threads(2)
+    cfg, model, b = _setup(batch=4)
+    # eps well above the fp32 summation-order noise of the gradients: Adam's first step is lr * g / (|g| + eps), which would
+    # otherwise turn a sign flip of a noise-level gradient into a 2 * lr difference
+    tr = train.EncoderTrainer(model, lr=1e-3, eps=1e-2, rowsparse=True)
+    tr.step(b)
+    torch.set_num_threads(nthreads)
+    dp = torch.load(out)
+    worst = max(float((dp[k] - v).abs().max()) for k, v in model.state_dict().items() if v.dtype.is_floating_point)
+    assert worst < 1e-6
+
