@@ -195,9 +195,14 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
     loss_host = torch.zeros(1).pin_memory()
     if args.mode == "graph":
+        trainer.stage(host_batches[0])
+
         def e2e_step(i):
-            # inputs of step i travel host -> static buffers, ordered with the compute stream; the loss comes back every step
-            trainer.load_static(host_batches[i & 1])
+            # every step: its inputs have travelled host -> staging on the copy stream while the previous step computed; they
+            # move into the graph's static buffers, the NEXT step's host batch starts travelling, the step runs, and the loss
+            # comes back to the host
+            trainer.commit()
+            trainer.stage(host_batches[(i + 1) & 1])
             l = trainer.replay()
             loss_host.copy_(l.reshape(1), non_blocking=True)
     else:

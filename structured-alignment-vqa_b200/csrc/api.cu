@@ -87,6 +87,11 @@ struct MapKeyHash {
 
 int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                          const uint32_t* box, bool swizzle128) {
+  return make_tensor_map(out, base, false, rank, dims, strides_bytes, box, swizzle128);
+}
+
+int make_tensor_map(CUtensorMap* out, const void* base, bool is_f32, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, bool swizzle128) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
@@ -103,7 +108,7 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
   MapKey key;
   memset(&key, 0, sizeof(key));
   key.w[0] = reinterpret_cast<uint64_t>(base);
-  key.w[1] = static_cast<uint64_t>(rank) | (swizzle128 ? 256u : 0u);
+  key.w[1] = static_cast<uint64_t>(rank) | (swizzle128 ? 256u : 0u) | (is_f32 ? 512u : 0u);
   for (int i = 0; i < rank; ++i) {
     key.w[2 + i] = dims[i];
     key.w[8 + i] = box[i];
@@ -135,7 +140,7 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   alignas(64) CUtensorMap m;
-  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bdim, estr,
+  CUresult r = fn(&m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bdim, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -1,0 +1,488 @@
+// CTA-pair bf16 GEMM for sm_100a: two CTAs of a cluster (one SM each) compute one 256 x BN tile with
+// tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and HALF of the B tile, so the L2 -> shared-memory
+// traffic per flop is 2/3 (BN = 256) of the single-CTA kernel's (gemm_tcgen05.cu), which is what bounds K = 512 GEMMs.
+//
+//   acc[m,n] = sum_k A[m,k] * B[n,k]          (nn.Linear of modules.py:227-229, 428-429; AttModel_x3.py:42-44)
+//
+// Warp roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator (both CTAs) + MMA issuer (leader CTA
+// only), warps 2..9 = epilogue (TMEM lane quadrant `warp & 3`, two warps per quadrant on alternating column chunks: with
+// K = 512 the epilogue of a tile costs as much as its MMAs, so it needs the issue slots of all four schedulers twice).
+// Pipelines:
+//   smem   full[s]  (leader's barrier collects the TMA bytes of BOTH CTAs)  /  empty[s] (multicast tcgen05.commit to both)
+//   TMEM   tmem_full[a] (multicast commit to both)  /  tmem_empty[a] (leader's barrier, 16 arrivals: 8 epilogue warps x 2 CTAs)
+// Epilogue: TMEM -> registers -> fused math -> 128B-swizzled smem staging -> TMA store (coalesced, asynchronous); the
+// operands it reads from HBM (residual / ReLU gate / bias) are prefetched one chunk ahead, the first chunk while the
+// tile's MMAs are still running.  Split-K partial sums (wgrad) go out with red.global.add.v4.f32.
+#include "common.cuh"
+
+namespace savqa {
+
+int gemm2_launch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
+                 const savqa_gemm_epilogue_t* epi, int split_k, cudaStream_t stream, bool* handled);
+
+namespace {
+
+constexpr int BM = 128;   // rows per CTA (256 per pair)
+constexpr int BK = 64;    // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kStagingBytes = 8 * 4096;      // 8 epilogue warps x [32 rows][128 B]
+constexpr int kBiasBytes = 2 * 256 * 4;      // the tile's bias slice, double buffered over the accumulator stages
+
+enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_ATOMIC = 2 };
+
+struct Gemm2Params {
+  int M, N, K;
+  int num_m, num_n, split_k, kb_per_split, num_kb;
+  savqa_gemm_epilogue_t e;
+};
+
+template <int BN>
+struct Cfg2 {
+  static constexpr int kABytes = BM * BK * 2;          // 16 KB
+  static constexpr int kBBytes = (BN / 2) * BK * 2;    // this CTA's half of the B tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kRoom = 227 * 1024 - kStagingBytes - kBiasBytes - 2048;  // 1 KB alignment slack + static smem
+  static constexpr int kStages = kRoom / kStageBytes > 8 ? 8 : kRoom / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBiasBytes + 1024;
+  static constexpr int kTmemCols = 2 * BN;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                  const Gemm2Params p) {
+  using C = Cfg2<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[C::kStages];
+  __shared__ __align__(8) uint64_t empty_bar[C::kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* staging = smem + C::kStages * C::kStageBytes;
+  float* sbias = reinterpret_cast<float*>(staging + kStagingBytes);  // [2][256]
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (EPI != EPI_ATOMIC) tma_prefetch_desc(&tmO);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 16);  // one arrive per epilogue warp of each CTA of the pair (leader's copy is the live one)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair<C::kTmemCols>(&tmem_base_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anything is signalled across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int tiles_mn = p.num_m * p.num_n;
+  const int num_tiles = tiles_mn * p.split_k;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one thread per CTA) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int n_blk = tile % p.num_n;
+        const int m_blk = (tile / p.num_n) % p.num_m;
+        const int ks = tile / tiles_mn;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int m0 = m_blk * 2 * BM + static_cast<int>(cta_rank) * BM;           // this CTA's 128 rows of A
+        const int n0 = n_blk * BN + static_cast<int>(cta_rank) * (BN / 2);         // this CTA's half of the B tile
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kABytes;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);  // bytes of both CTAs
+          const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);           // the leader's barrier
+          if constexpr (!A_MN) {
+            tma_load_2d_pair(sa, &tmA, bar, kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d_pair(sa + c * 8192, &tmA, bar, m0 + c * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_pair(sb, &tmB, bar, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 128; ++c) tma_load_2d_pair(sb + c * 8192, &tmB, bar, n0 + c * 64, kb * BK);
+          }
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int ks = tile / tiles_mn;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int as = it & 1;
+        mbar_wait(&tmem_empty_bar[as], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + C::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = A_MN ? umma_smem_desc(sa + k * (UMMA_K * 128), 8192, 1024) : umma_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc(sb + k * (UMMA_K * 128), 8192, 1024) : umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage], 0b11);  // frees the slot in BOTH CTAs once these MMAs have read it
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_pair(&tmem_full_bar[as], 0b11);  // accumulator complete -> both CTAs' epilogues
+      }
+    }
+  } else {
+    // ===================== epilogue warps (8: two per TMEM lane quadrant, alternating column chunks) =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const savqa_gemm_epilogue_t& e = p.e;
+    uint8_t* buf = staging + (warp - 2) * 4096;  // this warp's [32 rows][128 B] staging tile
+    const uint32_t srow = static_cast<uint32_t>(lane) * 128u;
+    const uint32_t sxor = static_cast<uint32_t>(lane & 7);
+    const __nv_bfloat16* gate = static_cast<const __nv_bfloat16*>(e.gate_bf16);
+    const uint32_t empty_remote0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
+    const uint32_t empty_remote1 = mapa_shared(smem_u32(&tmem_empty_bar[1]), 0);
+    constexpr int CW = (EPI == EPI_BF16) ? 64 : 32;  // columns per chunk = 128 bytes of output per row
+    constexpr int NCH = BN / CW;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int n_blk = tile % p.num_n;
+      const int m_blk = (tile / p.num_n) % p.num_m;
+      const int as = it & 1;
+      const int row0 = m_blk * 2 * BM + static_cast<int>(cta_rank) * BM + quad * 32;  // first row of this warp's slab
+      const long grow = static_cast<long>(row0) + lane;
+      const bool row_ok = grow < p.M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
+      const int ncol0 = n_blk * BN;
+      // the tile's bias slice -> smem (all epilogue warps; the named barrier also orders the reuse of the buffer)
+      const float* bias_s = sbias + as * 256;
+      if (e.bias) {
+        const int et = threadIdx.x - 64;  // 0..255
+        if (et < BN) sbias[as * 256 + et] = (ncol0 + et < p.N) ? __ldg(e.bias + ncol0 + et) : 0.0f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      const float* rowtab_row = (EPI != EPI_BF16 && e.rowtab != nullptr && row_ok) ? e.rowtab + static_cast<long>(grow % e.rowtab_period) * e.ld_rowtab : nullptr;
+
+      // operands read from HBM (ReLU gate: 64 bf16 = 8 x uint4; residual: 32 fp32 = 8 x float4), prefetched one chunk ahead
+      uint4 aux[8], aux_next[8];
+      auto load_aux = [&](int c, uint4 (&x)[8]) {
+        const int gcol = ncol0 + c * CW;
+        if (row_ok && gcol < p.N) {
+          if constexpr (EPI == EPI_BF16) {
+            if (gate) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = __ldg(reinterpret_cast<const uint4*>(gate + grow * e.ld_gate + gcol) + j);
+            }
+          } else {
+            if (e.res) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = __ldg(reinterpret_cast<const uint4*>(e.res + grow * e.ld_res + gcol) + j);
+            }
+          }
+        }
+      };
+      if (half < NCH) load_aux(half, aux);
+      mbar_wait(&tmem_full_bar[as], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half; c < NCH; c += 2) {
+        const int gcol = ncol0 + c * CW;
+        const bool last = c + 2 >= NCH;
+        if (!last) load_aux(c + 2, aux_next);
+        constexpr int NH = CW / 32;  // 32-column halves of the chunk (2 for bf16 output, 1 for fp32)
+        const bool active = gcol < p.N;  // warp-uniform
+        {
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            float v[32];
+            {
+              uint32_t racc[32];
+              __syncwarp();
+              tmem_ld_32x32(t_row + c * CW + 32 * h, racc);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(racc[j]) * e.alpha;
+            }
+            if (last && h == NH - 1) {
+              // this warp's last TMEM read of the accumulator buffer is done -> hand it back to the leader's MMA warp early
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(as ? empty_remote1 : empty_remote0);
+            }
+            if (!active) continue;
+            if constexpr (EPI != EPI_ATOMIC) {
+              if (h == 0) {
+                // staging tile free?  (the TMA store of this warp's previous chunk has finished reading it); asked as late as
+                // possible: the TMEM load and the wait above have already covered most of that store's latency
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+              }
+            }
+            if (e.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * CW + 32 * h + j);
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            }
+            if constexpr (EPI == EPI_BF16) {
+              if (e.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+              }
+              if (gate) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 g4 = aux[4 * h + j];
+                  const uint32_t w[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float2 f = unpack_bf16x2(w[q]);
+                    if (!(f.x > 0.0f)) v[8 * j + 2 * q] = 0.0f;
+                    if (!(f.y > 0.0f)) v[8 * j + 2 * q + 1] = 0.0f;
+                  }
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<uint4*>(buf + srow + ((static_cast<uint32_t>(4 * h + u) ^ sxor) << 4)) =
+                    make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                               pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+            } else {
+              if (e.res && row_ok) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[4 * j] += __uint_as_float(aux[j].x); v[4 * j + 1] += __uint_as_float(aux[j].y);
+                  v[4 * j + 2] += __uint_as_float(aux[j].z); v[4 * j + 3] += __uint_as_float(aux[j].w);
+                }
+              }
+              if (rowtab_row) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 t = __ldg(reinterpret_cast<const float4*>(rowtab_row + gcol) + j);
+                  v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                }
+              }
+              if (e.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+              }
+              if constexpr (EPI == EPI_ATOMIC) {
+                if (row_ok) {
+                  float* o = e.out_f32 + grow * e.ld_out_f32 + gcol;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) red_add_v4(o + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+              } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  *reinterpret_cast<float4*>(buf + srow + ((static_cast<uint32_t>(u) ^ sxor) << 4)) =
+                      make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+              }
+            }
+            if (e.colsum) {  // bias gradient: column sums of the valid rows (31 shuffles + one atomic per lane)
+              if (!row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+              }
+              const float cs = warp_colsum32(v, lane);
+              atomicAdd(e.colsum + gcol + 32 * h + lane, cs);
+            }
+          }
+          if constexpr (EPI != EPI_ATOMIC) {
+            if (active) fence_proxy_async_smem();
+            __syncwarp();
+            if (active && lane == 0) {
+              tma_store_2d(&tmO, buf, gcol, row0);  // rows past M / columns past N are clipped by the TMA unit
+              tma_store_commit();
+            }
+          }
+        }
+        if (!last) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) aux[j] = aux_next[j];
+        }
+      }
+    }
+    if (EPI != EPI_ATOMIC && lane == 0) tma_store_wait_all();  // the staging smem must outlive the last store's reads
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still signal / read across the pair
+  if (warp == 1) {
+    tc_fence_after();
+    __syncwarp();
+    tmem_dealloc_pair<C::kTmemCols>(tmem_base);
+  }
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const Gemm2Params& p, cudaStream_t stream) {
+  using C = Cfg2<BN>;
+  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN, EPI>;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "savqa_gemm_bf16 (CTA-pair kernel)")) return rc;
+  const int tiles = p.num_m * p.num_n * p.split_k;
+  const int max_pairs = sm_count() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  kern<<<2 * pairs, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmO, p);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+template <int BN, int EPI>
+int launch2_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const Gemm2Params& p,
+                  cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch2<BN, false, false, EPI>(tmA, tmB, tmO, p, s);
+  if (!a_mn && b_mn) return launch2<BN, false, true, EPI>(tmA, tmB, tmO, p, s);
+  return launch2<BN, true, true, EPI>(tmA, tmB, tmO, p, s);
+}
+
+template <int BN>
+int launch2_epi(int epi, bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const Gemm2Params& p,
+                cudaStream_t s) {
+  if (epi == EPI_BF16) return launch2_major<BN, EPI_BF16>(a_mn, b_mn, tmA, tmB, tmO, p, s);
+  if (epi == EPI_F32) return launch2_major<BN, EPI_F32>(a_mn, b_mn, tmA, tmB, tmO, p, s);
+  return launch2_major<BN, EPI_ATOMIC>(a_mn, b_mn, tmA, tmB, tmO, p, s);
+}
+
+}  // namespace
+
+// Takes the problem when the CTA-pair kernel supports it (sets *handled); otherwise leaves it to the single-CTA kernel.
+int gemm2_launch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
+                 const savqa_gemm_epilogue_t* epi, int split_k, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  const savqa_gemm_epilogue_t& e = *epi;
+  int mode;
+  if (e.accumulate == 2 && e.out_f32 && !e.out_bf16) mode = EPI_ATOMIC;
+  else if (e.accumulate == 0 && e.out_bf16 && !e.out_f32) mode = EPI_BF16;
+  else if (e.accumulate == 0 && e.out_f32 && !e.out_bf16) mode = EPI_F32;
+  else return SAVQA_OK;
+  if (a_mn && !b_mn) return SAVQA_OK;                       // combination not used by the path
+  if (M <= BM || N % 64 != 0 || (sm_count() & 1)) return SAVQA_OK;  // decoder-sized problems and ragged widths: single-CTA kernel
+  if (mode == EPI_BF16 && (e.res || e.rowtab)) return SAVQA_OK;
+  if (mode != EPI_BF16 && e.gate_bf16) return SAVQA_OK;
+  if (e.bias && !aligned16(e.bias)) return SAVQA_OK;
+  if (e.res && (!aligned16(e.res) || e.ld_res % 4)) return SAVQA_OK;
+  if (e.rowtab && (!aligned16(e.rowtab) || e.ld_rowtab % 4)) return SAVQA_OK;
+  if (e.gate_bf16 && (!aligned16(e.gate_bf16) || e.ld_gate % 8)) return SAVQA_OK;
+  if (e.out_f32 && (!aligned16(e.out_f32) || e.ld_out_f32 % 4)) return SAVQA_OK;
+  if (e.out_bf16 && (!aligned16(e.out_bf16) || e.ld_out_bf16 % 8)) return SAVQA_OK;
+  if (!aligned16(A) || !aligned16(B)) return SAVQA_OK;
+
+  Gemm2Params p;
+  p.M = M; p.N = N; p.K = K;
+  p.e = e;
+  p.num_kb = (K + BK - 1) / BK;
+  p.num_m = (M + 2 * BM - 1) / (2 * BM);
+  const int pairs = sm_count() / 2;
+  if (mode == EPI_ATOMIC && split_k != 1) {
+    // split-K (wgrad: few output tiles, long K): one round of work units over the CTA pairs, at least 4 k-blocks each
+    const long tiles256 = static_cast<long>(p.num_m) * ((N + 255) / 256);
+    int want = tiles256 >= pairs ? 1 : static_cast<int>(pairs / tiles256);
+    const int cap = p.num_kb / 4 > 0 ? p.num_kb / 4 : 1;
+    split_k = want < cap ? want : cap;
+  }
+  if (split_k < 1) split_k = 1;
+  if (split_k > p.num_kb) split_k = p.num_kb;
+  p.kb_per_split = (p.num_kb + split_k - 1) / split_k;
+  p.split_k = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+
+  // tile width: 256 halves the B traffic per flop; 128 when it loses fewer SM-rounds to wave quantisation
+  auto rounds = [&](int bn) {
+    const long tiles = static_cast<long>(p.num_m) * ((N + bn - 1) / bn) * p.split_k;
+    return (tiles + pairs - 1) / pairs * bn;  // ~ time in units of a 64-column slab
+  };
+  int BN = 256;
+  if (N % 256 != 0 || rounds(128) * 10 < rounds(256) * 9) BN = 128;
+  p.num_n = (N + BN - 1) / BN;
+
+  alignas(64) CUtensorMap tmA, tmB, tmO;
+  int rc;
+  if (!a_mn) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t str[1] = {static_cast<uint64_t>(lda) * 2};
+    const uint32_t box[2] = {BK, BM};
+    rc = make_tensor_map_bf16(&tmA, A, 2, dims, str, box, true);
+  } else {
+    const uint64_t dims[2] = {static_cast<uint64_t>(M), static_cast<uint64_t>(K)};
+    const uint64_t str[1] = {static_cast<uint64_t>(lda) * 2};
+    const uint32_t box[2] = {64, BK};
+    rc = make_tensor_map_bf16(&tmA, A, 2, dims, str, box, true);
+  }
+  if (rc) return rc;
+  if (!b_mn) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t str[1] = {static_cast<uint64_t>(ldb) * 2};
+    const uint32_t box[2] = {BK, static_cast<uint32_t>(BN / 2)};
+    rc = make_tensor_map_bf16(&tmB, B, 2, dims, str, box, true);
+  } else {
+    const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(K)};
+    const uint64_t str[1] = {static_cast<uint64_t>(ldb) * 2};
+    const uint32_t box[2] = {64, BK};
+    rc = make_tensor_map_bf16(&tmB, B, 2, dims, str, box, true);
+  }
+  if (rc) return rc;
+  if (mode == EPI_BF16) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    const uint64_t str[1] = {static_cast<uint64_t>(e.ld_out_bf16) * 2};
+    const uint32_t box[2] = {64, 32};
+    rc = make_tensor_map(&tmO, e.out_bf16, false, 2, dims, str, box, true);
+  } else if (mode == EPI_F32) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    const uint64_t str[1] = {static_cast<uint64_t>(e.ld_out_f32) * 4};
+    const uint32_t box[2] = {32, 32};
+    rc = make_tensor_map(&tmO, e.out_f32, true, 2, dims, str, box, true);
+  } else {
+    tmO = tmA;  // unused
+    rc = SAVQA_OK;
+  }
+  if (rc) return rc;
+  *handled = true;
+  if (BN == 256) return launch2_epi<256>(mode, a_mn != 0, b_mn != 0, tmA, tmB, tmO, p, stream);
+  return launch2_epi<128>(mode, a_mn != 0, b_mn != 0, tmA, tmB, tmO, p, stream);
+}
+
+}  // namespace savqa

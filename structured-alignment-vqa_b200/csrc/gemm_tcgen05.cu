@@ -9,9 +9,14 @@
 //
 // Operand majors: K-major (k contiguous, the forward / dgrad case) or MN-major (m or n contiguous: the wgrad
 // case dW = dY^T X, where both operands are read "transposed" straight from their row-major activations).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace savqa {
+
+int gemm2_launch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
+                 const savqa_gemm_epilogue_t* epi, int split_k, cudaStream_t stream, bool* handled);  // gemm2_tcgen05.cu
 
 namespace {
 
@@ -321,6 +326,16 @@ int launch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// SAVQA_GEMM_ENGINE=1 pins the single-CTA kernel (A/B comparison of the two kernels in tests and microbenchmarks)
+int engine_pref() {
+  static int pref = -1;
+  if (pref < 0) {
+    const char* s = getenv("SAVQA_GEMM_ENGINE");
+    pref = (s && s[0] == '1') ? 1 : 0;
+  }
+  return pref;
+}
+
 }  // namespace
 
 }  // namespace savqa
@@ -338,6 +353,14 @@ extern "C" int savqa_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const
   SAVQA_REQUIRE(split_k == 1 || (epi->accumulate == 2 && !epi->out_bf16 && !epi->relu && !epi->gate_bf16 && !epi->bias && !epi->res && !epi->rowtab),
                 "savqa_gemm_bf16: split_k > 1 needs accumulate == 2 and a linear epilogue");
   SAVQA_REQUIRE(!epi->rowtab || epi->rowtab_period > 0, "savqa_gemm_bf16: rowtab needs a period");
+  SAVQA_REQUIRE(!epi->colsum || split_k == 1, "savqa_gemm_bf16: colsum needs split_k == 1");
+
+  // large problems: the CTA-pair kernel (cta_group::2, TMA-store epilogue); everything else: the single-CTA kernel below
+  if (engine_pref() != 1) {
+    bool handled = false;
+    if (int rc = gemm2_launch(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, epi, split_k, stream, &handled)) return rc;
+    if (handled) return SAVQA_OK;
+  }
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;

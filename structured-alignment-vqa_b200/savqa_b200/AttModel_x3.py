@@ -31,6 +31,7 @@ INVALID = 400003
 VIS_PAD = -1
 LOC_PAD = -1
 VOCAB_ROWS = 407000  # hard-coded in the reference (AttModel_x3.py:36, 168, 293)
+_SIDE_STREAMS = {}   # device -> second stream of AttModel.encoder_step
 
 
 class _CastBf16(torch.autograd.Function):
@@ -265,6 +266,7 @@ class AttModel(nn.Module):
         self.cls_mcb = _head(self.mcb_out, hidden_size, num_classes, dropout_rate)
         self.label_smoothing = label_smoothing()
         self._pk = {k: (WeightPack(), WeightPack()) for k in ("cls", "cls_vis", "cls_syb")}
+        self.concurrent_branches = True  # encoder_step runs att_vis_grid and att_syb on two streams
 
     def _savqa_bind(self, fv):
         for name, (p0, p3) in self._pk.items():
@@ -291,8 +293,24 @@ class AttModel(nn.Module):
     def encoder_step(self, vis_fea, vis_mask, q_ipt, q_mask, q_graph, syb_ipt, macro_mask, macro_graph, decMask=True):
         """The accelerated path alone: both branch models + heads, with `syb_ipt` [B,M,2048] given (what MIL_NCE
         hands to att_syb at AttModel_x3.py:530)."""
+        if not (getattr(self, "concurrent_branches", True) and vis_fea.is_cuda):
+            fea_vis_grid = self.att_vis_grid(vis_fea, vis_mask, q_ipt, q_graph, q_mask, decMask)
+            fea_syb = self.att_syb(syb_ipt, macro_mask, macro_graph, q_ipt, q_graph, q_mask, decMask)
+            return self.answer_logits(fea_vis_grid, fea_syb)
+        # The two branch models are independent until the heads (AttModel_x3.py:529-531): fork the symbolic branch onto a
+        # second stream so that its kernels (and, through autograd, their backward) overlap the visual branch's -- the
+        # decoders' launch-bound M = B kernels of one branch hide under the encoder GEMMs of the other.  Inside a CUDA-graph
+        # capture this becomes two parallel branches of the graph.
+        main = torch.cuda.current_stream()
+        side = _SIDE_STREAMS.get(vis_fea.device)
+        if side is None:
+            side = _SIDE_STREAMS[vis_fea.device] = torch.cuda.Stream(device=vis_fea.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            fea_syb = self.att_syb(syb_ipt, macro_mask, macro_graph, q_ipt, q_graph, q_mask, decMask)
         fea_vis_grid = self.att_vis_grid(vis_fea, vis_mask, q_ipt, q_graph, q_mask, decMask)
-        fea_syb = self.att_syb(syb_ipt, macro_mask, macro_graph, q_ipt, q_graph, q_mask, decMask)
+        main.wait_stream(side)
+        fea_syb.record_stream(main)
         return self.answer_logits(fea_vis_grid, fea_syb)
 
     def forward(self, vis_fea, vis_mask, q_ipt, q_mask, q_graph, macro_ipt, macro_mask, macro_graph, macro_obj_loc,

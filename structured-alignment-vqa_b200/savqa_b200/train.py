@@ -204,6 +204,31 @@ class EncoderTrainer:
             for k in STEP_KEYS:
                 self.static[k].copy_(batch[k], non_blocking=True)
 
+    # ---- double-buffered host -> device input path (the loader hand-off of SURVEY.md 8(f2)) ---------------------
+    def stage(self, batch: Dict[str, torch.Tensor]) -> None:
+        """Starts the host -> device copy of the NEXT step's (pinned) batch on a copy stream, into a staging set of buffers,
+        while the current step computes; commit() then moves it into the graph's static inputs with device-to-device copies
+        (~0.1 ms for 164 MB) on the compute stream."""
+        if getattr(self, "staging", None) is None:
+            self.staging = {k: torch.empty_like(v) for k, v in self.static.items()}
+            self._copy_stream = torch.cuda.Stream()
+            self._staged = torch.cuda.Event()
+            self._staging_free = torch.cuda.Event()
+            self._staging_free.record(torch.cuda.current_stream())
+        cs = self._copy_stream
+        cs.wait_event(self._staging_free)  # the previous commit() has consumed the staging buffers
+        with torch.cuda.stream(cs):
+            for k in STEP_KEYS:
+                self.staging[k].copy_(batch[k], non_blocking=True)
+            self._staged.record(cs)
+
+    def commit(self) -> None:
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        for k in STEP_KEYS:
+            self.static[k].copy_(self.staging[k], non_blocking=True)
+        self._staging_free.record(cur)
+
     def replay(self) -> torch.Tensor:
         self.step_count += 1
         self._set_dyn()

@@ -178,7 +178,38 @@ def test_gemm_epilogues(ops):
     assert rel(big[:, N:2 * N], _gemm_ref(a, b)) < 4e-3 and float(big[:, :N].float().abs().sum()) == 0
 
 
-@pytest.mark.parametrize("M,Nout,Kin", [(300, 512, 2048), (7168, 2048, 512), (128, 1845, 512), (140, 2048, 300), (130, 1536, 512)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 128, 128), (7168, 1536, 512), (16384, 2048, 512), (1000, 512, 2048), (2560, 2048, 304),
+                                   (300, 192, 512), (7168, 1024, 512)])
+def test_gemm_pair_kernel_forward_epilogues(ops, M, N, K):
+    """The CTA-pair kernel (cta_group::2, TMA-store epilogue; taken for M > 128, N % 64 == 0, one output): bias + ReLU -> bf16,
+    bias + residual -> fp32, bias + positional row table -> fp32, with ragged M (rows past M are clipped by the TMA store)."""
+    a = GS.randn(f"gemm2/{M}/{K}/a", M, K).to(BF)
+    b = (GS.randn(f"gemm2/{N}/{K}/b", N, K) / math.sqrt(K)).to(BF)
+    bias = GS.randn(f"gemm2/{N}/bias", N)
+    res = GS.randn(f"gemm2/{M}/{N}/res", M, N)
+    rowtab = GS.randn(f"gemm2/{N}/rt", 64, N)
+    o16 = torch.full((M + 3, N), 7.0, device="cuda", dtype=BF)
+    ops.gemm(dev(a), dev(b), M, N, K, bias=dev(bias), relu=True, out_bf16=o16)
+    torch.cuda.synchronize()
+    assert rel(o16[:M], _gemm_ref(a, b, bias=bias, relu=True)) < 4e-3
+    assert float((o16[M:].float() - 7.0).abs().max()) == 0.0  # nothing written past row M
+    o32 = torch.full((M + 3, N), 7.0, device="cuda")
+    ops.gemm(dev(a), dev(b), M, N, K, bias=dev(bias), res=dev(res), out_f32=o32)
+    torch.cuda.synchronize()
+    assert rel(o32[:M], _gemm_ref(a, b, bias=bias, res=res)) < 2e-5
+    assert float((o32[M:] - 7.0).abs().max()) == 0.0
+    ops.gemm(dev(a), dev(b), M, N, K, bias=dev(bias), rowtab=dev(rowtab), rowtab_period=56, alpha=0.5, out_f32=o32)
+    torch.cuda.synchronize()
+    assert rel(o32[:M], _gemm_ref(a, b, bias=bias, rowtab=rowtab, period=56, alpha=0.5)) < 2e-5
+    # column-slice output of a wider buffer (fused QKV layout)
+    big = torch.zeros(M, 3 * N, device="cuda", dtype=BF)
+    ops.gemm(dev(a), dev(b), M, N, K, out_bf16=big[:, N:2 * N])
+    torch.cuda.synchronize()
+    assert rel(big[:, N:2 * N], _gemm_ref(a, b)) < 4e-3 and float(big[:, :N].float().abs().sum()) == 0 and float(big[:, 2 * N:].float().abs().sum()) == 0
+
+
+@pytest.mark.parametrize("M,Nout,Kin", [(300, 512, 2048), (7168, 2048, 512), (128, 1845, 512), (140, 2048, 300), (130, 1536, 512),
+                                        (16384, 512, 2048), (16384, 1536, 512), (1000, 2048, 512)])
 def test_gemm_dgrad_mn_major_b_and_colsum(ops, M, Nout, Kin):
     """dX[M,Kin] = dY[M,Nout] W[Nout,Kin] with W read MN-major from its forward staging [Nout, pad8(Kin)] (no transposed copy),
     ReLU gate and the bias-gradient column sums fused in the epilogue (functional.dgrad)."""
@@ -197,10 +228,20 @@ def test_gemm_dgrad_mn_major_b_and_colsum(ops, M, Nout, Kin):
     assert rel(out, ref) < 2e-5
     assert rel(outb[:, :Kin], ref) < 4e-3
     assert rel(cs, ref.sum(0)) < 1e-4  # fp32 atomics over the row tiles: order only
+    # single-output forms (the ones functional.dgrad issues; these run on the CTA-pair kernel when M > 128 and Kin % 64 == 0)
+    cs2 = torch.zeros(Kin, device="cuda")
+    outb2 = torch.zeros(M, ldw, device="cuda", dtype=BF)
+    ops.gemm(dev(dy), dev(w), M, Kin, Nout, b_mn=True, gate=dev(gate), out_bf16=outb2, colsum=cs2)
+    res = GS.randn(f"dg/{M}/{Kin}/res", M, Kin)
+    out2 = torch.empty(M, Kin, device="cuda")
+    ops.gemm(dev(dy), dev(w), M, Kin, Nout, b_mn=True, res=dev(res), out_f32=out2)
+    torch.cuda.synchronize()
+    assert rel(outb2[:, :Kin], ref) < 4e-3 and rel(cs2, ref.sum(0)) < 1e-4
+    assert rel(out2, dy[:, :Nout].float() @ w[:, :Kin].float() + res) < 2e-5
 
 
 @pytest.mark.parametrize("Mtok,Nout,Kin", [(256, 128, 128), (448, 1536, 512), (7168, 2048, 512), (7168, 512, 2048), (140, 2048, 300),
-                                           (128, 1845, 512)])
+                                           (128, 1845, 512), (16384, 1536, 512), (16384, 512, 2048), (1000, 1024, 512)])
 def test_gemm_wgrad_mn_major(ops, Mtok, Nout, Kin):
     """dW[Nout,Kin] = dY[Mtok,Nout]^T X[Mtok,Kin]: both operands MN-major, split-K with fp32 atomics."""
     ldy, ldx = ops.pad8(Nout), ops.pad8(Kin)

@@ -15,9 +15,10 @@ rm -f gpurun_out/summary.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.log 2>&1
 PT="python -m pytest -q -m gpu -p no:cacheprovider --timeout 240"
 run t_elem 600 $PT tests/test_gpu_kernels.py -k "masks or gather or casts or layernorm or loss"
+run t_gemm_pair 600 $PT tests/test_gpu_kernels.py -k "pair_kernel"
 run t_gemm_k 600 $PT tests/test_gpu_kernels.py -k "gemm_kmajor"
 run t_gemm_epi 300 $PT tests/test_gpu_kernels.py -k "gemm_epilogues"
-run t_gemm_wgrad 300 $PT tests/test_gpu_kernels.py -k "wgrad"
+run t_gemm_wgrad 300 $PT tests/test_gpu_kernels.py -k "wgrad or dgrad"
 run t_attn_simt 600 $PT tests/test_gpu_kernels.py -k "attention_forward and 1-"
 run t_attn_tc 600 $PT tests/test_gpu_kernels.py -k "attention_forward and 0-"
 run t_attn_bwd 600 $PT tests/test_gpu_kernels.py -k "attention_backward"
@@ -25,4 +26,5 @@ run t_parity 900 $PT tests/test_gpu_parity.py
 run smoke 300 python -c "import __graft_entry__ as g; g.smoke()"
 run bench_eager 600 python bench.py --mode eager --steps 5 --warmup 3 --no-cpu-baseline
 run bench_graph 600 python bench.py --mode graph --steps 10 --warmup 3 --no-cpu-baseline
+run kbench 600 python tools/bench_kernels.py
 cat gpurun_out/summary.log
