@@ -26,5 +26,4 @@ run t_parity 900 $PT tests/test_gpu_parity.py
 run smoke 300 python -c "import __graft_entry__ as g; g.smoke()"
 run bench_eager 600 python bench.py --mode eager --steps 5 --warmup 3 --no-cpu-baseline
 run bench_graph 600 python bench.py --mode graph --steps 10 --warmup 3 --no-cpu-baseline
-run kbench 600 python tools/bench_kernels.py
 cat gpurun_out/summary.log
