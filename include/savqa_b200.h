@@ -50,6 +50,11 @@ int savqa_build_masks(const void* first_mask, const void* q_mask, const void* q_
                       int in_is_float, int B, int V, int Q, int dec_mask_on,
                       float* graph_diag, float* graph, float* dec_mask, savqa_stream_t stream);
 
+/* bits[r, w] bit j = (graph[r, 32 w + j] != 0), zero past Tk, for r < rows, w < words_per_row (>= ceil(Tk / 32)).
+ * Only meaningful for graphs whose entries are exactly 0 or 1 (the outputs of savqa_build_masks): the attention kernels
+ * then read 4 bytes per 32 keys instead of 128. */
+int savqa_pack_graph_bits(const float* graph, int64_t rows, int Tk, uint32_t* bits, int words_per_row, savqa_stream_t stream);
+
 /* ---- a1/a2: embedding gathers (nn.Embedding at AttModel_x3.py:96,216; modules.py:32-46) ------------
  * out[r, 0:width] = table[idx[r], 0:width] * scale   (scale == 1.0f leaves the bits untouched).
  * out_f32 and/or out_bf16 may be NULL.  Columns [width, pad_to) of out_bf16 are zero-filled (TMA needs
@@ -150,6 +155,9 @@ typedef struct savqa_attn_args {
   float* scratch;                  /* fp32 [2, H*N, Tq, Tk] workspace (dS and W'); engine 1 with Tq > 1 only */
   /* optional bias gradients of the Q/K/V projections: db*[c] += sum_rows gated d*[row, c]  (fp32 [H*d], atomics) */
   float* dbq; float* dbk; float* dbv;
+  /* optional bit-packed form of a 0/1 `graph` (savqa_pack_graph_bits): word w of a row holds keys [32w, 32w+32); strides in
+   * 32-bit words (bits_q_stride = 0 broadcasts one row).  The tcgen05 engine reads it instead of the fp32 matrix. */
+  const uint32_t* graph_bits; int64_t bits_n_stride; int64_t bits_q_stride;
 } savqa_attn_args_t;
 
 int savqa_graph_attn_fwd(const savqa_attn_args_t* args, savqa_stream_t stream);

@@ -28,6 +28,7 @@ struct BwdParams {
   savqa_attn_args_t a;
   int tk_pad16;  // Tk rounded up to 16
   int kt;        // 128-key output tiles (1 or 2)
+  int kc;        // 64-key chunks of the dS / W' tiles
   int kv_rows;   // rows of the K / V smem tiles (= TMA box rows)
   int dw_off;    // TMEM column of the raw dW accumulator
   int tmem_cols;
@@ -75,9 +76,14 @@ __device__ __forceinline__ void store_gated_row32(const uint32_t (&r)[32], const
   }
 }
 
-// g[j] = graph weight of column c0 + j of this thread's query row (1 when there is no graph, 0 past Tk)
-__device__ __forceinline__ void load_graph32(const float* grow, bool use, int c0, int Tk, int gvec, float (&g)[32]) {
-  if (use && grow) {
+// g[j] = graph weight of column c0 + j of this thread's query row (1 when there is no graph, 0 past Tk); `bits_row`
+// (shared memory, one word per 32 keys) replaces the fp32 row when the graph came bit-packed
+__device__ __forceinline__ void load_graph32(const float* grow, const uint32_t* bits_row, bool use, int c0, int Tk, int gvec, float (&g)[32]) {
+  if (use && bits_row) {
+    const uint32_t word = bits_row[c0 >> 5];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) g[j] = ((word >> j) & 1u) ? 1.0f : 0.0f;
+  } else if (use && grow) {
     if (gvec && c0 + 32 <= Tk) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -94,29 +100,42 @@ __device__ __forceinline__ void load_graph32(const float* grow, bool use, int c0
   }
 }
 
-template <int D>
-__global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                                                         const __grid_constant__ CUtensorMap tmV, const BwdParams p) {
+// RS = thread-halves per query row: with RS == 2 (256 threads, chosen when Tk > 64 leaves room for only one CTA per SM) warps
+// w and w + 4 share TMEM lane quadrant w & 3 and split the key columns of every row pass and the head columns of the
+// epilogue; the row statistics are combined through shared memory.  One warp per scheduler cannot hide the exp / TMEM /
+// shared-memory latencies of these dependent passes; two can.
+template <int D, int RS>
+__global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                              const __grid_constant__ CUtensorMap tmV, const BwdParams p) {
   constexpr int DCH = D / 64;
+  constexpr int NT = 128 * RS;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_tma, bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
+  __shared__ float sStat[RS == 2 ? 2 * 128 * 4 : 1];  // per-half partial row statistics
   const savqa_attn_args_t& a = p.a;
-  const int t = threadIdx.x, warp = t >> 5;
+  const int tid = threadIdx.x;
+  const int t = tid & 127;       // query row / TMEM lane of this thread
+  const int half = tid >> 7;     // which half of the columns it works on
+  const int warp = t >> 5;       // TMEM lane quadrant
   const int hn = blockIdx.x;
   const int h = hn / a.N, n = hn % a.N;
-  const int kc2 = 2 * p.kt;  // 64-key chunks of the dS / W' tiles (whole 128-key tiles)
+  const int kc2 = p.kc;  // 64-key chunks of the dS / W' tiles that are written; the MMAs read whole 128-key tiles, so with an odd
+                         // count the last tile's second chunk is whatever follows in shared memory (finite bf16 data of the next
+                         // region): it only feeds dK / dV rows >= Tk, which are never stored
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;                            // DCH x [128][128 B]
+  uint8_t* sW = smem;                            // kc2 x [128][128 B]   W'
+  uint8_t* sP = sW + kc2 * 16384;                // kc2 x [128][128 B]   dS
+  uint8_t* sQ = sP + kc2 * 16384;                // DCH x [128][128 B]
   uint8_t* sdO = sQ + DCH * 16384;               // DCH x [128][128 B]
   uint8_t* sK = sdO + DCH * 16384;               // DCH x [kv_rows][128 B]
   uint8_t* sV = sK + DCH * p.kv_rows * 128;      // DCH x [kv_rows][128 B]
-  uint8_t* sP = sV + DCH * p.kv_rows * 128;      // kc2 x [128][128 B]   dS
-  uint8_t* sW = sP + kc2 * 16384;                // kc2 x [128][128 B]   W'
-  float* sKeyOn = reinterpret_cast<float*>(sW + kc2 * 16384);  // [Tk]
+  float* sKeyOn = reinterpret_cast<float*>(sV + DCH * p.kv_rows * 128);  // [Tk]
+  uint32_t* sBits = reinterpret_cast<uint32_t*>(sKeyOn + ((a.Tk + 3) & ~3));  // [128][wpr] bit-packed graph rows
+  const int wpr = (a.Tk + 31) >> 5;
 
-  if (t == 0) {
+  if (tid == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -134,23 +153,40 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
     }
   }
   __syncwarp();
-  if (warp == 0) tmem_alloc_rt(&tmem_slot, static_cast<uint32_t>(p.tmem_cols));
-  for (int j = t; j < a.Tk; j += 128) sKeyOn[j] = a.key_on ? a.key_on[static_cast<long>(n) * a.Tk + j] : 1.0f;
+  if (tid < 32) tmem_alloc_rt(&tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+  for (int j = tid; j < a.Tk; j += NT) sKeyOn[j] = a.key_on ? a.key_on[static_cast<long>(n) * a.Tk + j] : 1.0f;
+  if (a.graph_bits) {
+    for (int idx = tid; idx < 128 * wpr; idx += NT) {
+      const int row = idx / wpr, w = idx % wpr;
+      sBits[idx] = (row < a.Tq) ? __ldg(a.graph_bits + static_cast<long>(n) * a.bits_n_stride + static_cast<long>(row) * a.bits_q_stride + w) : 0u;
+    }
+  }
 
   // ---- dO: fp32 [Tq, D] head slice -> bf16 K-major swizzled tile (rows >= Tq are zero) ----
+  // all of a thread's loads are issued before the first conversion (the loop is latency bound otherwise: one HBM round trip
+  // per iteration)
   {
-    constexpr int V4 = D / 4;  // float4 per row
-    for (int idx = t; idx < 128 * V4; idx += 128) {
+    constexpr int V4 = D / 4;          // float4 per row
+    constexpr int kIters = V4 / RS;    // 128 * V4 float4 over the CTA's threads
+    float4 dv[kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int idx = tid + it * NT;
       const int row = idx / V4, col = (idx % V4) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      dv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row < a.Tq) {
         const float* src = a.dout + (static_cast<long>(n) * a.Tq + row) * a.ld_dout + h * D + col;
-        if (p.dvec) v = __ldg(reinterpret_cast<const float4*>(src));
-        else v = make_float4(src[0], src[1], src[2], src[3]);
+        if (p.dvec) dv[it] = __ldg(reinterpret_cast<const float4*>(src));
+        else dv[it] = make_float4(src[0], src[1], src[2], src[3]);
       }
+    }
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int idx = tid + it * NT;
+      const int row = idx / V4, col = (idx % V4) * 4;
       const int cc = col & 63;
       uint8_t* dst = sdO + (col >> 6) * 16384 + row * 128 + ((((cc >> 3) ^ (row & 7))) << 4) + (cc & 7) * 2;
-      *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(dv[it].x, dv[it].y), pack_bf16x2(dv[it].z, dv[it].w));
     }
   }
   fence_proxy_async_smem();
@@ -159,7 +195,7 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (t == 0) {
+  if (tid == 0) {
     mbar_wait(&bar_tma, 0);
     tc_fence_after();
     // S = Q K^T and raw dW = dO V^T (N up to 256 per instruction)
@@ -193,12 +229,17 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
   const long qrow = static_cast<long>(n) * a.Tq + (row_ok ? i : 0);
   const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
   const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
-  const int renorm = a.graph ? a.renorm : 0;
+  const int renorm = (a.graph || a.graph_bits) ? a.renorm : 0;
+  const uint32_t* bits_row = a.graph_bits ? sBits + t * wpr : nullptr;
   const float* grow = (a.graph && row_ok) ? a.graph + static_cast<long>(n) * a.graph_n_stride + static_cast<long>(i) * a.graph_q_stride : nullptr;
   const float qon = (a.query_on && row_ok) ? a.query_on[qrow] : 1.0f;
 
+  // this half's share of the 32-column chunks of the score row
+  const int nch = (a.Tk + 31) >> 5;
+  const int ch_lo = (RS == 2 && half == 1) ? (nch + 1) / 2 : 0;
+  const int ch_hi = (RS == 2 && half == 0) ? (nch + 1) / 2 : nch;
   float m = -INFINITY;
-  for (int c0 = 0; c0 < a.Tk; c0 += 32) {
+  for (int c0 = ch_lo * 32; c0 < ch_hi * 32; c0 += 32) {
     uint32_t r[32];
     __syncwarp();
     tmem_ld_32x32(t_lane + c0, r);
@@ -214,16 +255,22 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
       }
     }
   }
+  if constexpr (RS == 2) {  // row maximum over both halves
+    sStat[(half * 128 + t) * 4] = m;
+    __syncthreads();
+    m = fmaxf(m, sStat[((half ^ 1) * 128 + t) * 4]);
+    __syncthreads();
+  }
   // statistics: Z = sum e, R = sum |g e|, SA = sum g e, U = sum g e * raw dW
   float Z = 0.0f, R = 0.0f, SA = 0.0f, U = 0.0f;
-  for (int c0 = 0; c0 < a.Tk; c0 += 32) {
+  for (int c0 = ch_lo * 32; c0 < ch_hi * 32; c0 += 32) {
     uint32_t r[32], w[32];
     __syncwarp();
     tmem_ld_32x32(t_lane + c0, r);
     tmem_ld_32x32(t_lane + p.dw_off + c0, w);
     tmem_ld_wait();
     float g[32];
-    load_graph32(grow, renorm != 0, c0, a.Tk, p.gvec, g);
+    load_graph32(grow, bits_row, renorm != 0, c0, a.Tk, p.gvec, g);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int col = c0 + j;
@@ -239,6 +286,14 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
         U = fmaf(ge, __uint_as_float(w[j]), U);
       }
     }
+  }
+  if constexpr (RS == 2) {  // sums over both halves (added in the same order by both threads of a row: identical results)
+    float* mine = sStat + (half * 128 + t) * 4;
+    mine[0] = Z; mine[1] = R; mine[2] = SA; mine[3] = U;
+    __syncthreads();
+    const float* lo = sStat + t * 4;
+    const float* hi = sStat + (128 + t) * 4;
+    Z = lo[0] + hi[0]; R = lo[1] + hi[1]; SA = lo[2] + hi[2]; U = lo[3] + hi[3];
   }
   float scale;
   bool clamped = false;
@@ -256,7 +311,9 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
   const float beta = clamped ? 1.0f : (renorm == 2 ? 1.0f - scale * SA : 0.0f);
   const float inv_z = 1.0f / Z;
 
-  for (int c0 = 0; c0 < kc2 * 64; c0 += 32) {
+  const int wch_lo = (RS == 2 && half == 1) ? kc2 : 0;            // 2 * kc2 chunks of 32 columns, zero fill past Tk included
+  const int wch_hi = (RS == 2 && half == 0) ? kc2 : 2 * kc2;
+  for (int c0 = wch_lo * 32; c0 < wch_hi * 32; c0 += 32) {
     float ds[32], wq[32];
     if (c0 < a.Tk) {  // warp-uniform: the TMEM loads are .sync.aligned
       uint32_t r[32], w[32];
@@ -265,7 +322,7 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
       tmem_ld_32x32(t_lane + p.dw_off + c0, w);
       tmem_ld_wait();
       float g[32];
-      load_graph32(grow, renorm != 0, c0, a.Tk, p.gvec, g);
+      load_graph32(grow, bits_row, renorm != 0, c0, a.Tk, p.gvec, g);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int col = c0 + j;
@@ -307,7 +364,7 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
-  if (t == 0) {
+  if (tid == 0) {
     tc_fence_after();
     const uint32_t idesc_q = umma_idesc_bf16(128, 64, false, true);
     const uint32_t idesc_k = umma_idesc_bf16(128, 64, true, true);
@@ -344,7 +401,7 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
   const __nv_bfloat16* Qg = static_cast<const __nv_bfloat16*>(a.q) + qrow * a.ldq + h * D;
   __nv_bfloat16* dQg = static_cast<__nv_bfloat16*>(a.dq) + qrow * a.ld_dq + h * D;
 #pragma unroll 1
-  for (int c0 = 0; c0 < D; c0 += 32) {
+  for (int c0 = half * 32; c0 < D; c0 += 32 * RS) {
     uint32_t r[32];
     __syncwarp();
     tmem_ld_32x32(t_lane + dq_off + c0, r);
@@ -361,7 +418,7 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
     __nv_bfloat16* dKg = static_cast<__nv_bfloat16*>(a.dk) + krow * a.ld_dk + h * D;
     __nv_bfloat16* dVg = static_cast<__nv_bfloat16*>(a.dv) + krow * a.ld_dv + h * D;
 #pragma unroll 1
-    for (int c0 = 0; c0 < D; c0 += 32) {
+    for (int c0 = half * 32; c0 < D; c0 += 32 * RS) {
       uint32_t r[32];
       __syncwarp();
       tmem_ld_32x32(t_lane + dk_off + kt * D + c0, r);
@@ -375,7 +432,7 @@ __global__ void __launch_bounds__(128) attn_bwd_tc_kernel(const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (tid < 32) {
     tc_fence_after();
     __syncwarp();
     tmem_dealloc_rt(tmem, static_cast<uint32_t>(p.tmem_cols));
@@ -395,6 +452,7 @@ void fill_params(const savqa_attn_args_t* a, BwdParams& p, size_t& smem) {
   p.a = *a;
   p.tk_pad16 = (a->Tk + 15) / 16 * 16;
   p.kt = (a->Tk + 127) / 128;
+  p.kc = (p.tk_pad16 + 63) / 64;
   p.kv_rows = p.tk_pad16;
   p.dw_off = (p.tk_pad16 + 31) / 32 * 32;
   const int need = max(p.dw_off + p.tk_pad16, (1 + 2 * p.kt) * a->d);
@@ -405,7 +463,8 @@ void fill_params(const savqa_attn_args_t* a, BwdParams& p, size_t& smem) {
   p.dvec = (a->ld_dout % 4 == 0 && aligned16(a->dout) && a->d % 4 == 0) ? 1 : 0;
   const int dch = a->d / 64;
   smem = 1024 + static_cast<size_t>(2) * dch * 16384 + static_cast<size_t>(2) * dch * p.kv_rows * 128 +
-         static_cast<size_t>(2) * (2 * p.kt) * 16384 + static_cast<size_t>(a->Tk) * 4 + 16;
+         static_cast<size_t>(2) * p.kc * 16384 + static_cast<size_t>(a->Tk) * 4 + 16 +
+         (a->graph_bits ? static_cast<size_t>(128) * ((a->Tk + 31) / 32) * 4 : 0);
 }
 
 }  // namespace
@@ -438,13 +497,22 @@ int attn_bwd_tc(const savqa_attn_args_t* a, cudaStream_t stream) {
   if (int rc = make_map3(&tmK, a->k, a->ldk, a->Tk, a->N, p.kv_rows)) return rc;
   if (int rc = make_map3(&tmV, a->v, a->ldv, a->Tk, a->N, p.kv_rows)) return rc;
   dim3 grid(a->N * a->H);
+  // two CTAs fit an SM when the key tile is a single 64-key chunk (d = 64); otherwise one CTA with two threads per row
+  const bool split = smem > 112 * 1024;
+#define SAVQA_LAUNCH_BWD(DD, RR)                                                                                                           \
+  do {                                                                                                                                     \
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_bwd_tc_kernel<DD, RR>), smem, "savqa_graph_attn_bwd (tcgen05 engine)")) \
+      return rc;                                                                                                                           \
+    attn_bwd_tc_kernel<DD, RR><<<grid, 128 * RR, smem, stream>>>(tmQ, tmK, tmV, p);                                                        \
+  } while (0)
   if (a->d == 64) {
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_bwd_tc_kernel<64>), smem, "savqa_graph_attn_bwd (tcgen05 engine)")) return rc;
-    attn_bwd_tc_kernel<64><<<grid, 128, smem, stream>>>(tmQ, tmK, tmV, p);
+    if (split) SAVQA_LAUNCH_BWD(64, 2);
+    else SAVQA_LAUNCH_BWD(64, 1);
   } else {
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_bwd_tc_kernel<128>), smem, "savqa_graph_attn_bwd (tcgen05 engine)")) return rc;
-    attn_bwd_tc_kernel<128><<<grid, 128, smem, stream>>>(tmQ, tmK, tmV, p);
+    if (split) SAVQA_LAUNCH_BWD(128, 2);
+    else SAVQA_LAUNCH_BWD(128, 1);
   }
+#undef SAVQA_LAUNCH_BWD
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;
 }

@@ -459,6 +459,264 @@ __global__ void __launch_bounds__(kRowWarps * 32) attn_row1_bwd_kernel(const sav
   }
 }
 
+// ---- piece-parallel row kernels (head size a power of two, 16-byte aligned rows): lane = (key slot ks, 16-byte piece p) ----
+// A warp sweeps the keys 32 / P at a time (P = d / 8 pieces per row), every lane moving 16 bytes per load; four sweeps are in
+// flight at once.  Scores, dW and the weights travel through a per-warp shared-memory row.
+constexpr int kPieceWarps = 4;
+constexpr int kSweepUnroll = 4;
+
+__device__ __forceinline__ float dot8(const float* __restrict__ x, const uint4& u) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
+  float acc = x[0] * a.x;
+  acc = fmaf(x[1], a.y, acc); acc = fmaf(x[2], b.x, acc); acc = fmaf(x[3], b.y, acc);
+  acc = fmaf(x[4], c.x, acc); acc = fmaf(x[5], c.y, acc); acc = fmaf(x[6], e.x, acc); acc = fmaf(x[7], e.y, acc);
+  return acc;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = e.x; f[7] = e.y;
+}
+
+// dst[j] = scale * <x, M[j, head slice]> for every key j (M = K or V rows of this sample/head); result written by the p == 0 lanes
+__device__ __forceinline__ void sweep_dots(const __nv_bfloat16* __restrict__ base, long ld, int Tk, int P, int ks, int pc, const float* xp,
+                                           float scale, float* dst) {
+  const int kpi = 32 / P;
+  for (int j0 = 0; j0 < Tk; j0 += kpi * kSweepUnroll) {
+    uint4 u[kSweepUnroll];
+#pragma unroll
+    for (int i = 0; i < kSweepUnroll; ++i) {
+      const int j = j0 + i * kpi + ks;
+      u[i] = (j < Tk) ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<long>(j) * ld) + pc) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < kSweepUnroll; ++i) {
+      float part = dot8(xp, u[i]);
+      for (int o = 1; o < P; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const int j = j0 + i * kpi + ks;
+      if (pc == 0 && j < Tk) dst[j] = part * scale;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kPieceWarps * 32) attn_row1_fwd_piece_kernel(const savqa_attn_args_t a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int d = a.d, P = d >> 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sS = reinterpret_cast<float*>(smem) + warp * (a.Tk + d);  // [Tk] scores, then W'; [d] q
+  float* sq = sS + a.Tk;
+  const long hn = static_cast<long>(blockIdx.x) * kPieceWarps + warp;
+  if (hn >= static_cast<long>(a.N) * a.H) return;
+  const int h = static_cast<int>(hn / a.N), n = static_cast<int>(hn % a.N);
+  const int pc = lane % P, ks = lane / P;
+  const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q) + static_cast<long>(n) * a.ldq + h * d;
+  for (int c = lane; c < d; c += 32) sq[c] = __bfloat162float(Q[c]);
+  __syncwarp();
+  const __nv_bfloat16* Kb = static_cast<const __nv_bfloat16*>(a.k) + static_cast<long>(n) * a.Tk * a.ldk + h * d;
+  const __nv_bfloat16* Vb = static_cast<const __nv_bfloat16*>(a.v) + static_cast<long>(n) * a.Tk * a.ldv + h * d;
+  sweep_dots(Kb, a.ldk, a.Tk, P, ks, pc, sq + pc * 8, 1.0f, sS);
+  __syncwarp();
+  // softmax / graph / renormalisation: key j = jj*32 + lane (same arithmetic as the generic kernels)
+  const float sqrt_d = sqrtf(static_cast<float>(d));
+  float s[kMaxJ];
+#pragma unroll
+  for (int jj = 0; jj < kMaxJ; ++jj) {
+    const int j = jj * 32 + lane;
+    float v = kMaskFill;
+    if (j < a.Tk) {
+      v = sS[j] / sqrt_d;
+      if (a.key_on && a.key_on[static_cast<long>(n) * a.Tk + j] == 0.0f) v = kMaskFill;
+      if (a.causal && j > 0) v = kMaskFill;
+    }
+    s[jj] = v;
+  }
+  const float* grow = a.graph ? a.graph + static_cast<long>(n) * a.graph_n_stride : nullptr;
+  RowSoftmax rs;
+  row_weights(s, grow, a.Tk, a.graph ? a.renorm : 0, lane, rs);
+  const float qon = a.query_on ? a.query_on[n] : 1.0f;
+  __syncwarp();
+#pragma unroll
+  for (int jj = 0; jj < kMaxJ; ++jj) {
+    const int j = jj * 32 + lane;
+    if (j < a.Tk) {
+      if (a.att) a.att[hn * a.Tk + j] = rs.w[jj];
+      sS[j] = rs.w[jj] * qon;
+    }
+  }
+  __syncwarp();
+  // out[piece] = sum_j W'_j V[j][piece]
+  const int kpi = 32 / P;
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.0f;
+  for (int j0 = 0; j0 < a.Tk; j0 += kpi * kSweepUnroll) {
+    uint4 u[kSweepUnroll];
+#pragma unroll
+    for (int i = 0; i < kSweepUnroll; ++i) {
+      const int j = j0 + i * kpi + ks;
+      u[i] = (j < a.Tk) ? __ldg(reinterpret_cast<const uint4*>(Vb + static_cast<long>(j) * a.ldv) + pc) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < kSweepUnroll; ++i) {
+      const int j = j0 + i * kpi + ks;
+      const float w = (j < a.Tk) ? sS[j] : 0.0f;
+      float f[8];
+      unpack8(u[i], f);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = fmaf(w, f[c], acc[c]);
+    }
+  }
+  for (int o = P; o < 32; o <<= 1) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+  }
+  if (ks == 0) {
+    float* o = a.out + static_cast<long>(n) * a.ldo + h * d + pc * 8;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] = acc[c];
+  }
+}
+
+__global__ void __launch_bounds__(kPieceWarps * 32) attn_row1_bwd_piece_kernel(const savqa_attn_args_t a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int d = a.d, P = d >> 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sS = reinterpret_cast<float*>(smem) + warp * (3 * a.Tk + 2 * d);  // [Tk] scores -> dS/sqrt(d); [Tk] dW -> W'; [d] q; [d] dO
+  float* sD = sS + a.Tk;
+  float* sq = sD + a.Tk;
+  float* sg = sq + d;
+  const long hn = static_cast<long>(blockIdx.x) * kPieceWarps + warp;
+  if (hn >= static_cast<long>(a.N) * a.H) return;
+  const int h = static_cast<int>(hn / a.N), n = static_cast<int>(hn % a.N);
+  const int pc = lane % P, ks = lane / P;
+  const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q) + static_cast<long>(n) * a.ldq + h * d;
+  const float* dO = a.dout + static_cast<long>(n) * a.ld_dout + h * d;
+  for (int c = lane; c < d; c += 32) {
+    sq[c] = __bfloat162float(Q[c]);
+    sg[c] = dO[c];
+  }
+  __syncwarp();
+  const __nv_bfloat16* Kb = static_cast<const __nv_bfloat16*>(a.k) + static_cast<long>(n) * a.Tk * a.ldk + h * d;
+  const __nv_bfloat16* Vb = static_cast<const __nv_bfloat16*>(a.v) + static_cast<long>(n) * a.Tk * a.ldv + h * d;
+  const float qon = a.query_on ? a.query_on[n] : 1.0f;
+  sweep_dots(Kb, a.ldk, a.Tk, P, ks, pc, sq + pc * 8, 1.0f, sS);
+  sweep_dots(Vb, a.ldv, a.Tk, P, ks, pc, sg + pc * 8, qon, sD);  // dW_j = qm * <dO, V_j>
+  __syncwarp();
+  const float sqrt_d = sqrtf(static_cast<float>(d));
+  const int renorm = a.graph ? a.renorm : 0;
+  float s[kMaxJ], dw[kMaxJ];
+#pragma unroll
+  for (int jj = 0; jj < kMaxJ; ++jj) {
+    const int j = jj * 32 + lane;
+    float v = kMaskFill, w = 0.0f;
+    if (j < a.Tk) {
+      v = sS[j] / sqrt_d;
+      w = sD[j];
+      if (a.key_on && a.key_on[static_cast<long>(n) * a.Tk + j] == 0.0f) v = kMaskFill;
+      if (a.causal && j > 0) v = kMaskFill;
+    }
+    s[jj] = v;
+    dw[jj] = w;
+  }
+  const float* grow = a.graph ? a.graph + static_cast<long>(n) * a.graph_n_stride : nullptr;
+  RowSoftmax rs;
+  row_weights(s, grow, a.Tk, renorm, lane, rs);
+  float t = 0.0f;
+#pragma unroll
+  for (int jj = 0; jj < kMaxJ; ++jj) t += rs.w[jj] * dw[jj];
+  t = warp_sum(t);
+  const bool clamped = (renorm == 1) && (rs.r < 1e-12f);
+  __syncwarp();
+#pragma unroll
+  for (int jj = 0; jj < kMaxJ; ++jj) {
+    const int j = jj * 32 + lane;
+    if (j < a.Tk) {
+      float ds;
+      if (renorm == 1 && clamped) ds = rs.w[jj] * dw[jj] - rs.p[jj] * t;
+      else if (renorm == 2) ds = rs.w[jj] * (dw[jj] - t) - rs.p[jj] * t * (1.0f - rs.sumw);
+      else ds = rs.w[jj] * (dw[jj] - t);
+      if (s[jj] == kMaskFill) ds = 0.0f;  // masked scores are constants
+      sS[j] = ds / sqrt_d;
+      sD[j] = rs.w[jj] * qon;
+    }
+  }
+  __syncwarp();
+  // piece pass: dQ = sum_j dS_j K_j;  dK_j = dS_j q;  dV_j = W'_j dO   (ReLU gates of the projections; bias-gradient sums)
+  const int kpi = 32 / P;
+  float qf[8], gf[8], dq[8], bk[8], bv[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    qf[c] = sq[pc * 8 + c];
+    gf[c] = sg[pc * 8 + c];
+    dq[c] = bk[c] = bv[c] = 0.0f;
+  }
+  __nv_bfloat16* dK = static_cast<__nv_bfloat16*>(a.dk) + static_cast<long>(n) * a.Tk * a.ld_dk + h * d;
+  __nv_bfloat16* dV = static_cast<__nv_bfloat16*>(a.dv) + static_cast<long>(n) * a.Tk * a.ld_dv + h * d;
+  for (int j0 = 0; j0 < a.Tk; j0 += kpi * kSweepUnroll) {
+    uint4 uk[kSweepUnroll], uv[kSweepUnroll];
+#pragma unroll
+    for (int i = 0; i < kSweepUnroll; ++i) {
+      const int j = j0 + i * kpi + ks;
+      const bool ok = j < a.Tk;
+      uk[i] = ok ? __ldg(reinterpret_cast<const uint4*>(Kb + static_cast<long>(j) * a.ldk) + pc) : make_uint4(0u, 0u, 0u, 0u);
+      uv[i] = ok ? __ldg(reinterpret_cast<const uint4*>(Vb + static_cast<long>(j) * a.ldv) + pc) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < kSweepUnroll; ++i) {
+      const int j = j0 + i * kpi + ks;
+      if (j < a.Tk) {
+        const float ds = sS[j], w = sD[j];
+        float kf[8], vf[8], ok_[8], ov_[8];
+        unpack8(uk[i], kf);
+        unpack8(uv[i], vf);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          dq[c] = fmaf(ds, kf[c], dq[c]);
+          ok_[c] = kf[c] > 0.0f ? ds * qf[c] : 0.0f;
+          ov_[c] = vf[c] > 0.0f ? w * gf[c] : 0.0f;
+          bk[c] += ok_[c];
+          bv[c] += ov_[c];
+        }
+        *(reinterpret_cast<uint4*>(dK + static_cast<long>(j) * a.ld_dk) + pc) =
+            make_uint4(pack_bf16x2(ok_[0], ok_[1]), pack_bf16x2(ok_[2], ok_[3]), pack_bf16x2(ok_[4], ok_[5]), pack_bf16x2(ok_[6], ok_[7]));
+        *(reinterpret_cast<uint4*>(dV + static_cast<long>(j) * a.ld_dv) + pc) =
+            make_uint4(pack_bf16x2(ov_[0], ov_[1]), pack_bf16x2(ov_[2], ov_[3]), pack_bf16x2(ov_[4], ov_[5]), pack_bf16x2(ov_[6], ov_[7]));
+      }
+    }
+  }
+  for (int o = P; o < 32; o <<= 1) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      dq[c] += __shfl_xor_sync(0xffffffffu, dq[c], o);
+      bk[c] += __shfl_xor_sync(0xffffffffu, bk[c], o);
+      bv[c] += __shfl_xor_sync(0xffffffffu, bv[c], o);
+    }
+  }
+  if (ks == 0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (!(qf[c] > 0.0f)) dq[c] = 0.0f;  // ReLU of the Q projection
+    __nv_bfloat16* dQ = static_cast<__nv_bfloat16*>(a.dq) + static_cast<long>(n) * a.ld_dq + h * d;
+    *(reinterpret_cast<uint4*>(dQ) + pc) =
+        make_uint4(pack_bf16x2(dq[0], dq[1]), pack_bf16x2(dq[2], dq[3]), pack_bf16x2(dq[4], dq[5]), pack_bf16x2(dq[6], dq[7]));
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int col = h * d + pc * 8 + c;
+      if (a.dbq) atomicAdd(a.dbq + col, dq[c]);
+      if (a.dbk) atomicAdd(a.dbk + col, bk[c]);
+      if (a.dbv) atomicAdd(a.dbv + col, bv[c]);
+    }
+  }
+}
+
+bool row1_piece_ok(const savqa_attn_args_t* a, bool bwd) {
+  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const int d = a->d;
+  if (!(d == 8 || d == 16 || d == 32 || d == 64 || d == 128 || d == 256)) return false;
+  if (a->ldk % 8 || a->ldv % 8 || !a16(a->k) || !a16(a->v)) return false;
+  if (bwd && (a->ld_dq % 8 || a->ld_dk % 8 || a->ld_dv % 8 || !a16(a->dq) || !a16(a->dk) || !a16(a->dv))) return false;
+  return true;
+}
+
 bool row1_vec_ok(const savqa_attn_args_t* a) {
   auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   return a->d % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a16(a->k) && a16(a->v);
@@ -481,6 +739,14 @@ int check_common(const savqa_attn_args_t* a, const char* who) {
 int attn_fwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
   if (int rc = check_common(a, "savqa_graph_attn_fwd")) return rc;
   SAVQA_REQUIRE(a->out, "savqa_graph_attn_fwd: null out");
+  if (a->Tq == 1 && row1_piece_ok(a, false)) {
+    const size_t smem1 = static_cast<size_t>(kPieceWarps) * (a->Tk + a->d) * 4;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_row1_fwd_piece_kernel), smem1, "savqa_graph_attn_fwd (row kernel)")) return rc;
+    const long warps = static_cast<long>(a->N) * a->H;
+    attn_row1_fwd_piece_kernel<<<static_cast<unsigned>((warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, smem1, stream>>>(*a);
+    SAVQA_CHECK_CUDA(cudaGetLastError());
+    return SAVQA_OK;
+  }
   if (a->Tq == 1) {
     const size_t smem1 = static_cast<size_t>(kRowWarps) * (a->Tk + a->d) * 4;
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_row1_fwd_kernel), smem1, "savqa_graph_attn_fwd (row kernel)")) return rc;
@@ -502,6 +768,14 @@ int attn_bwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
   if (int rc = check_common(a, "savqa_graph_attn_bwd")) return rc;
   SAVQA_REQUIRE(a->dout && a->dq && a->dk && a->dv, "savqa_graph_attn_bwd: null gradient buffer");
   SAVQA_REQUIRE(a->ld_dq % 2 == 0 && a->ld_dk % 2 == 0 && a->ld_dv % 2 == 0, "savqa_graph_attn_bwd: odd leading dimension");
+  if (a->Tq == 1 && row1_piece_ok(a, true)) {
+    const size_t smem1 = static_cast<size_t>(kPieceWarps) * (3 * a->Tk + 2 * a->d) * 4;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_row1_bwd_piece_kernel), smem1, "savqa_graph_attn_bwd (row kernel)")) return rc;
+    const long warps = static_cast<long>(a->N) * a->H;
+    attn_row1_bwd_piece_kernel<<<static_cast<unsigned>((warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, smem1, stream>>>(*a);
+    SAVQA_CHECK_CUDA(cudaGetLastError());
+    return SAVQA_OK;
+  }
   if (a->Tq == 1) {
     const size_t smem1 = static_cast<size_t>(kRowWarps) * (2 * a->Tk + 2 * a->d) * 4;
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_row1_bwd_kernel), smem1, "savqa_graph_attn_bwd (row kernel)")) return rc;

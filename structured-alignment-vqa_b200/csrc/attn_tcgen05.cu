@@ -29,6 +29,7 @@ struct AttnTcParams {
   int kv_rows;    // rows of the K / V smem tiles (tk_pad16 rounded up to the TMA boxes)
   int kv_box;     // rows per K / V TMA box (<= 256)
   int tmem_cols;  // power of two >= max(tk_pad16, d), >= 32
+  int qk_bytes;   // max(Q + K tiles, P tile): the region the P tile shares with Q and K
   int gvec;       // graph rows can be read with float4
   int ovec;       // out rows can be written with float4
 };
@@ -58,9 +59,14 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                                   // DCH chunks of [128][128 B]
   uint8_t* sK = sQ + DCH * 16384;                       // DCH chunks of [kv_rows][128 B]
-  uint8_t* sV = sK + DCH * p.kv_rows * 128;             // DCH chunks of [kv_rows][128 B]
-  uint8_t* sP = sV + DCH * p.kv_rows * 128;             // tk_chunks chunks of [128][128 B]
-  float* sKeyOn = reinterpret_cast<float*>(sP + p.tk_chunks * 16384);  // [Tk]
+  uint8_t* sP = smem;                                   // tk_chunks chunks of [128][128 B]: OVER Q and K, which are dead once
+                                                        // S = Q K^T has completed (every thread waits for that before writing P);
+                                                        // the smaller footprint is what lets 4 CTAs share an SM and hide each
+                                                        // other's TMA / TMEM / exp latencies
+  uint8_t* sV = smem + p.qk_bytes;                      // DCH chunks of [kv_rows][128 B]
+  float* sKeyOn = reinterpret_cast<float*>(sV + DCH * p.kv_rows * 128);  // [Tk]
+  uint32_t* sBits = reinterpret_cast<uint32_t*>(sKeyOn + ((a.Tk + 3) & ~3));  // [128][wpr] bit-packed graph rows of this query tile
+  const int wpr = (a.Tk + 31) >> 5;
 
   if (t == 0) {
     tma_prefetch_desc(&tmQ);
@@ -73,6 +79,12 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
   }
   if (warp == 0) tmem_alloc_rt(&tmem_slot, static_cast<uint32_t>(p.tmem_cols));
   for (int j = t; j < a.Tk; j += 128) sKeyOn[j] = a.key_on ? a.key_on[static_cast<long>(n) * a.Tk + j] : 1.0f;
+  if (a.graph_bits) {
+    for (int idx = t; idx < 128 * wpr; idx += 128) {
+      const int row = idx / wpr, w = idx % wpr;
+      sBits[idx] = (q0 + row < a.Tq) ? __ldg(a.graph_bits + static_cast<long>(n) * a.bits_n_stride + static_cast<long>(q0 + row) * a.bits_q_stride + w) : 0u;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -115,7 +127,7 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
   const long qrow = static_cast<long>(n) * a.Tq + (row_ok ? i : 0);
   const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
   const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));  // exact for D = 64
-  const int renorm = a.graph ? a.renorm : 0;
+  const int renorm = (a.graph || a.graph_bits) ? a.renorm : 0;
   const float* grow = (a.graph && row_ok) ? a.graph + static_cast<long>(n) * a.graph_n_stride + static_cast<long>(i) * a.graph_q_stride : nullptr;
 
   float m = -INFINITY;
@@ -144,7 +156,11 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
       tmem_ld_32x32(t_lane + c0, r);
       tmem_ld_wait();
       float g[32];
-      if (grow && renorm != 0) {
+      if (a.graph_bits && renorm != 0) {
+        const uint32_t word = sBits[t * wpr + (c0 >> 5)];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) g[j] = ((word >> j) & 1u) ? 1.0f : 0.0f;
+      } else if (grow && renorm != 0) {
         if (p.gvec && c0 + 32 <= a.Tk) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -210,7 +226,7 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
             float s = __uint_as_float(r[j]) * inv_sqrt_d;
             if (sKeyOn[col] == 0.0f) s = kMaskFill;
             if (a.causal && col > i) s = kMaskFill;
-            const float g = (grow && renorm != 0) ? __ldg(grow + col) : 1.0f;
+            const float g = (renorm == 0) ? 1.0f : (a.graph_bits ? (((sBits[t * wpr + (col >> 5)] >> (col & 31)) & 1u) ? 1.0f : 0.0f) : (grow ? __ldg(grow + col) : 1.0f));
             arow[col] = g * __expf(s - m) * scale;
           }
         }
@@ -290,8 +306,10 @@ int attn_fwd_tc(const savqa_attn_args_t* a, cudaStream_t stream) {
                : 0;
   p.ovec = (a->ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0) ? 1 : 0;
   const int dch = a->d / 64;
-  const size_t smem = 1024 + static_cast<size_t>(dch) * 16384 + static_cast<size_t>(2) * dch * p.kv_rows * 128 +
-                      static_cast<size_t>(p.tk_chunks) * 16384 + static_cast<size_t>(a->Tk) * 4 + 16;
+  const int qk = dch * 16384 + dch * p.kv_rows * 128;
+  p.qk_bytes = qk > p.tk_chunks * 16384 ? qk : p.tk_chunks * 16384;
+  const size_t smem = 1024 + static_cast<size_t>(p.qk_bytes) + static_cast<size_t>(dch) * p.kv_rows * 128 +
+                      static_cast<size_t>(a->Tk) * 4 + 16 + (a->graph_bits ? static_cast<size_t>(128) * ((a->Tk + 31) / 32) * 4 : 0);
   alignas(64) CUtensorMap tmQ, tmK, tmV;
   if (int rc = make_map3(&tmQ, a->q, a->ldq, a->Tq, a->N, 128)) return rc;
   if (int rc = make_map3(&tmK, a->k, a->ldk, a->Tk, a->N, p.kv_box)) return rc;

@@ -52,6 +52,21 @@ __global__ void build_masks_kernel(const TIn* __restrict__ first_mask, const TIn
   }
 }
 
+// One warp per (row, word): a coalesced 128-byte read, one ballot, one 4-byte store.
+__global__ void pack_graph_bits_kernel(const float* __restrict__ graph, long rows, int Tk, uint32_t* __restrict__ bits, int wpr) {
+  const int lane = threadIdx.x & 31;
+  const long warp0 = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+  const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+  const long total = rows * wpr;
+  for (long i = warp0; i < total; i += nwarps) {
+    const long r = i / wpr;
+    const int col = static_cast<int>(i % wpr) * 32 + lane;
+    const bool on = col < Tk && graph[r * Tk + col] != 0.0f;
+    const uint32_t word = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) bits[i] = word;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // a1/a2: row gather.  One warp per output row; 16-byte loads when width % 4 == 0 (300 = 75 float4).
 // ------------------------------------------------------------------------------------------------------
@@ -384,6 +399,15 @@ extern "C" int savqa_build_masks(const void* first_mask, const void* q_mask, con
     build_masks_kernel<int><<<grid, 256, 0, stream>>>(static_cast<const int*>(first_mask), static_cast<const int*>(q_mask),
                                                       static_cast<const int*>(q_graph), static_cast<const int*>(first_graph), B, V, Q,
                                                       dec_mask_on, graph_diag, graph, dec_mask);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_pack_graph_bits(const float* graph, int64_t rows, int Tk, uint32_t* bits, int words_per_row, savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows == 0 || Tk == 0) return SAVQA_OK;
+  SAVQA_REQUIRE(graph && bits && rows > 0 && Tk > 0 && words_per_row * 32 >= Tk, "savqa_pack_graph_bits: bad argument");
+  pack_graph_bits_kernel<<<grid_for(rows * words_per_row * 32, 256), 256, 0, stream>>>(graph, rows, Tk, bits, words_per_row);
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;
 }

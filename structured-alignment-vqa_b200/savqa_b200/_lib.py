@@ -34,7 +34,8 @@ class AttnArgs(C.Structure):
                 ("causal", C.c_int), ("renorm", C.c_int), ("engine", C.c_int),
                 ("out", vp), ("ldo", i64), ("att", vp),
                 ("dout", vp), ("ld_dout", i64), ("dq", vp), ("ld_dq", i64), ("dk", vp), ("ld_dk", i64),
-                ("dv", vp), ("ld_dv", i64), ("scratch", vp), ("dbq", vp), ("dbk", vp), ("dbv", vp)]
+                ("dv", vp), ("ld_dv", i64), ("scratch", vp), ("dbq", vp), ("dbk", vp), ("dbv", vp),
+                ("graph_bits", vp), ("bits_n_stride", i64), ("bits_q_stride", i64)]
 
 
 #: every symbol include/savqa_b200.h declares: name -> argtypes (restype is int unless noted)
@@ -43,6 +44,7 @@ SIGNATURES = {
     "savqa_last_error": [],
     "savqa_device_check": [C.POINTER(C.c_int)],
     "savqa_build_masks": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp],
+    "savqa_pack_graph_bits": [vp, i64, C.c_int, vp, C.c_int, vp],
     "savqa_gather_rows": [vp, i64, C.c_int, vp, i64, C.c_float, vp, i64, vp, i64, C.c_int, vp],
     "savqa_scatter_add_rows": [vp, i64, C.c_int, vp, i64, vp, i64, C.c_float, i64, vp],
     "savqa_cast_bf16": [vp, i64, vp, i64, i64, C.c_int, C.c_int, vp],

@@ -36,7 +36,8 @@ def tc_attention_fits(d: int, Tk: int) -> bool:
     tk16 = (Tk + 15) // 16 * 16
     box = min(tk16, 256)
     kv_rows = (tk16 + box - 1) // box * box
-    smem = 1024 + dch * 16384 + 2 * dch * kv_rows * 128 + ((Tk + 63) // 64) * 16384 + Tk * 4 + 16
+    qk = max(dch * 16384 + dch * kv_rows * 128, ((Tk + 63) // 64) * 16384)  # the P tile overlays Q and K
+    smem = 1024 + qk + dch * kv_rows * 128 + Tk * 4 + 16 + 128 * ((Tk + 31) // 32) * 4
     return smem + 64 <= 227 * 1024
 
 
@@ -402,18 +403,23 @@ class GraphAttentionFn(Function):
                 mode = 2
 
         # ---- attention core ----
-        g = None
+        g = gbits = None
         if graph is not None and renorm != 0:
+            gbits = ops.graph_bits_of(graph)  # 0/1 graphs built by ops.build_masks carry their bit-packed form
             g = graph if graph.dtype == F32 else graph.float()
             g = g if g.is_contiguous() else g.contiguous()
+            if g is not graph:
+                gbits = None
         engine = ATTN_ENGINE if (tc_attention_fits(d, Tk) and Tq > 1) else 1  # Tq == 1: one-warp row kernel
-        o, att = ops.graph_attention_fwd(q, k, v, g, k_on, q_on, N, H, Tq, Tk, d, causal, renorm if g is not None else 0, want_att, engine)
+        o, att = ops.graph_attention_fwd(q, k, v, g, k_on, q_on, N, H, Tq, Tk, d, causal, renorm if g is not None else 0, want_att, engine,
+                                         graph_bits=gbits)
 
         # ---- residual (RAW queries) + LayerNorm (modules.py:304-307) ----
         y, pre, yb, y_on = ops.layernorm_fwd(o.reshape(N, Tq, C), xq, gamma.detach(), beta.detach(), eps, save_pre=True, want_bf16=True,
                                              want_on=True)
         ctx.cfg, ctx.mode, ctx.dims = cfg, mode, (N, Tq, Tk, C, H, d)
         ctx.renorm_eff = renorm if g is not None else 0
+        ctx.gbits = gbits
         ctx.save_for_backward(q_bf16, k_bf16, v_bf16, q, k, v, g, q_on, k_on, pre, gamma)
         outs = (y, yb, y_on) + ((att,) if want_att else ())
         ctx.mark_non_differentiable(yb, y_on, *((att,) if want_att else ()))
@@ -457,7 +463,7 @@ class GraphAttentionFn(Function):
             dv = torch.empty(Mk, C, device=dev, dtype=BF16)
             dbq, dbk, dbv = pq.bias_grad_buffer(C, dev), pk_.bias_grad_buffer(C, dev), pv_.bias_grad_buffer(C, dev)
         ops.graph_attention_bwd(q, k, v, g, k_on, q_on, N, H, Tq, Tk, d, cfg["causal"], ctx.renorm_eff, dpre2, dq, dk, dv,
-                                dbq=dbq, dbk=dbk, dbv=dbv)
+                                dbq=dbq, dbk=dbk, dbv=dbv, graph_bits=ctx.gbits)
 
         dxq = dxk = dxv = None
         if mode == 0:

@@ -66,7 +66,34 @@ def build_masks(first_mask: Tensor, q_mask: Tensor, q_graph: Tensor, first_graph
     dec_mask = torch.empty(B, 1, T, device=fm.device, dtype=F32)
     call("savqa_build_masks", ptr(fm), ptr(qm), ptr(qg), ptr(fg), int(is_float), B, V, Q, int(bool(dec_mask_on)),
          ptr(graph_diag), ptr(graph), ptr(dec_mask))
+    # these graphs are exactly 0/1: hand the attention kernels their bit-packed form as well (4 bytes per 32 keys)
+    for g in (graph_diag, graph):
+        attach_graph_bits(g)
     return graph_diag, graph, dec_mask
+
+
+def pack_graph_bits(graph: Tensor) -> Tensor:
+    """int32 [N, Tq, ceil(Tk / 32)]: bit j of word w of a row = (graph[row, 32 w + j] != 0).  For 0/1 graphs only."""
+    _check(graph, F32, "graph")
+    assert graph.dim() == 3 and graph.is_contiguous()
+    N, Tq, Tk = graph.shape
+    wpr = (Tk + 31) // 32
+    bits = torch.empty(N, Tq, wpr, device=graph.device, dtype=torch.int32)
+    call("savqa_pack_graph_bits", ptr(graph), N * Tq, Tk, ptr(bits), wpr)
+    return bits
+
+
+def attach_graph_bits(graph: Tensor) -> Tensor:
+    """Marks a 0/1 graph tensor with its bit-packed form; graph_bits_of() returns it while the tensor is unmodified."""
+    graph._savqa_bits = (pack_graph_bits(graph), graph._version, graph.data_ptr())
+    return graph
+
+
+def graph_bits_of(graph: Optional[Tensor]) -> Optional[Tensor]:
+    tag = getattr(graph, "_savqa_bits", None) if graph is not None else None
+    if tag is not None and tag[1] == graph._version and tag[2] == graph.data_ptr():
+        return tag[0]
+    return None
 
 
 def gather_rows(table: Tensor, idx: Tensor, scale: float = 1.0, want_f32: bool = True, want_bf16: bool = False):
@@ -287,8 +314,19 @@ def wgrad(dy: Tensor, x: Tensor, n_out: int, k_in: int, out: Tensor) -> None:
 
 
 # ------------------------------------------------------------------------------------------------------
+def _set_graph_bits(a: AttnArgs, graph_bits: Optional[Tensor], N: int, Tq: int, Tk: int) -> None:
+    if graph_bits is None:
+        return
+    _check(graph_bits, torch.int32, "graph_bits")
+    wpr = (Tk + 31) // 32
+    assert graph_bits.is_contiguous() and graph_bits.shape[0] == N and graph_bits.shape[1] in (Tq, 1) and graph_bits.shape[2] == wpr
+    a.graph_bits, a.bits_n_stride = ptr(graph_bits), graph_bits.shape[1] * wpr
+    a.bits_q_stride = wpr if graph_bits.shape[1] == Tq else 0
+
+
 def graph_attention_fwd(q: Tensor, k: Tensor, v: Tensor, graph: Optional[Tensor], key_on: Tensor, query_on: Tensor, N: int, H: int,
-                        Tq: int, Tk: int, d: int, causal: bool, renorm: int, want_att: bool, engine: int):
+                        Tq: int, Tk: int, d: int, causal: bool, renorm: int, want_att: bool, engine: int,
+                        graph_bits: Optional[Tensor] = None):
     """Attention core of modules.py:246-301.  q/k/v: bf16 2-D views [N*T, >= H*d].  Returns (out fp32 [N*Tq, H*d], att | None)."""
     for nm, t in (("q", q), ("k", k), ("v", v)):
         _check(t, BF16, nm)
@@ -303,6 +341,8 @@ def graph_attention_fwd(q: Tensor, k: Tensor, v: Tensor, graph: Optional[Tensor]
     a.key_on, a.query_on = ptr(key_on), ptr(query_on)
     a.N, a.H, a.Tq, a.Tk, a.d = N, H, Tq, Tk, d
     a.causal, a.renorm, a.engine = int(causal), int(renorm), int(engine)
+    if graph is not None:
+        _set_graph_bits(a, graph_bits, N, Tq, Tk)
     out = torch.empty(N * Tq, H * d, device=q.device, dtype=F32)
     att = torch.empty(H * N, Tq, Tk, device=q.device, dtype=F32) if want_att else None
     a.out, a.ldo, a.att = ptr(out), H * d, ptr(att)
@@ -321,13 +361,13 @@ def tc_attention_bwd_fits(d: int, Tq: int, Tk: int) -> bool:
     if max(dw_off + tk16, (1 + 2 * kt) * d) > 512:
         return False
     dch = d // 64
-    smem = 1024 + 2 * dch * 16384 + 2 * dch * tk16 * 128 + 2 * (2 * kt) * 16384 + Tk * 4 + 16
+    smem = 1024 + 2 * dch * 16384 + 2 * dch * tk16 * 128 + 2 * ((tk16 + 63) // 64) * 16384 + Tk * 4 + 16 + 128 * ((Tk + 31) // 32) * 4
     return smem + 64 <= 227 * 1024
 
 
 def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout: Tensor, dq: Tensor, dk: Tensor,
                         dv: Tensor, engine: Optional[int] = None, dbq: Optional[Tensor] = None, dbk: Optional[Tensor] = None,
-                        dbv: Optional[Tensor] = None) -> None:
+                        dbv: Optional[Tensor] = None, graph_bits: Optional[Tensor] = None) -> None:
     """Gradient of the attention core; dq/dk/dv are bf16 2-D views and come back ReLU-gated by q/k/v > 0.
     dbq/dbk/dbv (fp32 [H*d], optional) accumulate the column sums of dq/dk/dv: the projections' bias gradients.
     engine None: tcgen05 kernel when the shape fits, CUDA-core kernels otherwise (Tq == 1: the one-warp row kernel)."""
@@ -350,6 +390,8 @@ def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causa
         _check(t, F32, nm)
         assert t is None or (t.is_contiguous() and t.numel() == H * d)
     a.dbq, a.dbk, a.dbv = ptr(dbq), ptr(dbk), ptr(dbv)
+    if graph is not None:
+        _set_graph_bits(a, graph_bits, N, Tq, Tk)
     if engine == 1 and Tq > 1:
         scratch = torch.empty(2, H * N, Tq, Tk, device=q.device, dtype=F32)
         a.scratch = ptr(scratch)

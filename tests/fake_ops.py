@@ -30,6 +30,8 @@ def build_masks(first_mask, q_mask, q_graph, first_graph, dec_mask_on):
     if dec_mask_on:
         dm[:, 0, :V] = (first_mask.float().sum(-1) != 0).float()
         dm[:, 0, V:] = (q_mask.float().sum(-1) != 0).float()
+    attach_graph_bits(gd)
+    attach_graph_bits(g)
     return gd, g, dm
 
 
@@ -180,7 +182,35 @@ def _weights(q, k, graph, key_on, N, H, Tq, Tk, d, causal, renorm):
     return P, W, fixed, r, G
 
 
-def graph_attention_fwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, want_att, engine):
+def pack_graph_bits(graph):
+    N, Tq, Tk = graph.shape
+    wpr = (Tk + 31) // 32
+    padded = torch.zeros(N, Tq, wpr * 32, dtype=torch.int64)
+    padded[:, :, :Tk] = (graph != 0).long()
+    words = (padded.reshape(N, Tq, wpr, 32) << torch.arange(32)).sum(-1)
+    return torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+
+
+def attach_graph_bits(graph):
+    graph._savqa_bits = (pack_graph_bits(graph), graph._version, graph.data_ptr())
+    return graph
+
+
+def graph_bits_of(graph):
+    tag = getattr(graph, "_savqa_bits", None) if graph is not None else None
+    if tag is not None and tag[1] == graph._version and tag[2] == graph.data_ptr():
+        return tag[0]
+    return None
+
+
+def _check_bits(graph, graph_bits):
+    if graph_bits is not None:  # what the kernels would read instead of the fp32 graph must say the same thing
+        assert graph is not None and torch.equal(graph_bits, pack_graph_bits(graph.float()))
+        assert bool(((graph == 0) | (graph == 1)).all())
+
+
+def graph_attention_fwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, want_att, engine, graph_bits=None):
+    _check_bits(graph, graph_bits)
     P, W, _, _, _ = _weights(q, k, graph, key_on, N, H, Tq, Tk, d, causal, renorm)
     V = _heads(v, N, Tk, H, d)
     Wq = W * query_on.reshape(1, N, Tq, 1)
@@ -191,7 +221,8 @@ def graph_attention_fwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causa
 
 
 def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout, dq, dk, dv, engine=None, dbq=None,
-                        dbk=None, dbv=None):
+                        dbk=None, dbv=None, graph_bits=None):
+    _check_bits(graph, graph_bits)
     # the explicit formulas of csrc/attn_simt.cu (attn_bwd_rows_kernel / attn_bwd_keys_kernel)
     P, W, fixed, r, G = _weights(q, k, graph, key_on, N, H, Tq, Tk, d, causal, renorm)
     Q, K, V = _heads(q, N, Tq, H, d), _heads(k, N, Tk, H, d), _heads(v, N, Tk, H, d)

@@ -308,6 +308,20 @@ def test_attention_forward(ops, engine, N, H, Tq, Tk, d, renorm, causal):
         o2, _ = ops.graph_attention_fwd(dev(q), dev(k), dev(v), dev(g1.expand(N, Tq, Tk).contiguous()), dev(key_on), dev(query_on), N, H, Tq,
                                         Tk, d, causal, 1, False, engine)
         assert torch.equal(o1, o2)
+    # the bit-packed form of the (0/1) graph must give bit-identical results and is itself bit exact
+    if engine == 0 and renorm != 0 and Tq > 1:
+        import fake_ops
+        bits = ops.pack_graph_bits(dev(graph))
+        assert torch.equal(bits.cpu(), fake_ops.pack_graph_bits(graph))
+        ob, ab = ops.graph_attention_fwd(dev(q), dev(k), dev(v), dev(graph), dev(key_on), dev(query_on), N, H, Tq, Tk, d, causal, renorm, True,
+                                         engine, graph_bits=bits)
+        assert torch.equal(ob, out) and torch.equal(ab, att)
+        b1 = ops.pack_graph_bits(dev(graph[:, :1].contiguous()))
+        o3, _ = ops.graph_attention_fwd(dev(q), dev(k), dev(v), dev(graph[:, :1].contiguous()), dev(key_on), dev(query_on), N, H, Tq, Tk, d, causal,
+                                        renorm, False, engine, graph_bits=b1)
+        o4, _ = ops.graph_attention_fwd(dev(q), dev(k), dev(v), dev(graph[:, :1].contiguous()), dev(key_on), dev(query_on), N, H, Tq, Tk, d, causal,
+                                        renorm, False, engine)
+        assert torch.equal(o3, o4)
 
 
 @pytest.mark.parametrize("engine", [1, 0])
@@ -341,6 +355,11 @@ def test_attention_backward(ops, engine, N, H, Tq, Tk, d, renorm, causal):
     # feeds bf16 dO, dS and W' to the tensor cores (three more 2^-9 roundings, fp32 accumulation).
     tol = 2e-3 if engine == 1 else 6e-3
     assert rel(dq, rq) < tol and rel(dk, rk) < tol and rel(dv, rv) < tol, (rel(dq, rq), rel(dk, rk), rel(dv, rv))
+    if engine == 0 and g_in is not None:  # bit-packed graph: identical arithmetic, identical bits out
+        d2 = torch.zeros_like(dqkv)
+        ops.graph_attention_bwd(dev(q), dev(k), dev(v), dev(g_in), dev(key_on), dev(query_on), N, H, Tq, Tk, d, causal, renorm, dev(dout),
+                                d2[:N * Tq, :C], d2[:N * Tk, C:2 * C], d2[:N * Tk, 2 * C:], engine=engine, graph_bits=ops.pack_graph_bits(dev(g_in)))
+        assert torch.equal(d2, dqkv)
 
 
 # ------------------------------------------------------------------------------------------------ loss / adam

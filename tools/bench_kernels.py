@@ -105,14 +105,15 @@ def bench_attn():
         graph = (torch.rand(N, T, T, device="cuda") < 0.3).float()
         graph[:, torch.arange(T), torch.arange(T)] = 1
         on = torch.ones(N * T, device="cuda")
-        us = timeit(lambda: ops.graph_attention_fwd(q, k, v, graph, on, on, N, H, T, T, d, False, 1, False, 0))
+        bits = ops.pack_graph_bits(graph)
+        us = timeit(lambda: ops.graph_attention_fwd(q, k, v, graph, on, on, N, H, T, T, d, False, 1, False, 0, graph_bits=bits))
         by = M * 3 * C * 2 + N * T * T * 4 + M * C * 4
         report(f"attn fwd tc   N={N} T={T}", us, 4.0 * N * H * T * T * d, by)
         dout = torch.randn(M, C, device="cuda")
         dqkv = torch.empty(M, 3 * C, device="cuda", dtype=BF)
         db = torch.zeros(3, C, device="cuda")
         us = timeit(lambda: ops.graph_attention_bwd(q, k, v, graph, on, on, N, H, T, T, d, False, 1, dout, dqkv[:, :C], dqkv[:, C:2 * C],
-                                                    dqkv[:, 2 * C:], dbq=db[0], dbk=db[1], dbv=db[2]))
+                                                    dqkv[:, 2 * C:], dbq=db[0], dbk=db[1], dbv=db[2], graph_bits=bits))
         by = M * 3 * C * 2 * 2 + N * T * T * 4 + M * C * 4
         report(f"attn bwd tc   N={N} T={T}", us, 10.0 * N * H * T * T * d, by)
         # decoder cross-attention: one query per sample
