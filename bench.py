@@ -304,9 +304,15 @@ def main():
                                                   f"steps after one warm-up (oracle port, torch CPU fp32, {sec:.2f} s per step; no optimizer)"}
             except Exception as e:  # the GPU number must not die with the CPU leg
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing the NCCL communicator down: destroying it while CUDA graphs that captured its collectives are
+        # alive can block for minutes.  The ranks agree that everyone is done, then exit.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
