@@ -24,6 +24,26 @@ FORCE_RESTAGE = False
 WEIGHT_EPOCH = 0
 #: attention forward engine: 0 = tcgen05/TMEM kernel, 1 = CUDA-core verification kernel
 ATTN_ENGINE = 0
+#: bound weight packs launch their weight-gradient GEMMs on a second stream (see WeightPack.weight_grad)
+WGRAD_SIDE_STREAM = True
+_WGRAD_STREAMS = {}  # compute stream -> its weight-gradient stream
+_WGRAD_DIRTY = []    # weight-gradient streams with work launched since the last join
+
+
+def wgrad_stream_of(cur: "torch.cuda.Stream") -> "torch.cuda.Stream":
+    key = (cur.device_index, cur.cuda_stream)
+    s = _WGRAD_STREAMS.get(key)
+    if s is None:
+        s = _WGRAD_STREAMS[key] = torch.cuda.Stream(device=cur.device)
+    return s
+
+
+def join_wgrad_streams() -> None:
+    """Makes the current stream wait for every weight-gradient stream (before the gradients are reduced / applied)."""
+    cur = torch.cuda.current_stream()
+    for s in _WGRAD_DIRTY:  # only streams used since the last join (inside a graph capture: only captured ones)
+        cur.wait_stream(s)
+    _WGRAD_DIRTY.clear()
 
 
 def tc_attention_fits(d: int, Tk: int) -> bool:
@@ -113,9 +133,25 @@ class WeightPack:
         return self.gb if self.bound else torch.zeros(n, device=dev, dtype=F32)
 
     def weight_grad(self, dyb: Tensor, xb: Tensor, n_out: int, k_in: int) -> Tensor:
-        """dW[n_out, k_in] (+)= dY^T X on the tensor cores, into the flat-gradient view when bound."""
+        """dW[n_out, k_in] (+)= dY^T X on the tensor cores, into the flat-gradient view when bound.
+
+        Bound packs: nothing downstream in the backward pass reads dW (only the optimizer does), so the GEMM goes to a second
+        stream and leaves the dgrad chain -- which is a chain of launch-latency-bound M = B kernels in the decoder -- alone.
+        The trainer joins the streams before the all-reduce / Adam (join_wgrad_streams)."""
         if self.bound:
             dW = self.gw if self.gw.shape[1] == k_in else self.gw[:, :k_in]
+            if WGRAD_SIDE_STREAM and dyb.is_cuda:
+                cur = torch.cuda.current_stream()
+                side = wgrad_stream_of(cur)
+                side.wait_stream(cur)
+                if side not in _WGRAD_DIRTY:
+                    _WGRAD_DIRTY.append(side)
+                with torch.cuda.stream(side):
+                    ops.wgrad(dyb, xb, n_out, k_in, dW)
+                # the operands are temporaries of the caller: keep their memory from being re-used before the side stream is done
+                dyb.record_stream(side)
+                xb.record_stream(side)
+                return dW
         else:
             dW = torch.zeros(n_out, k_in, device=dyb.device, dtype=F32)
         ops.wgrad(dyb, xb, n_out, k_in, dW)

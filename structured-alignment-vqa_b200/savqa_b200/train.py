@@ -139,6 +139,8 @@ class EncoderTrainer:
 
     def _exchange_and_apply(self) -> None:
         b1, b2 = self.betas
+        if self.flat_param.is_cuda:
+            Fn.join_wgrad_streams()  # weight-gradient GEMMs run on side streams during the backward pass
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=self.pg)
         ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, b1, b2, self.eps, max(self.step_count, 1),

@@ -167,6 +167,9 @@ def test_trainer_bound_gradients_match_autograd_and_graph_replay(A):
     assert model.att_syb.enc_self_attention_3._packs["qkv"].bound and model.att_vis_grid.dec_feed_forward_5._packs["w2"].bound
     tr.flat_grad.zero_()
     loss = tr._forward_backward(batch)
+    from savqa_b200 import functional as Fn
+    Fn.join_wgrad_streams()  # bound packs run their weight-gradient GEMMs on side streams
+    torch.cuda.synchronize()
     for t_ in tr.tables:
         t_._savqa_rowlog.clear()
     assert abs(float(loss) - float(ref_loss)) < 1e-5 * abs(float(ref_loss))
