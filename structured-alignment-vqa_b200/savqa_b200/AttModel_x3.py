@@ -88,7 +88,7 @@ class _Branch(nn.Module):
             g = graph_diag if i < 2 else graph
             x = getattr(self, 'enc_self_attention_%d' % i)(x, x, x, g)
             x = getattr(self, 'enc_feed_forward_%d' % i)(x)
-        memory = x
+        memory = self._join_memory(x)
         # decoder input: class token 2 through dec_emb (scaled by sqrt C) + position 0 (:141-147); same for every sample
         dec = self.dec_emb.lookup_table[2] * (C ** 0.5) + self.dec_positional_encoding.lookup_table[0]
         dec = dec.reshape(1, 1, C).expand(B, 1, C).contiguous()
@@ -98,6 +98,25 @@ class _Branch(nn.Module):
             dec = getattr(self, 'dec_vanilla_attention_%d' % i)(dec, memory, memory, dec_mask)
             dec = getattr(self, 'dec_feed_forward_%d' % i)(dec)
         return dec
+
+    def _join_memory(self, x):
+        """Training on a B200 with bound weight packs: routes the cross-attention K/V projections of the encoder output (and
+        their backward) to a second stream, see functional.MemoryHolder.  Anything else: the plain tensor."""
+        pk = self.dec_vanilla_attention_0._packs["kv"] if self.num_blocks > 0 else None
+        if pk is None or not (pk.bound and Fn.WGRAD_SIDE_STREAM and x.is_cuda and x.requires_grad and torch.is_grad_enabled()):
+            return x
+        side_info = Fn.Side.of(x)
+        h = Fn.MemoryHolder()
+        cur = torch.cuda.current_stream()
+        h.side = Fn.wgrad_stream_of(cur)
+        h.shape = x.shape
+        memory = Fn.MemoryJoinFn.apply(x, h)
+        if side_info is not None:
+            memory._savqa_side = Fn.Side(memory, side_info.bf16, side_info.on)
+        h.ready = torch.cuda.Event()
+        h.ready.record(cur)
+        memory._savqa_kv_holder = h
+        return memory
 
     def _add_blocks(self, which, hidden_size):
         for i in range(self.num_blocks):

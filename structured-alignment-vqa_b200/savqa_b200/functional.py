@@ -380,6 +380,45 @@ class LayerNormFn(Function):
 # ======================================================================================================
 # attention modules  -- modules.py:119-207 (renorm 0), :210-311 (renorm 1), :314-403 (renorm 2)
 # ======================================================================================================
+class MemoryHolder:
+    """Side channel between the decoder's cross-attention layers and the encoder output they all read (`memory`,
+    AttModel_x3.py:148-152).  Their K/V projections of `memory` -- big GEMMs that depend on nothing in the decoder -- and the
+    matching dgrad / wgrad GEMMs run on a second stream next to the decoder's chain of launch-latency-bound M = B kernels;
+    the six layers' contributions to d(memory) accumulate in `dmem`, which MemoryJoinFn hands to autograd in one piece."""
+
+    def __init__(self):
+        self.ready: Optional["torch.cuda.Event"] = None   # memory (and its bf16 copy) are complete on the compute stream
+        self.dmem: Optional[Tensor] = None                # fp32 [N*T, C], accumulated on the side stream
+        self.side: Optional["torch.cuda.Stream"] = None
+
+
+class MemoryJoinFn(Function):
+    """Identity on `memory` whose backward returns the d(memory) that the cross-attention layers accumulated on the side
+    stream (they return no gradient for it themselves)."""
+
+    @staticmethod
+    def forward(ctx, x, holder: MemoryHolder):
+        ctx.holder = holder
+        ctx.set_materialize_grads(False)
+        return x.view_as(x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        h: MemoryHolder = ctx.holder
+        g = dy
+        if h.dmem is not None:
+            torch.cuda.current_stream().wait_stream(h.side)
+            d = h.dmem.reshape(ctx_shape(h))
+            g = d if g is None else g + d
+            h.dmem = None
+        return g, None
+
+
+def ctx_shape(h: MemoryHolder):
+    return h.shape
+
+
 def _same(a: Tensor, b: Tensor) -> bool:
     return a is b or (a.data_ptr() == b.data_ptr() and a.shape == b.shape and a.stride() == b.stride() and a._version == b._version)
 
@@ -414,6 +453,7 @@ class GraphAttentionFn(Function):
 
         # ---- projections: Linear + ReLU, fused along N when the inputs coincide (modules.py:241-243) ----
         dev = queries.device
+        holder = None
         if same_qk and same_kv:
             pk = packs["qkv"].refresh([Wq, Wk, Wv], [bq, bk, bv])
             qkv = torch.empty(Mq, 3 * C, device=dev, dtype=BF16)
@@ -427,7 +467,19 @@ class GraphAttentionFn(Function):
             if same_kv:
                 pkv = packs["kv"].refresh([Wk, Wv], [bk, bv])
                 kv = torch.empty(Mk, 2 * C, device=dev, dtype=BF16)
-                ops.gemm(k_bf16, pkv.w, Mk, 2 * C, C, bias=pkv.bias, relu=True, out_bf16=kv)
+                holder = cfg.get("kv_holder")
+                if holder is not None and not (pkv.bound and WGRAD_SIDE_STREAM and holder.ready is not None):
+                    holder = None
+                if holder is not None:
+                    # depends only on `memory`: off the decoder's kernel chain, onto the side stream
+                    cur = torch.cuda.current_stream()
+                    holder.side.wait_event(holder.ready)
+                    with torch.cuda.stream(holder.side):
+                        ops.gemm(k_bf16, pkv.w, Mk, 2 * C, C, bias=pkv.bias, relu=True, out_bf16=kv)
+                    kv.record_stream(holder.side)
+                    cur.wait_stream(holder.side)
+                else:
+                    ops.gemm(k_bf16, pkv.w, Mk, 2 * C, C, bias=pkv.bias, relu=True, out_bf16=kv)
                 k, v = kv[:, :C], kv[:, C:]
                 mode = 1
             else:
@@ -456,6 +508,7 @@ class GraphAttentionFn(Function):
         ctx.cfg, ctx.mode, ctx.dims = cfg, mode, (N, Tq, Tk, C, H, d)
         ctx.renorm_eff = renorm if g is not None else 0
         ctx.gbits = gbits
+        ctx.kv_holder = holder if mode == 1 else None
         ctx.save_for_backward(q_bf16, k_bf16, v_bf16, q, k, v, g, q_on, k_on, pre, gamma)
         outs = (y, yb, y_on) + ((att,) if want_att else ())
         ctx.mark_non_differentiable(yb, y_on, *((att,) if want_att else ()))
@@ -519,7 +572,21 @@ class GraphAttentionFn(Function):
             if mode == 1:
                 dW = pkv.weight_grad(dkv, k_bf16, 2 * C, C)
                 dWk, dWv = dW[:C], dW[C:]
-                if need[1] or need[2]:
+                holder = ctx.kv_holder
+                if holder is not None and (need[1] or need[2]):
+                    # d(memory) += dKV W_kv on the side stream (the six layers serialise there); MemoryJoinFn returns the sum
+                    cur = torch.cuda.current_stream()
+                    first = holder.dmem is None
+                    if first:
+                        holder.dmem = torch.empty(Mk, C, device=dev, dtype=F32)
+                        holder.dmem.record_stream(holder.side)
+                    holder.side.wait_stream(cur)
+                    if holder.side not in _WGRAD_DIRTY:
+                        _WGRAD_DIRTY.append(holder.side)
+                    with torch.cuda.stream(holder.side):
+                        ops.gemm(dkv, pkv.w, Mk, C, 2 * C, b_mn=True, out_f32=holder.dmem, accumulate=0 if first else 2)
+                    dkv.record_stream(holder.side)
+                elif need[1] or need[2]:
                     dxk = torch.empty(Mk, C, device=dev, dtype=F32)
                     dgrad(dkv, pkv, Mk, C, 2 * C, out_f32=dxk)
                     dxk = dxk.reshape(N, Tk, C)

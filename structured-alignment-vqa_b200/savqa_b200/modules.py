@@ -151,7 +151,8 @@ class _attention_base(nn.Module):
             raise NotImplementedError("savqa_b200: attention-probability dropout is not implemented in the fused kernel "
                                       "(AttModel_x3 constructs every attention with dropout_rate=0)")
         cfg = dict(heads=self.num_heads, causal=bool(self.causality), renorm=self._renorm, return_att=bool(self.return_att),
-                   packs=self._packs, eps=self.normalization.epsilon, norm_sink=self.normalization._sink)
+                   packs=self._packs, eps=self.normalization.epsilon, norm_sink=self.normalization._sink,
+                   kv_holder=getattr(keys, "_savqa_kv_holder", None) if keys is values else None)
         sq, sk = Side.of(queries), Side.of(keys)
         outs = Fn.GraphAttentionFn.apply(
             queries, keys, values, graph,
