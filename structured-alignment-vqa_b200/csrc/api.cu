@@ -2,6 +2,7 @@
 // resolved at run time so the .so links without libcuda and loads on a CPU-only box).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -43,6 +44,15 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes, const char* what) {
   if (bytes > 48 * 1024) SAVQA_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
   granted[kernel] = bytes;
   return SAVQA_OK;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SAVQA_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;  // measured on the training step: no gain over plain launches (two streams already overlap tails)
+  }
+  return on == 1;
 }
 
 int sm_count() {

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
   __shared__ __align__(8) uint64_t bar_tma, bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
   __shared__ float sStat[RS == 2 ? 2 * 128 * 4 : 1];  // per-half partial row statistics
+  pdl_trigger();
   const savqa_attn_args_t& a = p.a;
   const int tid = threadIdx.x;
   const int t = tid & 127;       // query row / TMEM lane of this thread
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
     mbar_init(&bar_s, 1);
     mbar_init(&bar_o, 1);
     fence_barrier_init();
+    pdl_wait();
     // Q / K / V travel while the CTA converts dO
     const uint32_t bytes = static_cast<uint32_t>(DCH) * (16384u + 2u * static_cast<uint32_t>(p.kv_rows) * 128u);
     mbar_arrive_expect_tx(&bar_tma, bytes);
@@ -154,6 +156,7 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
   }
   __syncwarp();
   if (tid < 32) tmem_alloc_rt(&tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+  pdl_wait();
   for (int j = tid; j < a.Tk; j += NT) sKeyOn[j] = a.key_on ? a.key_on[static_cast<long>(n) * a.Tk + j] : 1.0f;
   if (a.graph_bits) {
     for (int idx = tid; idx < 128 * wpr; idx += NT) {
@@ -503,7 +506,7 @@ int attn_bwd_tc(const savqa_attn_args_t* a, cudaStream_t stream) {
   do {                                                                                                                                     \
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_bwd_tc_kernel<DD, RR>), smem, "savqa_graph_attn_bwd (tcgen05 engine)")) \
       return rc;                                                                                                                           \
-    attn_bwd_tc_kernel<DD, RR><<<grid, 128 * RR, smem, stream>>>(tmQ, tmK, tmV, p);                                                        \
+    SAVQA_CHECK_CUDA(launch_kernel(true, attn_bwd_tc_kernel<DD, RR>, grid, dim3(128 * RR), smem, stream, tmQ, tmK, tmV, p));               \
   } while (0)
   if (a->d == 64) {
     if (split) SAVQA_LAUNCH_BWD(64, 2);

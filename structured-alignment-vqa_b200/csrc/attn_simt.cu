@@ -500,6 +500,8 @@ __device__ __forceinline__ void sweep_dots(const __nv_bfloat16* __restrict__ bas
 
 __global__ void __launch_bounds__(kPieceWarps * 32) attn_row1_fwd_piece_kernel(const savqa_attn_args_t a) {
   extern __shared__ __align__(16) uint8_t smem[];
+  pdl_trigger();
+  pdl_wait();
   const int d = a.d, P = d >> 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sS = reinterpret_cast<float*>(smem) + warp * (a.Tk + d);  // [Tk] scores, then W'; [d] q
@@ -578,6 +580,8 @@ __global__ void __launch_bounds__(kPieceWarps * 32) attn_row1_fwd_piece_kernel(c
 
 __global__ void __launch_bounds__(kPieceWarps * 32) attn_row1_bwd_piece_kernel(const savqa_attn_args_t a) {
   extern __shared__ __align__(16) uint8_t smem[];
+  pdl_trigger();
+  pdl_wait();
   const int d = a.d, P = d >> 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sS = reinterpret_cast<float*>(smem) + warp * (3 * a.Tk + 2 * d);  // [Tk] scores -> dS/sqrt(d); [Tk] dW -> W'; [d] q; [d] dO
@@ -743,8 +747,8 @@ int attn_fwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
     const size_t smem1 = static_cast<size_t>(kPieceWarps) * (a->Tk + a->d) * 4;
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_row1_fwd_piece_kernel), smem1, "savqa_graph_attn_fwd (row kernel)")) return rc;
     const long warps = static_cast<long>(a->N) * a->H;
-    attn_row1_fwd_piece_kernel<<<static_cast<unsigned>((warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, smem1, stream>>>(*a);
-    SAVQA_CHECK_CUDA(cudaGetLastError());
+    SAVQA_CHECK_CUDA(launch_kernel(true, attn_row1_fwd_piece_kernel, dim3(static_cast<unsigned>((warps + kPieceWarps - 1) / kPieceWarps)),
+                                   dim3(kPieceWarps * 32), smem1, stream, *a));
     return SAVQA_OK;
   }
   if (a->Tq == 1) {
@@ -772,8 +776,8 @@ int attn_bwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
     const size_t smem1 = static_cast<size_t>(kPieceWarps) * (3 * a->Tk + 2 * a->d) * 4;
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_row1_bwd_piece_kernel), smem1, "savqa_graph_attn_bwd (row kernel)")) return rc;
     const long warps = static_cast<long>(a->N) * a->H;
-    attn_row1_bwd_piece_kernel<<<static_cast<unsigned>((warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, smem1, stream>>>(*a);
-    SAVQA_CHECK_CUDA(cudaGetLastError());
+    SAVQA_CHECK_CUDA(launch_kernel(true, attn_row1_bwd_piece_kernel, dim3(static_cast<unsigned>((warps + kPieceWarps - 1) / kPieceWarps)),
+                                   dim3(kPieceWarps * 32), smem1, stream, *a));
     return SAVQA_OK;
   }
   if (a->Tq == 1) {

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_tma, bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
+  pdl_trigger();
   const savqa_attn_args_t& a = p.a;
   const int t = threadIdx.x, warp = t >> 5;
   const int hn = blockIdx.x;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc_rt(&tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+  pdl_wait();
   for (int j = t; j < a.Tk; j += 128) sKeyOn[j] = a.key_on ? a.key_on[static_cast<long>(n) * a.Tk + j] : 1.0f;
   if (a.graph_bits) {
     for (int idx = t; idx < 128 * wpr; idx += 128) {
@@ -317,10 +319,10 @@ int attn_fwd_tc(const savqa_attn_args_t* a, cudaStream_t stream) {
   dim3 grid(a->N * a->H, (a->Tq + 127) / 128);
   if (a->d == 64) {
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_fwd_tc_kernel<64>), smem, "savqa_graph_attn_fwd (tcgen05 engine)")) return rc;
-    attn_fwd_tc_kernel<64><<<grid, 128, smem, stream>>>(tmQ, tmK, tmV, p);
+    SAVQA_CHECK_CUDA(launch_kernel(true, attn_fwd_tc_kernel<64>, grid, dim3(128), smem, stream, tmQ, tmK, tmV, p));
   } else {
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_fwd_tc_kernel<128>), smem, "savqa_graph_attn_fwd (tcgen05 engine)")) return rc;
-    attn_fwd_tc_kernel<128><<<grid, 128, smem, stream>>>(tmQ, tmK, tmV, p);
+    SAVQA_CHECK_CUDA(launch_kernel(true, attn_fwd_tc_kernel<128>, grid, dim3(128), smem, stream, tmQ, tmK, tmV, p));
   }
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;

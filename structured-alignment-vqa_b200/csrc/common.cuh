@@ -34,6 +34,11 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int sm_count();
 
+// Programmatic dependent launch (opt-in: SAVQA_PDL=1): a kernel launched this way may start -- run its prologue: barrier
+// init, TMEM allocation, descriptor prefetch -- while the previous kernel of the stream is still draining; it must call
+// pdl_wait() before it touches global memory.  Only kernels written that way are launched through launch_kernel(pdl=true).
+bool pdl_enabled();
+
 // Opts a kernel into `bytes` of dynamic shared memory (monotonic, cached per kernel); fails with a message when
 // bytes + the kernel's static shared memory exceed the 227 KB per-CTA limit of sm_100.
 int ensure_dynamic_smem(const void* kernel, size_t bytes, const char* what);
@@ -51,6 +56,26 @@ int make_tensor_map(CUtensorMap* out, const void* base, bool is_f32, int rank, c
 // device helpers
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// wait until the kernels this one depends on have completed and their writes are visible (no-op for a plain launch)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// let the next kernel of the stream start its prologue (it still waits in pdl_wait() for this grid to complete)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 

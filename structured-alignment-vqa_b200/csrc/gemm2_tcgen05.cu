@@ -27,7 +27,7 @@ constexpr int BK = 64;    // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kStagingBytes = 8 * 4096;      // 8 epilogue warps x [32 rows][128 B]
-constexpr int kBiasBytes = 2 * 256 * 4;      // the tile's bias slice, double buffered over the accumulator stages
+constexpr int kBiasBytes = 8 * 128 * 4;      // per epilogue warp: the bias values of the (at most two) column chunks it owns in a tile
 
 enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_ATOMIC = 2 };
 
@@ -64,6 +64,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -72,7 +73,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_pairs = gridDim.x >> 1;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* staging = smem + C::kStages * C::kStageBytes;
-  float* sbias = reinterpret_cast<float*>(staging + kStagingBytes);  // [2][256]
+  float* sbias = reinterpret_cast<float*>(staging + kStagingBytes);  // [8 warps][128]
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -93,6 +94,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   cluster_sync_all();  // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only from here on
   const uint32_t tmem_base = tmem_base_slot;
 
   const int tiles_mn = p.num_m * p.num_n;
@@ -194,12 +196,20 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool row_ok = grow < p.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
       const int ncol0 = n_blk * BN;
-      // the tile's bias slice -> smem (all epilogue warps; the named barrier also orders the reuse of the buffer)
-      const float* bias_s = sbias + as * 256;
+      // this warp's bias values -> its private smem slice: chunk c = half + 2 i lives at [CW i, CW i + CW)  (warp-local: no
+      // barrier across the epilogue warps, whose slowest member would otherwise gate every tile)
+      float* bias_w = sbias + (warp - 2) * 128;
       if (e.bias) {
-        const int et = threadIdx.x - 64;  // 0..255
-        if (et < BN) sbias[as * 256 + et] = (ncol0 + et < p.N) ? __ldg(e.bias + ncol0 + et) : 0.0f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < (NCH + 1) / 2; ++i) {
+          const int c = half + 2 * i;
+          for (int j = lane; j < CW; j += 32) {
+            const int col = ncol0 + c * CW + j;
+            bias_w[CW * i + j] = (c < NCH && col < p.N) ? __ldg(e.bias + col) : 0.0f;
+          }
+        }
+        __syncwarp();
       }
       const float* rowtab_row = (EPI != EPI_BF16 && e.rowtab != nullptr && row_ok) ? e.rowtab + static_cast<long>(grow % e.rowtab_period) * e.ld_rowtab : nullptr;
 
@@ -261,7 +271,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (e.bias) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * CW + 32 * h + j);
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_w + CW * ((c - half) >> 1) + 32 * h + j);
                 v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
               }
             }
@@ -367,8 +377,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& t
   const int tiles = p.num_m * p.num_n * p.split_k;
   const int max_pairs = sm_count() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  kern<<<2 * pairs, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmO, p);
-  SAVQA_CHECK_CUDA(cudaGetLastError());
+  SAVQA_CHECK_CUDA(launch_kernel(true, kern, dim3(2 * pairs), dim3(kThreads), C::kSmemBytes, stream, tmA, tmB, tmO, p));
   return SAVQA_OK;
 }
 

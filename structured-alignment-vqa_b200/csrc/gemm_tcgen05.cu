@@ -57,6 +57,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -78,6 +79,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = tmem_base_slot;
 
   const int tiles_mn = p.num_m * p.num_n;
@@ -311,8 +313,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "savqa_gemm_bf16")) return rc;
   const int tiles = p.num_m * p.num_n * p.split_k;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
-  SAVQA_CHECK_CUDA(cudaGetLastError());
+  SAVQA_CHECK_CUDA(launch_kernel(true, kern, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, tmA, tmB, p));
   return SAVQA_OK;
 }
 

@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
                                                          long rows, float* __restrict__ pre, float* __restrict__ y,
                                                          __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ on) {
   constexpr int C = NV * 128;
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long warp0 = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
   const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
@@ -109,6 +111,8 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
                                                          float* __restrict__ dbeta, float* __restrict__ dxsum) {
   constexpr int C = NV * 128;
   __shared__ __align__(16) float red[8][NV * 128 + 4];  // per-warp partials of one parameter gradient at a time
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
   const long warp0 = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
@@ -254,7 +258,7 @@ extern "C" int savqa_residual_layernorm_fwd(const float* x, const float* res, co
   const int grid = ln_grid(rows, 8);
   if (vec) {
     switch (C / 128) {
-#define LN_CASE(NV) case NV: ln_fwd_vec_kernel<NV><<<grid, 256, 0, stream>>>(x, res, gamma, beta, eps, rows, pre, y, yb, on); break;
+#define LN_CASE(NV) case NV: SAVQA_CHECK_CUDA(launch_kernel(true, ln_fwd_vec_kernel<NV>, dim3(grid), dim3(256), 0, stream, x, res, gamma, beta, eps, static_cast<long>(rows), pre, y, yb, on)); break;
       LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
 #undef LN_CASE
     }
@@ -275,9 +279,9 @@ extern "C" int savqa_layernorm_bwd(const float* dy, const float* pre, const floa
   const bool vec = (C % 128 == 0) && (C / 128 <= 4) && a16(dy) && a16(pre) && a16(gamma) && a16(dx) && (!dres_in || a16(dres_in)) &&
                    (!db || a16(db));
   if (vec) {
-    const int grid = ln_grid(rows, 2);  // few, fat blocks: each ends with C atomics per parameter
+    const int grid = ln_grid(rows, 2);  // few, fat blocks: each ends with C atomics per parameter (4 per SM measured slower)
     switch (C / 128) {
-#define LN_CASE(NV) case NV: ln_bwd_vec_kernel<NV><<<grid, 256, 0, stream>>>(dy, pre, gamma, eps, rows, dres_in, dx, db, dgamma, dbeta, dxsum); break;
+#define LN_CASE(NV) case NV: SAVQA_CHECK_CUDA(launch_kernel(true, ln_bwd_vec_kernel<NV>, dim3(grid), dim3(256), 0, stream, dy, pre, gamma, eps, static_cast<long>(rows), dres_in, dx, db, dgamma, dbeta, dxsum)); break;
       LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4)
 #undef LN_CASE
     }
