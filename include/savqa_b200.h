@@ -158,6 +158,11 @@ typedef struct savqa_attn_args {
   /* optional bit-packed form of a 0/1 `graph` (savqa_pack_graph_bits): word w of a row holds keys [32w, 32w+32); strides in
    * 32-bit words (bits_q_stride = 0 broadcasts one row).  The tcgen05 engine reads it instead of the fp32 matrix. */
   const uint32_t* graph_bits; int64_t bits_n_stride; int64_t bits_q_stride;
+  /* softmax statistics of every (head, sample, query) row, fp32 [H*N*Tq, 4] = {row max m, 1/Z (negated when the 1e-12
+   * clamp of the L1 renormalisation bit), scale (W = G e scale), beta}: written by the tcgen05 forward when non-NULL, read
+   * -- together with the forward output `out` -- by the tcgen05 backward, which then needs ONE pass over the score tile
+   * (sum_j W_j dW_j == <dO_row, out_row>) instead of three. */
+  float* stats;
 } savqa_attn_args_t;
 
 int savqa_graph_attn_fwd(const savqa_attn_args_t* args, savqa_stream_t stream);

@@ -34,6 +34,7 @@ struct BwdParams {
   int tmem_cols;
   int gvec;      // graph rows readable as float4
   int dvec;      // dout rows readable as float4
+  int ovec;      // forward-output rows readable as float4 (statistics path)
 };
 
 __device__ __forceinline__ void tmem_alloc_rt(uint32_t* slot, uint32_t ncols) {
@@ -112,7 +113,8 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_tma, bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
-  __shared__ float sStat[RS == 2 ? 2 * 128 * 4 : 1];  // per-half partial row statistics
+  __shared__ float sStat[RS == 2 ? 2 * 128 * 4 : 1];  // per-half partial row statistics (recompute path only)
+  __shared__ float sT[128];                            // t_i = <dO_i, O_i> = sum_j W_ij dW_ij  (statistics path)
   pdl_trigger();
   const savqa_attn_args_t& a = p.a;
   const int tid = threadIdx.x;
@@ -183,6 +185,29 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
         else dv[it] = make_float4(src[0], src[1], src[2], src[3]);
       }
     }
+    if (a.stats) {
+      // t_row = <dO_row, O_row> over this head's columns: the V4 (16 or 32) consecutive threads that hold a row reduce it
+      float part[kIters];
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        const int idx = tid + it * NT;
+        const int row = idx / V4, col = (idx % V4) * 4;
+        part[it] = 0.0f;
+        if (row < a.Tq) {
+          const float* src = a.out + (static_cast<long>(n) * a.Tq + row) * a.ldo + h * D + col;
+          const float4 o = p.ovec ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(src[0], src[1], src[2], src[3]);
+          part[it] = (dv[it].x * o.x + dv[it].y * o.y) + (dv[it].z * o.z + dv[it].w * o.w);
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        float v = part[it];
+#pragma unroll
+        for (int o = (V4 < 32 ? V4 : 32) / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int idx = tid + it * NT;
+        if ((idx % V4) == 0) sT[idx / V4] = v;
+      }
+    }
 #pragma unroll
     for (int it = 0; it < kIters; ++it) {
       const int idx = tid + it * NT;
@@ -237,11 +262,22 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
   const float* grow = (a.graph && row_ok) ? a.graph + static_cast<long>(n) * a.graph_n_stride + static_cast<long>(i) * a.graph_q_stride : nullptr;
   const float qon = (a.query_on && row_ok) ? a.query_on[qrow] : 1.0f;
 
+  float m = -INFINITY, tsum, scale, alpha, beta, inv_z;
+  if (a.stats) {
+    // ---- statistics path: the forward kernel left {m, +-1/Z, scale, beta} per row, and t_i = <dO_i, O_i> ----
+    const float4 st = __ldg(reinterpret_cast<const float4*>(a.stats) + static_cast<long>(hn) * a.Tq + (row_ok ? i : 0));
+    m = st.x;
+    inv_z = fabsf(st.y);
+    scale = st.z;
+    beta = st.w;
+    alpha = st.y < 0.0f ? 0.0f : 1.0f;
+    tsum = sT[t];
+  } else {
+  // ---- recompute path (no forward statistics): row max, then Z / R / SA / U, then the clamp logic of the forward ----
   // this half's share of the 32-column chunks of the score row
   const int nch = (a.Tk + 31) >> 5;
   const int ch_lo = (RS == 2 && half == 1) ? (nch + 1) / 2 : 0;
   const int ch_hi = (RS == 2 && half == 0) ? (nch + 1) / 2 : nch;
-  float m = -INFINITY;
   for (int c0 = ch_lo * 32; c0 < ch_hi * 32; c0 += 32) {
     uint32_t r[32];
     __syncwarp();
@@ -298,7 +334,6 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
     const float* hi = sStat + (128 + t) * 4;
     Z = lo[0] + hi[0]; R = lo[1] + hi[1]; SA = lo[2] + hi[2]; U = lo[3] + hi[3];
   }
-  float scale;
   bool clamped = false;
   if (renorm == 1) {
     clamped = !(R / Z >= 1e-12f);
@@ -308,11 +343,12 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
   } else {
     scale = 1.0f / Z;
   }
-  const float tsum = scale * qon * U;  // sum_j W_j dW_j
+  tsum = scale * qon * U;  // sum_j W_j dW_j
   // dS_j = W_j (dW_j - alpha t) - beta P_j t
-  const float alpha = clamped ? 0.0f : 1.0f;
-  const float beta = clamped ? 1.0f : (renorm == 2 ? 1.0f - scale * SA : 0.0f);
-  const float inv_z = 1.0f / Z;
+  alpha = clamped ? 0.0f : 1.0f;
+  beta = clamped ? 1.0f : (renorm == 2 ? 1.0f - scale * SA : 0.0f);
+  inv_z = 1.0f / Z;
+  }  // recompute path
 
   const int wch_lo = (RS == 2 && half == 1) ? kc2 : 0;            // 2 * kc2 chunks of 32 columns, zero fill past Tk included
   const int wch_hi = (RS == 2 && half == 0) ? kc2 : 2 * kc2;
@@ -464,6 +500,7 @@ void fill_params(const savqa_attn_args_t* a, BwdParams& p, size_t& smem) {
   p.tmem_cols = cols;
   p.gvec = (a->graph && a->Tk % 4 == 0 && a->graph_n_stride % 4 == 0 && a->graph_q_stride % 4 == 0 && aligned16(a->graph)) ? 1 : 0;
   p.dvec = (a->ld_dout % 4 == 0 && aligned16(a->dout) && a->d % 4 == 0) ? 1 : 0;
+  p.ovec = (a->out && a->ldo % 4 == 0 && aligned16(a->out) && a->d % 4 == 0) ? 1 : 0;
   const int dch = a->d / 64;
   smem = 1024 + static_cast<size_t>(2) * dch * 16384 + static_cast<size_t>(2) * dch * p.kv_rows * 128 +
          static_cast<size_t>(2) * p.kc * 16384 + static_cast<size_t>(a->Tk) * 4 + 16 +

@@ -208,9 +208,20 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
     }
   }
   float scale;
-  if (renorm == 1) scale = (R / Z >= 1e-12f) ? 1.0f / R : 1.0f / (Z * 1e-12f);
-  else if (renorm == 2) scale = 1.0f / (SA + 1e-7f * Z);
-  else scale = 1.0f / Z;
+  bool clamped = false;
+  if (renorm == 1) {
+    clamped = !(R / Z >= 1e-12f);
+    scale = clamped ? 1.0f / (Z * 1e-12f) : 1.0f / R;
+  } else if (renorm == 2) {
+    scale = 1.0f / (SA + 1e-7f * Z);
+  } else {
+    scale = 1.0f / Z;
+  }
+  if (a.stats && row_ok) {  // for the backward kernel: dS_j = W_j (dW_j - alpha t) - beta (e_j / Z) t
+    const float beta = clamped ? 1.0f : (renorm == 2 ? 1.0f - scale * SA : 0.0f);
+    const float inv_z = 1.0f / Z;
+    reinterpret_cast<float4*>(a.stats)[static_cast<long>(hn) * a.Tq + i] = make_float4(m, clamped ? -inv_z : inv_z, scale, beta);
+  }
 
   // return_att: recompute W = G*e*scale in fp32 and stream it out (pre query mask); whole-warp TMEM loads
   if (a.att) {

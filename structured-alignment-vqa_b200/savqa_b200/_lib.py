@@ -35,7 +35,7 @@ class AttnArgs(C.Structure):
                 ("out", vp), ("ldo", i64), ("att", vp),
                 ("dout", vp), ("ld_dout", i64), ("dq", vp), ("ld_dq", i64), ("dk", vp), ("ld_dk", i64),
                 ("dv", vp), ("ld_dv", i64), ("scratch", vp), ("dbq", vp), ("dbk", vp), ("dbv", vp),
-                ("graph_bits", vp), ("bits_n_stride", i64), ("bits_q_stride", i64)]
+                ("graph_bits", vp), ("bits_n_stride", i64), ("bits_q_stride", i64), ("stats", vp)]
 
 
 #: every symbol include/savqa_b200.h declares: name -> argtypes (restype is int unless noted)

@@ -499,8 +499,12 @@ class GraphAttentionFn(Function):
             if g is not graph:
                 gbits = None
         engine = ATTN_ENGINE if (tc_attention_fits(d, Tk) and Tq > 1) else 1  # Tq == 1: one-warp row kernel
+        # training on the tensor-core engine: keep the softmax row statistics (and the core's output) for a one-pass backward
+        stats = None
+        if engine == 0 and any(ctx.needs_input_grad[:3]) and ops.tc_attention_bwd_fits(d, Tq, Tk):
+            stats = torch.empty(H * N * Tq, 4, device=dev, dtype=F32)
         o, att = ops.graph_attention_fwd(q, k, v, g, k_on, q_on, N, H, Tq, Tk, d, causal, renorm if g is not None else 0, want_att, engine,
-                                         graph_bits=gbits)
+                                         graph_bits=gbits, stats=stats)
 
         # ---- residual (RAW queries) + LayerNorm (modules.py:304-307) ----
         y, pre, yb, y_on = ops.layernorm_fwd(o.reshape(N, Tq, C), xq, gamma.detach(), beta.detach(), eps, save_pre=True, want_bf16=True,
@@ -509,7 +513,7 @@ class GraphAttentionFn(Function):
         ctx.renorm_eff = renorm if g is not None else 0
         ctx.gbits = gbits
         ctx.kv_holder = holder if mode == 1 else None
-        ctx.save_for_backward(q_bf16, k_bf16, v_bf16, q, k, v, g, q_on, k_on, pre, gamma)
+        ctx.save_for_backward(q_bf16, k_bf16, v_bf16, q, k, v, g, q_on, k_on, pre, gamma, stats, o if stats is not None else None)
         outs = (y, yb, y_on) + ((att,) if want_att else ())
         ctx.mark_non_differentiable(yb, y_on, *((att,) if want_att else ()))
         return outs
@@ -517,7 +521,7 @@ class GraphAttentionFn(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dy, *_unused):
-        q_bf16, k_bf16, v_bf16, q, k, v, g, q_on, k_on, pre, gamma = ctx.saved_tensors
+        q_bf16, k_bf16, v_bf16, q, k, v, g, q_on, k_on, pre, gamma, stats, fwd_o = ctx.saved_tensors
         cfg, mode = ctx.cfg, ctx.mode
         N, Tq, Tk, C, H, d = ctx.dims
         Mq, Mk = N * Tq, N * Tk
@@ -552,7 +556,7 @@ class GraphAttentionFn(Function):
             dv = torch.empty(Mk, C, device=dev, dtype=BF16)
             dbq, dbk, dbv = pq.bias_grad_buffer(C, dev), pk_.bias_grad_buffer(C, dev), pv_.bias_grad_buffer(C, dev)
         ops.graph_attention_bwd(q, k, v, g, k_on, q_on, N, H, Tq, Tk, d, cfg["causal"], ctx.renorm_eff, dpre2, dq, dk, dv,
-                                dbq=dbq, dbk=dbk, dbv=dbv, graph_bits=ctx.gbits)
+                                dbq=dbq, dbk=dbk, dbv=dbv, graph_bits=ctx.gbits, stats=stats, fwd_out=fwd_o)
 
         dxq = dxk = dxv = None
         if mode == 0:

@@ -326,7 +326,7 @@ def _set_graph_bits(a: AttnArgs, graph_bits: Optional[Tensor], N: int, Tq: int, 
 
 def graph_attention_fwd(q: Tensor, k: Tensor, v: Tensor, graph: Optional[Tensor], key_on: Tensor, query_on: Tensor, N: int, H: int,
                         Tq: int, Tk: int, d: int, causal: bool, renorm: int, want_att: bool, engine: int,
-                        graph_bits: Optional[Tensor] = None):
+                        graph_bits: Optional[Tensor] = None, stats: Optional[Tensor] = None):
     """Attention core of modules.py:246-301.  q/k/v: bf16 2-D views [N*T, >= H*d].  Returns (out fp32 [N*Tq, H*d], att | None)."""
     for nm, t in (("q", q), ("k", k), ("v", v)):
         _check(t, BF16, nm)
@@ -346,6 +346,10 @@ def graph_attention_fwd(q: Tensor, k: Tensor, v: Tensor, graph: Optional[Tensor]
     out = torch.empty(N * Tq, H * d, device=q.device, dtype=F32)
     att = torch.empty(H * N, Tq, Tk, device=q.device, dtype=F32) if want_att else None
     a.out, a.ldo, a.att = ptr(out), H * d, ptr(att)
+    if stats is not None:  # engine 0 only: {m, +-1/Z, scale, beta} per (head, sample, query) row, for the backward kernel
+        _check(stats, F32, "stats")
+        assert engine == 0 and stats.is_contiguous() and stats.numel() == H * N * Tq * 4
+        a.stats = ptr(stats)
     call("savqa_graph_attn_fwd", C.byref(a))
     return out, att
 
@@ -367,7 +371,8 @@ def tc_attention_bwd_fits(d: int, Tq: int, Tk: int) -> bool:
 
 def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout: Tensor, dq: Tensor, dk: Tensor,
                         dv: Tensor, engine: Optional[int] = None, dbq: Optional[Tensor] = None, dbk: Optional[Tensor] = None,
-                        dbv: Optional[Tensor] = None, graph_bits: Optional[Tensor] = None) -> None:
+                        dbv: Optional[Tensor] = None, graph_bits: Optional[Tensor] = None, stats: Optional[Tensor] = None,
+                        fwd_out: Optional[Tensor] = None) -> None:
     """Gradient of the attention core; dq/dk/dv are bf16 2-D views and come back ReLU-gated by q/k/v > 0.
     dbq/dbk/dbv (fp32 [H*d], optional) accumulate the column sums of dq/dk/dv: the projections' bias gradients.
     engine None: tcgen05 kernel when the shape fits, CUDA-core kernels otherwise (Tq == 1: the one-warp row kernel)."""
@@ -392,6 +397,13 @@ def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causa
     a.dbq, a.dbk, a.dbv = ptr(dbq), ptr(dbk), ptr(dbv)
     if graph is not None:
         _set_graph_bits(a, graph_bits, N, Tq, Tk)
+    if engine == 0 and stats is not None and fwd_out is not None:
+        # single-pass tcgen05 backward: the forward's row statistics and output replace the recomputation of max / Z / R / U
+        _check(stats, F32, "stats")
+        _check(fwd_out, F32, "fwd_out")
+        assert stats.is_contiguous() and stats.numel() == H * N * Tq * 4
+        assert fwd_out.dim() == 2 and fwd_out.stride(1) == 1 and fwd_out.shape[0] == N * Tq and fwd_out.shape[1] >= H * d
+        a.stats, a.out, a.ldo = ptr(stats), ptr(fwd_out), fwd_out.stride(0)
     if engine == 1 and Tq > 1:
         scratch = torch.empty(2, H * N, Tq, Tk, device=q.device, dtype=F32)
         a.scratch = ptr(scratch)

@@ -150,6 +150,10 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, bias=None, res=None, rowtab=N
         colsum[:N] += v.sum(0)
 
 
+def tc_attention_bwd_fits(d, Tq, Tk):
+    return False
+
+
 def split_k_for(tiles, k_blocks):
     return 1
 
@@ -209,7 +213,7 @@ def _check_bits(graph, graph_bits):
         assert bool(((graph == 0) | (graph == 1)).all())
 
 
-def graph_attention_fwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, want_att, engine, graph_bits=None):
+def graph_attention_fwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, want_att, engine, graph_bits=None, stats=None):
     _check_bits(graph, graph_bits)
     P, W, _, _, _ = _weights(q, k, graph, key_on, N, H, Tq, Tk, d, causal, renorm)
     V = _heads(v, N, Tk, H, d)
@@ -221,7 +225,7 @@ def graph_attention_fwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causa
 
 
 def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout, dq, dk, dv, engine=None, dbq=None,
-                        dbk=None, dbv=None, graph_bits=None):
+                        dbk=None, dbv=None, graph_bits=None, stats=None, fwd_out=None):
     _check_bits(graph, graph_bits)
     # the explicit formulas of csrc/attn_simt.cu (attn_bwd_rows_kernel / attn_bwd_keys_kernel)
     P, W, fixed, r, G = _weights(q, k, graph, key_on, N, H, Tq, Tk, d, causal, renorm)
