@@ -196,7 +196,9 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
         if (row < a.Tq) {
           const float* src = a.out + (static_cast<long>(n) * a.Tq + row) * a.ldo + h * D + col;
           const float4 o = p.ovec ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(src[0], src[1], src[2], src[3]);
-          part[it] = (dv[it].x * o.x + dv[it].y * o.y) + (dv[it].z * o.z + dv[it].w * o.w);
+          // the bf16-rounded dO that the dW = dO V^T MMA sees: t then equals sum_j W~_j dW_j with the forward's own (bf16) W~
+          const float2 d01 = unpack_bf16x2(pack_bf16x2(dv[it].x, dv[it].y)), d23 = unpack_bf16x2(pack_bf16x2(dv[it].z, dv[it].w));
+          part[it] = (d01.x * o.x + d01.y * o.y) + (d23.x * o.z + d23.y * o.w);
         }
       }
 #pragma unroll
@@ -372,7 +374,10 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
           if (sKeyOn[col] == 0.0f) { s = kMaskFill; masked = true; }
           if (a.causal && col > i) { s = kMaskFill; masked = true; }
           const float e = __expf(s - m);
-          const float W = g[j] * e * scale;
+          // statistics path: the weight exactly as the forward's P V MMA used it (bf16-rounded before the scale), so that
+          // sum_j dS_ij vanishes to fp32 accuracy against t = <dO~_i, O_i>
+          const float ge = a.stats ? __bfloat162float(__float2bfloat16_rn(g[j] * e)) : g[j] * e;
+          const float W = ge * scale;
           const float dW = __uint_as_float(w[j]) * qon;
           dsv = W * (dW - alpha * tsum) - beta * (e * inv_z) * tsum;
           if (masked) dsv = 0.0f;  // masked scores are constants
