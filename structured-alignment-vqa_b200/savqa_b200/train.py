@@ -36,6 +36,7 @@ class EncoderTrainer:
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.dec_mask = dec_mask
         self.step_count = 0
+        self.allreduce_chunks = 6
         self.tables = [model.att_vis_grid.syb_emb, model.att_syb.syb_emb]
         self.flat_param: Optional[torch.Tensor] = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -141,10 +142,22 @@ class EncoderTrainer:
         b1, b2 = self.betas
         if self.flat_param.is_cuda:
             Fn.join_wgrad_streams()  # weight-gradient GEMMs run on side streams during the backward pass
+        step = max(self.step_count, 1)
         if self.world > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=self.pg)
-        ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, b1, b2, self.eps, max(self.step_count, 1),
-                      dyn=self.dyn, param_bf16=self.flat_bf16)
+            # the all-reduce travels in chunks on NCCL's stream while the fused Adam kernel follows one chunk behind on the
+            # compute stream: only the first chunk's reduction and the last chunk's update are exposed
+            n = self.flat_grad.numel()
+            k = self.allreduce_chunks
+            bounds = [(n * i // k) // 8 * 8 for i in range(k)] + [n]
+            works = [dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
+                     for lo, hi in zip(bounds[:-1], bounds[1:])]
+            for w, lo, hi in zip(works, bounds[:-1], bounds[1:]):
+                w.wait()
+                ops.adam_step(self.flat_param[lo:hi], self.flat_grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.lr, b1, b2,
+                              self.eps, step, dyn=self.dyn, param_bf16=self.flat_bf16[lo:hi])
+        else:
+            ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, b1, b2, self.eps, step,
+                          dyn=self.dyn, param_bf16=self.flat_bf16)
         if self.rowsparse:
             for t, st in zip(self.tables, self.row_state):
                 log = t._savqa_rowlog
