@@ -198,3 +198,36 @@ def test_trainer_bound_gradients_match_autograd_and_graph_replay(A):
     assert abs(replayed[0] - eager[3]) < 2e-3 * abs(eager[3]) and abs(replayed[1] - eager[4]) < 2e-3 * abs(eager[4]), (eager, replayed)
     assert eager[4] < eager[0]  # the optimizer is actually descending on the repeated batch
     assert torch.equal(tr3.flat_bf16, tr3.flat_param.to(torch.bfloat16))
+
+
+def test_cfg2_inference_full_size_vs_oracle_and_batch_sharding(A):
+    """BASELINE configs[1]: AttModel_x3 inference, batch 256, 100 region nodes (T = 120 visual, T = 299 symbolic), 2048-d features.
+    (i) answer logits of the first samples against the CPU oracle (fp32) at the end-to-end bf16-operand tolerance of
+    SURVEY 8(c) (<= 1e-2 norm-relative); (ii) the size-independent property the data-parallel inference relies on: a batch
+    shard gives bit-identical logits to the same samples inside the full batch (no cross-sample arithmetic anywhere)."""
+    from savqa_b200 import synthetic
+    cfg = synthetic.CFG2
+    model = synthetic.build_model(cfg, vocab_rows=5000)
+    batch = synthetic.make_batch(cfg, batch_size=256, seed=7, vocab_rows=5000)
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    n_ref = 6
+    with torch.no_grad():
+        _, ref_logits, _, _ = O.encoder_step(params, {k: v[:n_ref] for k, v in batch.items()}, cfg["blocks"], cfg["heads"])
+    model = model.cuda().eval()
+    keys = ("vis_fea", "vis_fea_mask", "q_ipt", "q_ipt_mask", "q_ipt_graph", "syb_ipt", "macro_node_mask", "macro_graph_ipt")
+
+    def run(sl):
+        b = {k: batch[k][sl].cuda() for k in keys}
+        with torch.no_grad():
+            return model.encoder_step(b["vis_fea"], b["vis_fea_mask"], b["q_ipt"], b["q_ipt_mask"], b["q_ipt_graph"], b["syb_ipt"],
+                                      b["macro_node_mask"], b["macro_graph_ipt"], True)
+
+    full = run(slice(0, 256))
+    for got, ref, name in zip(full, ref_logits, ("concat", "vis", "syb")):
+        assert torch.isfinite(got).all()
+        err = O.rel_err(got[:n_ref].cpu(), ref)
+        assert err < 1e-2, f"logits_{name}: rel err {err:.3e} (bf16 MMA operands through 12 blocks; fp32 accumulate / softmax / LN)"
+    assert (full[0][:n_ref].argmax(-1).cpu() == ref_logits[0].argmax(-1)).float().mean() >= 0.8
+    shard = run(slice(128, 256))
+    for a_, b_ in zip(shard, full):
+        assert torch.equal(a_, b_[128:256])
