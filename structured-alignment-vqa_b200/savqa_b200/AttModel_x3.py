@@ -86,6 +86,7 @@ class _Branch(nn.Module):
         for i in range(self.num_blocks):
             # blocks 0,1: graph_diag; the reference aliases graph_cross and graph, so 2.. all see `graph` (:118-139)
             g = graph_diag if i < 2 else graph
+            x = Fn.bucket_mark(x, (id(self), "enc", i))  # multi-GPU: block i's gradients are final once backward passes here
             x = getattr(self, 'enc_self_attention_%d' % i)(x, x, x, g)
             x = getattr(self, 'enc_feed_forward_%d' % i)(x)
         memory = self._join_memory(x)
@@ -110,6 +111,7 @@ class _Branch(nn.Module):
         cur = torch.cuda.current_stream()
         h.side = Fn.wgrad_stream_of(cur)
         h.shape = x.shape
+        h.bucket = (id(self), "dec")
         memory = Fn.MemoryJoinFn.apply(x, h)
         if side_info is not None:
             memory._savqa_side = Fn.Side(memory, side_info.bf16, side_info.on)
@@ -315,7 +317,7 @@ class AttModel(nn.Module):
         if not (getattr(self, "concurrent_branches", True) and vis_fea.is_cuda):
             fea_vis_grid = self.att_vis_grid(vis_fea, vis_mask, q_ipt, q_graph, q_mask, decMask)
             fea_syb = self.att_syb(syb_ipt, macro_mask, macro_graph, q_ipt, q_graph, q_mask, decMask)
-            return self.answer_logits(fea_vis_grid, fea_syb)
+            return self.answer_logits(Fn.bucket_mark(fea_vis_grid, (id(self), "heads")), Fn.bucket_mark(fea_syb, (id(self), "heads")))
         # The two branch models are independent until the heads (AttModel_x3.py:529-531): fork the symbolic branch onto a
         # second stream so that its kernels (and, through autograd, their backward) overlap the visual branch's -- the
         # decoders' launch-bound M = B kernels of one branch hide under the encoder GEMMs of the other.  Inside a CUDA-graph
@@ -330,7 +332,7 @@ class AttModel(nn.Module):
         fea_vis_grid = self.att_vis_grid(vis_fea, vis_mask, q_ipt, q_graph, q_mask, decMask)
         main.wait_stream(side)
         fea_syb.record_stream(main)
-        return self.answer_logits(fea_vis_grid, fea_syb)
+        return self.answer_logits(Fn.bucket_mark(fea_vis_grid, (id(self), "heads")), Fn.bucket_mark(fea_syb, (id(self), "heads")))
 
     def forward(self, vis_fea, vis_mask, q_ipt, q_mask, q_graph, macro_ipt, macro_mask, macro_graph, macro_obj_loc,
                 micro_positive_obj, micro_negative_obj, micro_obj_mask, micro_positive_rel, micro_negative_rel,

@@ -380,6 +380,41 @@ class LayerNormFn(Function):
 # ======================================================================================================
 # attention modules  -- modules.py:119-207 (renorm 0), :210-311 (renorm 1), :314-403 (renorm 2)
 # ======================================================================================================
+#: set by train.EncoderTrainer when gradients are reduced across ranks: an object with `.ready(key)` that is told, from inside
+#: the backward pass, that every gradient of the parameter bucket `key` has been launched (train.GradReducer)
+GRAD_REDUCER = None
+
+
+class BucketMarkFn(Function):
+    """Identity whose backward reports that the parameters used DOWNSTREAM of this point (one encoder block, the heads ...)
+    have all had their gradient kernels launched, so that their all-reduce can start while the rest of the backward runs."""
+
+    @staticmethod
+    def forward(ctx, x, key):
+        ctx.key = key
+        ctx.set_materialize_grads(False)
+        y = x.view_as(x)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        if GRAD_REDUCER is not None:
+            GRAD_REDUCER.ready(ctx.key)
+        return dy, None
+
+
+def bucket_mark(x: Tensor, key) -> Tensor:
+    """Marks `x` (keeping its bf16 / row-mask side information) when a gradient reducer is active; otherwise returns it as is."""
+    if GRAD_REDUCER is None or not (x.requires_grad and torch.is_grad_enabled()):
+        return x
+    side = Side.of(x)
+    y = BucketMarkFn.apply(x, key)
+    if side is not None:
+        y._savqa_side = Side(y, side.bf16, side.on)
+    return y
+
+
 class MemoryHolder:
     """Side channel between the decoder's cross-attention layers and the encoder output they all read (`memory`,
     AttModel_x3.py:148-152).  Their K/V projections of `memory` -- big GEMMs that depend on nothing in the decoder -- and the
@@ -407,6 +442,8 @@ class MemoryJoinFn(Function):
     def backward(ctx, dy):
         h: MemoryHolder = ctx.holder
         g = dy
+        if GRAD_REDUCER is not None and getattr(h, "bucket", None) is not None:
+            GRAD_REDUCER.ready(h.bucket)  # the decoder's backward is complete
         if h.dmem is not None:
             torch.cuda.current_stream().wait_stream(h.side)
             d = h.dmem.reshape(ctx_shape(h))

@@ -23,6 +23,88 @@ from . import AttModel_x3 as A
 from . import functional as Fn
 from . import ops
 
+import os
+import re
+from collections import Counter
+
+
+class GradReducer:
+    """Bucketed gradient all-reduce that starts inside the backward pass (the role of DistributedDataParallel's reducer,
+    main_itp_ddp_tar_super_node.py:203).  The flat gradient buffer is laid out bucket by bucket -- heads, each branch's
+    decoder, each encoder block, the rest -- and the model reports, through functional.BucketMarkFn / MemoryJoinFn, the moment
+    the last gradient kernel of a bucket has been LAUNCHED; the bucket's all-reduce is then enqueued on NCCL's stream behind
+    the compute and weight-gradient streams that feed it, and overlaps the remaining backward.  finish() reduces whatever
+    was not reported and hands back the (range, work) list for the optimizer to follow."""
+
+    def __init__(self, flat_grad: torch.Tensor, buckets, need, group):
+        self.flat_grad, self.buckets, self.need, self.group = flat_grad, buckets, need, group
+        self.got, self.works, self.done = Counter(), [], set()
+        self.launch_stream = torch.cuda.Stream() if flat_grad.is_cuda else None
+
+    def begin_step(self) -> None:
+        self.got, self.works, self.done = Counter(), [], set()
+
+    def ready(self, key) -> None:
+        if key not in self.buckets or key in self.done:
+            return
+        self.got[key] += 1
+        if self.got[key] < self.need.get(key, 1):
+            return
+        lo, hi = self.buckets[key]
+        self.done.add(key)
+        if hi <= lo:
+            return
+        if self.launch_stream is not None:
+            cur = torch.cuda.current_stream()
+            r = self.launch_stream
+            r.wait_stream(cur)
+            w = Fn._WGRAD_STREAMS.get((cur.device_index, cur.cuda_stream))
+            if w is not None:
+                r.wait_stream(w)
+            with torch.cuda.stream(r):
+                work = dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        else:
+            work = dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        self.works.append((lo, hi, work))
+
+    def finish(self, chunks: int):
+        """All-reduces the ranges no bucket report covered (in `chunks` pieces so that the optimizer can follow one piece
+        behind) and returns every (lo, hi, work) in launch order."""
+        if self.launch_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.launch_stream)
+        covered = sorted(self.buckets[k] for k in self.done)
+        gaps, pos, n = [], 0, self.flat_grad.numel()
+        for lo, hi in covered:
+            if lo > pos:
+                gaps.append((pos, lo))
+            pos = max(pos, hi)
+        if pos < n:
+            gaps.append((pos, n))
+        total = sum(hi - lo for lo, hi in gaps)
+        piece = max((total // max(chunks, 1) + 7) // 8 * 8, 8)
+        for lo, hi in gaps:
+            p = lo
+            while p < hi:
+                q = min(hi, p + piece)
+                self.works.append((p, q, dist.all_reduce(self.flat_grad[p:q], op=dist.ReduceOp.AVG, group=self.group, async_op=True)))
+                p = q
+        return self.works
+
+
+_BUCKET_RE = re.compile(r"^(att_vis_grid|att_syb)\.(enc|dec)_[a-z_]+_(\d+)\.")
+
+
+def bucket_key_of(model, name: str):
+    """Which readiness bucket a parameter belongs to (see GradReducer): matches the marks placed in AttModel_x3._Branch."""
+    m = _BUCKET_RE.match(name)
+    if m:
+        branch = getattr(model, m.group(1))
+        return (id(branch), "enc", int(m.group(3))) if m.group(2) == "enc" else (id(branch), "dec")
+    if name.split(".")[0] in ("cls", "cls_vis", "cls_syb"):
+        return (id(model), "heads")
+    return None
+
+
 STEP_KEYS = ("vis_fea", "vis_fea_mask", "q_ipt", "q_ipt_mask", "q_ipt_graph", "syb_ipt", "macro_node_mask", "macro_graph_ipt", "answer")
 
 
@@ -37,6 +119,8 @@ class EncoderTrainer:
         self.dec_mask = dec_mask
         self.step_count = 0
         self.allreduce_chunks = 6
+        self.overlap_allreduce = os.environ.get("SAVQA_OVERLAP_ALLREDUCE", "1") != "0"  # world > 1: see GradReducer
+        self._debug_skip_allreduce = os.environ.get("SAVQA_DEBUG_SKIP_ALLREDUCE", "0") == "1"  # timing experiments only
         self.tables = [model.att_vis_grid.syb_emb, model.att_syb.syb_emb]
         self.flat_param: Optional[torch.Tensor] = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -82,12 +166,27 @@ class EncoderTrainer:
                     order.append(list(g))
                     placed.update(ids)
         order += [[p] for p in used if id(p) not in placed]
+        # bucket by readiness in the backward pass (heads, decoders, encoder blocks last-to-first, the rest), so that each
+        # bucket is one contiguous range of the flat gradient buffer that can be all-reduced as soon as it is final
+        names = {id(p): k for k, p in model.named_parameters()}
+        keys = []
+        for g in order:
+            k = bucket_key_of(model, names.get(id(g[0]), ""))
+            if k is not None and k not in keys:
+                keys.append(k)
+        rank = {k: i for i, k in enumerate(keys)}
+        order.sort(key=lambda g: rank.get(bucket_key_of(model, names.get(id(g[0]), "")), len(rank)))
         offsets, n = {}, 0
+        self.bucket_ranges = {}
         for g in order:
             n = (n + 7) // 8 * 8
+            k = bucket_key_of(model, names.get(id(g[0]), ""))
             for p in g:
                 offsets[id(p)] = (n, p.numel())
                 n += p.numel()
+            if k is not None:
+                lo, _ = self.bucket_ranges.get(k, (offsets[id(g[0])][0], 0))
+                self.bucket_ranges[k] = (lo, (n + 7) // 8 * 8)
         n_pad = (n + 7) // 8 * 8
         self.dense: List[torch.nn.Parameter] = [p for g in order for p in g]
         self.flat_param = torch.zeros(n_pad, device=dev)
@@ -118,6 +217,10 @@ class EncoderTrainer:
         self.dyn = torch.zeros(3, device=dev)
         self.dyn_host = torch.zeros(3).pin_memory() if dev.type == "cuda" else torch.zeros(3)
         Fn.WEIGHT_EPOCH += 1
+        self.reducer = None
+        if self.world > 1 and self.overlap_allreduce and not self._debug_skip_allreduce:
+            need = {k: (2 if k[1] == "heads" else 1) for k in self.bucket_ranges}  # both decoder outputs feed the heads
+            self.reducer = GradReducer(self.flat_grad, dict(self.bucket_ranges), need, self.pg)
 
     def sync_mirror(self) -> None:
         """Re-derives the bf16 mirror from the fp32 parameters (after prepare(), or after load_state_dict wrote into them)."""
@@ -143,15 +246,18 @@ class EncoderTrainer:
         if self.flat_param.is_cuda:
             Fn.join_wgrad_streams()  # weight-gradient GEMMs run on side streams during the backward pass
         step = max(self.step_count, 1)
-        if self.world > 1:
-            # the all-reduce travels in chunks on NCCL's stream while the fused Adam kernel follows one chunk behind on the
-            # compute stream: only the first chunk's reduction and the last chunk's update are exposed
-            n = self.flat_grad.numel()
-            k = self.allreduce_chunks
-            bounds = [(n * i // k) // 8 * 8 for i in range(k)] + [n]
-            works = [dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
-                     for lo, hi in zip(bounds[:-1], bounds[1:])]
-            for w, lo, hi in zip(works, bounds[:-1], bounds[1:]):
+        if self.world > 1 and not self._debug_skip_allreduce:
+            # the all-reduce travels in pieces on NCCL's stream -- the buckets the backward pass reported first (GradReducer),
+            # then the remainder in chunks -- while the fused Adam kernel follows one piece behind on the compute stream
+            if self.reducer is not None:
+                works = self.reducer.finish(self.allreduce_chunks)
+            else:
+                n = self.flat_grad.numel()
+                k = self.allreduce_chunks
+                bounds = [(n * i // k) // 8 * 8 for i in range(k)] + [n]
+                works = [(lo, hi, dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+                         for lo, hi in zip(bounds[:-1], bounds[1:])]
+            for lo, hi, w in works:
                 w.wait()
                 ops.adam_step(self.flat_param[lo:hi], self.flat_grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.lr, b1, b2,
                               self.eps, step, dyn=self.dyn, param_bf16=self.flat_bf16[lo:hi])
@@ -175,7 +281,13 @@ class EncoderTrainer:
 
     def _step_impl(self, b: Dict[str, torch.Tensor]) -> torch.Tensor:
         self.flat_grad.zero_()
-        loss = self._forward_backward(b)
+        if self.reducer is not None:
+            self.reducer.begin_step()
+            Fn.GRAD_REDUCER = self.reducer
+        try:
+            loss = self._forward_backward(b)
+        finally:
+            Fn.GRAD_REDUCER = None
         self._exchange_and_apply()
         return loss
 
