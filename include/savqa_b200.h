@@ -128,6 +128,20 @@ typedef struct savqa_gemm_epilogue {
 int savqa_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, int M, int N, int K,
                     const savqa_gemm_epilogue_t* epilogue, int split_k, savqa_stream_t stream);
 
+/* `count` (1 or 2) independent GEMMs with the same N, operand majors and kind of output in ONE launch: the same layer of the
+ * visual and the symbolic branch model (AttModel_x3.py:529-530) -- same shapes, different row counts (B*56 and B*128 tokens)
+ * and different weights.  One launch halves the fixed launch / pipeline-fill cost and spreads the tiles of both problems over
+ * the SMs together.  Falls back to one savqa_gemm_bf16 call per problem when the grouped kernel does not take the shapes. */
+typedef struct savqa_gemm_problem {
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  int M, K;
+  savqa_gemm_epilogue_t epilogue;
+} savqa_gemm_problem_t;
+
+int savqa_gemm_bf16_grouped(const savqa_gemm_problem_t* problems, int count, int a_mn_major, int b_mn_major, int N, int split_k,
+                            savqa_stream_t stream);
+
 /* ---- a5: graph-weighted attention core (modules.py:246-301 between the projections and the residual) ---
  * For each sample n and head h (channels [h*d,(h+1)*d) of q/k/v):
  *   S = Q K^T / sqrt(d);  S[:, j] = -4294967296 where !key_on[n,j];  optional causal tril mask;

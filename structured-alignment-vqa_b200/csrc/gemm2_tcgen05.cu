@@ -13,12 +13,16 @@
 // Epilogue: TMEM -> registers -> fused math -> 128B-swizzled smem staging -> TMA store (coalesced, asynchronous); the
 // operands it reads from HBM (residual / ReLU gate / bias) are prefetched one chunk ahead, the first chunk while the
 // tile's MMAs are still running.  Split-K partial sums (wgrad) go out with red.global.add.v4.f32.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace savqa {
 
 int gemm2_launch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
                  const savqa_gemm_epilogue_t* epi, int split_k, cudaStream_t stream, bool* handled);
+int gemm2_launch_group(const savqa_gemm_problem_t* probs, int count, int a_mn, int b_mn, int N, int split_k, cudaStream_t stream,
+                       bool* handled);
 
 namespace {
 
@@ -35,6 +39,16 @@ struct Gemm2Params {
   int M, N, K;
   int num_m, num_n, split_k, kb_per_split, num_kb;
   savqa_gemm_epilogue_t e;
+};
+
+// Up to two independent problems with the same N (and tile shape, operand majors, epilogue kind) in ONE launch: the tile
+// index space is the concatenation of the problems' tiles.  The step's two branch models issue the same GEMM shapes with
+// different row counts (7168 and 16384) and weights; one launch halves the fixed launch / pipeline-fill cost (~8 us on
+// 25-50 us of work at K = 512) and fills the 74 CTA pairs far more evenly than either problem alone.
+struct Gemm2Group {
+  int tiles0;       // tiles of problem 0; problem 1 owns [tiles0, tiles0 + tiles1)
+  int num_tiles;
+  Gemm2Params p[2];
 };
 
 template <int BN>
@@ -54,8 +68,9 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
-                  const Gemm2Params p) {
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmO0,
+                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmO1,
+                  const __grid_constant__ Gemm2Group g) {
   using C = Cfg2<BN>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C::kStages];
@@ -76,9 +91,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   float* sbias = reinterpret_cast<float*>(staging + kStagingBytes);  // [8 warps][128]
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    if (EPI != EPI_ATOMIC) tma_prefetch_desc(&tmO);
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (EPI != EPI_ATOMIC) tma_prefetch_desc(&tmO0);
+    if (g.num_tiles > g.tiles0) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+      if (EPI != EPI_ATOMIC) tma_prefetch_desc(&tmO1);
+    }
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -97,15 +117,20 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only from here on
   const uint32_t tmem_base = tmem_base_slot;
 
-  const int tiles_mn = p.num_m * p.num_n;
-  const int num_tiles = tiles_mn * p.split_k;
+  const int num_tiles = g.num_tiles;
 
   if (warp == 0) {
     // ===================== TMA producer (one thread per CTA) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int gtile = pair; gtile < num_tiles; gtile += num_pairs) {
+        const int gi = gtile >= g.tiles0 ? 1 : 0;
+        const Gemm2Params& p = g.p[gi];
+        const CUtensorMap* tmA = gi ? &tmA1 : &tmA0;
+        const CUtensorMap* tmB = gi ? &tmB1 : &tmB0;
+        const int tile = gtile - (gi ? g.tiles0 : 0);
+        const int tiles_mn = p.num_m * p.num_n;
         const int n_blk = tile % p.num_n;
         const int m_blk = (tile / p.num_n) % p.num_m;
         const int ks = tile / tiles_mn;
@@ -120,16 +145,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);  // bytes of both CTAs
           const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);           // the leader's barrier
           if constexpr (!A_MN) {
-            tma_load_2d_pair(sa, &tmA, bar, kb * BK, m0);
+            tma_load_2d_pair(sa, tmA, bar, kb * BK, m0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d_pair(sa + c * 8192, &tmA, bar, m0 + c * 64, kb * BK);
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d_pair(sa + c * 8192, tmA, bar, m0 + c * 64, kb * BK);
           }
           if constexpr (!B_MN) {
-            tma_load_2d_pair(sb, &tmB, bar, kb * BK, n0);
+            tma_load_2d_pair(sb, tmB, bar, kb * BK, n0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 128; ++c) tma_load_2d_pair(sb + c * 8192, &tmB, bar, n0 + c * 64, kb * BK);
+            for (int c = 0; c < BN / 128; ++c) tma_load_2d_pair(sb + c * 8192, tmB, bar, n0 + c * 64, kb * BK);
           }
           if (++stage == C::kStages) {
             stage = 0;
@@ -145,8 +170,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-        const int ks = tile / tiles_mn;
+      for (int gtile = pair; gtile < num_tiles; gtile += num_pairs, ++it) {
+        const int gi = gtile >= g.tiles0 ? 1 : 0;
+        const Gemm2Params& p = g.p[gi];
+        const int tile = gtile - (gi ? g.tiles0 : 0);
+        const int ks = tile / (p.num_m * p.num_n);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         const int as = it & 1;
@@ -177,17 +205,21 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== epilogue warps (8: two per TMEM lane quadrant, alternating column chunks) =====================
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
-    const savqa_gemm_epilogue_t& e = p.e;
     uint8_t* buf = staging + (warp - 2) * 4096;  // this warp's [32 rows][128 B] staging tile
     const uint32_t srow = static_cast<uint32_t>(lane) * 128u;
     const uint32_t sxor = static_cast<uint32_t>(lane & 7);
-    const __nv_bfloat16* gate = static_cast<const __nv_bfloat16*>(e.gate_bf16);
     const uint32_t empty_remote0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t empty_remote1 = mapa_shared(smem_u32(&tmem_empty_bar[1]), 0);
     constexpr int CW = (EPI == EPI_BF16) ? 64 : 32;  // columns per chunk = 128 bytes of output per row
     constexpr int NCH = BN / CW;
     int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+    for (int gtile = pair; gtile < num_tiles; gtile += num_pairs, ++it) {
+      const int gi = gtile >= g.tiles0 ? 1 : 0;
+      const Gemm2Params& p = g.p[gi];
+      const savqa_gemm_epilogue_t& e = p.e;
+      const CUtensorMap* tmO = gi ? &tmO1 : &tmO0;
+      const __nv_bfloat16* gate = static_cast<const __nv_bfloat16*>(e.gate_bf16);
+      const int tile = gtile - (gi ? g.tiles0 : 0);
       const int n_blk = tile % p.num_n;
       const int m_blk = (tile / p.num_n) % p.num_m;
       const int as = it & 1;
@@ -343,7 +375,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (active) fence_proxy_async_smem();
             __syncwarp();
             if (active && lane == 0) {
-              tma_store_2d(&tmO, buf, gcol, row0);  // rows past M / columns past N are clipped by the TMA unit
+              tma_store_2d(tmO, buf, gcol, row0);  // rows past M / columns past N are clipped by the TMA unit
               tma_store_commit();
             }
           }
@@ -369,129 +401,175 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+struct Maps {
+  alignas(64) CUtensorMap a[2], b[2], o[2];
+};
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const Gemm2Params& p, cudaStream_t stream) {
+int launch2(const Maps& m, const Gemm2Group& g, cudaStream_t stream) {
   using C = Cfg2<BN>;
   auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN, EPI>;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "savqa_gemm_bf16 (CTA-pair kernel)")) return rc;
-  const int tiles = p.num_m * p.num_n * p.split_k;
   const int max_pairs = sm_count() / 2;
-  const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  SAVQA_CHECK_CUDA(launch_kernel(true, kern, dim3(2 * pairs), dim3(kThreads), C::kSmemBytes, stream, tmA, tmB, tmO, p));
+  const int pairs = g.num_tiles < max_pairs ? g.num_tiles : max_pairs;
+  SAVQA_CHECK_CUDA(launch_kernel(true, kern, dim3(2 * pairs), dim3(kThreads), C::kSmemBytes, stream, m.a[0], m.b[0], m.o[0], m.a[1], m.b[1],
+                                 m.o[1], g));
   return SAVQA_OK;
 }
 
 template <int BN, int EPI>
-int launch2_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const Gemm2Params& p,
-                  cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch2<BN, false, false, EPI>(tmA, tmB, tmO, p, s);
-  if (!a_mn && b_mn) return launch2<BN, false, true, EPI>(tmA, tmB, tmO, p, s);
-  return launch2<BN, true, true, EPI>(tmA, tmB, tmO, p, s);
+int launch2_major(bool a_mn, bool b_mn, const Maps& m, const Gemm2Group& g, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch2<BN, false, false, EPI>(m, g, s);
+  if (!a_mn && b_mn) return launch2<BN, false, true, EPI>(m, g, s);
+  return launch2<BN, true, true, EPI>(m, g, s);
 }
 
 template <int BN>
-int launch2_epi(int epi, bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const Gemm2Params& p,
-                cudaStream_t s) {
-  if (epi == EPI_BF16) return launch2_major<BN, EPI_BF16>(a_mn, b_mn, tmA, tmB, tmO, p, s);
-  if (epi == EPI_F32) return launch2_major<BN, EPI_F32>(a_mn, b_mn, tmA, tmB, tmO, p, s);
-  return launch2_major<BN, EPI_ATOMIC>(a_mn, b_mn, tmA, tmB, tmO, p, s);
+int launch2_epi(int epi, bool a_mn, bool b_mn, const Maps& m, const Gemm2Group& g, cudaStream_t s) {
+  if (epi == EPI_BF16) return launch2_major<BN, EPI_BF16>(a_mn, b_mn, m, g, s);
+  if (epi == EPI_F32) return launch2_major<BN, EPI_F32>(a_mn, b_mn, m, g, s);
+  return launch2_major<BN, EPI_ATOMIC>(a_mn, b_mn, m, g, s);
 }
 
-}  // namespace
-
-// Takes the problem when the CTA-pair kernel supports it (sets *handled); otherwise leaves it to the single-CTA kernel.
-int gemm2_launch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
-                 const savqa_gemm_epilogue_t* epi, int split_k, cudaStream_t stream, bool* handled) {
-  *handled = false;
-  const savqa_gemm_epilogue_t& e = *epi;
+// epilogue kind the pair kernel would run this problem with, or -1 when it does not take it
+int pair_mode(const void* A, const void* B, int a_mn, int b_mn, int M, int N, const savqa_gemm_epilogue_t& e) {
   int mode;
   if (e.accumulate == 2 && e.out_f32 && !e.out_bf16) mode = EPI_ATOMIC;
   else if (e.accumulate == 0 && e.out_bf16 && !e.out_f32) mode = EPI_BF16;
   else if (e.accumulate == 0 && e.out_f32 && !e.out_bf16) mode = EPI_F32;
-  else return SAVQA_OK;
-  if (a_mn && !b_mn) return SAVQA_OK;                       // combination not used by the path
-  if (M <= BM || N % 64 != 0 || (sm_count() & 1)) return SAVQA_OK;  // decoder-sized problems and ragged widths: single-CTA kernel
-  if (mode == EPI_BF16 && (e.res || e.rowtab)) return SAVQA_OK;
-  if (mode != EPI_BF16 && e.gate_bf16) return SAVQA_OK;
-  if (e.bias && !aligned16(e.bias)) return SAVQA_OK;
-  if (e.res && (!aligned16(e.res) || e.ld_res % 4)) return SAVQA_OK;
-  if (e.rowtab && (!aligned16(e.rowtab) || e.ld_rowtab % 4)) return SAVQA_OK;
-  if (e.gate_bf16 && (!aligned16(e.gate_bf16) || e.ld_gate % 8)) return SAVQA_OK;
-  if (e.out_f32 && (!aligned16(e.out_f32) || e.ld_out_f32 % 4)) return SAVQA_OK;
-  if (e.out_bf16 && (!aligned16(e.out_bf16) || e.ld_out_bf16 % 8)) return SAVQA_OK;
-  if (!aligned16(A) || !aligned16(B)) return SAVQA_OK;
+  else return -1;
+  if (a_mn && !b_mn) return -1;                                  // combination not used by the path
+  if (M <= BM || N % 64 != 0 || (sm_count() & 1)) return -1;     // decoder-sized problems and ragged widths: single-CTA kernel
+  if (mode == EPI_BF16 && (e.res || e.rowtab)) return -1;
+  if (mode != EPI_BF16 && e.gate_bf16) return -1;
+  if (e.bias && !aligned16(e.bias)) return -1;
+  if (e.res && (!aligned16(e.res) || e.ld_res % 4)) return -1;
+  if (e.rowtab && (!aligned16(e.rowtab) || e.ld_rowtab % 4)) return -1;
+  if (e.gate_bf16 && (!aligned16(e.gate_bf16) || e.ld_gate % 8)) return -1;
+  if (e.out_f32 && (!aligned16(e.out_f32) || e.ld_out_f32 % 4)) return -1;
+  if (e.out_bf16 && (!aligned16(e.out_bf16) || e.ld_out_bf16 % 8)) return -1;
+  if (!aligned16(A) || !aligned16(B)) return -1;
+  return mode;
+}
 
-  Gemm2Params p;
-  p.M = M; p.N = N; p.K = K;
-  p.e = e;
-  p.num_kb = (K + BK - 1) / BK;
-  p.num_m = (M + 2 * BM - 1) / (2 * BM);
-  const int pairs = sm_count() / 2;
-  if (mode == EPI_ATOMIC && split_k != 1) {
-    // split-K (wgrad: few output tiles, long K): one round of work units over the CTA pairs, at least 4 k-blocks each
-    const long tiles256 = static_cast<long>(p.num_m) * ((N + 255) / 256);
-    int want = tiles256 >= pairs ? 1 : static_cast<int>(pairs / tiles256);
-    const int cap = p.num_kb / 4 > 0 ? p.num_kb / 4 : 1;
-    split_k = want < cap ? want : cap;
-  }
-  if (split_k < 1) split_k = 1;
-  if (split_k > p.num_kb) split_k = p.num_kb;
-  p.kb_per_split = (p.num_kb + split_k - 1) / split_k;
-  p.split_k = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
-
-  // tile width: 256 halves the B traffic per flop; 128 when it loses fewer SM-rounds to wave quantisation
-  auto rounds = [&](int bn) {
-    const long tiles = static_cast<long>(p.num_m) * ((N + bn - 1) / bn) * p.split_k;
-    return (tiles + pairs - 1) / pairs * bn;  // ~ time in units of a 64-column slab
-  };
-  int BN = 256;
-  if (N % 256 != 0 || rounds(128) * 10 < rounds(256) * 9) BN = 128;
-  p.num_n = (N + BN - 1) / BN;
-
-  alignas(64) CUtensorMap tmA, tmB, tmO;
+int make_maps(Maps& m, int i, const savqa_gemm_problem_t& pr, int a_mn, int b_mn, int N, int BN, int mode) {
+  const int M = pr.M, K = pr.K;
+  const savqa_gemm_epilogue_t& e = pr.epilogue;
   int rc;
   if (!a_mn) {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
-    const uint64_t str[1] = {static_cast<uint64_t>(lda) * 2};
+    const uint64_t str[1] = {static_cast<uint64_t>(pr.lda) * 2};
     const uint32_t box[2] = {BK, BM};
-    rc = make_tensor_map_bf16(&tmA, A, 2, dims, str, box, true);
+    rc = make_tensor_map_bf16(&m.a[i], pr.A, 2, dims, str, box, true);
   } else {
     const uint64_t dims[2] = {static_cast<uint64_t>(M), static_cast<uint64_t>(K)};
-    const uint64_t str[1] = {static_cast<uint64_t>(lda) * 2};
+    const uint64_t str[1] = {static_cast<uint64_t>(pr.lda) * 2};
     const uint32_t box[2] = {64, BK};
-    rc = make_tensor_map_bf16(&tmA, A, 2, dims, str, box, true);
+    rc = make_tensor_map_bf16(&m.a[i], pr.A, 2, dims, str, box, true);
   }
   if (rc) return rc;
   if (!b_mn) {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
-    const uint64_t str[1] = {static_cast<uint64_t>(ldb) * 2};
+    const uint64_t str[1] = {static_cast<uint64_t>(pr.ldb) * 2};
     const uint32_t box[2] = {BK, static_cast<uint32_t>(BN / 2)};
-    rc = make_tensor_map_bf16(&tmB, B, 2, dims, str, box, true);
+    rc = make_tensor_map_bf16(&m.b[i], pr.B, 2, dims, str, box, true);
   } else {
     const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(K)};
-    const uint64_t str[1] = {static_cast<uint64_t>(ldb) * 2};
+    const uint64_t str[1] = {static_cast<uint64_t>(pr.ldb) * 2};
     const uint32_t box[2] = {64, BK};
-    rc = make_tensor_map_bf16(&tmB, B, 2, dims, str, box, true);
+    rc = make_tensor_map_bf16(&m.b[i], pr.B, 2, dims, str, box, true);
   }
   if (rc) return rc;
   if (mode == EPI_BF16) {
     const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
     const uint64_t str[1] = {static_cast<uint64_t>(e.ld_out_bf16) * 2};
     const uint32_t box[2] = {64, 32};
-    rc = make_tensor_map(&tmO, e.out_bf16, false, 2, dims, str, box, true);
+    rc = make_tensor_map(&m.o[i], e.out_bf16, false, 2, dims, str, box, true);
   } else if (mode == EPI_F32) {
     const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
     const uint64_t str[1] = {static_cast<uint64_t>(e.ld_out_f32) * 4};
     const uint32_t box[2] = {32, 32};
-    rc = make_tensor_map(&tmO, e.out_f32, true, 2, dims, str, box, true);
+    rc = make_tensor_map(&m.o[i], e.out_f32, true, 2, dims, str, box, true);
   } else {
-    tmO = tmA;  // unused
+    m.o[i] = m.a[i];  // unused
     rc = SAVQA_OK;
   }
-  if (rc) return rc;
+  return rc;
+}
+
+}  // namespace
+
+// Takes the problems (one, or two with the same N / operand majors / epilogue kind) when the CTA-pair kernel supports them
+// (sets *handled); otherwise leaves them to the caller (single-CTA kernel, one launch per problem).
+int gemm2_launch_group(const savqa_gemm_problem_t* probs, int count, int a_mn, int b_mn, int N, int split_k, cudaStream_t stream,
+                       bool* handled) {
+  *handled = false;
+  if (count < 1 || count > 2) return SAVQA_OK;
+  const int mode = pair_mode(probs[0].A, probs[0].B, a_mn, b_mn, probs[0].M, N, probs[0].epilogue);
+  if (mode < 0) return SAVQA_OK;
+  for (int i = 1; i < count; ++i)
+    if (pair_mode(probs[i].A, probs[i].B, a_mn, b_mn, probs[i].M, N, probs[i].epilogue) != mode) return SAVQA_OK;
+
+  const int pairs = sm_count() / 2;
+  Gemm2Group g;
+  memset(&g, 0, sizeof(g));
+  long tiles256 = 0;
+  for (int i = 0; i < count; ++i) {
+    Gemm2Params& p = g.p[i];
+    p.M = probs[i].M; p.N = N; p.K = probs[i].K;
+    p.e = probs[i].epilogue;
+    p.num_kb = (p.K + BK - 1) / BK;
+    p.num_m = (p.M + 2 * BM - 1) / (2 * BM);
+    tiles256 += static_cast<long>(p.num_m) * ((N + 255) / 256);
+  }
+  for (int i = 0; i < count; ++i) {
+    Gemm2Params& p = g.p[i];
+    int sk = split_k;
+    if (mode == EPI_ATOMIC && split_k != 1) {
+      // split-K (wgrad: few output tiles, long K): about one round of work units over the CTA pairs, >= 4 k-blocks each
+      int want = tiles256 >= pairs ? 1 : static_cast<int>(pairs / tiles256);
+      const int cap = p.num_kb / 4 > 0 ? p.num_kb / 4 : 1;
+      sk = want < cap ? want : cap;
+    }
+    if (sk < 1) sk = 1;
+    if (sk > p.num_kb) sk = p.num_kb;
+    p.kb_per_split = (p.num_kb + sk - 1) / sk;
+    p.split_k = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  }
+  // tile width: 256 halves the B traffic per flop; 128 when it loses fewer SM-rounds to wave quantisation
+  auto rounds = [&](int bn) {
+    long tiles = 0;
+    for (int i = 0; i < count; ++i) tiles += static_cast<long>(g.p[i].num_m) * ((N + bn - 1) / bn) * g.p[i].split_k;
+    return (tiles + pairs - 1) / pairs * bn;  // ~ time in units of a 64-column slab
+  };
+  int BN = 256;
+  if (N % 256 != 0 || rounds(128) * 10 < rounds(256) * 9) BN = 128;
+  Maps m;
+  int total = 0;
+  for (int i = 0; i < count; ++i) {
+    g.p[i].num_n = (N + BN - 1) / BN;
+    const int t = g.p[i].num_m * g.p[i].num_n * g.p[i].split_k;
+    if (i == 0) g.tiles0 = t;
+    total += t;
+    if (int rc = make_maps(m, i, probs[i], a_mn, b_mn, N, BN, mode)) return rc;
+  }
+  if (count == 1) {
+    m.a[1] = m.a[0];
+    m.b[1] = m.b[0];
+    m.o[1] = m.o[0];
+  }
+  g.num_tiles = total;
   *handled = true;
-  if (BN == 256) return launch2_epi<256>(mode, a_mn != 0, b_mn != 0, tmA, tmB, tmO, p, stream);
-  return launch2_epi<128>(mode, a_mn != 0, b_mn != 0, tmA, tmB, tmO, p, stream);
+  if (BN == 256) return launch2_epi<256>(mode, a_mn != 0, b_mn != 0, m, g, stream);
+  return launch2_epi<128>(mode, a_mn != 0, b_mn != 0, m, g, stream);
+}
+
+int gemm2_launch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
+                 const savqa_gemm_epilogue_t* epi, int split_k, cudaStream_t stream, bool* handled) {
+  savqa_gemm_problem_t pr;
+  pr.A = A; pr.lda = lda; pr.B = B; pr.ldb = ldb; pr.M = M; pr.K = K;
+  pr.epilogue = *epi;
+  return gemm2_launch_group(&pr, 1, a_mn, b_mn, N, split_k, stream, handled);
 }
 
 }  // namespace savqa

@@ -18,6 +18,9 @@ namespace savqa {
 int gemm2_launch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
                  const savqa_gemm_epilogue_t* epi, int split_k, cudaStream_t stream, bool* handled);  // gemm2_tcgen05.cu
 
+int gemm2_launch_group(const savqa_gemm_problem_t* probs, int count, int a_mn, int b_mn, int N, int split_k, cudaStream_t stream,
+                       bool* handled);  // gemm2_tcgen05.cu
+
 namespace {
 
 constexpr int BM = 128;
@@ -420,4 +423,25 @@ extern "C" int savqa_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const
     case 256: return launch_major<256>(a_mn_major != 0, b_mn_major != 0, tmA, tmB, p, stream);
     default: return launch_major<128>(a_mn_major != 0, b_mn_major != 0, tmA, tmB, p, stream);
   }
+}
+
+extern "C" int savqa_gemm_bf16_grouped(const savqa_gemm_problem_t* problems, int count, int a_mn_major, int b_mn_major, int N, int split_k,
+                                       savqa_stream_t stream_) {
+  using namespace savqa;
+  SAVQA_REQUIRE(problems && count >= 1, "savqa_gemm_bf16_grouped: no problems");
+  bool handled = false;
+  if (count <= 2 && engine_pref() != 1) {
+    bool ok = true;
+    for (int i = 0; i < count; ++i) ok = ok && problems[i].A && problems[i].B && problems[i].M > 0 && problems[i].K > 0 &&
+                                         problems[i].lda % 8 == 0 && problems[i].ldb % 8 == 0 && (!problems[i].epilogue.colsum || split_k == 1) &&
+                                         (problems[i].epilogue.out_f32 || problems[i].epilogue.out_bf16);
+    if (ok)
+      if (int rc = gemm2_launch_group(problems, count, a_mn_major, b_mn_major, N, split_k, static_cast<cudaStream_t>(stream_), &handled)) return rc;
+  }
+  if (handled) return SAVQA_OK;
+  for (int i = 0; i < count; ++i)
+    if (int rc = savqa_gemm_bf16(problems[i].A, problems[i].lda, a_mn_major, problems[i].B, problems[i].ldb, b_mn_major, problems[i].M, N,
+                                 problems[i].K, &problems[i].epilogue, split_k, stream_))
+      return rc;
+  return SAVQA_OK;
 }

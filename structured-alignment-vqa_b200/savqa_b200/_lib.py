@@ -25,6 +25,11 @@ class GemmEpilogue(C.Structure):
                 ("out_bf16", vp), ("ld_out_bf16", i64), ("colsum", vp)]
 
 
+class GemmProblem(C.Structure):
+    """savqa_gemm_problem_t"""
+    _fields_ = [("A", vp), ("lda", i64), ("B", vp), ("ldb", i64), ("M", C.c_int), ("K", C.c_int), ("epilogue", GemmEpilogue)]
+
+
 class AttnArgs(C.Structure):
     """savqa_attn_args_t"""
     _fields_ = [("q", vp), ("ldq", i64), ("k", vp), ("ldk", i64), ("v", vp), ("ldv", i64),
@@ -55,6 +60,7 @@ SIGNATURES = {
     "savqa_residual_layernorm_fwd": [vp, vp, vp, vp, C.c_float, i64, C.c_int, vp, vp, vp, vp, vp],
     "savqa_layernorm_bwd": [vp, vp, vp, C.c_float, i64, C.c_int, vp, vp, vp, vp, vp, vp, vp],
     "savqa_gemm_bf16": [vp, i64, C.c_int, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(GemmEpilogue), C.c_int, vp],
+    "savqa_gemm_bf16_grouped": [C.POINTER(GemmProblem), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "savqa_graph_attn_fwd": [C.POINTER(AttnArgs), vp],
     "savqa_graph_attn_bwd": [C.POINTER(AttnArgs), vp],
     "savqa_answer_loss": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp, vp],

@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import AttnArgs, GemmEpilogue, call, ptr
+from ._lib import AttnArgs, GemmEpilogue, GemmProblem, call, ptr
 
 Tensor = torch.Tensor
 BF16 = torch.bfloat16
@@ -244,6 +244,15 @@ def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_
     else:
         assert b.shape[0] >= N and b.shape[1] >= K, (b.shape, N, K)
     e = GemmEpilogue()
+    _fill_epilogue(e, M, N, bias, res, rowtab, rowtab_period, gate, relu, alpha, out_f32, out_bf16, accumulate, split_k, colsum)
+    if _DEBUG_GEMM == "torch":
+        assert colsum is None
+        _gemm_debug_torch(a, b, M, N, K, a_mn, b_mn, bias, res, rowtab, rowtab_period, gate, relu, alpha, out_f32, out_bf16, accumulate)
+        return
+    call("savqa_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), M, N, K, C.byref(e), int(split_k))
+
+
+def _fill_epilogue(e, M, N, bias, res, rowtab, rowtab_period, gate, relu, alpha, out_f32, out_bf16, accumulate, split_k, colsum) -> None:
     e.alpha, e.relu, e.accumulate, e.rowtab_period = float(alpha), int(relu), int(accumulate), int(rowtab_period)
     e.bias = ptr(bias)
     if bias is not None:
@@ -266,11 +275,40 @@ def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_
     if colsum is not None:
         assert colsum.is_contiguous() and colsum.numel() >= N and split_k == 1
         e.colsum = ptr(colsum)
-    if _DEBUG_GEMM == "torch":
-        assert colsum is None
-        _gemm_debug_torch(a, b, M, N, K, a_mn, b_mn, bias, res, rowtab, rowtab_period, gate, relu, alpha, out_f32, out_bf16, accumulate)
+
+
+def gemm_grouped(problems, N: int, *, a_mn: bool = False, b_mn: bool = False, split_k: int = 1) -> None:
+    """Several independent GEMMs with the same N / operand majors / kind of output in ONE launch (savqa_gemm_bf16_grouped): the
+    same layer of the two branch models.  `problems`: dicts with a, b, M, K and the epilogue keywords of gemm()."""
+    if len(problems) == 1 or _DEBUG_GEMM == "torch" or len(problems) > 2:
+        for p in problems:
+            kw = {k: v for k, v in p.items() if k not in ("a", "b", "M", "K")}
+            gemm(p["a"], p["b"], p["M"], N, p["K"], a_mn=a_mn, b_mn=b_mn, split_k=split_k, **kw)
         return
-    call("savqa_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), M, N, K, C.byref(e), int(split_k))
+    arr = (GemmProblem * len(problems))()
+    for i, p in enumerate(problems):
+        a, b, M, K = p["a"], p["b"], p["M"], p["K"]
+        _check(a, BF16, "A")
+        _check(b, BF16, "B")
+        assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+        for nm in ("bias", "res", "rowtab", "out_f32", "colsum"):
+            _check(p.get(nm), F32, nm)
+        _check(p.get("gate"), BF16, "gate")
+        _check(p.get("out_bf16"), BF16, "out_bf16")
+        arr[i].A, arr[i].lda, arr[i].B, arr[i].ldb, arr[i].M, arr[i].K = ptr(a), a.stride(0), ptr(b), b.stride(0), M, K
+        _fill_epilogue(arr[i].epilogue, M, N, p.get("bias"), p.get("res"), p.get("rowtab"), p.get("rowtab_period", 0), p.get("gate"),
+                       p.get("relu", False), p.get("alpha", 1.0), p.get("out_f32"), p.get("out_bf16"), p.get("accumulate", 0), split_k,
+                       p.get("colsum"))
+    call("savqa_gemm_bf16_grouped", arr, len(problems), int(a_mn), int(b_mn), N, int(split_k))
+
+
+def wgrad_grouped(items) -> None:
+    """[(dy, x, n_out, k_in, out)], same n_out / k_in: out += dy^T x for each, in one launch."""
+    n_out, k_in = items[0][2], items[0][3]
+    tiles = ((n_out + 127) // 128) * ((k_in + 127) // 128)
+    sk = min(split_k_for(tiles, (it[0].shape[0] + 63) // 64) for it in items)
+    gemm_grouped([dict(a=dy, b=x, M=n_out, K=dy.shape[0], out_f32=out, accumulate=2) for dy, x, _, _, out in items], k_in,
+                 a_mn=True, b_mn=True, split_k=sk)
 
 
 def _gemm_debug_torch(a, b, M, N, K, a_mn, b_mn, bias, res, rowtab, period, gate, relu, alpha, out_f32, out_bf16, accumulate):

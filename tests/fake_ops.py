@@ -154,6 +154,17 @@ def tc_attention_bwd_fits(d, Tq, Tk):
     return False
 
 
+def gemm_grouped(problems, N, *, a_mn=False, b_mn=False, split_k=1):
+    for p in problems:
+        kw = {k: v for k, v in p.items() if k not in ("a", "b", "M", "K")}
+        gemm(p["a"], p["b"], p["M"], N, p["K"], a_mn=a_mn, b_mn=b_mn, **kw)
+
+
+def wgrad_grouped(items):
+    for dy, x, n_out, k_in, out in items:
+        wgrad(dy, x, n_out, k_in, out)
+
+
 def split_k_for(tiles, k_blocks):
     return 1
 

@@ -208,6 +208,53 @@ def test_gemm_pair_kernel_forward_epilogues(ops, M, N, K):
     assert rel(big[:, N:2 * N], _gemm_ref(a, b)) < 4e-3 and float(big[:, :N].float().abs().sum()) == 0 and float(big[:, 2 * N:].float().abs().sum()) == 0
 
 
+@pytest.mark.parametrize("M0,M1,N,K", [(7168, 16384, 1536, 512), (7168, 16384, 512, 2048), (1000, 300, 256, 128), (2560, 2560, 2048, 304)])
+def test_gemm_grouped_two_problems(ops, M0, M1, N, K):
+    """One launch for the same layer of the two branch models (different row counts and weights): every output equals the
+    single-problem launch bit for bit (same K order per tile); split-K weight gradients agree to fp32 summation order."""
+    P = []
+    for i, M in enumerate((M0, M1)):
+        a = GS.randn(f"gg/{i}/{M}/{K}/a", M, K).to(BF)
+        b = (GS.randn(f"gg/{i}/{N}/{K}/b", N, K) / math.sqrt(K)).to(BF)
+        bias = GS.randn(f"gg/{i}/{N}/bias", N)
+        res = GS.randn(f"gg/{i}/{M}/{N}/res", M, N)
+        gate = GS.randn(f"gg/{i}/{M}/{N}/gate", M, N).to(BF)
+        P.append(dict(a=dev(a), b=dev(b), bias=dev(bias), res=dev(res), gate=dev(gate), M=M))
+    # forward kind: bias + ReLU -> bf16
+    outs = [torch.empty(p["M"], N, device="cuda", dtype=BF) for p in P]
+    ops.gemm_grouped([dict(a=p["a"], b=p["b"], M=p["M"], K=K, bias=p["bias"], relu=True, out_bf16=o) for p, o in zip(P, outs)], N)
+    for p, o in zip(P, outs):
+        single = torch.empty_like(o)
+        ops.gemm(p["a"], p["b"], p["M"], N, K, bias=p["bias"], relu=True, out_bf16=single)
+        assert torch.equal(o, single)
+        assert rel(o, _gemm_ref(p["a"].cpu(), p["b"].cpu(), bias=p["bias"].cpu(), relu=True)) < 4e-3
+    # residual kind -> fp32
+    outs = [torch.empty(p["M"], N, device="cuda") for p in P]
+    ops.gemm_grouped([dict(a=p["a"], b=p["b"], M=p["M"], K=K, bias=p["bias"], res=p["res"], out_f32=o) for p, o in zip(P, outs)], N)
+    for p, o in zip(P, outs):
+        single = torch.empty_like(o)
+        ops.gemm(p["a"], p["b"], p["M"], N, K, bias=p["bias"], res=p["res"], out_f32=single)
+        assert torch.equal(o, single)
+    # dgrad kind: dX = dY W (W read MN-major), ReLU gate + column sums
+    if K % 64 == 0:
+        outs = [torch.empty(p["M"], K, device="cuda", dtype=BF) for p in P]
+        cs = [torch.zeros(K, device="cuda") for _ in P]
+        dys = [dev(GS.randn(f"gg/{i}/dy", p["M"], N).to(BF)) for i, p in enumerate(P)]
+        gates = [dev(GS.randn(f"gg/{i}/g2", p["M"], K).to(BF)) for i, p in enumerate(P)]
+        ops.gemm_grouped([dict(a=dy, b=p["b"], M=p["M"], K=N, gate=g_, out_bf16=o, colsum=c) for p, dy, g_, o, c in zip(P, dys, gates, outs, cs)],
+                         K, b_mn=True)
+        for p, dy, g_, o, c in zip(P, dys, gates, outs, cs):
+            single, c1 = torch.empty_like(o), torch.zeros(K, device="cuda")
+            ops.gemm(dy, p["b"], p["M"], K, N, b_mn=True, gate=g_, out_bf16=single, colsum=c1)
+            assert torch.equal(o, single) and rel(c, c1) < 1e-5
+    # wgrad kind
+    dws = [torch.zeros(N, K, device="cuda") for _ in P]
+    dys = [dev(GS.randn(f"gg/{i}/dyw", p["M"], N).to(BF)) for i, p in enumerate(P)]
+    ops.wgrad_grouped([(dy, p["a"], N, K, dw) for p, dy, dw in zip(P, dys, dws)])
+    for p, dy, dw in zip(P, dys, dws):
+        assert rel(dw, dy.float().t() @ p["a"].float()) < 2e-5
+
+
 @pytest.mark.parametrize("M,Nout,Kin", [(300, 512, 2048), (7168, 2048, 512), (128, 1845, 512), (140, 2048, 300), (130, 1536, 512),
                                         (16384, 512, 2048), (16384, 1536, 512), (1000, 2048, 512)])
 def test_gemm_dgrad_mn_major_b_and_colsum(ops, M, Nout, Kin):
