@@ -142,6 +142,12 @@ typedef struct savqa_gemm_problem {
 int savqa_gemm_bf16_grouped(const savqa_gemm_problem_t* problems, int count, int a_mn_major, int b_mn_major, int N, int split_k,
                             savqa_stream_t stream);
 
+/* Scheduling hint for the calling thread's NEXT savqa_gemm_bf16* launches: the persistent CTA-pair kernel takes at most `sms`
+ * SMs (0 = all).  The training step sets it around the GEMMs it puts on side streams (weight gradients, the decoder's K/V
+ * projections of the encoder output, AttModel_x3.py:148-152): a persistent GEMM on every SM would make the decoder's chain of
+ * small kernels on the main stream queue behind whole GEMMs.  Results do not depend on it.  Returns the previous value. */
+int savqa_set_gemm_sm_limit(int sms);
+
 /* ---- a5: graph-weighted attention core (modules.py:246-301 between the projections and the residual) ---
  * For each sample n and head h (channels [h*d,(h+1)*d) of q/k/v):
  *   S = Q K^T / sqrt(d);  S[:, j] = -4294967296 where !key_on[n,j];  optional causal tril mask;

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
   __shared__ uint32_t tmem_slot;
   __shared__ float sStat[RS == 2 ? 2 * 128 * 4 : 1];  // per-half partial row statistics (recompute path only)
   __shared__ float sT[128];                            // t_i = <dO_i, O_i> = sum_j W_ij dW_ij  (statistics path)
+  __shared__ uint32_t sKeyBits[8];                     // bit j of word w: key 32 w + j exists and is switched on (Tk <= 256)
   pdl_trigger();
   const savqa_attn_args_t& a = p.a;
   const int tid = threadIdx.x;
@@ -160,6 +161,12 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
   if (tid < 32) tmem_alloc_rt(&tmem_slot, static_cast<uint32_t>(p.tmem_cols));
   pdl_wait();
   for (int j = tid; j < a.Tk; j += NT) sKeyOn[j] = a.key_on ? a.key_on[static_cast<long>(n) * a.Tk + j] : 1.0f;
+  for (int w = tid >> 5; w < wpr; w += NT / 32) {
+    const int col = w * 32 + (tid & 31);
+    const bool on = col < a.Tk && (a.key_on == nullptr || a.key_on[static_cast<long>(n) * a.Tk + col] != 0.0f);
+    const uint32_t word = __ballot_sync(0xffffffffu, on);
+    if ((tid & 31) == 0) sKeyBits[w] = word;
+  }
   if (a.graph_bits) {
     for (int idx = tid; idx < 128 * wpr; idx += NT) {
       const int row = idx / wpr, w = idx % wpr;
@@ -319,7 +326,7 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
         float s = __uint_as_float(r[j]) * inv_sqrt_d;
         if (sKeyOn[col] == 0.0f) s = kMaskFill;
         if (a.causal && col > i) s = kMaskFill;
-        const float e = __expf(s - m);
+        const float e = ex2_approx(s == kMaskFill ? (kMaskFill - m) * kLog2e : fmaf(__uint_as_float(r[j]), inv_sqrt_d * kLog2e, -m * kLog2e));
         const float ge = g[j] * e;
         Z += e;
         R += fabsf(ge);
@@ -354,9 +361,45 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
 
   const int wch_lo = (RS == 2 && half == 1) ? kc2 : 0;            // 2 * kc2 chunks of 32 columns, zero fill past Tk included
   const int wch_hi = (RS == 2 && half == 0) ? kc2 : 2 * kc2;
+  // Fast row pass (the training step): forward statistics, no causal mask, 0/1 graph bit-packed (or none).  Same e = 2^(raw c2 - m2)
+  // as the forward kernel; the per-row factors are folded so that a score costs ~14 instructions (was ~40).
+  const bool fast = a.stats != nullptr && !a.causal && (a.graph_bits != nullptr || renorm == 0);
+  const float okf = row_ok ? 1.0f : 0.0f;
+  const float c2 = inv_sqrt_d * kLog2e, m2 = m * kLog2e, marg = (kMaskFill - m) * kLog2e;
+  const float sq = scale * qon * okf;                          // W' = ge sq
+  const float ca = sq * inv_sqrt_d;                            // dS = ge (dW_raw ca - cb) - cc e, zero on masked keys
+  const float cb = scale * alpha * tsum * inv_sqrt_d * okf;
+  const float cc = beta * inv_z * tsum * inv_sqrt_d * okf;
   for (int c0 = wch_lo * 32; c0 < wch_hi * 32; c0 += 32) {
     float ds[32], wq[32];
-    if (c0 < a.Tk) {  // warp-uniform: the TMEM loads are .sync.aligned
+    if (fast && c0 < a.Tk) {
+      uint32_t r[32], w[32];
+      __syncwarp();
+      tmem_ld_32x32(t_lane + c0, r);
+      tmem_ld_32x32(t_lane + p.dw_off + c0, w);
+      const uint32_t vw = (c0 + 32 <= a.Tk) ? 0xffffffffu : ((1u << (a.Tk - c0)) - 1u);
+      const uint32_t kw = sKeyBits[c0 >> 5];
+      const uint32_t gw = renorm != 0 ? bits_row[c0 >> 5] : 0xffffffffu;
+      tmem_ld_wait();
+      float e[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float arg = fmaf(__uint_as_float(r[j]), c2, -m2);
+        e[j] = ex2_approx(((kw >> j) & 1u) ? arg : marg);
+      }
+      if (vw != 0xffffffffu) {  // last, partial chunk (warp-uniform)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) e[j] = ((vw >> j) & 1u) ? e[j] : 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        // the weight exactly as the forward's P V MMA used it (bf16-rounded before the scale)
+        const float ge = __bfloat162float(__float2bfloat16_rn(((gw >> j) & 1u) ? e[j] : 0.0f));
+        const float dsv = fmaf(ge, fmaf(__uint_as_float(w[j]), ca, -cb), -cc * e[j]);
+        ds[j] = ((kw >> j) & 1u) ? dsv : 0.0f;  // masked scores are constants
+        wq[j] = ge * sq;
+      }
+    } else if (c0 < a.Tk) {  // warp-uniform: the TMEM loads are .sync.aligned
       uint32_t r[32], w[32];
       __syncwarp();
       tmem_ld_32x32(t_lane + c0, r);
@@ -373,7 +416,7 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
           bool masked = false;
           if (sKeyOn[col] == 0.0f) { s = kMaskFill; masked = true; }
           if (a.causal && col > i) { s = kMaskFill; masked = true; }
-          const float e = __expf(s - m);
+          const float e = ex2_approx(s == kMaskFill ? (kMaskFill - m) * kLog2e : fmaf(__uint_as_float(r[j]), inv_sqrt_d * kLog2e, -m * kLog2e));
           // statistics path: the weight exactly as the forward's P V MMA used it (bf16-rounded before the scale), so that
           // sum_j dS_ij vanishes to fp32 accuracy against t = <dO~_i, O_i>
           const float ge = a.stats ? __bfloat162float(__float2bfloat16_rn(g[j] * e)) : g[j] * e;

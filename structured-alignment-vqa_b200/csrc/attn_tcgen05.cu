@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_tma, bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t sKeyBits[16];  // bit j of word w: key 32 w + j exists and is switched on (Tk <= 512)
   pdl_trigger();
   const savqa_attn_args_t& a = p.a;
   const int t = threadIdx.x, warp = t >> 5;
@@ -81,6 +82,12 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
   if (warp == 0) tmem_alloc_rt(&tmem_slot, static_cast<uint32_t>(p.tmem_cols));
   pdl_wait();
   for (int j = t; j < a.Tk; j += 128) sKeyOn[j] = a.key_on ? a.key_on[static_cast<long>(n) * a.Tk + j] : 1.0f;
+  for (int w = warp; w < wpr; w += 4) {
+    const int col = w * 32 + (t & 31);
+    const bool on = col < a.Tk && (a.key_on == nullptr || a.key_on[static_cast<long>(n) * a.Tk + col] != 0.0f);
+    const uint32_t word = __ballot_sync(0xffffffffu, on);
+    if ((t & 31) == 0) sKeyBits[w] = word;
+  }
   if (a.graph_bits) {
     for (int idx = t; idx < 128 * wpr; idx += 128) {
       const int row = idx / wpr, w = idx % wpr;
@@ -133,6 +140,71 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
   const float* grow = (a.graph && row_ok) ? a.graph + static_cast<long>(n) * a.graph_n_stride + static_cast<long>(i) * a.graph_q_stride : nullptr;
 
   float m = -INFINITY;
+  float Z = 0.0f, R = 0.0f, SA = 0.0f;
+  // Fast row pass (what the training step runs): no causal mask and a 0/1 graph that came bit-packed (or no graph).  The key
+  // mask, the validity of the last chunk and the graph are three 32-bit words per 32-column chunk; e = 2^(raw c2 - m2), the
+  // same expression in attn_bwd_tcgen05.cu.  ~12 instructions per score instead of ~50 (profiles/r1_06_attn_fwd_lines.txt).
+  const bool fast = !a.causal && (a.graph_bits != nullptr || renorm == 0);
+  if (fast) {
+    float mraw = -INFINITY;
+    uint32_t any_off = 0;
+    for (int c0 = 0; c0 < a.Tk; c0 += 32) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld_32x32(t_lane + c0, r);
+      const uint32_t vw = (c0 + 32 <= a.Tk) ? 0xffffffffu : ((1u << (a.Tk - c0)) - 1u);
+      const uint32_t kw = sKeyBits[c0 >> 5];
+      any_off |= vw & ~kw;
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mraw = fmaxf(mraw, ((kw >> j) & 1u) ? __uint_as_float(r[j]) : -INFINITY);
+    }
+    m = mraw * inv_sqrt_d;                      // max and the positive scale commute exactly
+    if (any_off) m = fmaxf(m, kMaskFill);       // a masked key takes part in the row maximum with the fill value (modules.py:269-274)
+    const float c2 = inv_sqrt_d * kLog2e, m2 = m * kLog2e;
+    const float marg = (kMaskFill - m) * kLog2e;  // exponent of a masked key: 0 when every key is masked (uniform row), else e = 0
+    for (int c0 = 0; c0 < p.tk_chunks * 64; c0 += 32) {
+      float ge[32];
+      if (c0 < a.Tk) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld_32x32(t_lane + c0, r);
+        const uint32_t vw = (c0 + 32 <= a.Tk) ? 0xffffffffu : ((1u << (a.Tk - c0)) - 1u);
+        const uint32_t kw = sKeyBits[c0 >> 5];
+        const uint32_t gw = renorm != 0 ? sBits[t * wpr + (c0 >> 5)] : 0xffffffffu;
+        tmem_ld_wait();
+        float e[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float arg = fmaf(__uint_as_float(r[j]), c2, -m2);
+          e[j] = ex2_approx(((kw >> j) & 1u) ? arg : marg);
+        }
+        if (vw != 0xffffffffu) {  // last, partial chunk (warp-uniform)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) e[j] = ((vw >> j) & 1u) ? e[j] : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float w = ((gw >> j) & 1u) ? e[j] : 0.0f;
+          Z += e[j];
+          SA += w;
+          ge[j] = w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ge[j] = 0.0f;
+      }
+      uint8_t* prow = sP + (c0 >> 6) * 16384 + t * 128;
+      const int u0 = (c0 & 63) >> 3;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint4 v = make_uint4(pack_bf16x2(ge[8 * u], ge[8 * u + 1]), pack_bf16x2(ge[8 * u + 2], ge[8 * u + 3]),
+                                   pack_bf16x2(ge[8 * u + 4], ge[8 * u + 5]), pack_bf16x2(ge[8 * u + 6], ge[8 * u + 7]));
+        *reinterpret_cast<uint4*>(prow + (((u0 + u) ^ (t & 7)) << 4)) = v;
+      }
+    }
+    R = SA;  // 0/1 graph: |G e| = G e
+  } else {
   for (int c0 = 0; c0 < a.Tk; c0 += 32) {
     uint32_t r[32];
     __syncwarp();
@@ -149,7 +221,6 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
       }
     }
   }
-  float Z = 0.0f, R = 0.0f, SA = 0.0f;
   for (int c0 = 0; c0 < p.tk_chunks * 64; c0 += 32) {
     uint32_t r[32];
     float ge[32];
@@ -185,7 +256,7 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
           float s = __uint_as_float(r[j]) * inv_sqrt_d;
           if (sKeyOn[col] == 0.0f) s = kMaskFill;
           if (a.causal && col > i) s = kMaskFill;
-          e = __expf(s - m);
+          e = ex2_approx(s == kMaskFill ? (kMaskFill - m) * kLog2e : fmaf(__uint_as_float(r[j]), inv_sqrt_d * kLog2e, -m * kLog2e));
           w = g[j] * e;
         }
         Z += e;
@@ -207,6 +278,7 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
       *reinterpret_cast<uint4*>(prow + (((u0 + u) ^ (t & 7)) << 4)) = v;
     }
   }
+  }  // generic row pass
   float scale;
   bool clamped = false;
   if (renorm == 1) {
@@ -240,7 +312,7 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
             if (sKeyOn[col] == 0.0f) s = kMaskFill;
             if (a.causal && col > i) s = kMaskFill;
             const float g = (renorm == 0) ? 1.0f : (a.graph_bits ? (((sBits[t * wpr + (col >> 5)] >> (col & 31)) & 1u) ? 1.0f : 0.0f) : (grow ? __ldg(grow + col) : 1.0f));
-            arow[col] = g * __expf(s - m) * scale;
+            arow[col] = g * ex2_approx(s == kMaskFill ? (kMaskFill - m) * kLog2e : fmaf(__uint_as_float(r[j]), inv_sqrt_d * kLog2e, -m * kLog2e)) * scale;
           }
         }
       }

@@ -19,12 +19,19 @@
 
 namespace savqa {
 
+int gemm2_set_sm_limit(int sms);
 int gemm2_launch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
                  const savqa_gemm_epilogue_t* epi, int split_k, cudaStream_t stream, bool* handled);
 int gemm2_launch_group(const savqa_gemm_problem_t* probs, int count, int a_mn, int b_mn, int N, int split_k, cudaStream_t stream,
                        bool* handled);
 
 namespace {
+
+thread_local int t_sm_limit = 0;  // savqa_set_gemm_sm_limit: SMs the next launches of this thread may occupy (0 = all)
+
+#ifndef SAVQA_GEMM2_DIAG
+#define SAVQA_GEMM2_DIAG 0  // bring-up aid (tools/build_variants.sh): 1 = no TMA stores, 2 = no staging writes either, 3 = TMEM loads only
+#endif
 
 constexpr int BM = 128;   // rows per CTA (256 per pair)
 constexpr int BK = 64;    // 64 bf16 = one 128-byte swizzle row
@@ -213,6 +220,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     constexpr int CW = (EPI == EPI_BF16) ? 64 : 32;  // columns per chunk = 128 bytes of output per row
     constexpr int NCH = BN / CW;
     int it = 0;
+#if SAVQA_GEMM2_DIAG
+    uint32_t sink = 0;
+#endif
     for (int gtile = pair; gtile < num_tiles; gtile += num_pairs, ++it) {
       const int gi = gtile >= g.tiles0 ? 1 : 0;
       const Gemm2Params& p = g.p[gi];
@@ -263,6 +273,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
         }
       };
+      constexpr int NH = CW / 32;  // 32-column halves of a chunk (2 for bf16 output, 1 for fp32)
       if (half < NCH) load_aux(half, aux);
       mbar_wait(&tmem_full_bar[as], (it >> 1) & 1);
       tc_fence_after();
@@ -271,7 +282,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int gcol = ncol0 + c * CW;
         const bool last = c + 2 >= NCH;
         if (!last) load_aux(c + 2, aux_next);
-        constexpr int NH = CW / 32;  // 32-column halves of the chunk (2 for bf16 output, 1 for fp32)
         const bool active = gcol < p.N;  // warp-uniform
         {
 #pragma unroll
@@ -292,7 +302,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               if (lane == 0) mbar_arrive_cluster(as ? empty_remote1 : empty_remote0);
             }
             if (!active) continue;
-            if constexpr (EPI != EPI_ATOMIC) {
+#if SAVQA_GEMM2_DIAG >= 3
+            sink ^= __float_as_uint(v[0]) ^ __float_as_uint(v[31]);
+            continue;
+#endif
+            if constexpr (EPI != EPI_ATOMIC && SAVQA_GEMM2_DIAG == 0) {
               if (h == 0) {
                 // staging tile free?  (the TMA store of this warp's previous chunk has finished reading it); asked as late as
                 // possible: the TMEM load and the wait above have already covered most of that store's latency
@@ -326,10 +340,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 }
               }
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
-                *reinterpret_cast<uint4*>(buf + srow + ((static_cast<uint32_t>(4 * h + u) ^ sxor) << 4)) =
-                    make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
-                               pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+              for (int u = 0; u < 4; ++u) {
+                const uint4 pk = make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                                            pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+#if SAVQA_GEMM2_DIAG >= 2
+                sink ^= pk.x ^ pk.y ^ pk.z ^ pk.w;
+#else
+                *reinterpret_cast<uint4*>(buf + srow + ((static_cast<uint32_t>(4 * h + u) ^ sxor) << 4)) = pk;
+#endif
+              }
             } else {
               if (e.res && row_ok) {
 #pragma unroll
@@ -371,10 +390,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               atomicAdd(e.colsum + gcol + 32 * h + lane, cs);
             }
           }
-          if constexpr (EPI != EPI_ATOMIC) {
+          if constexpr (EPI != EPI_ATOMIC && SAVQA_GEMM2_DIAG <= 1) {
             if (active) fence_proxy_async_smem();
             __syncwarp();
-            if (active && lane == 0) {
+            if (SAVQA_GEMM2_DIAG == 0 && active && lane == 0) {
               tma_store_2d(tmO, buf, gcol, row0);  // rows past M / columns past N are clipped by the TMA unit
               tma_store_commit();
             }
@@ -387,6 +406,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
     }
     if (EPI != EPI_ATOMIC && lane == 0) tma_store_wait_all();  // the staging smem must outlive the last store's reads
+#if SAVQA_GEMM2_DIAG
+    if (sink == 0x12345677u) buf[0] = 1;  // keeps the diagnostic variants' arithmetic alive
+#endif
   }
 
   tc_fence_before();
@@ -410,7 +432,8 @@ int launch2(const Maps& m, const Gemm2Group& g, cudaStream_t stream) {
   using C = Cfg2<BN>;
   auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN, EPI>;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "savqa_gemm_bf16 (CTA-pair kernel)")) return rc;
-  const int max_pairs = sm_count() / 2;
+  int max_pairs = sm_count() / 2;
+  if (t_sm_limit > 0 && t_sm_limit / 2 < max_pairs) max_pairs = t_sm_limit / 2 > 0 ? t_sm_limit / 2 : 1;
   const int pairs = g.num_tiles < max_pairs ? g.num_tiles : max_pairs;
   SAVQA_CHECK_CUDA(launch_kernel(true, kern, dim3(2 * pairs), dim3(kThreads), C::kSmemBytes, stream, m.a[0], m.b[0], m.o[0], m.a[1], m.b[1],
                                  m.o[1], g));
@@ -510,7 +533,8 @@ int gemm2_launch_group(const savqa_gemm_problem_t* probs, int count, int a_mn, i
   for (int i = 1; i < count; ++i)
     if (pair_mode(probs[i].A, probs[i].B, a_mn, b_mn, probs[i].M, N, probs[i].epilogue) != mode) return SAVQA_OK;
 
-  const int pairs = sm_count() / 2;
+  int pairs = sm_count() / 2;
+  if (t_sm_limit > 0 && t_sm_limit / 2 < pairs) pairs = t_sm_limit / 2 > 0 ? t_sm_limit / 2 : 1;
   Gemm2Group g;
   memset(&g, 0, sizeof(g));
   long tiles256 = 0;
@@ -562,6 +586,12 @@ int gemm2_launch_group(const savqa_gemm_problem_t* probs, int count, int a_mn, i
   *handled = true;
   if (BN == 256) return launch2_epi<256>(mode, a_mn != 0, b_mn != 0, m, g, stream);
   return launch2_epi<128>(mode, a_mn != 0, b_mn != 0, m, g, stream);
+}
+
+int gemm2_set_sm_limit(int sms) {
+  const int old = t_sm_limit;
+  t_sm_limit = sms > 0 ? sms : 0;
+  return old;
 }
 
 int gemm2_launch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,

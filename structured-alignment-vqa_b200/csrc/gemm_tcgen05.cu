@@ -425,6 +425,9 @@ extern "C" int savqa_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const
   }
 }
 
+namespace savqa { int gemm2_set_sm_limit(int sms); }
+extern "C" int savqa_set_gemm_sm_limit(int sms) { return savqa::gemm2_set_sm_limit(sms); }
+
 extern "C" int savqa_gemm_bf16_grouped(const savqa_gemm_problem_t* problems, int count, int a_mn_major, int b_mn_major, int N, int split_k,
                                        savqa_stream_t stream_) {
   using namespace savqa;

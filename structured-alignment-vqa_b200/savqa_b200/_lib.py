@@ -11,7 +11,8 @@ from typing import Optional
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_PKG), "lib", "libsavqa_b200.so")
+# SAVQA_LIB: another build of the SAME library (kernel experiments, tools/build_variants.sh); never a different backend
+LIB_PATH = os.environ.get("SAVQA_LIB") or os.path.join(os.path.dirname(_PKG), "lib", "libsavqa_b200.so")
 
 i64 = C.c_int64
 vp = C.c_void_p
@@ -61,6 +62,7 @@ SIGNATURES = {
     "savqa_layernorm_bwd": [vp, vp, vp, C.c_float, i64, C.c_int, vp, vp, vp, vp, vp, vp, vp],
     "savqa_gemm_bf16": [vp, i64, C.c_int, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(GemmEpilogue), C.c_int, vp],
     "savqa_gemm_bf16_grouped": [C.POINTER(GemmProblem), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "savqa_set_gemm_sm_limit": [C.c_int],
     "savqa_graph_attn_fwd": [C.POINTER(AttnArgs), vp],
     "savqa_graph_attn_bwd": [C.POINTER(AttnArgs), vp],
     "savqa_answer_loss": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp, vp],

@@ -7,6 +7,7 @@ MMA operands (activations / weights / probabilities) are bf16, accumulation is f
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -26,6 +27,9 @@ WEIGHT_EPOCH = 0
 ATTN_ENGINE = 0
 #: bound weight packs launch their weight-gradient GEMMs on a second stream (see WeightPack.weight_grad)
 WGRAD_SIDE_STREAM = True
+#: SMs the persistent GEMMs on the side streams may occupy (0 = all): the rest stays free for the main streams' kernels, so the
+#: decoder's chain of small launches does not queue behind whole GEMMs (savqa_set_gemm_sm_limit)
+SIDE_GEMM_SMS = int(os.environ.get("SAVQA_SIDE_SMS", "116"))
 _WGRAD_STREAMS = {}  # compute stream -> its weight-gradient stream
 _WGRAD_DIRTY = []    # weight-gradient streams with work launched since the last join
 
@@ -132,8 +136,10 @@ class WeightPack:
         """fp32 [n] that the producer of dY accumulates the bias gradient into (the flat-gradient view when bound)."""
         return self.gb if self.bound else torch.zeros(n, device=dev, dtype=F32)
 
-    def weight_grad(self, dyb: Tensor, xb: Tensor, n_out: int, k_in: int) -> Tensor:
-        """dW[n_out, k_in] (+)= dY^T X on the tensor cores, into the flat-gradient view when bound.
+    def weight_grad(self, dyb: Tensor, xb: Tensor, n_out: int, k_in: int, bias_grad: Optional[Tensor] = None) -> Tensor:
+        """dW[n_out, k_in] (+)= dY^T X on the tensor cores, into the flat-gradient view when bound.  `bias_grad` (fp32 [n_out],
+        optional) += the column sums of dY on the same stream: a bias gradient that no epilogue upstream could produce cheaply
+        (the K = 512 dgrad GEMM that writes dY is epilogue-bound: the in-epilogue column sums cost it 40 % -- profiles/r1_06).
 
         Bound packs: nothing downstream in the backward pass reads dW (only the optimizer does), so the GEMM goes to a second
         stream and leaves the dgrad chain -- which is a chain of launch-latency-bound M = B kernels in the decoder -- alone.
@@ -146,8 +152,10 @@ class WeightPack:
                 side.wait_stream(cur)
                 if side not in _WGRAD_DIRTY:
                     _WGRAD_DIRTY.append(side)
-                with torch.cuda.stream(side):
+                with torch.cuda.stream(side), ops.gemm_sm_limit(SIDE_GEMM_SMS):
                     ops.wgrad(dyb, xb, n_out, k_in, dW)
+                    if bias_grad is not None:
+                        ops.colsum_bf16(dyb[:, :n_out], bias_grad)
                 # the operands are temporaries of the caller: keep their memory from being re-used before the side stream is done
                 dyb.record_stream(side)
                 xb.record_stream(side)
@@ -155,6 +163,8 @@ class WeightPack:
         else:
             dW = torch.zeros(n_out, k_in, device=dyb.device, dtype=F32)
         ops.wgrad(dyb, xb, n_out, k_in, dW)
+        if bias_grad is not None:
+            ops.colsum_bf16(dyb[:, :n_out], bias_grad)
         return dW
 
     def out(self, t: Optional[Tensor]) -> Optional[Tensor]:
@@ -366,11 +376,14 @@ class LayerNormFn(Function):
         ctx.eps = eps
         ctx.sink = sink or _NO_SINK
         ctx.mark_non_differentiable(yb, on)
+        ctx.set_materialize_grads(False)  # no zero-fill launches for the gradients of the non-differentiable outputs
         return y, yb, on
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy, _dyb, _don):
+        if dy is None:
+            return None, None, None, None, None
         x, gamma = ctx.saved_tensors
         dg, db = ctx.sink.buffers(gamma)
         dx, _ = ops.layernorm_bwd(dy.contiguous(), x, gamma.detach(), ctx.eps, dg, db)
@@ -511,7 +524,7 @@ class GraphAttentionFn(Function):
                     # depends only on `memory`: off the decoder's kernel chain, onto the side stream
                     cur = torch.cuda.current_stream()
                     holder.side.wait_event(holder.ready)
-                    with torch.cuda.stream(holder.side):
+                    with torch.cuda.stream(holder.side), ops.gemm_sm_limit(SIDE_GEMM_SMS):
                         ops.gemm(k_bf16, pkv.w, Mk, 2 * C, C, bias=pkv.bias, relu=True, out_bf16=kv)
                     kv.record_stream(holder.side)
                     cur.wait_stream(holder.side)
@@ -553,11 +566,14 @@ class GraphAttentionFn(Function):
         ctx.save_for_backward(q_bf16, k_bf16, v_bf16, q, k, v, g, q_on, k_on, pre, gamma, stats, o if stats is not None else None)
         outs = (y, yb, y_on) + ((att,) if want_att else ())
         ctx.mark_non_differentiable(yb, y_on, *((att,) if want_att else ()))
+        ctx.set_materialize_grads(False)  # autograd would otherwise zero-fill a gradient for yb / y_on / att (two launches per module)
         return outs
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy, *_unused):
+        if dy is None:
+            return (None,) * 17
         q_bf16, k_bf16, v_bf16, q, k, v, g, q_on, k_on, pre, gamma, stats, fwd_o = ctx.saved_tensors
         cfg, mode = ctx.cfg, ctx.mode
         N, Tq, Tk, C, H, d = ctx.dims
@@ -592,12 +608,17 @@ class GraphAttentionFn(Function):
             dk = torch.empty(Mk, C, device=dev, dtype=BF16)
             dv = torch.empty(Mk, C, device=dev, dtype=BF16)
             dbq, dbk, dbv = pq.bias_grad_buffer(C, dev), pk_.bias_grad_buffer(C, dev), pv_.bias_grad_buffer(C, dev)
+        # encoder self-attention (fused QKV, Tq > 1): the bias gradient is one column-sum launch over dqkv next to the weight
+        # gradient on the side stream -- inside the attention kernel the 6 warp-transpose reductions per thread were ~17 % of its
+        # instructions (profiles/r1_06_attn_bwd_lines.txt); the one-query decoder kernels keep theirs
+        bias_outside = mode == 0 and Tq > 1
         ops.graph_attention_bwd(q, k, v, g, k_on, q_on, N, H, Tq, Tk, d, cfg["causal"], ctx.renorm_eff, dpre2, dq, dk, dv,
-                                dbq=dbq, dbk=dbk, dbv=dbv, graph_bits=ctx.gbits, stats=stats, fwd_out=fwd_o)
+                                dbq=None if bias_outside else dbq, dbk=None if bias_outside else dbk, dbv=None if bias_outside else dbv,
+                                graph_bits=ctx.gbits, stats=stats, fwd_out=fwd_o)
 
         dxq = dxk = dxv = None
         if mode == 0:
-            dW = pqkv.weight_grad(dqkv, q_bf16, 3 * C, C)
+            dW = pqkv.weight_grad(dqkv, q_bf16, 3 * C, C, bias_grad=db if bias_outside else None)
             dWq, dWk, dWv = dW[:C], dW[C:2 * C], dW[2 * C:]
             if need[0] or need[1] or need[2]:
                 dxq = torch.empty(Mq, C, device=dev, dtype=F32)
@@ -624,7 +645,7 @@ class GraphAttentionFn(Function):
                     holder.side.wait_stream(cur)
                     if holder.side not in _WGRAD_DIRTY:
                         _WGRAD_DIRTY.append(holder.side)
-                    with torch.cuda.stream(holder.side):
+                    with torch.cuda.stream(holder.side), ops.gemm_sm_limit(SIDE_GEMM_SMS):
                         ops.gemm(dkv, pkv.w, Mk, C, 2 * C, b_mn=True, out_f32=holder.dmem, accumulate=0 if first else 2)
                     dkv.record_stream(holder.side)
                 elif need[1] or need[2]:
@@ -675,11 +696,14 @@ class FeedForwardFn(Function):
         ctx.cfg, ctx.dims = cfg, (M, C, Hd)
         ctx.save_for_backward(xb, h, z, gamma)
         ctx.mark_non_differentiable(yb, y_on)
+        ctx.set_materialize_grads(False)
         return y, yb, y_on
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy, *_unused):
+        if dy is None:
+            return (None,) * 9
         xb, h, z, gamma = ctx.saved_tensors
         cfg = ctx.cfg
         M, C, Hd = ctx.dims
@@ -691,11 +715,12 @@ class FeedForwardFn(Function):
         db2 = p2.bias_grad_buffer(C, dev)
         dz, dzb = ops.layernorm_bwd(dy.contiguous().reshape(M, C), z, gamma.detach(), cfg["eps"], dgamma, dbeta, want_bf16=True, dxsum=db2)
         dW2 = p2.weight_grad(dzb, h, C, Hd)
-        # conv1: h = relu(x W1^T + b1).  ReLU backward and db1 = column sums of dh fused in the dgrad epilogue
+        # conv1: h = relu(x W1^T + b1).  ReLU backward fused in the dgrad epilogue; db1 = column sums of dh next to the weight
+        # gradient (off the dgrad chain)
         db1 = p1.bias_grad_buffer(Hd, dev)
         dh = torch.empty(M, Hd, device=dev, dtype=BF16)
-        dgrad(dzb, p2, M, Hd, C, gate=h, out_bf16=dh, colsum=db1)
-        dW1 = p1.weight_grad(dh, xb, Hd, C)
+        dgrad(dzb, p2, M, Hd, C, gate=h, out_bf16=dh)
+        dW1 = p1.weight_grad(dh, xb, Hd, C, bias_grad=db1)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, C, device=dev, dtype=F32)

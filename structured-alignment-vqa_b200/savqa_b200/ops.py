@@ -4,6 +4,7 @@ No function in this file computes anything with torch ops.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 from typing import Optional, Tuple
@@ -275,6 +276,20 @@ def _fill_epilogue(e, M, N, bias, res, rowtab, rowtab_period, gate, relu, alpha,
     if colsum is not None:
         assert colsum.is_contiguous() and colsum.numel() >= N and split_k == 1
         e.colsum = ptr(colsum)
+
+
+@contextlib.contextmanager
+def gemm_sm_limit(sms: int):
+    """The GEMMs launched inside (by this thread) leave 148 - sms SMs to kernels of other streams: savqa_set_gemm_sm_limit."""
+    if not sms:
+        yield
+        return
+    lib = _lib.load()
+    old = lib.savqa_set_gemm_sm_limit(int(sms))
+    try:
+        yield
+    finally:
+        lib.savqa_set_gemm_sm_limit(old)
 
 
 def gemm_grouped(problems, N: int, *, a_mn: bool = False, b_mn: bool = False, split_k: int = 1) -> None:

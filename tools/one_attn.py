@@ -30,11 +30,15 @@ g1 = torch.ones(N, 1, T, device="cuda")
 on1 = torch.ones(N, device="cuda")
 dout1 = torch.randn(N, C, device="cuda")
 dq1 = torch.empty(N, C, device="cuda", dtype=BF)
+# as the training step drives them: bit-packed graph, forward row statistics reused by the backward
+bits = ops.pack_graph_bits(graph)
+stats = torch.empty(H * N * T * 4, device="cuda")
 if kind == "fwd":
-    fn = lambda: ops.graph_attention_fwd(q, k, v, graph, on, on, N, H, T, T, d, False, 1, False, 0)  # noqa: E731
+    fn = lambda: ops.graph_attention_fwd(q, k, v, graph, on, on, N, H, T, T, d, False, 1, False, 0, graph_bits=bits, stats=stats)  # noqa: E731
 elif kind == "bwd":
+    fwd_out, _ = ops.graph_attention_fwd(q, k, v, graph, on, on, N, H, T, T, d, False, 1, False, 0, graph_bits=bits, stats=stats)
     fn = lambda: ops.graph_attention_bwd(q, k, v, graph, on, on, N, H, T, T, d, False, 1, dout, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:],  # noqa: E731
-                                         dbq=db[0], dbk=db[1], dbv=db[2])
+                                         dbq=db[0], dbk=db[1], dbv=db[2], graph_bits=bits, stats=stats, fwd_out=fwd_out)
 elif kind == "row1f":
     fn = lambda: ops.graph_attention_fwd(q1, k, v, g1, on, on1, N, H, 1, T, d, False, 1, False, 1)  # noqa: E731
 else:
