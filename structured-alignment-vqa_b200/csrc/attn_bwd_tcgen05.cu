@@ -13,6 +13,8 @@
 //   epilogue  ReLU gates of the Q/K/V projections (modules.py:227-229) applied from q/k/v, bf16 stores into the
 //             fused [.., 3C] gradient layout.
 // Formulas: SURVEY.md Appendix A (verified against autograd); attn_simt.cu is the fp32 restatement of the same maths.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace savqa {
@@ -526,6 +528,311 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two-CTAs-per-SM variant for the training step's symbolic branch (64 < Tk <= 128, Tq <= 128, d = 64, forward statistics,
+// no causal mask, 0/1 graph bit-packed or absent).  The W' and dS tiles share ONE shared-memory tile: the row pass writes W'
+// and keeps its 64 dS values packed in 32 registers; dV = W'^T dO is issued alone; once it has read the tile the dS values
+// overwrite it and dQ / dK follow, while the dV accumulator is already being stored.  96 KB of tiles instead of 128 KB and
+// 128 registers x 256 threads let two CTAs share an SM, so that one CTA's TMA / MMA / epilogue latencies hide under the
+// other's row pass (the one-CTA kernel ran at IPC 0.24 with 42 % of its stalls on memory: profiles/r1_06_attn_bwd_lines.txt).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256, 2) attn_bwd_tc1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                             const __grid_constant__ CUtensorMap tmV, const BwdParams p) {
+  constexpr int DCH = D / 64;
+  constexpr int NT = 256;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_tma, bar_s, bar_v, bar_o;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float sT[128];           // t_i = <dO_i, O_i>
+  __shared__ uint32_t sKeyBits[4];    // bit j of word w: key 32 w + j exists and is switched on
+  pdl_trigger();
+  const savqa_attn_args_t& a = p.a;
+  const int tid = threadIdx.x;
+  const int t = tid & 127;       // query row / key row / TMEM lane of this thread
+  const int half = tid >> 7;     // which 64 key columns (row pass) / which 32 head columns (epilogue) it works on
+  const int warp = t >> 5;       // TMEM lane quadrant
+  const int hn = blockIdx.x;
+  const int h = hn / a.N, n = hn % a.N;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sX = smem;                            // 2 x [128][128 B]   W', then dS
+  uint8_t* sQ = sX + 2 * 16384;                  // DCH x [128][128 B]
+  uint8_t* sdO = sQ + DCH * 16384;               // DCH x [128][128 B]
+  uint8_t* sK = sdO + DCH * 16384;               // DCH x [kv_rows][128 B]
+  uint8_t* sV = sK + DCH * p.kv_rows * 128;      // DCH x [kv_rows][128 B]
+  const int wpr = (a.Tk + 31) >> 5;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(&bar_tma, 1);
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_v, 1);
+    mbar_init(&bar_o, 1);
+    fence_barrier_init();
+    pdl_wait();
+    const uint32_t bytes = static_cast<uint32_t>(DCH) * (16384u + 2u * static_cast<uint32_t>(p.kv_rows) * 128u);
+    mbar_arrive_expect_tx(&bar_tma, bytes);
+    for (int c = 0; c < DCH; ++c) {
+      tma_load_3d(sQ + c * 16384, &tmQ, &bar_tma, h * D + c * 64, 0, n);
+      tma_load_3d(sK + c * p.kv_rows * 128, &tmK, &bar_tma, h * D + c * 64, 0, n);
+      tma_load_3d(sV + c * p.kv_rows * 128, &tmV, &bar_tma, h * D + c * 64, 0, n);
+    }
+  }
+  __syncwarp();
+  if (tid < 32) tmem_alloc_rt(&tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+  pdl_wait();
+  for (int w = tid >> 5; w < wpr; w += NT / 32) {
+    const int col = w * 32 + (tid & 31);
+    const bool on = col < a.Tk && (a.key_on == nullptr || a.key_on[static_cast<long>(n) * a.Tk + col] != 0.0f);
+    const uint32_t word = __ballot_sync(0xffffffffu, on);
+    if ((tid & 31) == 0) sKeyBits[w] = word;
+  }
+  const int i = t;
+  const bool row_ok = i < a.Tq;
+  // this thread's two graph words (its 64 key columns of query row i), straight from global memory
+  uint32_t gwd[2] = {0xffffffffu, 0xffffffffu};
+  if (a.graph_bits && a.renorm != 0) {
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int w = half * 2 + cc;
+      gwd[cc] = (row_ok && w < wpr) ? __ldg(a.graph_bits + static_cast<long>(n) * a.bits_n_stride + static_cast<long>(i) * a.bits_q_stride + w) : 0u;
+    }
+  }
+
+  // ---- dO: fp32 [Tq, D] head slice -> bf16 K-major swizzled tile (rows >= Tq are zero), and t = <dO~, O> ----
+  {
+    constexpr int V4 = D / 4;
+    constexpr int kIters = V4 / 2;
+    float4 dv[kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int idx = tid + it * NT;
+      const int row = idx / V4, col = (idx % V4) * 4;
+      dv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < a.Tq) {
+        const float* src = a.dout + (static_cast<long>(n) * a.Tq + row) * a.ld_dout + h * D + col;
+        if (p.dvec) dv[it] = __ldg(reinterpret_cast<const float4*>(src));
+        else dv[it] = make_float4(src[0], src[1], src[2], src[3]);
+      }
+    }
+    float part[kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int idx = tid + it * NT;
+      const int row = idx / V4, col = (idx % V4) * 4;
+      part[it] = 0.0f;
+      if (row < a.Tq) {
+        const float* src = a.out + (static_cast<long>(n) * a.Tq + row) * a.ldo + h * D + col;
+        const float4 o = p.ovec ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(src[0], src[1], src[2], src[3]);
+        const float2 d01 = unpack_bf16x2(pack_bf16x2(dv[it].x, dv[it].y)), d23 = unpack_bf16x2(pack_bf16x2(dv[it].z, dv[it].w));
+        part[it] = (d01.x * o.x + d01.y * o.y) + (d23.x * o.z + d23.y * o.w);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      float v = part[it];
+#pragma unroll
+      for (int o = (V4 < 32 ? V4 : 32) / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      const int idx = tid + it * NT;
+      if ((idx % V4) == 0) sT[idx / V4] = v;
+    }
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int idx = tid + it * NT;
+      const int row = idx / V4, col = (idx % V4) * 4;
+      const int cc = col & 63;
+      uint8_t* dst = sdO + (col >> 6) * 16384 + row * 128 + ((((cc >> 3) ^ (row & 7))) << 4) + (cc & 7) * 2;
+      *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(dv[it].x, dv[it].y), pack_bf16x2(dv[it].z, dv[it].w));
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (tid == 0) {
+    mbar_wait(&bar_tma, 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, p.tk_pad16, false, false);
+#pragma unroll
+    for (int k = 0; k < D / 16; ++k) {
+      const int c = k / 4, kk = k % 4;
+      umma_bf16_ss(tmem, umma_smem_desc(smem_u32(sQ + c * 16384) + kk * 32, 16, 1024),
+                   umma_smem_desc(smem_u32(sK + c * p.kv_rows * 128) + kk * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < D / 16; ++k) {
+      const int c = k / 4, kk = k % 4;
+      umma_bf16_ss(tmem + p.dw_off, umma_smem_desc(smem_u32(sdO + c * 16384) + kk * 32, 16, 1024),
+                   umma_smem_desc(smem_u32(sV + c * p.kv_rows * 128) + kk * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(&bar_s);
+  }
+  __syncwarp();
+
+  // ---- row pass: thread (t, half) <-> query row t, key columns [64 half, 64 half + 64) ----
+  mbar_wait(&bar_s, 0);
+  tc_fence_after();
+  const long qrow = static_cast<long>(n) * a.Tq + (row_ok ? i : 0);
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
+  const float qon = (a.query_on && row_ok) ? a.query_on[qrow] : 1.0f;
+  const float4 st = __ldg(reinterpret_cast<const float4*>(a.stats) + static_cast<long>(hn) * a.Tq + (row_ok ? i : 0));
+  const float m = st.x, inv_z = fabsf(st.y), scale = st.z, beta = st.w, alpha = st.y < 0.0f ? 0.0f : 1.0f;
+  const float tsum = sT[t];
+  const float okf = row_ok ? 1.0f : 0.0f;
+  const float c2 = inv_sqrt_d * kLog2e, m2 = m * kLog2e, marg = (kMaskFill - m) * kLog2e;
+  const float sq = scale * qon * okf;                          // W' = ge sq
+  const float ca = sq * inv_sqrt_d;                            // dS = ge (dW_raw ca - cb) - cc e, zero on masked keys
+  const float cb = scale * alpha * tsum * inv_sqrt_d * okf;
+  const float cc_ = beta * inv_z * tsum * inv_sqrt_d * okf;
+  uint32_t dsp[2][16];  // this thread's 64 dS values, bf16 pairs: written to the shared tile once dV = W'^T dO has read W' from it
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c0 = (half * 2 + cc) * 32;
+    float wq[32];
+    if (c0 < a.Tk) {  // warp-uniform
+      uint32_t r[32], w[32];
+      __syncwarp();
+      tmem_ld_32x32(t_lane + c0, r);
+      tmem_ld_32x32(t_lane + p.dw_off + c0, w);
+      const uint32_t vw = (c0 + 32 <= a.Tk) ? 0xffffffffu : ((1u << (a.Tk - c0)) - 1u);
+      const uint32_t kw = sKeyBits[c0 >> 5];
+      const uint32_t gw = gwd[cc];
+      tmem_ld_wait();
+      float e[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float arg = fmaf(__uint_as_float(r[j]), c2, -m2);
+        e[j] = ex2_approx(((kw >> j) & 1u) ? arg : marg);
+      }
+      if (vw != 0xffffffffu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) e[j] = ((vw >> j) & 1u) ? e[j] : 0.0f;
+      }
+      float ds[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float ge = __bfloat162float(__float2bfloat16_rn(((gw >> j) & 1u) ? e[j] : 0.0f));
+        const float dsv = fmaf(ge, fmaf(__uint_as_float(w[j]), ca, -cb), -cc_ * e[j]);
+        ds[j] = ((kw >> j) & 1u) ? dsv : 0.0f;
+        wq[j] = ge * sq;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) dsp[cc][u] = pack_bf16x2(ds[2 * u], ds[2 * u + 1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) wq[j] = 0.0f;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) dsp[cc][u] = 0u;
+    }
+    const int off = (c0 >> 6) * 16384 + t * 128;
+    const int u0 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      *reinterpret_cast<uint4*>(sX + off + (((u0 + u) ^ (t & 7)) << 4)) =
+          make_uint4(pack_bf16x2(wq[8 * u], wq[8 * u + 1]), pack_bf16x2(wq[8 * u + 2], wq[8 * u + 3]),
+                     pack_bf16x2(wq[8 * u + 4], wq[8 * u + 5]), pack_bf16x2(wq[8 * u + 6], wq[8 * u + 7]));
+  }
+
+  // ---- dV = W'^T dO ----
+  const int dq_off = 0, dk_off = D, dv_off = 2 * D;
+  const int ksteps_rows = (a.Tq + 15) / 16;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc_k = umma_idesc_bf16(128, 64, true, true);
+    for (int c = 0; c < DCH; ++c)
+      for (int k = 0; k < ksteps_rows; ++k)
+        umma_bf16_ss(tmem + dv_off + c * 64, umma_smem_desc(smem_u32(sX) + k * 2048, 16384, 1024),
+                     umma_smem_desc(smem_u32(sdO + c * 16384) + k * 2048, 8192, 1024), idesc_k, k > 0 ? 1u : 0u);
+    umma_commit(&bar_v);
+  }
+  __syncwarp();
+  mbar_wait(&bar_v, 0);  // the MMAs have read W': the tile is free for dS
+  tc_fence_after();
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c0 = (half * 2 + cc) * 32;
+    const int off = (c0 >> 6) * 16384 + t * 128;
+    const int u0 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      *reinterpret_cast<uint4*>(sX + off + (((u0 + u) ^ (t & 7)) << 4)) =
+          make_uint4(dsp[cc][4 * u], dsp[cc][4 * u + 1], dsp[cc][4 * u + 2], dsp[cc][4 * u + 3]);
+  }
+  // ---- dQ = dS K, dK = dS^T Q ----
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc_q = umma_idesc_bf16(128, 64, false, true);
+    const uint32_t idesc_k = umma_idesc_bf16(128, 64, true, true);
+    const int ksteps_keys = p.tk_pad16 / 16;
+    for (int c = 0; c < DCH; ++c)
+      for (int k = 0; k < ksteps_keys; ++k)
+        umma_bf16_ss(tmem + dq_off + c * 64, umma_smem_desc(smem_u32(sX + (k >> 2) * 16384) + (k & 3) * 32, 16, 1024),
+                     umma_smem_desc(smem_u32(sK + c * p.kv_rows * 128) + k * 2048, 8192, 1024), idesc_q, k > 0 ? 1u : 0u);
+    for (int c = 0; c < DCH; ++c)
+      for (int k = 0; k < ksteps_rows; ++k)
+        umma_bf16_ss(tmem + dk_off + c * 64, umma_smem_desc(smem_u32(sX) + k * 2048, 16384, 1024),
+                     umma_smem_desc(smem_u32(sQ + c * 16384) + k * 2048, 8192, 1024), idesc_k, k > 0 ? 1u : 0u);
+    umma_commit(&bar_o);
+  }
+  __syncwarp();
+
+  // ---- epilogue: dV while dQ / dK are still being computed, then dQ and dK (ReLU gates + bf16 stores) ----
+  const int j = t;
+  const bool key_ok = j < a.Tk;
+  const long krow = static_cast<long>(n) * a.Tk + (key_ok ? j : 0);
+  {
+    const __nv_bfloat16* Vg = static_cast<const __nv_bfloat16*>(a.v) + krow * a.ldv + h * D;
+    __nv_bfloat16* dVg = static_cast<__nv_bfloat16*>(a.dv) + krow * a.ld_dv + h * D;
+#pragma unroll 1
+    for (int c0 = half * 32; c0 < D; c0 += 64) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld_32x32(t_lane + dv_off + c0, r);
+      tmem_ld_wait();
+      store_gated_row32(r, Vg + c0, dVg + c0, key_ok, a.dbv ? a.dbv + h * D + c0 : nullptr, t & 31);
+    }
+  }
+  mbar_wait(&bar_o, 0);
+  tc_fence_after();
+  {
+    const __nv_bfloat16* Qg = static_cast<const __nv_bfloat16*>(a.q) + qrow * a.ldq + h * D;
+    __nv_bfloat16* dQg = static_cast<__nv_bfloat16*>(a.dq) + qrow * a.ld_dq + h * D;
+    const __nv_bfloat16* Kg = static_cast<const __nv_bfloat16*>(a.k) + krow * a.ldk + h * D;
+    __nv_bfloat16* dKg = static_cast<__nv_bfloat16*>(a.dk) + krow * a.ld_dk + h * D;
+#pragma unroll 1
+    for (int c0 = half * 32; c0 < D; c0 += 64) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld_32x32(t_lane + dq_off + c0, r);
+      tmem_ld_wait();
+      store_gated_row32(r, Qg + c0, dQg + c0, row_ok, a.dbq ? a.dbq + h * D + c0 : nullptr, t & 31);
+      __syncwarp();
+      tmem_ld_32x32(t_lane + dk_off + c0, r);
+      tmem_ld_wait();
+      store_gated_row32(r, Kg + c0, dKg + c0, key_ok, a.dbk ? a.dbk + h * D + c0 : nullptr, t & 31);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) {
+    tc_fence_after();
+    __syncwarp();
+    tmem_dealloc_rt(tmem, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
 int make_map3(CUtensorMap* m, const void* base, int64_t ld, int T, int N, int box_rows) {
   const uint64_t dims[3] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(T), static_cast<uint64_t>(N)};
   const uint64_t str[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * static_cast<uint64_t>(T)};
@@ -585,6 +892,17 @@ int attn_bwd_tc(const savqa_attn_args_t* a, cudaStream_t stream) {
   if (int rc = make_map3(&tmK, a->k, a->ldk, a->Tk, a->N, p.kv_rows)) return rc;
   if (int rc = make_map3(&tmV, a->v, a->ldv, a->Tk, a->N, p.kv_rows)) return rc;
   dim3 grid(a->N * a->H);
+  // the training step's symbolic branch: two CTAs per SM with the shared W' / dS tile (attn_bwd_tc1_kernel)
+  const bool one_tile = a->d == 64 && p.kc == 2 && p.kt == 1 && a->stats && a->out && !a->causal &&
+                        (a->graph_bits || !a->graph || a->renorm == 0) && p.tmem_cols <= 256 && getenv("SAVQA_ATTN_BWD_ONE_TILE_OFF") == nullptr;
+  if (one_tile) {
+    const size_t smem1 = 1024 + static_cast<size_t>(2) * 16384 + static_cast<size_t>(2) * 16384 + static_cast<size_t>(2) * p.kv_rows * 128;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_bwd_tc1_kernel<64>), smem1, "savqa_graph_attn_bwd (tcgen05 engine, shared tile)"))
+      return rc;
+    SAVQA_CHECK_CUDA(launch_kernel(true, attn_bwd_tc1_kernel<64>, grid, dim3(256), smem1, stream, tmQ, tmK, tmV, p));
+    SAVQA_CHECK_CUDA(cudaGetLastError());
+    return SAVQA_OK;
+  }
   // two CTAs fit an SM when the key tile is a single 64-key chunk (d = 64); otherwise one CTA with two threads per row
   const bool split = smem > 112 * 1024;
 #define SAVQA_LAUNCH_BWD(DD, RR)                                                                                                           \

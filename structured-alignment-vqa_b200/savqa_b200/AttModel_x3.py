@@ -14,6 +14,8 @@ from __future__ import annotations
 
 import math
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -61,9 +63,31 @@ def _linear(x, lin: nn.Linear, pack: WeightPack, relu=False, out_bf16=False, row
 class _Branch(nn.Module):
     """Shared forward of the two branch models (they differ in the top-left block of `graph` and in table sizes)."""
 
+    def _cross_layers(self):
+        return [getattr(self, 'dec_vanilla_attention_%d' % i) for i in range(self.num_blocks)]
+
+    def _savqa_groups(self):
+        """[Wk_0; Wv_0; ...; Wk_{L-1}; Wv_{L-1}] of the decoder's cross-attention layers as ONE [2 L C, C] block (and their biases
+        as one [2 L C] vector): every layer projects the same encoder output (AttModel_x3.py:148-152), so the L K/V projections
+        are one GEMM with N = 2 L C forward, one dgrad with K = 2 L C and one wgrad backward (functional.MemoryHolder)."""
+        ws, bs = [], []
+        for m in self._cross_layers():
+            ws += [m.K_proj[0].weight, m.V_proj[0].weight]
+            bs += [m.K_proj[0].bias, m.V_proj[0].bias]
+        return [ws, bs] if ws else []
+
     def _savqa_bind(self, fv):
         Fn.bind_linear(self._pk["mlp"], self.syb_mlp[0], fv)    # K = 300: stays on the per-step staging path
         Fn.bind_linear(self._pk["mlp2"], self.syb_mlp2, fv)
+        pk = self._pk.setdefault("kv_all", WeightPack())
+        if fv is None:
+            pk.unbind()
+            return
+        g = self._savqa_groups()
+        C = self.hidden_size
+        if g and C % 8 == 0 and fv.has(g[0]) and fv.has(g[1]):
+            n = 2 * self.num_blocks * C
+            pk.bind(fv.bf16(g[0]).view(n, C), fv.param(g[1]), fv.grad(g[0]).view(n, C), fv.grad(g[1]))
 
     def _input_stage(self, first_ipt, q_ids, pos_table, pos_dropout_p):
         B = first_ipt.shape[0]
@@ -118,6 +142,21 @@ class _Branch(nn.Module):
         h.ready = torch.cuda.Event()
         h.ready.record(cur)
         memory._savqa_kv_holder = h
+        pall = self._pk.get("kv_all")
+        if pall is not None and pall.bound and side_info is not None and side_info.bf16 is not None:
+            # all L cross-attention layers' K/V projections of the encoder output in one GEMM, on the side stream
+            C = x.shape[-1]
+            Mk, n = x.numel() // C, pall.w.shape[0]
+            mem_bf16 = side_info.bf16.reshape(Mk, C)
+            kv_all = torch.empty(Mk, n, device=x.device, dtype=torch.bfloat16)
+            h.side.wait_event(h.ready)
+            with torch.cuda.stream(h.side), Fn.ops.gemm_sm_limit(Fn.SIDE_GEMM_SMS):
+                Fn.ops.gemm(mem_bf16, pall.w, Mk, n, C, bias=pall.bias, relu=True, out_bf16=kv_all)
+            kv_all.record_stream(h.side)
+            mem_bf16.record_stream(h.side)
+            h.kv_done = torch.cuda.Event()
+            h.kv_done.record(h.side)
+            h.kv_all, h.pack_all, h.mem_bf16 = kv_all, pall, mem_bf16
         return memory
 
     def _add_blocks(self, which, hidden_size):
@@ -131,6 +170,8 @@ class _Branch(nn.Module):
                                                                                 dropout_rate=0, causality=True))
                 setattr(self, 'dec_vanilla_attention_%d' % i, new_multihead_attention(num_units=hidden_size, num_heads=self.num_heads,
                                                                                        dropout_rate=0, causality=False))
+                m = getattr(self, 'dec_vanilla_attention_%d' % i)
+                m._kv_external, m._kv_index = True, i
                 setattr(self, 'dec_feed_forward_%d' % i, feedforward(hidden_size, [4 * hidden_size, hidden_size]))
 
 

@@ -29,7 +29,7 @@ ATTN_ENGINE = 0
 WGRAD_SIDE_STREAM = True
 #: SMs the persistent GEMMs on the side streams may occupy (0 = all): the rest stays free for the main streams' kernels, so the
 #: decoder's chain of small launches does not queue behind whole GEMMs (savqa_set_gemm_sm_limit)
-SIDE_GEMM_SMS = int(os.environ.get("SAVQA_SIDE_SMS", "116"))
+SIDE_GEMM_SMS = int(os.environ.get("SAVQA_SIDE_SMS", "132"))
 _WGRAD_STREAMS = {}  # compute stream -> its weight-gradient stream
 _WGRAD_DIRTY = []    # weight-gradient streams with work launched since the last join
 
@@ -438,6 +438,12 @@ class MemoryHolder:
         self.ready: Optional["torch.cuda.Event"] = None   # memory (and its bf16 copy) are complete on the compute stream
         self.dmem: Optional[Tensor] = None                # fp32 [N*T, C], accumulated on the side stream
         self.side: Optional["torch.cuda.Stream"] = None
+        # fused form (the branch model's [2 L C, C] K/V block is bound): ONE projection GEMM for all L layers ...
+        self.kv_all: Optional[Tensor] = None              # bf16 [N*T, 2 L C]: layer i reads columns [2 C i, 2 C (i + 1))
+        self.kv_done: Optional["torch.cuda.Event"] = None
+        self.pack_all: Optional[WeightPack] = None
+        self.mem_bf16: Optional[Tensor] = None
+        self.dkv_all: Optional[Tensor] = None             # ... and one dgrad (K = 2 L C) + one wgrad once every layer has written its slice
 
 
 class MemoryJoinFn(Function):
@@ -455,6 +461,17 @@ class MemoryJoinFn(Function):
     def backward(ctx, dy):
         h: MemoryHolder = ctx.holder
         g = dy
+        if h.dkv_all is not None:
+            # every cross-attention layer has written its slice of dkv_all: d(memory) = dKV_all W_all in one GEMM (K = 2 L C) on
+            # this stream (the encoder's backward is next), the weight gradient of the whole block on the side stream
+            pk, dkv = h.pack_all, h.dkv_all
+            Mk, n = dkv.shape
+            C = pk.w.shape[1]
+            d = torch.empty(Mk, C, device=dkv.device, dtype=F32)
+            ops.gemm(dkv, pk.w, Mk, C, n, b_mn=True, res=None if g is None else g.reshape(Mk, C), out_f32=d)
+            pk.weight_grad(dkv, h.mem_bf16, n, C)
+            g = d.reshape(ctx_shape(h))
+            h.dkv_all = h.kv_all = None
         if GRAD_REDUCER is not None and getattr(h, "bucket", None) is not None:
             GRAD_REDUCER.ready(h.bucket)  # the decoder's backward is complete
         if h.dmem is not None:
@@ -504,6 +521,7 @@ class GraphAttentionFn(Function):
         # ---- projections: Linear + ReLU, fused along N when the inputs coincide (modules.py:241-243) ----
         dev = queries.device
         holder = None
+        fused_kv = False
         if same_qk and same_kv:
             pk = packs["qkv"].refresh([Wq, Wk, Wv], [bq, bk, bv])
             qkv = torch.empty(Mq, 3 * C, device=dev, dtype=BF16)
@@ -520,7 +538,14 @@ class GraphAttentionFn(Function):
                 holder = cfg.get("kv_holder")
                 if holder is not None and not (pkv.bound and WGRAD_SIDE_STREAM and holder.ready is not None):
                     holder = None
-                if holder is not None:
+                if holder is not None and holder.kv_all is not None:
+                    # projected for all layers at once when the encoder finished (AttModel_x3._Branch._join_memory)
+                    C2 = 2 * C
+                    i0 = cfg.get("kv_index", 0) * C2
+                    torch.cuda.current_stream().wait_event(holder.kv_done)
+                    kv = holder.kv_all[:, i0:i0 + C2]
+                    fused_kv = True
+                elif holder is not None:
                     # depends only on `memory`: off the decoder's kernel chain, onto the side stream
                     cur = torch.cuda.current_stream()
                     holder.side.wait_event(holder.ready)
@@ -563,6 +588,7 @@ class GraphAttentionFn(Function):
         ctx.renorm_eff = renorm if g is not None else 0
         ctx.gbits = gbits
         ctx.kv_holder = holder if mode == 1 else None
+        ctx.kv_fused = fused_kv
         ctx.save_for_backward(q_bf16, k_bf16, v_bf16, q, k, v, g, q_on, k_on, pre, gamma, stats, o if stats is not None else None)
         outs = (y, yb, y_on) + ((att,) if want_att else ())
         ctx.mark_non_differentiable(yb, y_on, *((att,) if want_att else ()))
@@ -597,7 +623,14 @@ class GraphAttentionFn(Function):
         elif mode == 1:
             pq, pkv = packs["q"], packs["kv"]
             dq = torch.empty(Mq, C, device=dev, dtype=BF16)
-            dkv = torch.empty(Mk, 2 * C, device=dev, dtype=BF16)
+            if ctx.kv_fused:  # this layer's slice of the gradient of the fused K/V projection (MemoryJoinFn.backward consumes it)
+                hold = ctx.kv_holder
+                if hold.dkv_all is None:
+                    hold.dkv_all = torch.empty(Mk, hold.pack_all.w.shape[0], device=dev, dtype=BF16)
+                i0 = cfg.get("kv_index", 0) * 2 * C
+                dkv = hold.dkv_all[:, i0:i0 + 2 * C]
+            else:
+                dkv = torch.empty(Mk, 2 * C, device=dev, dtype=BF16)
             dk, dv = dkv[:, :C], dkv[:, C:]
             dbq = pq.bias_grad_buffer(C, dev)
             dbkv = pkv.bias_grad_buffer(2 * C, dev)
@@ -631,7 +664,9 @@ class GraphAttentionFn(Function):
                 dxq = torch.empty(Mq, C, device=dev, dtype=F32)
                 dgrad(dq, pq, Mq, C, C, res=dpre2, out_f32=dxq)
                 dxq = dxq.reshape(N, Tq, C)
-            if mode == 1:
+            if mode == 1 and ctx.kv_fused:
+                dWk = dWv = None  # weight gradient and d(memory) of all layers together: MemoryJoinFn.backward
+            elif mode == 1:
                 dW = pkv.weight_grad(dkv, k_bf16, 2 * C, C)
                 dWk, dWv = dW[:C], dW[C:]
                 holder = ctx.kv_holder

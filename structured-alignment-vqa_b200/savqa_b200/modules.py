@@ -126,8 +126,14 @@ class _attention_base(nn.Module):
         self.output_dropout = nn.Dropout(p=dropout_rate)
         self.normalization = layer_normalization(num_units)
         self._packs = {k: WeightPack() for k in ("qkv", "q", "kv", "k", "v")}
+        # decoder cross-attention layers of one branch model: their [Wk; Wv] blocks sit side by side in the trainer's flat buffers
+        # so that ONE GEMM projects the encoder output for all of them (AttModel_x3._Branch._savqa_groups); layer index there
+        self._kv_external = False
+        self._kv_index = 0
 
     def _savqa_groups(self):
+        if self._kv_external:
+            return []  # K / V are placed by the branch model; Wq, bq go with the ungrouped parameters
         q, k, v = self.Q_proj[0], self.K_proj[0], self.V_proj[0]
         return [[q.weight, k.weight, v.weight], [q.bias, k.bias, v.bias]]
 
@@ -137,8 +143,19 @@ class _attention_base(nn.Module):
             for pk in self._packs.values():
                 pk.unbind()
             return
-        gw, gb = self._savqa_groups()
         C = self.num_units
+        if self._kv_external:
+            q, k, v = self.Q_proj[0], self.K_proj[0], self.V_proj[0]
+            ok = C % 8 == 0 and fv.has([q.weight]) and fv.has([q.bias]) and fv.has([k.weight, v.weight]) and fv.has([k.bias, v.bias])
+            if not ok:
+                return
+            self._packs["q"].bind(fv.bf16([q.weight]).view(C, C), fv.param([q.bias]), fv.grad([q.weight]).view(C, C), fv.grad([q.bias]))
+            w, b = fv.bf16([k.weight, v.weight]).view(2 * C, C), fv.param([k.bias, v.bias])
+            dw, db = fv.grad([k.weight, v.weight]).view(2 * C, C), fv.grad([k.bias, v.bias])
+            for name, lo, hi in (("kv", 0, 2 * C), ("k", 0, C), ("v", C, 2 * C)):
+                self._packs[name].bind(w[lo:hi], b[lo:hi], dw[lo:hi], db[lo:hi])
+            return
+        gw, gb = self._savqa_groups()
         if not fv.has(gw + gb) or C % 8:
             return
         w, b = fv.bf16(gw).view(3 * C, C), fv.param(gb)
@@ -152,7 +169,7 @@ class _attention_base(nn.Module):
                                       "(AttModel_x3 constructs every attention with dropout_rate=0)")
         cfg = dict(heads=self.num_heads, causal=bool(self.causality), renorm=self._renorm, return_att=bool(self.return_att),
                    packs=self._packs, eps=self.normalization.epsilon, norm_sink=self.normalization._sink,
-                   kv_holder=getattr(keys, "_savqa_kv_holder", None) if keys is values else None)
+                   kv_holder=getattr(keys, "_savqa_kv_holder", None) if keys is values else None, kv_index=self._kv_index)
         sq, sk = Side.of(queries), Side.of(keys)
         outs = Fn.GraphAttentionFn.apply(
             queries, keys, values, graph,

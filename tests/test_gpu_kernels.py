@@ -426,6 +426,44 @@ def test_attention_backward(ops, engine, N, H, Tq, Tk, d, renorm, causal):
         assert max(e3) < (1e-2 if Tq < 8 else tol), e3
 
 
+@pytest.mark.parametrize("N,H,Tq,Tk", [(3, 8, 128, 128), (2, 8, 100, 100), (2, 8, 72, 72), (2, 8, 40, 120), (130, 8, 128, 128)])
+def test_attention_backward_shared_tile_kernel(ops, N, H, Tq, Tk):
+    """The step's symbolic-branch backward (64 < Tk <= 128, bit-packed graph, forward statistics): the two-CTAs-per-SM kernel
+    that shares one tile between W' and dS must agree with the fp32 restatement and -- bit for bit -- with the one-CTA kernel
+    (same arithmetic, different schedule), masked keys and query rows included."""
+    import os
+    import fake_ops
+    d, C = 64, H * 64
+    q, k, v, graph, key_on, query_on = _attn_inputs(f"attb1/{N}/{H}/{Tq}/{Tk}", N, H, Tq, Tk, d, False)
+    dout = GS.randn(f"attb1/{N}/{Tq}/{C}/dout", N * Tq, C)
+    rq, rk, rv = torch.zeros(N * Tq, C, dtype=BF), torch.zeros(N * Tk, C, dtype=BF), torch.zeros(N * Tk, C, dtype=BF)
+    fake_ops.graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, False, 1, dout, rq, rk, rv)
+    bits = ops.pack_graph_bits(dev(graph))
+    stats = torch.empty(H * N * Tq, 4, device="cuda")
+    o_f, _ = ops.graph_attention_fwd(dev(q), dev(k), dev(v), dev(graph), dev(key_on), dev(query_on), N, H, Tq, Tk, d, False, 1, False, 0,
+                                     graph_bits=bits, stats=stats)
+    outs = []
+    for off in (False, True):
+        if off:
+            os.environ["SAVQA_ATTN_BWD_ONE_TILE_OFF"] = "1"
+        try:
+            dqkv = torch.zeros(N * max(Tq, Tk), 3 * C, dtype=BF, device="cuda")
+            db = torch.zeros(3, C, device="cuda")
+            ops.graph_attention_bwd(dev(q), dev(k), dev(v), dev(graph), dev(key_on), dev(query_on), N, H, Tq, Tk, d, False, 1, dev(dout),
+                                    dqkv[:N * Tq, :C], dqkv[:N * Tk, C:2 * C], dqkv[:N * Tk, 2 * C:], engine=0, dbq=db[0], dbk=db[1], dbv=db[2],
+                                    graph_bits=bits, stats=stats, fwd_out=o_f)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("SAVQA_ATTN_BWD_ONE_TILE_OFF", None)
+        outs.append((dqkv, db))
+    (g1, b1), (g0, b0) = outs
+    e = (rel(g1[:N * Tq, :C], rq), rel(g1[:N * Tk, C:2 * C], rk), rel(g1[:N * Tk, 2 * C:], rv))
+    assert max(e) < 6e-3, e
+    assert torch.equal(g1, g0)
+    for x, y in zip(b1, b0):  # bias gradients: same addends, atomics in a different order
+        assert float((x - y).abs().max()) <= 1e-5 * float(y.abs().max()) + 1e-6
+
+
 # ------------------------------------------------------------------------------------------------ loss / adam
 def test_answer_loss_and_adam(ops):
     B, ncls = 37, 1845

@@ -181,9 +181,12 @@ def test_trainer_bound_gradients_match_autograd_and_graph_replay(A):
         err = float((p.grad - ref_grads[k]).abs().max()) / (scale + 1e-12)
         if err > worst[1]:
             worst = (k, err)
-    # same kernels on the same operands: only the fp32 accumulation order differs (atomics; bias sums taken from the fp32
-    # values instead of the bf16-rounded stores: 2^-9 per element before averaging over the rows)
-    assert worst[1] < 5e-3, worst
+    # Same kernels on the same operands up to the ORDER of fp32 sums: atomics, and the trainer's fused decoder K/V backward
+    # (one K = 2 L C dgrad GEMM where the unbound modules accumulate L GEMMs).  A 1-ulp fp32 difference in d(memory) flips a few
+    # bf16 roundings of the MMA operands in each of the 6 encoder blocks behind it, so the deepest blocks' gradients agree to a
+    # few 2^-9 of max|grad| (measured worst: 6e-3, on the cancellation-dominated K-projection bias of block 1); an indexing or
+    # layout error would show up as O(1).
+    assert worst[1] < 1e-2, worst
 
     # eager step == replayed graph step (same static batch), and the mirror follows the parameters
     tr2_model = copy.deepcopy(ref)

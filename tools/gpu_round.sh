@@ -7,4 +7,3 @@ timeout -k 10 900 python -m pytest -q -m gpu -p no:cacheprovider --timeout 300 -
 grep -E "FAILED|Error|assert" gpurun_out/t_all.log | head -20
 for T in 128 56; do for KIND in fwd bwd; do python tools/one_attn.py 128 $T $KIND 6 2>&1 | tail -1; done; done
 timeout -k 10 300 python bench.py --mode graph --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | cut -c1-230
-timeout -k 10 300 python tools/trace_step.py 2>&1 | tail -12

@@ -49,7 +49,7 @@ if ks:
     hi = ends[1] + 1 if len(ends) >= 2 else len(ks)
     one = ks[lo:hi]
     t0 = one[0]["ts"]
-    rows = [dict(n=e["name"][:70], s=e["args"].get("stream", -1), t=round(e["ts"] - t0, 2), d=round(e["dur"], 2)) for e in one]
+    rows = [dict(n=e["name"].replace("void ", "").replace("savqa::(anonymous namespace)::", "")[:90], s=e["args"].get("stream", -1), t=round(e["ts"] - t0, 2), d=round(e["dur"], 2)) for e in one]
     with gzip.open(os.path.join(ROOT, "gpurun_out", "trace_step.json.gz"), "wt") as f:
         json.dump(rows, f)
     span = one[-1]["ts"] + one[-1]["dur"] - t0
