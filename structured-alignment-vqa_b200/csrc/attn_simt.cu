@@ -4,6 +4,8 @@
 // kernel (attn_tcgen05.cu), (iii) head sizes the tensor-core kernel does not take (d not in {32,64,128}).
 // Semantics follow modules.py:246-301 exactly, including the fp32 key-mask constant, softmax over ALL keys,
 // multiplicative graph after the softmax, L1 renormalisation with the 1e-12 clamp, and the query mask.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace savqa {
@@ -712,6 +714,337 @@ __global__ void __launch_bounds__(kPieceWarps * 32) attn_row1_bwd_piece_kernel(c
   }
 }
 
+// ---- key-split row kernels: one CTA of kSplitWarps warps per (sample, head); every warp sweeps its own slice of the keys with
+// all of its 16-byte loads in flight at once (the one-warp kernels above walk the keys in dependent rounds of 16: the decoder's
+// cross-attention is a chain link, and its latency -- not its bandwidth -- is what the step pays).  The softmax of the whole row
+// is recomputed by every warp from the shared score row (identical arithmetic, so the redundant writes agree bit for bit). ----
+constexpr int kSplitWarps = 4;
+constexpr int kSplitLoads = 8;
+
+template <int MJ>
+struct RowSoftmaxT {
+  float w[MJ], p[MJ], r, sumw;
+};
+
+template <int MJ>
+__device__ __forceinline__ void row_weights_t(const float (&s)[MJ], const float* __restrict__ grow, int Tk, int renorm, int lane,
+                                              RowSoftmaxT<MJ>& o) {  // row_weights() for MJ * 32 keys
+  float m = -INFINITY;
+#pragma unroll
+  for (int jj = 0; jj < MJ; ++jj)
+    if (jj * 32 + lane < Tk) m = fmaxf(m, s[jj]);
+  m = warp_max(m);
+  float z = 0.0f;
+#pragma unroll
+  for (int jj = 0; jj < MJ; ++jj) {
+    const int j = jj * 32 + lane;
+    o.p[jj] = (j < Tk) ? expf(s[jj] - m) : 0.0f;
+    z += o.p[jj];
+  }
+  z = warp_sum(z);
+  const float iz = 1.0f / z;
+  float r = 0.0f, sa = 0.0f;
+#pragma unroll
+  for (int jj = 0; jj < MJ; ++jj) {
+    const int j = jj * 32 + lane;
+    o.p[jj] *= iz;
+    float a = o.p[jj];
+    if (renorm != 0) a *= (j < Tk) ? grow[j] : 0.0f;
+    o.w[jj] = a;
+    r += fabsf(a);
+    sa += a;
+  }
+  r = warp_sum(r);
+  sa = warp_sum(sa);
+  o.r = r;
+  float scale = 1.0f;
+  if (renorm == 1) scale = 1.0f / fmaxf(r, 1e-12f);
+  else if (renorm == 2) scale = 1.0f / (sa + 1e-7f);
+  float sw = 0.0f;
+#pragma unroll
+  for (int jj = 0; jj < MJ; ++jj) {
+    o.w[jj] *= scale;
+    sw += o.w[jj];
+  }
+  o.sumw = warp_sum(sw);
+}
+
+template <int MJ>
+__global__ void __launch_bounds__(kSplitWarps * 32) attn_row1_fwd_split_kernel(const savqa_attn_args_t a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  pdl_trigger();
+  pdl_wait();
+  const int d = a.d, P = d >> 3, kpi = 32 / P;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sS = reinterpret_cast<float*>(smem);  // [Tk] raw scores
+  float* sW = sS + a.Tk;                       // [Tk] W' = W * query mask
+  float* sq = sW + a.Tk;                       // [d]  q
+  float* sO = sq + d;                          // [kSplitWarps][d] partial outputs
+  const long hn = blockIdx.x;
+  const int h = static_cast<int>(hn / a.N), n = static_cast<int>(hn % a.N);
+  const int pc = lane % P, ks = lane / P;
+  const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q) + static_cast<long>(n) * a.ldq + h * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) sq[c] = __bfloat162float(Q[c]);
+  __syncthreads();
+  const __nv_bfloat16* Kb = static_cast<const __nv_bfloat16*>(a.k) + static_cast<long>(n) * a.Tk * a.ldk + h * d;
+  const __nv_bfloat16* Vb = static_cast<const __nv_bfloat16*>(a.v) + static_cast<long>(n) * a.Tk * a.ldv + h * d;
+  const int per = ((a.Tk + kSplitWarps - 1) / kSplitWarps + kpi - 1) / kpi * kpi;  // keys per warp, a multiple of the keys per load
+  const int j_lo = warp * per, j_hi = min(a.Tk, j_lo + per);
+  for (int j0 = j_lo; j0 < j_hi; j0 += kpi * kSplitLoads) {
+    uint4 u[kSplitLoads];
+#pragma unroll
+    for (int i = 0; i < kSplitLoads; ++i) {
+      const int j = j0 + i * kpi + ks;
+      u[i] = (j < j_hi) ? __ldg(reinterpret_cast<const uint4*>(Kb + static_cast<long>(j) * a.ldk) + pc) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < kSplitLoads; ++i) {
+      float part = dot8(sq + pc * 8, u[i]);
+      for (int o = 1; o < P; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const int j = j0 + i * kpi + ks;
+      if (pc == 0 && j < j_hi) sS[j] = part;
+    }
+  }
+  __syncthreads();
+  const float sqrt_d = sqrtf(static_cast<float>(d));
+  float s[MJ];
+#pragma unroll
+  for (int jj = 0; jj < MJ; ++jj) {
+    const int j = jj * 32 + lane;
+    float v = kMaskFill;
+    if (j < a.Tk) {
+      v = sS[j] / sqrt_d;
+      if (a.key_on && a.key_on[static_cast<long>(n) * a.Tk + j] == 0.0f) v = kMaskFill;
+      if (a.causal && j > 0) v = kMaskFill;
+    }
+    s[jj] = v;
+  }
+  const float* grow = a.graph ? a.graph + static_cast<long>(n) * a.graph_n_stride : nullptr;
+  RowSoftmaxT<MJ> rs;
+  row_weights_t<MJ>(s, grow, a.Tk, a.graph ? a.renorm : 0, lane, rs);
+  const float qon = a.query_on ? a.query_on[n] : 1.0f;
+#pragma unroll
+  for (int jj = 0; jj < MJ; ++jj) {
+    const int j = jj * 32 + lane;
+    if (j < a.Tk) {
+      if (a.att && warp == 0) a.att[hn * a.Tk + j] = rs.w[jj];
+      sW[j] = rs.w[jj] * qon;  // every warp writes the same value; it reads back only what it wrote itself
+    }
+  }
+  __syncwarp();
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.0f;
+  for (int j0 = j_lo; j0 < j_hi; j0 += kpi * kSplitLoads) {
+    uint4 u[kSplitLoads];
+#pragma unroll
+    for (int i = 0; i < kSplitLoads; ++i) {
+      const int j = j0 + i * kpi + ks;
+      u[i] = (j < j_hi) ? __ldg(reinterpret_cast<const uint4*>(Vb + static_cast<long>(j) * a.ldv) + pc) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < kSplitLoads; ++i) {
+      const int j = j0 + i * kpi + ks;
+      const float w = (j < j_hi) ? sW[j] : 0.0f;
+      float f[8];
+      unpack8(u[i], f);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = fmaf(w, f[c], acc[c]);
+    }
+  }
+  for (int o = P; o < 32; o <<= 1) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+  }
+  if (ks == 0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sO[warp * d + pc * 8 + c] = acc[c];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float o = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kSplitWarps; ++w) o += sO[w * d + c];
+    a.out[static_cast<long>(n) * a.ldo + h * d + c] = o;
+  }
+}
+
+template <int MJ>
+__global__ void __launch_bounds__(kSplitWarps * 32, 4) attn_row1_bwd_split_kernel(const savqa_attn_args_t a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  pdl_trigger();
+  pdl_wait();
+  const int d = a.d, P = d >> 3, kpi = 32 / P;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sS = reinterpret_cast<float*>(smem);  // [Tk] raw scores
+  float* sD = sS + a.Tk;                       // [Tk] dW = qm <dO, V_j>
+  float* sG = sD + a.Tk;                       // [Tk] dS / sqrt(d)
+  float* sW = sG + a.Tk;                       // [Tk] W'
+  float* sq = sW + a.Tk;                       // [d]  q
+  float* sg = sq + d;                          // [d]  dO
+  float* sP = sg + d;                          // [kSplitWarps][3][d] partial dQ, bias-gradient sums of dK, dV
+  const long hn = blockIdx.x;
+  const int h = static_cast<int>(hn / a.N), n = static_cast<int>(hn % a.N);
+  const int pc = lane % P, ks = lane / P;
+  const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q) + static_cast<long>(n) * a.ldq + h * d;
+  const float* dO = a.dout + static_cast<long>(n) * a.ld_dout + h * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    sq[c] = __bfloat162float(Q[c]);
+    sg[c] = dO[c];
+  }
+  __syncthreads();
+  const __nv_bfloat16* Kb = static_cast<const __nv_bfloat16*>(a.k) + static_cast<long>(n) * a.Tk * a.ldk + h * d;
+  const __nv_bfloat16* Vb = static_cast<const __nv_bfloat16*>(a.v) + static_cast<long>(n) * a.Tk * a.ldv + h * d;
+  const float qon = a.query_on ? a.query_on[n] : 1.0f;
+  const int per = ((a.Tk + kSplitWarps - 1) / kSplitWarps + kpi - 1) / kpi * kpi;
+  const int j_lo = warp * per, j_hi = min(a.Tk, j_lo + per);
+  for (int j0 = j_lo; j0 < j_hi; j0 += kpi * kSplitLoads) {
+    uint4 uk[kSplitLoads], uv[kSplitLoads];
+#pragma unroll
+    for (int i = 0; i < kSplitLoads; ++i) {
+      const int j = j0 + i * kpi + ks;
+      const bool ok = j < j_hi;
+      uk[i] = ok ? __ldg(reinterpret_cast<const uint4*>(Kb + static_cast<long>(j) * a.ldk) + pc) : make_uint4(0u, 0u, 0u, 0u);
+      uv[i] = ok ? __ldg(reinterpret_cast<const uint4*>(Vb + static_cast<long>(j) * a.ldv) + pc) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < kSplitLoads; ++i) {
+      float ps = dot8(sq + pc * 8, uk[i]), pd = dot8(sg + pc * 8, uv[i]);
+      for (int o = 1; o < P; o <<= 1) {
+        ps += __shfl_xor_sync(0xffffffffu, ps, o);
+        pd += __shfl_xor_sync(0xffffffffu, pd, o);
+      }
+      const int j = j0 + i * kpi + ks;
+      if (pc == 0 && j < j_hi) {
+        sS[j] = ps;
+        sD[j] = pd * qon;
+      }
+    }
+  }
+  __syncthreads();
+  const float sqrt_d = sqrtf(static_cast<float>(d));
+  const int renorm = a.graph ? a.renorm : 0;
+  float s[MJ], dw[MJ];
+#pragma unroll
+  for (int jj = 0; jj < MJ; ++jj) {
+    const int j = jj * 32 + lane;
+    float v = kMaskFill, w = 0.0f;
+    if (j < a.Tk) {
+      v = sS[j] / sqrt_d;
+      w = sD[j];
+      if (a.key_on && a.key_on[static_cast<long>(n) * a.Tk + j] == 0.0f) v = kMaskFill;
+      if (a.causal && j > 0) v = kMaskFill;
+    }
+    s[jj] = v;
+    dw[jj] = w;
+  }
+  const float* grow = a.graph ? a.graph + static_cast<long>(n) * a.graph_n_stride : nullptr;
+  RowSoftmaxT<MJ> rs;
+  row_weights_t<MJ>(s, grow, a.Tk, renorm, lane, rs);
+  float t = 0.0f;
+#pragma unroll
+  for (int jj = 0; jj < MJ; ++jj) t += rs.w[jj] * dw[jj];
+  t = warp_sum(t);
+  const bool clamped = (renorm == 1) && (rs.r < 1e-12f);
+#pragma unroll
+  for (int jj = 0; jj < MJ; ++jj) {
+    const int j = jj * 32 + lane;
+    if (j < a.Tk) {
+      float ds;
+      if (renorm == 1 && clamped) ds = rs.w[jj] * dw[jj] - rs.p[jj] * t;
+      else if (renorm == 2) ds = rs.w[jj] * (dw[jj] - t) - rs.p[jj] * t * (1.0f - rs.sumw);
+      else ds = rs.w[jj] * (dw[jj] - t);
+      if (s[jj] == kMaskFill) ds = 0.0f;  // masked scores are constants
+      sG[j] = ds / sqrt_d;                // every warp writes the same values; it reads back only its own
+      sW[j] = rs.w[jj] * qon;
+    }
+  }
+  __syncwarp();
+  // piece pass over this warp's keys: dQ += dS_j K_j;  dK_j = dS_j q;  dV_j = W'_j dO  (ReLU gates of the projections, bias sums)
+  float qf[8], gf[8], dq[8], bk[8], bv[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    qf[c] = sq[pc * 8 + c];
+    gf[c] = sg[pc * 8 + c];
+    dq[c] = bk[c] = bv[c] = 0.0f;
+  }
+  __nv_bfloat16* dK = static_cast<__nv_bfloat16*>(a.dk) + static_cast<long>(n) * a.Tk * a.ld_dk + h * d;
+  __nv_bfloat16* dV = static_cast<__nv_bfloat16*>(a.dv) + static_cast<long>(n) * a.Tk * a.ld_dv + h * d;
+  for (int j0 = j_lo; j0 < j_hi; j0 += kpi * kSplitLoads) {
+    uint4 uk[kSplitLoads], uv[kSplitLoads];
+#pragma unroll
+    for (int i = 0; i < kSplitLoads; ++i) {  // second read of the slice: L1 hits
+      const int j = j0 + i * kpi + ks;
+      const bool ok = j < j_hi;
+      uk[i] = ok ? __ldg(reinterpret_cast<const uint4*>(Kb + static_cast<long>(j) * a.ldk) + pc) : make_uint4(0u, 0u, 0u, 0u);
+      uv[i] = ok ? __ldg(reinterpret_cast<const uint4*>(Vb + static_cast<long>(j) * a.ldv) + pc) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < kSplitLoads; ++i) {
+      const int j = j0 + i * kpi + ks;
+      if (j < j_hi) {
+        const float ds = sG[j], w = sW[j];
+        float kf[8], vf[8], ok_[8], ov_[8];
+        unpack8(uk[i], kf);
+        unpack8(uv[i], vf);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          dq[c] = fmaf(ds, kf[c], dq[c]);
+          ok_[c] = kf[c] > 0.0f ? ds * qf[c] : 0.0f;
+          ov_[c] = vf[c] > 0.0f ? w * gf[c] : 0.0f;
+          bk[c] += ok_[c];
+          bv[c] += ov_[c];
+        }
+        *(reinterpret_cast<uint4*>(dK + static_cast<long>(j) * a.ld_dk) + pc) =
+            make_uint4(pack_bf16x2(ok_[0], ok_[1]), pack_bf16x2(ok_[2], ok_[3]), pack_bf16x2(ok_[4], ok_[5]), pack_bf16x2(ok_[6], ok_[7]));
+        *(reinterpret_cast<uint4*>(dV + static_cast<long>(j) * a.ld_dv) + pc) =
+            make_uint4(pack_bf16x2(ov_[0], ov_[1]), pack_bf16x2(ov_[2], ov_[3]), pack_bf16x2(ov_[4], ov_[5]), pack_bf16x2(ov_[6], ov_[7]));
+      }
+    }
+  }
+  for (int o = P; o < 32; o <<= 1) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      dq[c] += __shfl_xor_sync(0xffffffffu, dq[c], o);
+      bk[c] += __shfl_xor_sync(0xffffffffu, bk[c], o);
+      bv[c] += __shfl_xor_sync(0xffffffffu, bv[c], o);
+    }
+  }
+  if (ks == 0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      sP[(warp * 3 + 0) * d + pc * 8 + c] = dq[c];
+      sP[(warp * 3 + 1) * d + pc * 8 + c] = bk[c];
+      sP[(warp * 3 + 2) * d + pc * 8 + c] = bv[c];
+    }
+  }
+  __syncthreads();
+  if (warp == 0 && lane < P) {  // lane = piece: the four warps' partial sums in a fixed order, ReLU gate of the Q projection
+    float tq[8], tk[8], tv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      tq[c] = tk[c] = tv[c] = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kSplitWarps; ++w) {
+        tq[c] += sP[(w * 3 + 0) * d + lane * 8 + c];
+        tk[c] += sP[(w * 3 + 1) * d + lane * 8 + c];
+        tv[c] += sP[(w * 3 + 2) * d + lane * 8 + c];
+      }
+      if (!(sq[lane * 8 + c] > 0.0f)) tq[c] = 0.0f;
+    }
+    __nv_bfloat16* dQ = static_cast<__nv_bfloat16*>(a.dq) + static_cast<long>(n) * a.ld_dq + h * d;
+    *(reinterpret_cast<uint4*>(dQ) + lane) =
+        make_uint4(pack_bf16x2(tq[0], tq[1]), pack_bf16x2(tq[2], tq[3]), pack_bf16x2(tq[4], tq[5]), pack_bf16x2(tq[6], tq[7]));
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int col = h * d + lane * 8 + c;
+      if (a.dbq) atomicAdd(a.dbq + col, tq[c]);
+      if (a.dbk) atomicAdd(a.dbk + col, tk[c]);
+      if (a.dbv) atomicAdd(a.dbv + col, tv[c]);
+    }
+  }
+}
+
 bool row1_piece_ok(const savqa_attn_args_t* a, bool bwd) {
   auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const int d = a->d;
@@ -743,6 +1076,22 @@ int check_common(const savqa_attn_args_t* a, const char* who) {
 int attn_fwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
   if (int rc = check_common(a, "savqa_graph_attn_fwd")) return rc;
   SAVQA_REQUIRE(a->out, "savqa_graph_attn_fwd: null out");
+  if (a->Tq == 1 && row1_piece_ok(a, false) && a->Tk >= 32 && getenv("SAVQA_ROW1_SPLIT_OFF") == nullptr) {
+    const size_t smem1 = (static_cast<size_t>(2) * a->Tk + static_cast<size_t>(1 + kSplitWarps) * a->d) * 4;
+    const dim3 grid(static_cast<unsigned>(static_cast<long>(a->N) * a->H)), block(kSplitWarps * 32);
+#define SAVQA_ROW1_FWD(MJ)                                                                                                            \
+  do {                                                                                                                                \
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_row1_fwd_split_kernel<MJ>), smem1, "savqa_graph_attn_fwd (row kernel)")) \
+      return rc;                                                                                                                      \
+    SAVQA_CHECK_CUDA(launch_kernel(true, attn_row1_fwd_split_kernel<MJ>, grid, block, smem1, stream, *a));                            \
+  } while (0)
+    if (a->Tk <= 64) SAVQA_ROW1_FWD(2);
+    else if (a->Tk <= 128) SAVQA_ROW1_FWD(4);
+    else if (a->Tk <= 256) SAVQA_ROW1_FWD(8);
+    else SAVQA_ROW1_FWD(16);
+#undef SAVQA_ROW1_FWD
+    return SAVQA_OK;
+  }
   if (a->Tq == 1 && row1_piece_ok(a, false)) {
     const size_t smem1 = static_cast<size_t>(kPieceWarps) * (a->Tk + a->d) * 4;
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_row1_fwd_piece_kernel), smem1, "savqa_graph_attn_fwd (row kernel)")) return rc;
@@ -772,6 +1121,22 @@ int attn_bwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
   if (int rc = check_common(a, "savqa_graph_attn_bwd")) return rc;
   SAVQA_REQUIRE(a->dout && a->dq && a->dk && a->dv, "savqa_graph_attn_bwd: null gradient buffer");
   SAVQA_REQUIRE(a->ld_dq % 2 == 0 && a->ld_dk % 2 == 0 && a->ld_dv % 2 == 0, "savqa_graph_attn_bwd: odd leading dimension");
+  if (a->Tq == 1 && row1_piece_ok(a, true) && a->Tk >= 32 && getenv("SAVQA_ROW1_SPLIT_OFF") == nullptr) {
+    const size_t smem1 = (static_cast<size_t>(4) * a->Tk + static_cast<size_t>(2 + 3 * kSplitWarps) * a->d) * 4;
+    const dim3 grid(static_cast<unsigned>(static_cast<long>(a->N) * a->H)), block(kSplitWarps * 32);
+#define SAVQA_ROW1_BWD(MJ)                                                                                                            \
+  do {                                                                                                                                \
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_row1_bwd_split_kernel<MJ>), smem1, "savqa_graph_attn_bwd (row kernel)")) \
+      return rc;                                                                                                                      \
+    SAVQA_CHECK_CUDA(launch_kernel(true, attn_row1_bwd_split_kernel<MJ>, grid, block, smem1, stream, *a));                            \
+  } while (0)
+    if (a->Tk <= 64) SAVQA_ROW1_BWD(2);
+    else if (a->Tk <= 128) SAVQA_ROW1_BWD(4);
+    else if (a->Tk <= 256) SAVQA_ROW1_BWD(8);
+    else SAVQA_ROW1_BWD(16);
+#undef SAVQA_ROW1_BWD
+    return SAVQA_OK;
+  }
   if (a->Tq == 1 && row1_piece_ok(a, true)) {
     const size_t smem1 = static_cast<size_t>(kPieceWarps) * (3 * a->Tk + 2 * a->d) * 4;
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_row1_bwd_piece_kernel), smem1, "savqa_graph_attn_bwd (row kernel)")) return rc;

@@ -31,24 +31,25 @@ __global__ void build_masks_kernel(const TIn* __restrict__ first_mask, const TIn
     graph_diag[i] = gd;
     graph[i] = g;
   }
-  // dec_mask[b,0,j] = (sum_k mask[b,j,k] != 0); the sum is taken in fp32 like the reference (exact for 0/1 inputs)
+  // dec_mask[b,0,j] = (sum_k mask[b,j,k] != 0); the sum is taken in fp32 like the reference (exact for 0/1 inputs in any
+  // order).  One warp per mask row: coalesced reads, one shuffle reduction.
   const long rows = static_cast<long>(B) * T;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < rows; i += static_cast<long>(gridDim.x) * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const long warp0 = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+  const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+  for (long i = warp0; i < rows; i += nwarps) {
     const int j = static_cast<int>(i % T);
     const long b = i / T;
     float on = 0.0f;
     if (dec_mask_on) {
+      const TIn* row = (j < V) ? first_mask + (b * V + j) * V : q_mask + (b * Q + (j - V)) * Q;
+      const int len = (j < V) ? V : Q;
       float s = 0.0f;
-      if (j < V) {
-        const TIn* row = first_mask + (b * V + j) * V;
-        for (int k = 0; k < V; ++k) s += static_cast<float>(row[k]);
-      } else {
-        const TIn* row = q_mask + (b * Q + (j - V)) * Q;
-        for (int k = 0; k < Q; ++k) s += static_cast<float>(row[k]);
-      }
+      for (int k = lane; k < len; k += 32) s += static_cast<float>(row[k]);
+      s = warp_sum(s);
       on = (s != 0.0f) ? 1.0f : 0.0f;
     }
-    dec_mask[i] = on;
+    if (lane == 0) dec_mask[i] = on;
   }
 }
 

@@ -287,14 +287,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
           for (int h = 0; h < NH; ++h) {
             float v[32];
-            {
-              uint32_t racc[32];
-              __syncwarp();
-              tmem_ld_32x32(t_row + c * CW + 32 * h, racc);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(racc[j]) * e.alpha;
-            }
+            uint32_t racc[32];
+            __syncwarp();
+            tmem_ld_32x32(t_row + c * CW + 32 * h, racc);
+            tmem_ld_wait();
             if (last && h == NH - 1) {
               // this warp's last TMEM read of the accumulator buffer is done -> hand it back to the leader's MMA warp early
               tc_fence_before();
@@ -303,7 +299,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             }
             if (!active) continue;
 #if SAVQA_GEMM2_DIAG >= 3
-            sink ^= __float_as_uint(v[0]) ^ __float_as_uint(v[31]);
+            sink ^= racc[0] ^ racc[31];
             continue;
 #endif
             if constexpr (EPI != EPI_ATOMIC && SAVQA_GEMM2_DIAG == 0) {
@@ -314,17 +310,22 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 __syncwarp();
               }
             }
-            if (e.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias_w + CW * ((c - half) >> 1) + 32 * h + j);
-                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-              }
-            }
             if constexpr (EPI == EPI_BF16) {
-              if (e.relu) {
+              // bf16 output: acc * alpha + bias in one FMA per value, the ReLU inside the bf16 conversion, the ReLU gate of a
+              // dgrad as an integer test on the packed activation (the epilogue is what bounds the K = 512 GEMMs: every
+              // instruction here is paid once per output element)
+              if (e.bias) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(bias_w + CW * ((c - half) >> 1) + 32 * h + j);
+                  v[j] = fmaf(__uint_as_float(racc[j]), e.alpha, b4.x);
+                  v[j + 1] = fmaf(__uint_as_float(racc[j + 1]), e.alpha, b4.y);
+                  v[j + 2] = fmaf(__uint_as_float(racc[j + 2]), e.alpha, b4.z);
+                  v[j + 3] = fmaf(__uint_as_float(racc[j + 3]), e.alpha, b4.w);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(racc[j]) * e.alpha;
               }
               if (gate) {
 #pragma unroll
@@ -333,23 +334,38 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                   const uint32_t w[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
-                    const float2 f = unpack_bf16x2(w[q]);
-                    if (!(f.x > 0.0f)) v[8 * j + 2 * q] = 0.0f;
-                    if (!(f.y > 0.0f)) v[8 * j + 2 * q + 1] = 0.0f;
+                    // bf16 > 0  <=>  its 16 bits, read as a signed integer, are > 0 (activations are finite ReLU outputs)
+                    if (!(static_cast<int>(w[q] << 16) > 0)) v[8 * j + 2 * q] = 0.0f;
+                    if (!(static_cast<int>(w[q]) > 0xffff)) v[8 * j + 2 * q + 1] = 0.0f;
                   }
                 }
               }
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                const uint4 pk = make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
-                                            pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+                const uint4 pk = e.relu ? make_uint4(pack_bf16x2_relu(v[8 * u], v[8 * u + 1]), pack_bf16x2_relu(v[8 * u + 2], v[8 * u + 3]),
+                                                     pack_bf16x2_relu(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2_relu(v[8 * u + 6], v[8 * u + 7]))
+                                        : make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                                                     pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
 #if SAVQA_GEMM2_DIAG >= 2
                 sink ^= pk.x ^ pk.y ^ pk.z ^ pk.w;
 #else
                 *reinterpret_cast<uint4*>(buf + srow + ((static_cast<uint32_t>(4 * h + u) ^ sxor) << 4)) = pk;
 #endif
               }
+              if (e.colsum && e.relu) {  // the column sums below are taken from v: apply the ReLU there too
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+              }
             } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(racc[j]) * e.alpha;
+              if (e.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(bias_w + CW * ((c - half) >> 1) + 32 * h + j);
+                  v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                }
+              }
               if (e.res && row_ok) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {

@@ -705,6 +705,63 @@ class GraphAttentionFn(Function):
                 None, None, None, None, None)
 
 
+class TokenSelfAttentionFn(Function):
+    """multihead_attention (modules.py:119-207) on ONE token per sample attending to itself -- the decoder's self-attention
+    (AttModel_x3.py:148): the softmax over a single key is 1 whatever Q and K are (a masked key gives the uniform row, also 1), so
+        y = LN( relu(x Wv^T + bv) * query_mask + x )
+    and W_q, b_q, W_k, b_k receive exactly zero gradient (as in the reference, where d softmax = p (1 - p) = 0).  One N = C GEMM
+    instead of the N = 3C projection + the attention core, forward and backward: the decoder is a chain of launch-latency-bound
+    kernels, every link counts."""
+
+    @staticmethod
+    def forward(ctx, x, Wq, bq, Wk, bk, Wv, bv, gamma, beta, x_bf16, x_on, cfg):
+        packs, eps = cfg["packs"], cfg["eps"]
+        N, T, C = x.shape
+        assert T == 1
+        xc = x if x.is_contiguous() else x.contiguous()
+        if x_bf16 is None or x_on is None:
+            x_on, x_bf16 = ops.row_nonzero(xc.reshape(N, C))
+        x_bf16 = x_bf16.reshape(N, C)
+        pv = packs["v"].refresh([Wv], [bv])
+        vb = torch.empty(N, C, device=x.device, dtype=BF16)
+        ops.gemm(x_bf16, pv.w, N, C, C, bias=pv.bias, relu=True, out_bf16=vb)
+        o = torch.mul(vb, x_on.reshape(N, 1))  # fp32: the bf16 V row times the query mask, what W' V gives for a single key
+        y, pre, yb, y_on = ops.layernorm_fwd(o.reshape(N, 1, C), xc, gamma.detach(), beta.detach(), eps, save_pre=True, want_bf16=True,
+                                             want_on=True)
+        ctx.cfg, ctx.dims = cfg, (N, C)
+        ctx.save_for_backward(x_bf16, vb, x_on, pre, gamma, Wq, bq, Wk, bk)
+        ctx.mark_non_differentiable(yb, y_on)
+        ctx.set_materialize_grads(False)
+        return y, yb, y_on
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, *_unused):
+        if dy is None:
+            return (None,) * 12
+        x_bf16, vb, x_on, pre, gamma, Wq, bq, Wk, bk = ctx.saved_tensors
+        cfg = ctx.cfg
+        N, C = ctx.dims
+        pv = cfg["packs"]["v"]
+        sink: NormSink = cfg.get("norm_sink") or _NO_SINK
+        dgamma, dbeta = sink.buffers(gamma)
+        dpre, _ = ops.layernorm_bwd(dy.contiguous(), pre, gamma.detach(), cfg["eps"], dgamma, dbeta)
+        dpre2 = dpre.reshape(N, C)
+        dvb = ops.relu_gate_bf16(dpre2 * x_on.reshape(N, 1), vb)
+        dbv = pv.bias_grad_buffer(C, dy.device)
+        dWv = pv.weight_grad(dvb, x_bf16, C, C, bias_grad=dbv)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(N, C, device=dy.device, dtype=F32)
+            dgrad(dvb, pv, N, C, C, res=dpre2, out_f32=dx)  # + residual branch
+            dx = dx.reshape(N, 1, C)
+        o = pv.out
+        # unbound modules hand autograd explicit zeros for the Q / K projections, like the reference's autograd does (the trainer
+        # discovers the parameters of its flat buffers by their gradients); bound ones leave the zero-filled flat gradient alone
+        z = (lambda t: None) if pv.bound else torch.zeros_like
+        return (dx, z(Wq), z(bq), z(Wk), z(bk), o(dWv), o(dbv), sink.out(dgamma), sink.out(dbeta), None, None, None)
+
+
 # ======================================================================================================
 # feedforward  -- modules.py:405-447
 # ======================================================================================================

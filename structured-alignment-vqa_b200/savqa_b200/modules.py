@@ -171,6 +171,14 @@ class _attention_base(nn.Module):
                    packs=self._packs, eps=self.normalization.epsilon, norm_sink=self.normalization._sink,
                    kv_holder=getattr(keys, "_savqa_kv_holder", None) if keys is values else None, kv_index=self._kv_index)
         sq, sk = Side.of(queries), Side.of(keys)
+        if (graph is None and self._renorm == 0 and not self.return_att and queries is keys and keys is values and queries.dim() == 3
+                and queries.shape[1] == 1 and queries.is_cuda == self.Q_proj[0].weight.is_cuda):
+            # one token attending to itself (the decoder's self-attention): the attention weight is identically 1
+            y, yb, on = Fn.TokenSelfAttentionFn.apply(
+                queries, self.Q_proj[0].weight, self.Q_proj[0].bias, self.K_proj[0].weight, self.K_proj[0].bias,
+                self.V_proj[0].weight, self.V_proj[0].bias, self.normalization.gamma, self.normalization.beta,
+                sq.bf16 if sq else None, sq.on if sq else None, cfg)
+            return _attach(y, yb, on)
         outs = Fn.GraphAttentionFn.apply(
             queries, keys, values, graph,
             self.Q_proj[0].weight, self.Q_proj[0].bias, self.K_proj[0].weight, self.K_proj[0].bias,
