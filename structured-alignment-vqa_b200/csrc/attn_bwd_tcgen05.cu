@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Two-CTAs-per-SM variant for the training step's symbolic branch (64 < Tk <= 128, Tq <= 128, d = 64, forward statistics,
+// Two-CTAs-per-SM variant for the training step (32 < Tk <= 128, Tq <= 128, d = 64, forward statistics,
 // no causal mask, 0/1 graph bit-packed or absent).  The W' and dS tiles share ONE shared-memory tile: the row pass writes W'
 // and keeps its 64 dS values packed in 32 registers; dV = W'^T dO is issued alone; once it has read the tile the dS values
 // overwrite it and dQ / dK follow, while the dV accumulator is already being stored.  96 KB of tiles instead of 128 KB and
@@ -556,8 +556,10 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_tc1_kernel(const __grid_const
   const int h = hn / a.N, n = hn % a.N;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sX = smem;                            // 2 x [128][128 B]   W', then dS
-  uint8_t* sQ = sX + 2 * 16384;                  // DCH x [128][128 B]
+  const int kc = p.kc;                           // 64-key chunks of the tile (1 or 2); each thread owns kc 32-column chunks of its row
+  uint8_t* sX = smem;                            // kc x [128][128 B]   W', then dS  (kc == 1: the MN-major MMAs read a second chunk,
+                                                 // the Q tile behind it -- finite values that only reach key rows >= Tk, never stored)
+  uint8_t* sQ = sX + kc * 16384;                 // DCH x [128][128 B]
   uint8_t* sdO = sQ + DCH * 16384;               // DCH x [128][128 B]
   uint8_t* sK = sdO + DCH * 16384;               // DCH x [kv_rows][128 B]
   uint8_t* sV = sK + DCH * p.kv_rows * 128;      // DCH x [kv_rows][128 B]
@@ -597,8 +599,8 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_tc1_kernel(const __grid_const
   if (a.graph_bits && a.renorm != 0) {
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
-      const int w = half * 2 + cc;
-      gwd[cc] = (row_ok && w < wpr) ? __ldg(a.graph_bits + static_cast<long>(n) * a.bits_n_stride + static_cast<long>(i) * a.bits_q_stride + w) : 0u;
+      const int w = half * kc + cc;
+      gwd[cc] = (row_ok && cc < kc && w < wpr) ? __ldg(a.graph_bits + static_cast<long>(n) * a.bits_n_stride + static_cast<long>(i) * a.bits_q_stride + w) : 0u;
     }
   }
 
@@ -693,7 +695,8 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_tc1_kernel(const __grid_const
   uint32_t dsp[2][16];  // this thread's 64 dS values, bf16 pairs: written to the shared tile once dV = W'^T dO has read W' from it
 #pragma unroll
   for (int cc = 0; cc < 2; ++cc) {
-    const int c0 = (half * 2 + cc) * 32;
+    if (cc >= kc) break;
+    const int c0 = (half * kc + cc) * 32;
     float wq[32];
     if (c0 < a.Tk) {  // warp-uniform
       uint32_t r[32], w[32];
@@ -759,7 +762,8 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_tc1_kernel(const __grid_const
   tc_fence_after();
 #pragma unroll
   for (int cc = 0; cc < 2; ++cc) {
-    const int c0 = (half * 2 + cc) * 32;
+    if (cc >= kc) break;
+    const int c0 = (half * kc + cc) * 32;
     const int off = (c0 >> 6) * 16384 + t * 128;
     const int u0 = (c0 & 63) >> 3;
 #pragma unroll
@@ -893,10 +897,10 @@ int attn_bwd_tc(const savqa_attn_args_t* a, cudaStream_t stream) {
   if (int rc = make_map3(&tmV, a->v, a->ldv, a->Tk, a->N, p.kv_rows)) return rc;
   dim3 grid(a->N * a->H);
   // the training step's symbolic branch: two CTAs per SM with the shared W' / dS tile (attn_bwd_tc1_kernel)
-  const bool one_tile = a->d == 64 && p.kc == 2 && p.kt == 1 && a->stats && a->out && !a->causal &&
+  const bool one_tile = a->d == 64 && p.kc <= 2 && p.kt == 1 && a->Tk > 32 && a->stats && a->out && !a->causal &&
                         (a->graph_bits || !a->graph || a->renorm == 0) && p.tmem_cols <= 256 && getenv("SAVQA_ATTN_BWD_ONE_TILE_OFF") == nullptr;
   if (one_tile) {
-    const size_t smem1 = 1024 + static_cast<size_t>(2) * 16384 + static_cast<size_t>(2) * 16384 + static_cast<size_t>(2) * p.kv_rows * 128;
+    const size_t smem1 = 1024 + static_cast<size_t>(p.kc) * 16384 + static_cast<size_t>(2) * 16384 + static_cast<size_t>(2) * p.kv_rows * 128;
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_bwd_tc1_kernel<64>), smem1, "savqa_graph_attn_bwd (tcgen05 engine, shared tile)"))
       return rc;
     SAVQA_CHECK_CUDA(launch_kernel(true, attn_bwd_tc1_kernel<64>, grid, dim3(256), smem1, stream, tmQ, tmK, tmV, p));

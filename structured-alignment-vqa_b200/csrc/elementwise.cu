@@ -209,7 +209,22 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long ld,
   float a0 = 0.0f, a1 = 0.0f;
   if (c < cols) {
     const bool pair = (c + 1 < cols) && (ld % 2 == 0);
-    for (long r = static_cast<long>(blockIdx.y) * blockDim.y + threadIdx.y; r < rows; r += static_cast<long>(gridDim.y) * blockDim.y) {
+    long r = static_cast<long>(blockIdx.y) * blockDim.y + threadIdx.y;
+    const long stride = static_cast<long>(gridDim.y) * blockDim.y;
+    if (pair) {  // four rows in flight per thread: the kernel is a pure stream, its loads must not wait for each other
+      float b0 = 0.0f, b1 = 0.0f, c0 = 0.0f, c1 = 0.0f, d0 = 0.0f, d1 = 0.0f;
+      for (; r + 3 * stride < rows; r += 4 * stride) {
+        const uint32_t u0 = *reinterpret_cast<const uint32_t*>(x + r * ld + c);
+        const uint32_t u1 = *reinterpret_cast<const uint32_t*>(x + (r + stride) * ld + c);
+        const uint32_t u2 = *reinterpret_cast<const uint32_t*>(x + (r + 2 * stride) * ld + c);
+        const uint32_t u3 = *reinterpret_cast<const uint32_t*>(x + (r + 3 * stride) * ld + c);
+        const float2 f0 = unpack_bf16x2(u0), f1 = unpack_bf16x2(u1), f2 = unpack_bf16x2(u2), f3 = unpack_bf16x2(u3);
+        a0 += f0.x; a1 += f0.y; b0 += f1.x; b1 += f1.y; c0 += f2.x; c1 += f2.y; d0 += f3.x; d1 += f3.y;
+      }
+      a0 = (a0 + b0) + (c0 + d0);
+      a1 = (a1 + b1) + (c1 + d1);
+    }
+    for (; r < rows; r += stride) {
       if (pair) {
         const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
         a0 += f.x;

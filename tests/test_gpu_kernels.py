@@ -426,9 +426,10 @@ def test_attention_backward(ops, engine, N, H, Tq, Tk, d, renorm, causal):
         assert max(e3) < (1e-2 if Tq < 8 else tol), e3
 
 
-@pytest.mark.parametrize("N,H,Tq,Tk", [(3, 8, 128, 128), (2, 8, 100, 100), (2, 8, 72, 72), (2, 8, 40, 120), (130, 8, 128, 128)])
+@pytest.mark.parametrize("N,H,Tq,Tk", [(3, 8, 128, 128), (2, 8, 100, 100), (2, 8, 72, 72), (2, 8, 40, 120), (130, 8, 128, 128),
+                                       (3, 8, 56, 56), (2, 8, 64, 64), (2, 8, 36, 36), (2, 8, 20, 50)])
 def test_attention_backward_shared_tile_kernel(ops, N, H, Tq, Tk):
-    """The step's symbolic-branch backward (64 < Tk <= 128, bit-packed graph, forward statistics): the two-CTAs-per-SM kernel
+    """The step's encoder backward (32 < Tk <= 128, bit-packed graph, forward statistics): the two-CTAs-per-SM kernel
     that shares one tile between W' and dS must agree with the fp32 restatement and -- bit for bit -- with the one-CTA kernel
     (same arithmetic, different schedule), masked keys and query rows included."""
     import os
