@@ -89,6 +89,25 @@ class _Branch(nn.Module):
             n = 2 * self.num_blocks * C
             pk.bind(fv.bf16(g[0]).view(n, C), fv.param(g[1]), fv.grad(g[0]).view(n, C), fv.grad(g[1]))
 
+    def _masks_aside(self, first_mask, q_mask, q_graph, first_graph, dec_on):
+        """Mask construction (AttModel_x3.py:103-122 / :229-247) depends on nothing the input MLPs produce: on a GPU it runs on a
+        helper stream next to them; the caller joins with the returned event before the first attention."""
+        if not first_mask.is_cuda:
+            return ops.build_masks(first_mask, q_mask, q_graph, first_graph, dec_on), None
+        cur = torch.cuda.current_stream()
+        aside = Fn.wgrad_stream_of(cur)
+        aside.wait_stream(cur)
+        with torch.cuda.stream(aside):
+            masks = ops.build_masks(first_mask, q_mask, q_graph, first_graph, dec_on)  # (+ the bit-packed forms of the two graphs)
+            done = torch.cuda.Event()
+            done.record(aside)
+        for m in masks:
+            m.record_stream(cur)
+            bits = ops.graph_bits_of(m)
+            if bits is not None:
+                bits.record_stream(cur)
+        return masks, done
+
     def _input_stage(self, first_ipt, q_ids, pos_table, pos_dropout_p):
         B = first_ipt.shape[0]
         q = Fn.EmbeddingFn.apply(q_ids, self.syb_emb.weight, 1.0, -1, getattr(self.syb_emb, "_savqa_rowlog", None))  # :96 / :216
@@ -205,8 +224,10 @@ class AttModel_vis_grid(_Branch):
     def forward(self, vis_fea, vis_mask, q_fea, q_graph, q_mask, decMask):
         if vis_fea.dim() == 4:  # bs x gridx x gridy x fea_size
             vis_fea = vis_fea.reshape(-1, vis_fea.size(1) * vis_fea.size(2), vis_fea.size(3))
+        (graph_diag, graph, dec_mask), done = self._masks_aside(vis_mask, q_mask, q_graph, None, decMask != False)  # noqa: E712
         x = self._input_stage(vis_fea, q_fea, self.syb_positional_encoding[0].lookup_table, self.dropout_rate)
-        graph_diag, graph, dec_mask = ops.build_masks(vis_mask, q_mask, q_graph, None, decMask != False)  # noqa: E712
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
         return self._encode_decode(x, graph_diag, graph, dec_mask)
 
 
@@ -234,8 +255,10 @@ class AttModel_syb(_Branch):
         self._pk = {"mlp": WeightPack(), "mlp2": WeightPack()}
 
     def forward(self, syb_ipt, syb_mask, syb_graph, q_fea, q_graph, q_mask, decMask):
+        (graph_diag, graph, dec_mask), done = self._masks_aside(syb_mask, q_mask, q_graph, syb_graph, decMask != False)  # noqa: E712
         x = self._input_stage(syb_ipt, q_fea, self.syb_positional_encoding.lookup_table, 0.0)
-        graph_diag, graph, dec_mask = ops.build_masks(syb_mask, q_mask, q_graph, syb_graph, decMask != False)  # noqa: E712
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
         return self._encode_decode(x, graph_diag, graph, dec_mask)
 
 
