@@ -52,7 +52,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        """Samples from here on count (the sampler is started early: nvidia-smi needs ~1 s before its first line)."""
+        self.t_mark = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -60,7 +64,10 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        t0 = getattr(self, "t_mark", 0.0)
+        for ts, r in self.rows:
+            if ts < t0:
+                continue
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -208,6 +215,9 @@ def main():
     host_batches = [synthetic.make_batch(cfg, args.batch, seed=100 + rank * 16 + i, pin=True) for i in range(2)]
     host_batches = [{k: b[k] for k in train.STEP_KEYS} for b in host_batches]
     dev_batch = {k: v.to(dev) for k, v in host_batches[0].items()}
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # early: nvidia-smi needs a second or two before its first line; only samples after mark() count
     trainer = train.EncoderTrainer(model, lr=1e-4, rowsparse=not args.dense_tables)
     trainer.prepare(dev_batch)
 
@@ -228,9 +238,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         run_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -238,7 +246,6 @@ def main():
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
     loss_val = float(loss)
 
     # ---- end to end through the public API with HOST (pinned) inputs: `e2e` ----
@@ -272,6 +279,8 @@ def main():
     t1.record()
     barrier()
     e2e_ms = t0.elapsed_time(t1)
+    # clocks / throttle reasons sampled under load: from the start of the device-timed region to the end of the end-to-end one
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- max over ranks ----
     if world > 1:

@@ -36,13 +36,30 @@ class GradReducer:
     the compute and weight-gradient streams that feed it, and overlaps the remaining backward.  finish() reduces whatever
     was not reported and hands back the (range, work) list for the optimizer to follow."""
 
-    def __init__(self, flat_grad: torch.Tensor, buckets, need, group):
+    def __init__(self, flat_grad: torch.Tensor, buckets, need, group, world: int = 2, apply_fn=None):
         self.flat_grad, self.buckets, self.need, self.group = flat_grad, buckets, need, group
-        self.got, self.works, self.done = Counter(), [], set()
+        self.world = world
+        # apply_fn(lo, hi): the optimizer update of flat range [lo, hi).  Under graph capture it is launched per bucket, right
+        # behind the bucket's all-reduce (world 1: behind its last gradient kernel) on a stream of its own, so that the
+        # HBM-bound Adam kernel runs under the rest of the backward pass instead of after it.  Safe: once a bucket's gradients
+        # are final every kernel that reads the bucket's weights in this step (its dgrad GEMMs) has completed.
+        self.apply_fn = apply_fn
+        self.got, self.works, self.done, self.pending = Counter(), [], set(), []
         self.launch_stream = torch.cuda.Stream() if flat_grad.is_cuda else None
+        self.apply_stream = torch.cuda.Stream() if (flat_grad.is_cuda and apply_fn is not None) else None
 
     def begin_step(self) -> None:
-        self.got, self.works, self.done = Counter(), [], set()
+        self.got, self.works, self.done, self.pending = Counter(), [], set(), []
+
+    @staticmethod
+    def _stage(key) -> tuple:
+        """Position of a bucket in the backward pass: heads, decoders, encoder blocks last to first."""
+        kind = key[1]
+        if kind == "heads":
+            return (0, 0)
+        if kind == "dec":
+            return (1, 0)
+        return (2, -int(key[2]))
 
     def ready(self, key) -> None:
         if key not in self.buckets or key in self.done:
@@ -54,23 +71,62 @@ class GradReducer:
         self.done.add(key)
         if hi <= lo:
             return
-        if self.launch_stream is not None:
-            cur = torch.cuda.current_stream()
-            r = self.launch_stream
-            r.wait_stream(cur)
-            w = Fn._WGRAD_STREAMS.get((cur.device_index, cur.cuda_stream))
+        if self.launch_stream is None:
+            self.works.append((lo, hi, self._all_reduce(lo, hi), False))
+            return
+        cur = torch.cuda.current_stream()
+        w = Fn._WGRAD_STREAMS.get((cur.device_index, cur.cuda_stream))
+        if torch.cuda.is_current_stream_capturing():
+            # Inside a graph capture the HOST order of the launches is irrelevant to when the kernels run -- but collectives of
+            # one communicator execute in launch order, and autograd walks the whole visual branch before the symbolic one: launched
+            # from here, every symbolic-branch bucket would queue behind the visual branch's LAST bucket (seen in the 2-GPU kernel
+            # trace: half of the all-reduce volume ran after the backward pass).  Record the readiness events now; finish() launches
+            # the buckets in the order in which the GPU completes them (stage by stage, both branches alternating).
+            evs = [torch.cuda.Event()]
+            evs[0].record(cur)
             if w is not None:
-                r.wait_stream(w)
+                evs.append(torch.cuda.Event())
+                evs[1].record(w)
+            self.pending.append((self._stage(key), len(self.pending), lo, hi, evs))
+            return
+        r = self.launch_stream
+        r.wait_stream(cur)
+        if w is not None:
+            r.wait_stream(w)
+        with torch.cuda.stream(r):
+            work = self._all_reduce(lo, hi)
+        self.works.append((lo, hi, work, False))
+
+    def _all_reduce(self, lo: int, hi: int):
+        if self.world <= 1:
+            return None
+        return dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+
+    def _launch_pending(self) -> None:
+        r, a = self.launch_stream, self.apply_stream
+        for _, _, lo, hi, evs in sorted(self.pending, key=lambda t: (t[0], t[1])):
+            for ev in evs:
+                r.wait_event(ev)
             with torch.cuda.stream(r):
-                work = dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-        else:
-            work = dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-        self.works.append((lo, hi, work))
+                work = self._all_reduce(lo, hi)
+            applied = False
+            if a is not None:
+                if work is None:
+                    for ev in evs:
+                        a.wait_event(ev)
+                with torch.cuda.stream(a):
+                    if work is not None:
+                        work.wait()
+                    self.apply_fn(lo, hi)
+                applied = True
+            self.works.append((lo, hi, work, applied))
+        self.pending = []
 
     def finish(self, chunks: int):
         """All-reduces the ranges no bucket report covered (in `chunks` pieces so that the optimizer can follow one piece
-        behind) and returns every (lo, hi, work) in launch order."""
+        behind) and returns every (lo, hi, work | None, already_applied) in launch order."""
         if self.launch_stream is not None:
+            self._launch_pending()
             torch.cuda.current_stream().wait_stream(self.launch_stream)
         covered = sorted(self.buckets[k] for k in self.done)
         gaps, pos, n = [], 0, self.flat_grad.numel()
@@ -86,7 +142,7 @@ class GradReducer:
             p = lo
             while p < hi:
                 q = min(hi, p + piece)
-                self.works.append((p, q, dist.all_reduce(self.flat_grad[p:q], op=dist.ReduceOp.AVG, group=self.group, async_op=True)))
+                self.works.append((p, q, self._all_reduce(p, q), False))
                 p = q
         return self.works
 
@@ -222,9 +278,10 @@ class EncoderTrainer:
         self.dyn_host = torch.zeros(3).pin_memory() if dev.type == "cuda" else torch.zeros(3)
         Fn.WEIGHT_EPOCH += 1
         self.reducer = None
-        if self.world > 1 and self.overlap_allreduce and not self._debug_skip_allreduce:
+        if (self.world > 1 or self.flat_grad.is_cuda) and self.overlap_allreduce and not self._debug_skip_allreduce:
             need = {k: (2 if k[1] == "heads" else 1) for k in self.bucket_ranges}  # both decoder outputs feed the heads
-            self.reducer = GradReducer(self.flat_grad, dict(self.bucket_ranges), need, self.pg)
+            self.reducer = GradReducer(self.flat_grad, dict(self.bucket_ranges), need, self.pg, self.world,
+                                       self._adam_range if self.flat_grad.is_cuda else None)
 
     def sync_mirror(self) -> None:
         """Re-derives the bf16 mirror from the fp32 parameters (after prepare(), or after load_state_dict wrote into them)."""
@@ -250,30 +307,40 @@ class EncoderTrainer:
         if self.flat_param.is_cuda:
             Fn.join_wgrad_streams()  # weight-gradient GEMMs run on side streams during the backward pass
         step = max(self.step_count, 1)
+        works = None
+        if self.world > 1 and not self._debug_skip_allreduce:
+            # the all-reduce travels in pieces on NCCL's stream -- the buckets the backward pass reported (GradReducer), then the
+            # remainder -- while the fused Adam kernel follows one piece behind on the compute stream.  Launched BEFORE the word
+            # tables' all-gathers: collectives of one communicator run in launch order, and those wait for the end of the backward
+            if self.reducer is not None:
+                works = self.reducer.finish(2)  # what no bucket covers is small (input MLPs, tables): two pieces, latency bound
+            else:
+                n = self.flat_grad.numel()
+                k = self.allreduce_chunks
+                bounds = [(n * i // k) // 8 * 8 for i in range(k)] + [n]
+                works = [(lo, hi, dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.AVG, group=self.pg, async_op=True), False)
+                         for lo, hi in zip(bounds[:-1], bounds[1:])]
+        elif self.reducer is not None:
+            works = self.reducer.finish(1)  # single GPU: per-bucket Adam launched under the backward pass, the remainder here
         rows_done = False
-        if self.rowsparse and self.world == 1 and self.flat_param.is_cuda:
-            # single GPU: the word tables' row updates touch nothing the flat Adam kernel touches -> on a helper stream, under it
+        if self.rowsparse and self.flat_param.is_cuda:
+            # the word tables' row updates (and, multi-GPU, the all-gathers of their row lists) touch nothing the flat gradient
+            # all-reduce / Adam kernel touch -> on a helper stream, under them
             cur = torch.cuda.current_stream()
             aside = Fn.wgrad_stream_of(cur)
             aside.wait_stream(cur)
             with torch.cuda.stream(aside):
                 self._apply_rows()
             rows_done, self._rows_stream = True, aside
-        if self.world > 1 and not self._debug_skip_allreduce:
-            # the all-reduce travels in pieces on NCCL's stream -- the buckets the backward pass reported first (GradReducer),
-            # then the remainder in chunks -- while the fused Adam kernel follows one piece behind on the compute stream
-            if self.reducer is not None:
-                works = self.reducer.finish(self.allreduce_chunks)
-            else:
-                n = self.flat_grad.numel()
-                k = self.allreduce_chunks
-                bounds = [(n * i // k) // 8 * 8 for i in range(k)] + [n]
-                works = [(lo, hi, dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
-                         for lo, hi in zip(bounds[:-1], bounds[1:])]
-            for lo, hi, w in works:
-                w.wait()
-                ops.adam_step(self.flat_param[lo:hi], self.flat_grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.lr, b1, b2,
-                              self.eps, step, dyn=self.dyn, param_bf16=self.flat_bf16[lo:hi])
+        if works is not None:
+            for lo, hi, w, applied in works:
+                if applied:
+                    continue
+                if w is not None:
+                    w.wait()
+                self._adam_range(lo, hi)
+            if self.reducer is not None and self.reducer.apply_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.reducer.apply_stream)
         else:
             ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, b1, b2, self.eps, step,
                           dyn=self.dyn, param_bf16=self.flat_bf16)
@@ -281,6 +348,11 @@ class EncoderTrainer:
             self._apply_rows()
         elif rows_done:
             torch.cuda.current_stream().wait_stream(self._rows_stream)
+
+    def _adam_range(self, lo: int, hi: int) -> None:
+        b1, b2 = self.betas
+        ops.adam_step(self.flat_param[lo:hi], self.flat_grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.lr, b1, b2,
+                      self.eps, max(self.step_count, 1), dyn=self.dyn, param_bf16=self.flat_bf16[lo:hi])
 
     def _apply_rows(self) -> None:
         """Row-sparse update of the 407000 x 300 word tables: (row id, row gradient) lists -> lazy row-wise Adam."""

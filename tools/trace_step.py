@@ -18,12 +18,17 @@ from savqa_b200 import _lib, synthetic, train  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=128)
 args = ap.parse_args()
+rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
 _lib.require_device()
-dev = torch.device("cuda", 0)
+dev = torch.device("cuda", local)
+if world > 1:  # under torchrun: every rank runs the step, rank 0 records its own timeline (NCCL kernels included)
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
 cfg = synthetic.GQA_SHAPED
 model = synthetic.build_model(cfg, seed=0).to(dev)
 model.train()
-b = synthetic.make_batch(cfg, args.batch, seed=100, pin=True)
+b = synthetic.make_batch(cfg, args.batch, seed=100 + rank * 16, pin=True)
 dev_batch = {k: b[k].to(dev) for k in train.STEP_KEYS}
 trainer = train.EncoderTrainer(model, lr=1e-4, rowsparse=True)
 trainer.prepare(dev_batch)
@@ -31,10 +36,14 @@ trainer.capture(dev_batch, warmup=2)
 for _ in range(5):
     trainer.replay()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+import contextlib  # noqa: E402
+with (profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) if rank == 0 else contextlib.nullcontext()) as prof:
     for _ in range(3):
         trainer.replay()
     torch.cuda.synchronize()
+if rank != 0:
+    torch.distributed.barrier()
+    os._exit(0)
 path = os.path.join(ROOT, "gpurun_out", "trace_full.json")
 os.makedirs(os.path.dirname(path), exist_ok=True)
 prof.export_chrome_trace(path)
@@ -43,10 +52,11 @@ ks = [e for e in ev if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") an
 ks.sort(key=lambda e: e["ts"])
 print("gpu activities:", len(ks))
 if ks:
-    # split into replays at the adam kernel (last kernel of a step)
-    ends = [i for i, e in enumerate(ks) if "adam_kernel" in e["name"]]
-    lo = ends[0] + 1 if len(ends) >= 2 else 0
-    hi = ends[1] + 1 if len(ends) >= 2 else len(ks)
+    # split into replays at the host-to-device copy of the optimizer's per-step scalars (EncoderTrainer._set_dyn: the first
+    # activity of every replay)
+    starts = [i for i, e in enumerate(ks) if e.get("cat") == "gpu_memcpy" and "HtoD" in e["name"]]
+    lo = starts[1] if len(starts) >= 3 else 0
+    hi = starts[2] if len(starts) >= 3 else len(ks)
     one = ks[lo:hi]
     t0 = one[0]["ts"]
     rows = [dict(n=e["name"].replace("void ", "").replace("savqa::(anonymous namespace)::", "")[:90], s=e["args"].get("stream", -1), t=round(e["ts"] - t0, 2), d=round(e["dur"], 2)) for e in one]
@@ -71,3 +81,7 @@ if ks:
     busy += cur_e - cur_s
     print(f"  union busy {busy / 1e3:.3f} ms, idle {(span - busy) / 1e3:.3f} ms")
 os.remove(path)
+if world > 1:
+    torch.distributed.barrier()
+    sys.stdout.flush()
+    os._exit(0)
