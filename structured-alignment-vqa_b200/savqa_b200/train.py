@@ -278,10 +278,14 @@ class EncoderTrainer:
         self.dyn_host = torch.zeros(3).pin_memory() if dev.type == "cuda" else torch.zeros(3)
         Fn.WEIGHT_EPOCH += 1
         self.reducer = None
-        if (self.world > 1 or self.flat_grad.is_cuda) and self.overlap_allreduce and not self._debug_skip_allreduce:
+        # Per-bucket Adam under the backward pass (GradReducer.apply_fn) is implemented but OFF: measured on B200 it moves the
+        # 0.44 ms of Adam under the backward and the backward slows down by as much (1 GPU: 7.65 -> 7.65 ms; 2 GPUs: 8.07 ->
+        # 8.39 ms) -- the step is bound by the aggregate HBM / SM time of its kernels, not by its critical path.
+        per_bucket_adam = os.environ.get("SAVQA_ADAM_PER_BUCKET", "0") == "1" and self.flat_grad.is_cuda
+        if (self.world > 1 or per_bucket_adam) and self.overlap_allreduce and not self._debug_skip_allreduce:
             need = {k: (2 if k[1] == "heads" else 1) for k in self.bucket_ranges}  # both decoder outputs feed the heads
             self.reducer = GradReducer(self.flat_grad, dict(self.bucket_ranges), need, self.pg, self.world,
-                                       self._adam_range if self.flat_grad.is_cuda else None)
+                                       self._adam_range if per_bucket_adam else None)
 
     def sync_mirror(self) -> None:
         """Re-derives the bf16 mirror from the fp32 parameters (after prepare(), or after load_state_dict wrote into them)."""
