@@ -121,3 +121,16 @@ def test_data_parallel_world2_gloo(monkeypatch, tmp_path):
     worst = max(float((dp[k] - v).abs().max()) for k, v in model.state_dict().items() if v.dtype.is_floating_point)
     assert worst < 1e-6
 
+
+
+def test_grad_reducer_launch_order_follows_the_backward_pass():
+    """Under graph capture the reducer launches the bucket all-reduces in finish(), ordered by the stage of the backward pass that
+    completes them -- heads, decoders, encoder blocks last to first, the two branches alternating -- not in the order autograd
+    happened to report them (the whole visual branch first): collectives of one communicator run in launch order."""
+    from savqa_b200.train import GradReducer
+    a, b = 111, 222  # ids of the two branch models
+    reported = [(a, "dec")] + [(a, "enc", i) for i in range(5, -1, -1)] + [(0, "heads")] + [(b, "dec")] + [(b, "enc", i) for i in range(5, -1, -1)]
+    pending = [(GradReducer._stage(k), n, k) for n, k in enumerate(reported)]
+    order = [k for _, _, k in sorted(pending, key=lambda t: (t[0], t[1]))]
+    assert order[0] == (0, "heads") and order[1:3] == [(a, "dec"), (b, "dec")]
+    assert order[3:] == [(br, "enc", i) for i in range(5, -1, -1) for br in (a, b)]
