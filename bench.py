@@ -85,7 +85,7 @@ def dominant_kernel_roofline(batch, cfg, peaks, iters=10):
     ~60 % of the step's kernel time, 98 % of its FLOPs) -- on the forward GEMM shapes of both branch models' encoder blocks
     (fused QKV projection, feedforward conv1 and conv2), each launched alone on the current stream with the L2 flushed
     between launches.  achieved = algorithmic 2*M*N*K FLOPs per launch / mean launch duration; peak = the measured BURST
-    bf16 figure (a kernel timed alone).  `traffic` is the ncu dram__bytes_read+write of the conv1 launch (profiles/)."""
+    bf16 figure (a kernel timed alone).  `traffic` is the ncu dram__bytes_read+write of the conv1 launch (profiles/r1_07_ncu_gemm2_conv1.txt)."""
     import torch
     from savqa_b200 import ops
     C, Hd = cfg["hidden"], 4 * cfg["hidden"]
@@ -124,10 +124,11 @@ def dominant_kernel_roofline(batch, cfg, peaks, iters=10):
             shapes.append(f"{name} M={M} N={N} K={K}: {mean_us:.1f} us")
     achieved = total_flops / total_us / 1e6  # TFLOP/s
     return {"bound": "tensor", "kernel": "gemm2_bf16_kernel (tcgen05 cta_group::2, TMA, TMEM)", "achieved": achieved, "peak": peaks["tf_burst"],
-            "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"], "traffic": 28.57e6,
+            "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"], "traffic": 29.9e6,
             "note": f"FLOP-weighted over {n_launch} forward GEMM shapes of the encoder blocks, each timed alone with CUDA events on the "
                     f"launching stream, L2 flushed between launches; peak = {peaks['source']} burst bf16 figure; traffic = ncu "
-                    "dram bytes of the conv1 M=16384 launch (profiles/r1_03_ncu_gemm2_conv1.txt; writes still in L2 when ncu stops counting)",
+                    "dram bytes of the conv1 M=16384 launch (profiles/r1_07_ncu_gemm2_conv1.txt: 18.9 MB read + 11.0 MB written while ncu counts; the 67 MB bf16 output "
+                    "is still in the 126 MB L2 when the kernel ends; algorithmic bytes 86 MB)",
             "shapes": shapes}
 
 

@@ -104,7 +104,7 @@ __global__ void ln_fwd_generic_kernel(const float* __restrict__ x, const float* 
 // backward: dx = (g - mean g)/s - c * dot(g,c) / ((C-1) sigma s^2)  [second term dropped when sigma == 0, like autograd]
 //           dgamma += sum_rows dy * c / s ; dbeta += sum_rows dy
 template <int NV>
-__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict__ pre,
+__global__ void __launch_bounds__(256, 2) ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict__ pre,
                                                          const float* __restrict__ gamma, float eps, long rows,
                                                          const float* __restrict__ dres_in, float* __restrict__ dx,
                                                          __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
