@@ -68,6 +68,18 @@ def test_bound_trainer_matches_autograd_adam(monkeypatch, rowsparse, steps):
     assert model.att_vis_grid.enc_feed_forward_0._packs["w1"].bound
     assert not model.att_vis_grid._pk["mlp"].bound  # K = 300 is not a multiple of 8: stays on the staging path
     assert model.att_syb._pk["mlp2"].bound and model._pk["cls"][0].bound
+    # the decoder's cross-attention layers keep [Wk_0; Wv_0; ...; Wk_5; Wv_5] as ONE block of the flat buffers (one K/V GEMM for
+    # the six layers); every layer's own packs are slices of it, and its Wq / bq are bound on their own
+    br = model.att_vis_grid
+    C, L = br.hidden_size, br.num_blocks
+    pall = br._pk["kv_all"]
+    assert pall.bound and pall.w.shape == (2 * L * C, C) and pall.gb.shape == (2 * L * C,)
+    for i in range(L):
+        lay = getattr(br, "dec_vanilla_attention_%d" % i)
+        assert lay._kv_external and lay._kv_index == i and lay._packs["q"].bound and not lay._packs["qkv"].bound
+        assert lay._packs["kv"].w.data_ptr() == pall.w[2 * C * i:].data_ptr() and lay._packs["kv"].gw.data_ptr() == pall.gw[2 * C * i:].data_ptr()
+        assert lay._packs["kv"].gw.data_ptr() == lay.K_proj[0].weight.grad.data_ptr()
+        assert lay._packs["v"].gb.data_ptr() == lay.V_proj[0].bias.grad.data_ptr()
     assert losses == pytest.approx(ref_losses, rel=1e-5)
     # bf16 operands make the two runs differ only through rounding noise inside identical arithmetic: same stand-in kernels
     assert _max_param_diff(model, ref) < 2e-5
