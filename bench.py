@@ -132,6 +132,61 @@ def dominant_kernel_roofline(batch, cfg, peaks, iters=10):
             "shapes": shapes}
 
 
+def attention_roofline(batch, cfg, peaks, iters=10):
+    """BASELINE.json's second figure, "attn % of tensor-core peak": the fused graph-masked attention core (csrc/attn_tcgen05.cu,
+    attn_bwd_tcgen05.cu) timed alone with CUDA events at the step's two shapes (T = V+Q and M+Q keys per sample, 8 heads, d = 64,
+    bit-packed graph, forward statistics reused by the backward), L2 flushed between launches.  Dense-equivalent FLOPs
+    (4 T^2 d forward, 10 T^2 d backward per sample and head) against the measured burst bf16 peak, and algorithmic bytes against
+    the measured HBM peak -- at these sizes (AI 28..130 flop/B, ridge 212) the core is memory/latency bound, so the tensor
+    fraction is small by construction."""
+    import torch
+    from savqa_b200 import ops
+    C, H = cfg["hidden"], cfg["heads"]
+    d = C // H
+    BF = torch.bfloat16
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    out = {}
+    tot_flops = tot_us = 0.0
+    for T in (cfg["V"] + cfg["Q"], cfg["M"] + cfg["Q"]):
+        N, M = batch, batch * T
+        qkv = torch.randn(M, 3 * C, device="cuda").relu().to(BF)
+        q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+        graph = (torch.rand(N, T, T, device="cuda") < 0.3).float()
+        graph[:, torch.arange(T), torch.arange(T)] = 1
+        on = torch.ones(M, device="cuda")
+        bits = ops.pack_graph_bits(graph)
+        stats = torch.empty(H * N * T * 4, device="cuda")
+        dout = torch.randn(M, C, device="cuda")
+        dqkv = torch.empty(M, 3 * C, device="cuda", dtype=BF)
+        fwd = lambda: ops.graph_attention_fwd(q, k, v, graph, on, on, N, H, T, T, d, False, 1, False, 0, graph_bits=bits, stats=stats)  # noqa: E731
+        o, _ = fwd()
+        bwd = lambda: ops.graph_attention_bwd(q, k, v, graph, on, on, N, H, T, T, d, False, 1, dout, dqkv[:, :C], dqkv[:, C:2 * C],  # noqa: E731
+                                              dqkv[:, 2 * C:], graph_bits=bits, stats=stats, fwd_out=o)
+        for name, fn, flops, nbytes in (("fwd", fwd, 4.0 * N * H * T * T * d, M * 3 * C * 2 + N * T * T / 8 + M * C * 4),
+                                        ("bwd", bwd, 10.0 * N * H * T * T * d, M * 3 * C * 2 * 2 + N * T * T / 8 + 2 * M * C * 4)):
+            for _ in range(3):
+                fn()
+            us = []
+            for _ in range(iters):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                us.append(e0.elapsed_time(e1) * 1e3)
+            mean_us = sum(us) / len(us)
+            tot_flops += flops
+            tot_us += mean_us
+            out[f"{name}_T{T}"] = {"us": round(mean_us, 1), "tflops": round(flops / mean_us / 1e6, 1),
+                                   "pct_tensor_peak": round(100 * flops / mean_us / 1e6 / peaks["tf_burst"], 2),
+                                   "gbs": round(nbytes / mean_us / 1e3, 1), "pct_hbm_peak": round(100 * nbytes / mean_us / 1e3 / peaks["hbm_gbs"], 1)}
+    out["pct_tensor_peak"] = round(100 * tot_flops / tot_us / 1e6 / peaks["tf_burst"], 2)
+    out["note"] = ("fused adjacency-masked attention core, forward and backward at the step's two shapes, each launch timed alone (CUDA events, "
+                   "L2 flushed); dense-equivalent FLOPs vs the measured burst bf16 peak; HBM/latency bound at these sizes")
+    return out
+
+
 def cpu_reference_run(cfg, steps, warmup, batch_size, threads=None):
     """The reference's own CPU implementation of the path = the oracle port (the reference is Python and cannot be
     shipped to the box; oracle/savqa_oracle.py restates it op for op and is pinned to it by tests/golden)."""
@@ -302,6 +357,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches_per_step * args.steps,
                 "roofline": dominant_kernel_roofline(args.batch, cfg, peaks),
+                "attn_roofline": attention_roofline(args.batch, cfg, peaks),
                 "step_roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                                   "frac": achieved / peaks["tf_sustained"],
                                   "note": f"whole step: algorithmic dense-equivalent FLOPs {flops / 1e12:.3f} TFLOP/step/GPU over the "
