@@ -13,6 +13,7 @@
 // Epilogue: TMEM -> registers -> fused math -> 128B-swizzled smem staging -> TMA store (coalesced, asynchronous); the
 // operands it reads from HBM (residual / ReLU gate / bias) are prefetched one chunk ahead, the first chunk while the
 // tile's MMAs are still running.  Split-K partial sums (wgrad) go out with red.global.add.v4.f32.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -584,6 +585,10 @@ int gemm2_launch_group(const savqa_gemm_problem_t* probs, int count, int a_mn, i
   };
   int BN = 256;
   if (N % 256 != 0 || rounds(128) * 10 < rounds(256) * 9) BN = 128;
+  {  // experiment knob (tools/gpu_env_sweep.sh): SAVQA_GEMM2_BN = 128 | 256 forces the tile width where it is legal
+    static const int forced = [] { const char* e = getenv("SAVQA_GEMM2_BN"); return e ? atoi(e) : 0; }();
+    if (forced == 128 || (forced == 256 && N % 256 == 0)) BN = forced;
+  }
   Maps m;
   int total = 0;
   for (int i = 0; i < count; ++i) {

@@ -9,8 +9,11 @@ namespace {
 
 constexpr int kMaxV4 = 8;  // row cached in registers up to C = 8 * 128 = 1024
 
+#ifndef SAVQA_LN_FWD_BLOCKS
+#define SAVQA_LN_FWD_BLOCKS 1  // resident 256-thread blocks per SM the forward kernel is compiled for (register cap)
+#endif
 template <int NV>  // NV float4 per lane, C == NV * 128
-__global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ res,
+__global__ void __launch_bounds__(256, SAVQA_LN_FWD_BLOCKS) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                          long rows, float* __restrict__ pre, float* __restrict__ y,
                                                          __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ on) {
