@@ -219,7 +219,6 @@ def layernorm_bwd(dy: Tensor, pre: Tensor, gamma: Tensor, eps: float, dgamma: Op
 
 
 # ------------------------------------------------------------------------------------------------------
-_DEBUG_GEMM = os.environ.get("SAVQA_DEBUG_GEMM", "")  # "torch": bring-up aid ONLY (never set in tests/bench)
 
 
 def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False, bias: Optional[Tensor] = None,
@@ -246,10 +245,6 @@ def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_
         assert b.shape[0] >= N and b.shape[1] >= K, (b.shape, N, K)
     e = GemmEpilogue()
     _fill_epilogue(e, M, N, bias, res, rowtab, rowtab_period, gate, relu, alpha, out_f32, out_bf16, accumulate, split_k, colsum)
-    if _DEBUG_GEMM == "torch":
-        assert colsum is None
-        _gemm_debug_torch(a, b, M, N, K, a_mn, b_mn, bias, res, rowtab, rowtab_period, gate, relu, alpha, out_f32, out_bf16, accumulate)
-        return
     call("savqa_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), M, N, K, C.byref(e), int(split_k))
 
 
@@ -295,7 +290,7 @@ def gemm_sm_limit(sms: int):
 def gemm_grouped(problems, N: int, *, a_mn: bool = False, b_mn: bool = False, split_k: int = 1) -> None:
     """Several independent GEMMs with the same N / operand majors / kind of output in ONE launch (savqa_gemm_bf16_grouped): the
     same layer of the two branch models.  `problems`: dicts with a, b, M, K and the epilogue keywords of gemm()."""
-    if len(problems) == 1 or _DEBUG_GEMM == "torch" or len(problems) > 2:
+    if len(problems) == 1 or len(problems) > 2:
         for p in problems:
             kw = {k: v for k, v in p.items() if k not in ("a", "b", "M", "K")}
             gemm(p["a"], p["b"], p["M"], N, p["K"], a_mn=a_mn, b_mn=b_mn, split_k=split_k, **kw)
@@ -324,30 +319,6 @@ def wgrad_grouped(items) -> None:
     sk = min(split_k_for(tiles, (it[0].shape[0] + 63) // 64) for it in items)
     gemm_grouped([dict(a=dy, b=x, M=n_out, K=dy.shape[0], out_f32=out, accumulate=2) for dy, x, _, _, out in items], k_in,
                  a_mn=True, b_mn=True, split_k=sk)
-
-
-def _gemm_debug_torch(a, b, M, N, K, a_mn, b_mn, bias, res, rowtab, period, gate, relu, alpha, out_f32, out_bf16, accumulate):
-    """Bring-up aid for the GPU box (SAVQA_DEBUG_GEMM=torch): same contract through torch.matmul, to bisect a kernel bug."""
-    A = a[:K, :M].float().t() if a_mn else a[:M, :K].float()
-    Bm = b[:K, :N].float() if b_mn else b[:N, :K].float().t()
-    v = alpha * (A @ Bm)
-    if bias is not None:
-        v = v + bias[:N]
-    if res is not None:
-        v = v + res[:M, :N]
-    if rowtab is not None:
-        v = v + rowtab[:period, :N].repeat((M + period - 1) // period, 1)[:M]
-    if relu:
-        v = torch.relu(v)
-    if gate is not None:
-        v = v * (gate[:M, :N].float() > 0)
-    if out_f32 is not None:
-        if accumulate:
-            out_f32[:M, :N] += v
-        else:
-            out_f32[:M, :N] = v
-    if out_bf16 is not None:
-        out_bf16[:M, :N] = v.to(BF16)
 
 
 def split_k_for(tiles: int, k_blocks: int) -> int:
