@@ -34,6 +34,8 @@ VIS_PAD = -1
 LOC_PAD = -1
 VOCAB_ROWS = 407000  # hard-coded in the reference (AttModel_x3.py:36, 168, 293)
 _SIDE_STREAMS = {}   # device -> second stream of AttModel.encoder_step
+_HEAD_STREAMS = {}   # device -> the two extra streams of AttModel.answer_logits
+_HEADS_PARALLEL = os.environ.get("SAVQA_HEADS_PARALLEL", "1") != "0"
 
 
 class _CastBf16(torch.autograd.Function):
@@ -369,10 +371,30 @@ class AttModel(nn.Module):
 
     def answer_logits(self, fea_vis_grid, fea_syb):
         """Classifier heads of AttModel_x3.py:531-541 on the two [B,1,C] decoder outputs."""
-        logits_vis = self._classify("cls_vis", fea_vis_grid).squeeze(1)
-        logits_syb = self._classify("cls_syb", fea_syb).squeeze(1)
+        if not (fea_vis_grid.is_cuda and _HEADS_PARALLEL):
+            logits_vis = self._classify("cls_vis", fea_vis_grid).squeeze(1)
+            logits_syb = self._classify("cls_syb", fea_syb).squeeze(1)
+            fea = torch.cat((fea_syb.squeeze(1), fea_vis_grid.squeeze(1)), 1)
+            logits_concat = self._classify("cls", fea)
+            return logits_concat, logits_vis, logits_syb
+        # The three heads are independent chains of two M = B GEMMs (the second one 1845 classes wide): on a GPU they run side by
+        # side on three streams, forward and -- through autograd -- backward, instead of back to back while the SMs idle.
+        main = torch.cuda.current_stream()
+        hs = _HEAD_STREAMS.get(fea_vis_grid.device)
+        if hs is None:
+            hs = _HEAD_STREAMS[fea_vis_grid.device] = (torch.cuda.Stream(device=fea_vis_grid.device), torch.cuda.Stream(device=fea_vis_grid.device))
+        for st, fea_ in zip(hs, (fea_vis_grid, fea_syb)):
+            st.wait_stream(main)
+            fea_.record_stream(st)
+        with torch.cuda.stream(hs[0]):
+            logits_vis = self._classify("cls_vis", fea_vis_grid).squeeze(1)
+        with torch.cuda.stream(hs[1]):
+            logits_syb = self._classify("cls_syb", fea_syb).squeeze(1)
         fea = torch.cat((fea_syb.squeeze(1), fea_vis_grid.squeeze(1)), 1)
         logits_concat = self._classify("cls", fea)
+        for st, lg in zip(hs, (logits_vis, logits_syb)):
+            main.wait_stream(st)
+            lg.record_stream(main)
         return logits_concat, logits_vis, logits_syb
 
     def encoder_step(self, vis_fea, vis_mask, q_ipt, q_mask, q_graph, syb_ipt, macro_mask, macro_graph, decMask=True):

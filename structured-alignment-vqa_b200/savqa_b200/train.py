@@ -76,6 +76,8 @@ class GradReducer:
             return
         cur = torch.cuda.current_stream()
         w = Fn._WGRAD_STREAMS.get((cur.device_index, cur.cuda_stream))
+        # the heads run on streams of their own (AttModel.answer_logits): their bucket waits for every weight-gradient stream in use
+        extra = [s_ for s_ in Fn._WGRAD_DIRTY if s_ is not w] if key[1] == "heads" else []
         if torch.cuda.is_current_stream_capturing():
             # Inside a graph capture the HOST order of the launches is irrelevant to when the kernels run -- but collectives of
             # one communicator execute in launch order, and autograd walks the whole visual branch before the symbolic one: launched
@@ -84,15 +86,15 @@ class GradReducer:
             # the buckets in the order in which the GPU completes them (stage by stage, both branches alternating).
             evs = [torch.cuda.Event()]
             evs[0].record(cur)
-            if w is not None:
+            for s_ in ([w] if w is not None else []) + extra:
                 evs.append(torch.cuda.Event())
-                evs[1].record(w)
+                evs[-1].record(s_)
             self.pending.append((self._stage(key), len(self.pending), lo, hi, evs))
             return
         r = self.launch_stream
         r.wait_stream(cur)
-        if w is not None:
-            r.wait_stream(w)
+        for s_ in ([w] if w is not None else []) + extra:
+            r.wait_stream(s_)
         with torch.cuda.stream(r):
             work = self._all_reduce(lo, hi)
         self.works.append((lo, hi, work, False))
