@@ -12,8 +12,10 @@ timeout -k 10 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_ou
 ( time timeout -k 10 600 python bench.py --impl reference --steps 3 --warmup 1 ) > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "reference rc=$?"; cut -c1-160 gpurun_out/bench_reference.json
 timeout -k 10 300 python tools/trace_step.py 2>&1 | tail -4
 timeout -k 10 300 python tools/bench_kernels.py gemm attn ln adam > gpurun_out/kbench_${TAG}.log 2>&1; echo "kbench rc=$?"
-timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_${TAG}.csv \
-  python bench.py --mode eager --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_${TAG}.log 2>&1; echo "ncu launch list rc=$?"
+# (round 1: with -c 6000 and 3 warm-up steps this pass ran into a 900 s limit -- ~15 GPU-minutes -- after the step had long been
+#  written; one eager step is ~650 launches: stop ncu after the first few steps and cap the pass at 5 minutes)
+timeout -k 10 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 3200 --csv --log-file gpurun_out/launches_${TAG}.csv \
+  python bench.py --mode eager --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_${TAG}.log 2>&1; echo "ncu launch list rc=$?"
 python tools/summarize_launches.py gpurun_out/launches_${TAG}.csv > gpurun_out/launches_${TAG}.txt 2>&1; head -30 gpurun_out/launches_${TAG}.txt
 python tools/one_gemm.py 16384 2048 512 fwd 4 > gpurun_out/one_gemm_${TAG}.log 2>&1 && \
 timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:gemm2_bf16 -s 1 -c 2 -f -o gpurun_out/prof_gemm2_conv1_${TAG} python tools/one_gemm.py 16384 2048 512 fwd 4 > gpurun_out/ncu_gemm_${TAG}.log 2>&1; echo "ncu gemm rc=$?"
