@@ -282,17 +282,38 @@ def branch_goldens(M, A, out_dir):
          checksum=GS.checksum(Ph))
 
 
+def token_goldens(M, out_dir):
+    """multihead_attention (causal) on ONE token per sample attending to itself -- the decoder's self-attention
+    (AttModel_x3.py:148): the degenerate case savqa_b200 runs as a single N = C GEMM (functional.TokenSelfAttentionFn)."""
+    for tag, C, H in (("c64", 64, 4), ("c512", GS.WIDE["C"], GS.WIDE["heads"])):
+        N = 5 if C == 64 else 3
+        case = f"mha_token_{tag}"
+        P = GS.make_params(case, GS.attention_shapes(C))
+        q, _, _ = GS.attention_case(case, C, N, 1, 1, self_att=True)
+        m = M.multihead_attention(C, H, causality=True)
+        load_params(m, P)
+        x = q.clone().requires_grad_(True)
+        y = m(x, x, x)
+        w = GS.randn(f"{case}/dy", *y.shape)
+        (y * w).sum().backward()
+        g = grads_of(m, list(P.keys()))
+        save(os.path.join(out_dir, f"{case}.npz"), y=y, dx=x.grad, checksum=GS.checksum({**P, "q": q}), **GS.pack_grads(case, g))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
+    ap.add_argument("--only", default="", help="'token': (re)generate only the one-token self-attention fixtures")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(1)  # bit-stable reductions while generating
     M, A = import_reference(args.ref)
-    attention_goldens(M, args.out)
-    branch_goldens(M, A, args.out)
+    if args.only != "token":
+        attention_goldens(M, args.out)
+        branch_goldens(M, A, args.out)
+    token_goldens(M, args.out)
     with open(os.path.join(args.out, "MANIFEST.json"), "w") as f:
         json.dump({"torch": torch.__version__, "generator": "oracle/make_golden.py", "reference": "Peixixiong/Structured-Alignment-VQA",
                    "files": sorted(x for x in os.listdir(args.out) if x.endswith(".npz"))}, f, indent=1)

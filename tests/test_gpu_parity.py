@@ -41,6 +41,13 @@ def test_mha_causal(M, golden_dir, tag, C, H, N):
     PC.attention_case(M, golden_dir, "cuda", f"mha_causal_{tag}", C, H, N, 6, 6, True, kind="mha")
 
 
+@pytest.mark.parametrize("tag,C,H,N", [("c64", 64, 4, 5), ("c512", 512, 8, 3)])
+def test_mha_single_token(M, golden_dir, tag, C, H, N):
+    """The decoder's self-attention (one token attending to itself) runs as ONE N = C GEMM (functional.TokenSelfAttentionFn):
+    output, input gradient and parameter gradients (exact zeros for the Q / K projections) against the live reference's golden."""
+    PC.attention_case(M, golden_dir, "cuda", f"mha_token_{tag}", C, H, N, 1, 1, True, kind="mha")
+
+
 @pytest.mark.parametrize("tag,C,H,N,T", [("c64", 64, 4, 3, 10), ("c512", 512, 8, 2, 24)])
 def test_attention_graphmask(M, golden_dir, tag, C, H, N, T):
     PC.attention_case(M, golden_dir, "cuda", f"attn_graphmask_{tag}", C, H, N, T, T, True, kind="gm")

@@ -41,6 +41,7 @@ def test_attention_cross_wiring(fake, golden_dir, tq):
 def test_mha_causal_and_graphmask_wiring(fake, golden_dir):
     from savqa_b200 import modules as M
     PC.attention_case(M, golden_dir, "cpu", "mha_causal_c64", 64, 4, 3, 6, 6, True, kind="mha")
+    PC.attention_case(M, golden_dir, "cpu", "mha_token_c64", 64, 4, 5, 1, 1, True, kind="mha")  # one token: the single-GEMM form
     PC.attention_case(M, golden_dir, "cpu", "attn_graphmask_c64", 64, 4, 3, 10, 10, True, kind="gm")
     m = M.new_multihead_attention_with_graph_mask(64, 4)
     q = torch.randn(2, 3, 64)

@@ -82,6 +82,22 @@ def test_mha_causal(golden_dir, tag, C, H, N):
     GS.compare_grads(case, {k_: v.grad for k_, v in P.items()}, g, 1e-5)
 
 
+@pytest.mark.parametrize("tag,C,H,N", [("c64", 64, 4, 5), ("c512", 512, 8, 3)])
+def test_mha_single_token(golden_dir, tag, C, H, N):
+    case = f"mha_token_{tag}"  # one token attending to itself: the decoder's self-attention (AttModel_x3.py:148)
+    g = load(golden_dir, case)
+    P = GS.make_params(case, GS.attention_shapes(C))
+    q, _, _ = GS.attention_case(case, C, N, 1, 1, self_att=True)
+    check_checksum(g, {**P, "q": q})
+    P = {k_: v.clone().requires_grad_(True) for k_, v in P.items()}
+    x = q.clone().requires_grad_(True)
+    y, _ = O.attention(x, x, x, None, P, H, causality=True, renorm="none")
+    assert O.rel_err(y, t(g["y"])) < FP32_TOL
+    (y * GS.randn(f"{case}/dy", *y.shape)).sum().backward()
+    assert O.rel_err(x.grad, t(g["dx"])) < 1e-5
+    GS.compare_grads(case, {k_: v.grad for k_, v in P.items()}, g, 1e-5)
+
+
 @pytest.mark.parametrize("tag,C,H,N,T", [("c64", 64, 4, 3, 10), ("c512", 512, 8, 2, 24)])
 def test_attention_graphmask(golden_dir, tag, C, H, N, T):
     case = f"attn_graphmask_{tag}"
