@@ -29,7 +29,7 @@ extern "C" {
 #define SAVQA_ERR_CUDA 2
 #define SAVQA_ERR_UNSUPPORTED 3
 
-#define SAVQA_ABI_VERSION 2
+#define SAVQA_ABI_VERSION 3
 
 typedef void* savqa_stream_t; /* cudaStream_t */
 
@@ -203,6 +203,12 @@ int savqa_answer_loss(const float* logits_concat, const float* logits_vis, const
  * GEMMs read, so no per-step staging casts are needed. */
 int savqa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                     float beta2, float eps, int step, const float* dyn, void* param_bf16, savqa_stream_t stream);
+
+/* dyn[2] += 1 (the step counter lives on the DEVICE), then dyn[0] = lr / (1 - beta1^step), dyn[1] = sqrt(1 - beta2^step).
+ * One launch at the head of every step (captured in the step graph): a host that queues several steps ahead of the GPU, or a
+ * replayed graph, can then never hand a step the scalars of another one.  Replaces the `state['step'] += 1` of torch.optim.Adam
+ * (main_itp_ddp_tar_super_node.py:206, 366). */
+int savqa_adam_advance(float* dyn, float lr, float beta1, float beta2, savqa_stream_t stream);
 
 /* Row-sparse ("lazy") Adam for the 407000 x 300 word tables: only rows named in idx[0..n_idx) are updated, each exactly
  * once per call even if it occurs several times (row_stamp[row] is set to `step` by the first claimant).  grad is the

@@ -350,6 +350,15 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+// One thread: advances the device-resident step counter and derives the step's scalars from it, so that a replayed CUDA graph
+// (and a host that runs several steps ahead of the GPU) always sees the values of ITS step: dyn = {lr / (1 - b1^s), sqrt(1 - b2^s), s}.
+__global__ void adam_advance_kernel(float* __restrict__ dyn, float lr, float b1, float b2) {
+  const double s = static_cast<double>(dyn[2]) + 1.0;
+  dyn[0] = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), s)));
+  dyn[1] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), s)));
+  dyn[2] = static_cast<float>(s);
+}
+
 __global__ void adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                  int* __restrict__ stamp, long table_rows, int width, const int64_t* __restrict__ idx, long n_idx, float lr,
                                  float b1, float b2, float eps, float bc1, float bc2_sqrt, int step, const float* __restrict__ dyn) {
@@ -544,6 +553,14 @@ extern "C" int savqa_adam_step(float* param, const float* grad, float* exp_avg, 
   const int vec = (a16(param) && a16(grad) && a16(exp_avg) && a16(exp_avg_sq) && (!param_bf16 || (reinterpret_cast<uintptr_t>(param_bf16) & 7) == 0)) ? 1 : 0;
   adam_kernel<<<grid_for((n + 3) / 4, 256, 16), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2),
                                                                   dyn, static_cast<__nv_bfloat16*>(param_bf16), vec);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_adam_advance(float* dyn, float lr, float beta1, float beta2, savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SAVQA_REQUIRE(dyn && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, "savqa_adam_advance: bad argument");
+  adam_advance_kernel<<<1, 1, 0, stream>>>(dyn, lr, beta1, beta2);
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;
 }

@@ -121,7 +121,11 @@ class _Branch(nn.Module):
             raise IndexError("index out of range in self")  # positional table too short, as F.embedding would report
         if self.training and pos_dropout_p > 0:
             x = _linear(x_in, self.syb_mlp2, self._pk["mlp2"])
-            x = x + F.dropout(pos_table[:T], pos_dropout_p, True).unsqueeze(0)             # :100-101 (vis only)
+            pos = pos_table[:T]
+            if T == pos_table.shape[0]:  # padding_idx=-1: the table's last row is frozen (modules.py:34-41)
+                pos = torch.cat([pos[:-1], pos[-1:].detach()], 0)
+            # Sequential(embedding, Dropout) drops the gathered [B,T,C] tensor: an independent mask per sample (:100-101, vis only)
+            x = x + F.dropout(pos.unsqueeze(0).expand(B, T, -1), pos_dropout_p, True)
         else:
             x = _linear(x_in, self.syb_mlp2, self._pk["mlp2"], rowtab=pos_table, period=T)  # :99-101 fused
         return self.enc_dropout(x)                                                         # :102

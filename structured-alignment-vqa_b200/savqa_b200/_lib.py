@@ -67,6 +67,7 @@ SIGNATURES = {
     "savqa_graph_attn_bwd": [C.POINTER(AttnArgs), vp],
     "savqa_answer_loss": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp, vp],
     "savqa_adam_rows": [vp, vp, vp, vp, vp, i64, C.c_int, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp],
+    "savqa_adam_advance": [vp, C.c_float, C.c_float, C.c_float, vp],
     "savqa_adam_step": [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, vp],
 }
 

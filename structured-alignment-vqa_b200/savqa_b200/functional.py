@@ -323,6 +323,8 @@ class LinearFn(Function):
             # d rowtab[t] = sum_b dy[b, t]; tiny fp32 reduction over the batch (positional table, AttModel_x3.py:100)
             drowtab = torch.zeros(ctx.rowtab_shape, device=dev, dtype=F32)
             drowtab[:ctx.period] = dy2.float().reshape(-1, ctx.period, N).sum(0)
+            if ctx.period == ctx.rowtab_shape[0]:
+                drowtab[-1] = 0  # `embedding(zeros_pad=False)` passes padding_idx=-1: the LAST row is frozen (modules.py:34-41)
         return dx, dW, db, drowtab, None, None, None, None
 
 

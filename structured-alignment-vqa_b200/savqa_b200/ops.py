@@ -67,9 +67,12 @@ def build_masks(first_mask: Tensor, q_mask: Tensor, q_graph: Tensor, first_graph
     dec_mask = torch.empty(B, 1, T, device=fm.device, dtype=F32)
     call("savqa_build_masks", ptr(fm), ptr(qm), ptr(qg), ptr(fg), int(is_float), B, V, Q, int(bool(dec_mask_on)),
          ptr(graph_diag), ptr(graph), ptr(dec_mask))
-    # these graphs are exactly 0/1: hand the attention kernels their bit-packed form as well (4 bytes per 32 keys)
-    for g in (graph_diag, graph):
-        attach_graph_bits(g)
+    # integer / bool inputs (what collate_fn emits: int32 0/1) give graphs that are exactly 0/1: hand the attention kernels their
+    # bit-packed form as well (4 bytes per 32 keys).  Float inputs may carry weights (the reference multiplies by the graph
+    # VALUES, modules.py:281-284): those stay on the fp32 graph path.
+    if not is_float:
+        for g in (graph_diag, graph):
+            attach_graph_bits(g)
     return graph_diag, graph, dec_mask
 
 
@@ -458,6 +461,13 @@ def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, 
     assert param_bf16 is None or (param_bf16.is_contiguous() and param_bf16.numel() == param.numel())
     call("savqa_adam_step", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2, eps, int(step), ptr(dyn),
          ptr(param_bf16))
+
+
+def adam_advance(dyn: Tensor, lr: float, beta1: float, beta2: float) -> None:
+    """dyn = {lr / (1 - beta1^step), sqrt(1 - beta2^step), step} with step = dyn[2] + 1, computed ON the device."""
+    _check(dyn, F32, "dyn")
+    assert dyn.numel() == 3 and dyn.is_contiguous()
+    call("savqa_adam_advance", ptr(dyn), float(lr), float(beta1), float(beta2))
 
 
 def adam_rows(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, row_stamp: Tensor, idx: Tensor, lr: float, beta1: float,

@@ -262,6 +262,12 @@ class EncoderTrainer:
                 self.flat_param[o:o + k].copy_(p.reshape(-1))
                 p.data = self.flat_param[o:o + k].view(p.shape)
                 p.grad = self.flat_grad[o:o + k].view(p.shape)
+        if self.world > 1:
+            # what DistributedDataParallel's constructor does (main_itp_ddp_tar_super_node.py:203): every rank starts from rank 0's
+            # parameters -- the reference does not seed the ranks identically, and Xavier / Kaiming initialisation depends on the RNG
+            dist.broadcast(self.flat_param, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+            for t in self.tables:
+                dist.broadcast(t.weight.data, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
         self.sync_mirror()
         # the modules' weight packs / LayerNorm sinks now read the mirror and write their gradients straight into flat_grad
         self.views = Fn.FlatViews(self.flat_param, self.flat_grad, self.flat_bf16, offsets)
@@ -276,8 +282,10 @@ class EncoderTrainer:
                 w.grad = None
                 self.row_state.append(dict(grad=torch.zeros_like(w), m=torch.zeros_like(w), v=torch.zeros_like(w),
                                            stamp=torch.zeros(w.shape[0], dtype=torch.int32, device=dev)))
+        # {lr / (1 - b1^s), sqrt(1 - b2^s), s}: the step counter lives on the DEVICE and is advanced by a kernel at the head of
+        # every step (ops.adam_advance, part of the captured graph), so a host that queues steps ahead of the GPU cannot hand a
+        # step the scalars -- or the row stamp of savqa_adam_rows -- of another one
         self.dyn = torch.zeros(3, device=dev)
-        self.dyn_host = torch.zeros(3).pin_memory() if dev.type == "cuda" else torch.zeros(3)
         Fn.WEIGHT_EPOCH += 1
         self.reducer = None
         # Per-bucket Adam under the backward pass (GradReducer.apply_fn) is implemented but OFF: measured on B200 it moves the
@@ -300,14 +308,6 @@ class EncoderTrainer:
                 mod._savqa_bind(None)
 
     # ------------------------------------------------------------------------------------------------
-    def _set_dyn(self) -> None:
-        b1, b2 = self.betas
-        s = self.step_count
-        self.dyn_host[0] = self.lr / (1.0 - b1 ** s)
-        self.dyn_host[1] = (1.0 - b2 ** s) ** 0.5
-        self.dyn_host[2] = float(s)
-        self.dyn.copy_(self.dyn_host, non_blocking=True)
-
     def _exchange_and_apply(self) -> None:
         b1, b2 = self.betas
         if self.flat_param.is_cuda:
@@ -378,6 +378,7 @@ class EncoderTrainer:
             log.clear()
 
     def _step_impl(self, b: Dict[str, torch.Tensor]) -> torch.Tensor:
+        ops.adam_advance(self.dyn, self.lr, self.betas[0], self.betas[1])  # step += 1 on the device; read by the Adam kernels below
         if self.flat_grad.is_cuda:
             # 356 MB of zeros (48 us at HBM speed) that nothing reads before the backward pass: on a helper stream, next to the forward
             cur = torch.cuda.current_stream()
@@ -405,7 +406,6 @@ class EncoderTrainer:
         if self.flat_param is None:
             self.prepare(batch)
         self.step_count += 1
-        self._set_dyn()
         from . import _lib
         n0 = _lib.launch_count
         loss = self._step_impl(batch)
@@ -466,7 +466,6 @@ class EncoderTrainer:
         self._staging_free.record(cur)
 
     def replay(self) -> torch.Tensor:
-        self.step_count += 1
-        self._set_dyn()
+        self.step_count += 1  # host-side bookkeeping only: the kernels read the device counter
         self.graph.replay()
         return self.static_loss

@@ -284,7 +284,16 @@ def answer_loss(lc, lv, ls, answer, epsilon, grad_scale, want_grads):
     return loss, (tuple(grads) if want_grads else None)
 
 
+def adam_advance(dyn, lr, beta1, beta2):
+    s = float(dyn[2]) + 1.0
+    dyn[0] = lr / (1.0 - beta1 ** s)
+    dyn[1] = (1.0 - beta2 ** s) ** 0.5
+    dyn[2] = s
+
+
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, dyn=None, param_bf16=None):
+    if dyn is not None:
+        step = int(dyn[2])  # the device-resident step counter wins (savqa_adam_advance)
     exp_avg.mul_(beta1).add_(grad, alpha=1 - beta1)
     exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
     bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
@@ -294,6 +303,8 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, dyn
 
 
 def adam_rows(param, grad, exp_avg, exp_avg_sq, row_stamp, idx, lr, beta1, beta2, eps, step, dyn=None):
+    if dyn is not None:
+        step = int(dyn[2])
     rows = torch.unique(idx.reshape(-1))
     g = grad[rows]
     exp_avg[rows] = beta1 * exp_avg[rows] + (1 - beta1) * g
