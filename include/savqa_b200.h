@@ -39,6 +39,12 @@ const char* savqa_last_error(void);
 /* 0 if the current device is sm_100 (B200); error otherwise.  *sm_count receives the SM count. */
 int savqa_device_check(int* sm_count);
 
+/* Cumulative number of launches by kernel family since the library was loaded, in this order: gemm_pair (CTA-pair tcgen05 GEMM),
+ * gemm_single, attn_fwd_tc, attn_bwd_tc_shared (two-CTAs-per-SM shared-tile backward), attn_bwd_tc, attn_fwd_simt, attn_bwd_simt,
+ * attn_row1_fwd, attn_row1_bwd, rowln_gemm, mil_nce.  Writes min(n, families) values and returns the number of families.  Test /
+ * diagnostic aid: the parity tests assert which engine a shape actually took. */
+int savqa_launch_counts(int64_t* out, int n);
+
 /* ---- a4: scene-graph mask construction (AttModel_x3.py:103-122 vis, :229-247 syb) ------------------
  * first_mask [B,V,V], q_mask [B,Q,Q], q_graph [B,Q,Q], first_graph [B,V,V] or NULL (vis branch: top-left
  * block of `graph` is all ones).  Inputs are int32 when in_is_float == 0 (collate_fn output), fp32 otherwise.
@@ -210,13 +216,20 @@ int savqa_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
  * (main_itp_ddp_tar_super_node.py:206, 366). */
 int savqa_adam_advance(float* dyn, float lr, float beta1, float beta2, savqa_stream_t stream);
 
-/* Row-sparse ("lazy") Adam for the 407000 x 300 word tables: only rows named in idx[0..n_idx) are updated, each exactly
- * once per call even if it occurs several times (row_stamp[row] is set to `step` by the first claimant).  grad is the
- * dense fp32 gradient table that savqa_scatter_add_rows accumulated into; consumed rows are zeroed again, so the table
- * never needs a 488 MB memset. */
+/* Row-sparse Adam for the 407000 x 300 word tables with the semantics of the reference's DENSE torch.optim.Adam ("deferred"
+ * Adam).  row_stamp[row] = last step the row is current through (0: never touched).  Each row named in idx[0..n_idx) is handled
+ * exactly once per call even if it occurs several times: the steps it missed since row_stamp are replayed with a zero gradient
+ * (m *= beta1, v *= beta2, p -= lr_s m / (sqrt(v) / sqrt(1 - beta2^s) + eps): what dense Adam does to a row that is absent from a
+ * batch), then
+ *   apply != 0: the step-`step` update with grad (the dense fp32 table savqa_scatter_add_rows accumulated into; consumed rows
+ *               are zeroed again, so the table never needs a 488 MB memset);
+ *   apply == 0: nothing more -- the catch-up through step - 1, run BEFORE the step's gathers read the rows; idx == NULL brings
+ *               every row of the table up to date (before a checkpoint or an evaluation pass).
+ * step is read from dyn[2] when dyn != NULL.  Replays longer than 256 steps apply the oldest part in closed form to the moments
+ * only (their parameter updates are below fp32 resolution). */
 int savqa_adam_rows(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int32_t* row_stamp, int64_t table_rows, int width,
                     const int64_t* idx, int64_t n_idx, float lr, float beta1, float beta2, float eps, int step, const float* dyn,
-                    savqa_stream_t stream);
+                    int apply, savqa_stream_t stream);
 
 #ifdef __cplusplus
 }

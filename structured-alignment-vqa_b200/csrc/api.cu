@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
@@ -53,6 +54,11 @@ bool pdl_enabled() {
     on = (e && e[0] == '1') ? 1 : 0;  // measured on the training step: no gain over plain launches (two streams already overlap tails)
   }
   return on == 1;
+}
+
+static std::atomic<long long> g_launch_counts[LK_COUNT];
+void count_launch(int kind) {
+  if (kind >= 0 && kind < LK_COUNT) g_launch_counts[kind].fetch_add(1, std::memory_order_relaxed);
 }
 
 int sm_count() {
@@ -175,6 +181,14 @@ extern "C" {
 int savqa_abi_version(void) { return SAVQA_ABI_VERSION; }
 
 const char* savqa_last_error(void) { return savqa::g_err; }
+
+int savqa_launch_counts(int64_t* out, int n) {
+  static const char* names = "gemm_pair,gemm_single,attn_fwd_tc,attn_bwd_tc_shared,attn_bwd_tc,attn_fwd_simt,attn_bwd_simt,attn_row1_fwd,"
+                             "attn_row1_bwd,rowln_gemm,mil_nce";
+  (void)names;
+  for (int i = 0; i < n; ++i) out[i] = i < savqa::LK_COUNT ? static_cast<int64_t>(savqa::g_launch_counts[i].load(std::memory_order_relaxed)) : 0;
+  return savqa::LK_COUNT;
+}
 
 int savqa_device_check(int* sm_count_out) {
   int dev = 0;

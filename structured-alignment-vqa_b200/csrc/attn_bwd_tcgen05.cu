@@ -899,6 +899,7 @@ int attn_bwd_tc(const savqa_attn_args_t* a, cudaStream_t stream) {
   // the training step's symbolic branch: two CTAs per SM with the shared W' / dS tile (attn_bwd_tc1_kernel)
   const bool one_tile = a->d == 64 && p.kc <= 2 && p.kt == 1 && a->Tk > 32 && a->stats && a->out && !a->causal &&
                         (a->graph_bits || !a->graph || a->renorm == 0) && p.tmem_cols <= 256 && getenv("SAVQA_ATTN_BWD_ONE_TILE_OFF") == nullptr;
+  count_launch(one_tile ? LK_ATTN_BWD_TC_SHARED : LK_ATTN_BWD_TC);
   if (one_tile) {
     const size_t smem1 = 1024 + static_cast<size_t>(p.kc) * 16384 + static_cast<size_t>(2) * 16384 + static_cast<size_t>(2) * p.kv_rows * 128;
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_bwd_tc1_kernel<64>), smem1, "savqa_graph_attn_bwd (tcgen05 engine, shared tile)"))

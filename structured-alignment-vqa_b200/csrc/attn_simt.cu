@@ -1076,6 +1076,7 @@ int check_common(const savqa_attn_args_t* a, const char* who) {
 int attn_fwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
   if (int rc = check_common(a, "savqa_graph_attn_fwd")) return rc;
   SAVQA_REQUIRE(a->out, "savqa_graph_attn_fwd: null out");
+  count_launch(a->Tq == 1 ? LK_ATTN_ROW1_FWD : LK_ATTN_FWD_SIMT);
   if (a->Tq == 1 && row1_piece_ok(a, false) && a->Tk >= 32 && getenv("SAVQA_ROW1_SPLIT_OFF") == nullptr) {
     const size_t smem1 = (static_cast<size_t>(2) * a->Tk + static_cast<size_t>(1 + kSplitWarps) * a->d) * 4;
     const dim3 grid(static_cast<unsigned>(static_cast<long>(a->N) * a->H)), block(kSplitWarps * 32);
@@ -1121,6 +1122,7 @@ int attn_bwd_simt(const savqa_attn_args_t* a, cudaStream_t stream) {
   if (int rc = check_common(a, "savqa_graph_attn_bwd")) return rc;
   SAVQA_REQUIRE(a->dout && a->dq && a->dk && a->dv, "savqa_graph_attn_bwd: null gradient buffer");
   SAVQA_REQUIRE(a->ld_dq % 2 == 0 && a->ld_dk % 2 == 0 && a->ld_dv % 2 == 0, "savqa_graph_attn_bwd: odd leading dimension");
+  count_launch(a->Tq == 1 ? LK_ATTN_ROW1_BWD : LK_ATTN_BWD_SIMT);
   // (measured, N = 128: Tk = 128 52 -> 45 us, but Tk = 56 35 -> 38 us: short rows stay on the one-warp kernel)
   if (a->Tq == 1 && row1_piece_ok(a, true) && a->Tk >= 64 && getenv("SAVQA_ROW1_SPLIT_OFF") == nullptr) {
     const size_t smem1 = (static_cast<size_t>(4) * a->Tk + static_cast<size_t>(2 + 3 * kSplitWarps) * a->d) * 4;

@@ -400,6 +400,7 @@ int attn_fwd_tc(const savqa_attn_args_t* a, cudaStream_t stream) {
   if (int rc = make_map3(&tmK, a->k, a->ldk, a->Tk, a->N, p.kv_box)) return rc;
   if (int rc = make_map3(&tmV, a->v, a->ldv, a->Tk, a->N, p.kv_box)) return rc;
   dim3 grid(a->N * a->H, (a->Tq + 127) / 128);
+  count_launch(LK_ATTN_FWD_TC);
   if (a->d == 64) {
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_fwd_tc_kernel<64>), smem, "savqa_graph_attn_fwd (tcgen05 engine)")) return rc;
     SAVQA_CHECK_CUDA(launch_kernel(true, attn_fwd_tc_kernel<64>, grid, dim3(128), smem, stream, tmQ, tmK, tmV, p));

@@ -34,6 +34,13 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int sm_count();
 
+// Cumulative launch counters by kernel family (savqa_launch_counts): lets the parity tests assert WHICH engine a shape took.
+enum LaunchKind {
+  LK_GEMM_PAIR = 0, LK_GEMM_SINGLE, LK_ATTN_FWD_TC, LK_ATTN_BWD_TC_SHARED, LK_ATTN_BWD_TC, LK_ATTN_FWD_SIMT, LK_ATTN_BWD_SIMT,
+  LK_ATTN_ROW1_FWD, LK_ATTN_ROW1_BWD, LK_ROWLN_GEMM, LK_MILNCE, LK_COUNT
+};
+void count_launch(int kind);
+
 // Programmatic dependent launch (opt-in: SAVQA_PDL=1): a kernel launched this way may start -- run its prologue: barrier
 // init, TMEM allocation, descriptor prefetch -- while the previous kernel of the stream is still draining; it must call
 // pdl_wait() before it touches global memory.  Only kernels written that way are launched through launch_kernel(pdl=true).

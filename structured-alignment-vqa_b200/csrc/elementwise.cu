@@ -359,34 +359,62 @@ __global__ void adam_advance_kernel(float* __restrict__ dyn, float lr, float b1,
   dyn[2] = static_cast<float>(s);
 }
 
+// Row-sparse Adam with the semantics of DENSE torch.optim.Adam ("deferred" Adam): stamp[row] = the last step the row is current
+// through (0: never touched, moments zero).  A row named at step t is first brought up to date -- the steps it missed are
+// replayed with a zero gradient, exactly what the dense optimizer did to it in the meantime (m *= b1, v *= b2,
+// p -= lr_s m / (sqrt(v) / sqrt(bc2_s) + eps)) -- and then (apply != 0) takes its step-t update with the accumulated gradient,
+// which is zeroed again.  apply == 0 is the catch-up alone (through step t - 1), run before the step's gathers read the row.
+// The replay is cut after kReplayMax steps (the update has decayed by (b1 / sqrt(b2))^k < 1e-11 by then; the remaining decay of
+// the moments is applied in closed form).  idx == nullptr: every row of the table (flush before a checkpoint / evaluation).
+constexpr int kReplayMax = 256;
+
 __global__ void adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                  int* __restrict__ stamp, long table_rows, int width, const int64_t* __restrict__ idx, long n_idx, float lr,
-                                 float b1, float b2, float eps, float bc1, float bc2_sqrt, int step, const float* __restrict__ dyn) {
-  float step_size = lr / bc1;
-  if (dyn) {
-    step_size = dyn[0];
-    bc2_sqrt = dyn[1];
-    step = static_cast<int>(dyn[2]);
-  }
+                                 float b1, float b2, float eps, int step, const float* __restrict__ dyn, int apply) {
+  if (dyn) step = static_cast<int>(dyn[2]);
+  const int target = apply ? step : step - 1;   // the row is current through `target` when this kernel is done with it
+  if (target < 1) return;
   const int lane = threadIdx.x & 31;
   const long warp0 = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
   const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
   for (long r = warp0; r < n_idx; r += nwarps) {
-    const long row = idx[r];
+    const long row = idx ? idx[r] : r;
     if (row < 0 || row >= table_rows) continue;
-    int first = 0;
-    if (lane == 0) first = (atomicExch(stamp + row, step) != step) ? 1 : 0;
-    first = __shfl_sync(0xffffffffu, first, 0);
-    if (!first) continue;  // another occurrence of this row already took it
+    int old = 0;
+    if (lane == 0) old = atomicMax(stamp + row, target);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old >= target) continue;  // another occurrence of this row took it (or it is already current)
     const long base = row * static_cast<long>(width);
+    // steps old+1 .. last_zero see a zero gradient; step `target` sees g when apply
+    const int last_zero = apply ? target - 1 : target;
+    int first = old + 1;
+    float decay_m = 1.0f, decay_v = 1.0f;
+    if (old == 0) {
+      first = last_zero + 1;  // never touched: moments are zero, nothing to replay
+    } else if (last_zero - first + 1 > kReplayMax) {
+      const int skip = last_zero - first + 1 - kReplayMax;  // oldest missed steps: update below fp32 resolution, decay in closed form
+      decay_m = static_cast<float>(pow(static_cast<double>(b1), static_cast<double>(skip)));
+      decay_v = static_cast<float>(pow(static_cast<double>(b2), static_cast<double>(skip)));
+      first += skip;
+    }
     for (int c = lane; c < width; c += 32) {
-      const float gi = g[base + c];
-      const float mi = b1 * m[base + c] + (1.0f - b1) * gi;
-      const float vi = b2 * v[base + c] + (1.0f - b2) * gi * gi;
+      float pi = p[base + c], mi = m[base + c] * decay_m, vi = v[base + c] * decay_v;
+      for (int s = first; s <= last_zero; ++s) {
+        const double sd = static_cast<double>(s);
+        const float step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), sd)));
+        const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), sd)));
+        adam_one(pi, 0.0f, mi, vi, b1, b2, eps, step_size, bc2_sqrt);
+      }
+      if (apply) {
+        const double sd = static_cast<double>(target);
+        const float step_size = dyn ? dyn[0] : static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), sd)));
+        const float bc2_sqrt = dyn ? dyn[1] : static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), sd)));
+        adam_one(pi, g[base + c], mi, vi, b1, b2, eps, step_size, bc2_sqrt);
+        g[base + c] = 0.0f;
+      }
+      p[base + c] = pi;
       m[base + c] = mi;
       v[base + c] = vi;
-      p[base + c] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
-      g[base + c] = 0.0f;
     }
   }
 }
@@ -567,14 +595,14 @@ extern "C" int savqa_adam_advance(float* dyn, float lr, float beta1, float beta2
 
 extern "C" int savqa_adam_rows(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int32_t* row_stamp, int64_t table_rows,
                                int width, const int64_t* idx, int64_t n_idx, float lr, float beta1, float beta2, float eps, int step,
-                               const float* dyn, savqa_stream_t stream_) {
+                               const float* dyn, int apply, savqa_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (idx == nullptr) n_idx = table_rows;
   if (n_idx == 0) return SAVQA_OK;
-  SAVQA_REQUIRE(param && grad && exp_avg && exp_avg_sq && row_stamp && idx && width > 0 && step >= 1, "savqa_adam_rows: bad argument");
-  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
-  const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  SAVQA_REQUIRE(param && exp_avg && exp_avg_sq && row_stamp && width > 0 && step >= 1 && (grad || !apply), "savqa_adam_rows: bad argument");
+  SAVQA_REQUIRE(idx || !apply, "savqa_adam_rows: the whole-table form is the catch-up alone (apply == 0)");
   adam_rows_kernel<<<grid_for(n_idx * 32, 256), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, row_stamp, table_rows, width, idx, n_idx,
-                                                                   lr, beta1, beta2, eps, bc1, sqrtf(bc2), step, dyn);
+                                                                   lr, beta1, beta2, eps, step, dyn, apply);
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;
 }

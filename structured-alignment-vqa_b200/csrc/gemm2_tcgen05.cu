@@ -452,6 +452,7 @@ int launch2(const Maps& m, const Gemm2Group& g, cudaStream_t stream) {
   int max_pairs = sm_count() / 2;
   if (t_sm_limit > 0 && t_sm_limit / 2 < max_pairs) max_pairs = t_sm_limit / 2 > 0 ? t_sm_limit / 2 : 1;
   const int pairs = g.num_tiles < max_pairs ? g.num_tiles : max_pairs;
+  count_launch(LK_GEMM_PAIR);
   SAVQA_CHECK_CUDA(launch_kernel(true, kern, dim3(2 * pairs), dim3(kThreads), C::kSmemBytes, stream, m.a[0], m.b[0], m.o[0], m.a[1], m.b[1],
                                  m.o[1], g));
   return SAVQA_OK;

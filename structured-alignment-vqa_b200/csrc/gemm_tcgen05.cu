@@ -316,6 +316,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "savqa_gemm_bf16")) return rc;
   const int tiles = p.num_m * p.num_n * p.split_k;
   const int grid = tiles < sm_count() ? tiles : sm_count();
+  count_launch(LK_GEMM_SINGLE);
   SAVQA_CHECK_CUDA(launch_kernel(true, kern, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, tmA, tmB, p));
   return SAVQA_OK;
 }

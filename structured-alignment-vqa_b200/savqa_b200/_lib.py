@@ -49,6 +49,7 @@ SIGNATURES = {
     "savqa_abi_version": [],
     "savqa_last_error": [],
     "savqa_device_check": [C.POINTER(C.c_int)],
+    "savqa_launch_counts": [C.POINTER(i64), C.c_int],
     "savqa_build_masks": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp],
     "savqa_pack_graph_bits": [vp, i64, C.c_int, vp, C.c_int, vp],
     "savqa_gather_rows": [vp, i64, C.c_int, vp, i64, C.c_float, vp, i64, vp, i64, C.c_int, vp],
@@ -66,7 +67,7 @@ SIGNATURES = {
     "savqa_graph_attn_fwd": [C.POINTER(AttnArgs), vp],
     "savqa_graph_attn_bwd": [C.POINTER(AttnArgs), vp],
     "savqa_answer_loss": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp, vp],
-    "savqa_adam_rows": [vp, vp, vp, vp, vp, i64, C.c_int, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp],
+    "savqa_adam_rows": [vp, vp, vp, vp, vp, i64, C.c_int, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, C.c_int, vp],
     "savqa_adam_advance": [vp, C.c_float, C.c_float, C.c_float, vp],
     "savqa_adam_step": [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, vp],
 }
@@ -107,6 +108,17 @@ def require_device() -> None:
     if rc != 0:
         raise RuntimeError("savqa_b200: " + lib.savqa_last_error().decode())
     _device_ok = True
+
+
+LAUNCH_KINDS = ("gemm_pair", "gemm_single", "attn_fwd_tc", "attn_bwd_tc_shared", "attn_bwd_tc", "attn_fwd_simt", "attn_bwd_simt",
+                "attn_row1_fwd", "attn_row1_bwd", "rowln_gemm", "mil_nce")
+
+
+def launch_counts() -> dict:
+    """Cumulative launches per kernel family (savqa_launch_counts): which engine did a shape take?"""
+    buf = (i64 * len(LAUNCH_KINDS))()
+    load().savqa_launch_counts(buf, len(LAUNCH_KINDS))
+    return {k: int(buf[i]) for i, k in enumerate(LAUNCH_KINDS)}
 
 
 def check(rc: int) -> None:

@@ -470,14 +470,17 @@ def adam_advance(dyn: Tensor, lr: float, beta1: float, beta2: float) -> None:
     call("savqa_adam_advance", ptr(dyn), float(lr), float(beta1), float(beta2))
 
 
-def adam_rows(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, row_stamp: Tensor, idx: Tensor, lr: float, beta1: float,
-              beta2: float, eps: float, step: int, dyn: Optional[Tensor] = None) -> None:
-    """Row-sparse Adam over the rows named in idx (each once); consumed gradient rows are zeroed."""
+def adam_rows(param: Tensor, grad: Optional[Tensor], exp_avg: Tensor, exp_avg_sq: Tensor, row_stamp: Tensor, idx: Optional[Tensor], lr: float,
+              beta1: float, beta2: float, eps: float, step: int, dyn: Optional[Tensor] = None, apply: bool = True) -> None:
+    """Row-sparse Adam with dense-Adam semantics (savqa_adam_rows): rows named in idx (each once) first replay the zero-gradient
+    steps they missed, then -- apply=True -- take this step's update (their gradient rows are zeroed).  apply=False is the
+    catch-up alone (through step - 1); idx=None then covers the whole table."""
     for nm, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
         _check(t, F32, nm)
-        assert t.is_contiguous() and t.shape == param.shape
+        assert t is None or (t.is_contiguous() and t.shape == param.shape)
     _check(row_stamp, torch.int32, "row_stamp")
     _check(idx, torch.int64, "idx")
-    idx = idx.contiguous()
+    assert idx is not None or not apply
+    idx = idx.contiguous() if idx is not None else None
     call("savqa_adam_rows", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(row_stamp), param.shape[0], param.shape[1], ptr(idx),
-         idx.numel(), lr, beta1, beta2, eps, int(step), ptr(dyn))
+         idx.numel() if idx is not None else 0, lr, beta1, beta2, eps, int(step), ptr(dyn), int(bool(apply)))

@@ -5,10 +5,11 @@ Replaces, for this path, the reference's `DistributedDataParallel(find_unused_pa
 
   * the dense parameters that the step actually uses live in ONE flat fp32 buffer (parameter views), their gradients
     in another: one NCCL all-reduce (AVG) over NVLink and one fused Adam kernel per step;
-  * the two 407000 x 300 word tables exchange row-sparse gradients: all-gather of (row id, row gradient) lists, local
-    scatter-add, row-wise Adam on the touched rows (savqa_adam_rows).  `rowsparse=False` restores the reference's dense
-    table gradients (and dense Adam) for comparison.  Lazy row-wise Adam differs from dense Adam for rows that are
-    absent from a batch (their moments do not decay); documented in DESIGN.md;
+  * the 407000 x 300 word tables exchange row-sparse gradients: all-gather of (row id, row gradient) lists, local
+    scatter-add, and DEFERRED row-wise Adam (savqa_adam_rows): a row replays the zero-gradient updates it missed the next time it
+    is read or updated, so the tables follow dense torch.optim.Adam (the reference's optimizer) without touching 1.5 GB of
+    parameters, gradients and moments every step; flush_tables() brings every row up to date before a checkpoint.
+    `rowsparse=False` keeps the tables in the dense flat buffers (dense gradients, dense Adam) for comparison;
   * the whole step (bf16 weight staging, forward, backward, all-reduce, optimizer) can be captured into one CUDA graph
     and replayed, which removes the Python / launch overhead of ~1500 kernel launches per step.
 """
@@ -360,8 +361,32 @@ class EncoderTrainer:
         ops.adam_step(self.flat_param[lo:hi], self.flat_grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.lr, b1, b2,
                       self.eps, max(self.step_count, 1), dyn=self.dyn, param_bf16=self.flat_bf16[lo:hi])
 
+    def _table_ids(self, b: Dict[str, torch.Tensor]):
+        """Word ids each table is gathered with in a step (AttModel_x3.py:96, 216): the rows the forward pass will read."""
+        return [[b["q_ipt"]] for _ in self.tables]
+
+    def _catch_up_rows(self, b: Dict[str, torch.Tensor]) -> None:
+        """Deferred Adam, part 1 (before the step's gathers): the rows this step reads replay the zero-gradient updates dense
+        Adam applied to them while they were absent from the batches (savqa_adam_rows, apply=0)."""
+        b1, b2 = self.betas
+        for t, st, id_list in zip(self.tables, self.row_state, self._table_ids(b)):
+            for ids in id_list:
+                ops.adam_rows(t.weight.data, None, st["m"], st["v"], st["stamp"], ids.reshape(-1), self.lr, b1, b2, self.eps,
+                              max(self.step_count, 1), dyn=self.dyn, apply=False)
+
+    def flush_tables(self) -> None:
+        """Brings EVERY row of the word tables up to date with the current step (before state_dict() / evaluation): after it the
+        tables hold exactly what dense torch.optim.Adam would (main_itp_ddp_tar_super_node.py:206, 366, 428)."""
+        if not self.rowsparse or self.flat_param is None:
+            return
+        b1, b2 = self.betas
+        for t, st in zip(self.tables, self.row_state):
+            ops.adam_rows(t.weight.data, None, st["m"], st["v"], st["stamp"], None, self.lr, b1, b2, self.eps, self.step_count + 1,
+                          dyn=None, apply=False)
+
     def _apply_rows(self) -> None:
-        """Row-sparse update of the 407000 x 300 word tables: (row id, row gradient) lists -> lazy row-wise Adam."""
+        """Deferred Adam, part 2: (row id, row gradient) lists -> scatter-add -> this step's update of the touched rows (rows that
+        another rank read are caught up here first)."""
         b1, b2 = self.betas
         for t, st in zip(self.tables, self.row_state):
             log = t._savqa_rowlog
@@ -374,11 +399,13 @@ class EncoderTrainer:
                     idx, rows, scale = idx_all, rows_all, scale / self.world
                 ops.scatter_add_rows(st["grad"], idx, rows, scale=scale, skip_row=skip)
                 ops.adam_rows(t.weight.data, st["grad"], st["m"], st["v"], st["stamp"], idx, self.lr, b1, b2, self.eps,
-                              max(self.step_count, 1), dyn=self.dyn)
+                              max(self.step_count, 1), dyn=self.dyn, apply=True)
             log.clear()
 
     def _step_impl(self, b: Dict[str, torch.Tensor]) -> torch.Tensor:
         ops.adam_advance(self.dyn, self.lr, self.betas[0], self.betas[1])  # step += 1 on the device; read by the Adam kernels below
+        if self.rowsparse:
+            self._catch_up_rows(b)
         if self.flat_grad.is_cuda:
             # 356 MB of zeros (48 us at HBM speed) that nothing reads before the backward pass: on a helper stream, next to the forward
             cur = torch.cuda.current_stream()

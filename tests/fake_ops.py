@@ -302,17 +302,34 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, dyn
         param_bf16.copy_(param.to(BF16))
 
 
-def adam_rows(param, grad, exp_avg, exp_avg_sq, row_stamp, idx, lr, beta1, beta2, eps, step, dyn=None):
+def adam_rows(param, grad, exp_avg, exp_avg_sq, row_stamp, idx, lr, beta1, beta2, eps, step, dyn=None, apply=True):
+    """Deferred Adam: replay the zero-gradient steps a row missed (dense torch.optim.Adam semantics), then this step's update."""
     if dyn is not None:
         step = int(dyn[2])
-    rows = torch.unique(idx.reshape(-1))
-    g = grad[rows]
-    exp_avg[rows] = beta1 * exp_avg[rows] + (1 - beta1) * g
-    exp_avg_sq[rows] = beta2 * exp_avg_sq[rows] + (1 - beta2) * g * g
-    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
-    param[rows] -= (lr / bc1) * exp_avg[rows] / (exp_avg_sq[rows].sqrt() / (bc2 ** 0.5) + eps)
-    grad[rows] = 0
-    row_stamp[rows] = step
+    target = step if apply else step - 1
+    if target < 1:
+        return
+    rows = torch.unique(idx.reshape(-1)) if idx is not None else torch.arange(param.shape[0])
+    rows = rows[(rows >= 0) & (rows < param.shape[0])]
+    for r in rows.tolist():
+        old = int(row_stamp[r])
+        if old >= target:
+            continue
+        last_zero = target - 1 if apply else target
+        if old > 0:
+            for s_ in range(old + 1, last_zero + 1):
+                exp_avg[r] *= beta1
+                exp_avg_sq[r] *= beta2
+                bc1, bc2 = 1 - beta1 ** s_, 1 - beta2 ** s_
+                param[r] -= (lr / bc1) * exp_avg[r] / (exp_avg_sq[r].sqrt() / (bc2 ** 0.5) + eps)
+        if apply:
+            g = grad[r]
+            exp_avg[r] = beta1 * exp_avg[r] + (1 - beta1) * g
+            exp_avg_sq[r] = beta2 * exp_avg_sq[r] + (1 - beta2) * g * g
+            bc1, bc2 = 1 - beta1 ** target, 1 - beta2 ** target
+            param[r] -= (lr / bc1) * exp_avg[r] / (exp_avg_sq[r].sqrt() / (bc2 ** 0.5) + eps)
+            grad[r] = 0
+        row_stamp[r] = target
 
 
 def install(monkeypatch):

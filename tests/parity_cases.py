@@ -202,3 +202,135 @@ def branch_case(A, golden_dir, device, kind):
         # 12 stacked bf16-operand blocks: the emulation itself sits at 1e-2..5e-2 on the K/Q projection gradients
         errs[k_] = check(f"{case}: grad {k_}", ours[k_], ref[k_], emu[k_], floor=2e-2, factor=6.0)
     return errs
+
+
+def headline_step_case(device, batch_size=128, vocab_rows=5000, seed=11, floor=2e-2, factor=6.0, verbose=False):
+    """The composition the headline number runs, against the oracle: GQA-shaped batch (T = 56 visual / 128 symbolic tokens per
+    sample, C = 512, 8 heads, 6 + 6 blocks per branch), the REAL 12-block model (small vocabulary), train.EncoderTrainer's bound
+    path (flat buffers, bf16 mirror, fused decoder K/V, side-stream weight gradients): loss, the three logit tensors, every
+    dense parameter gradient of the flat buffer and the row-sparse word-table gradients vs O.encoder_step(...).backward() in
+    CPU fp32 (main_itp_ddp_tar_super_node.py:321-345, 363), tolerances calibrated by the oracle's bf16-operand emulation."""
+    from savqa_b200 import functional as Fn
+    from savqa_b200 import ops, synthetic, train
+    cfg = synthetic.GQA_SHAPED
+    model = synthetic.build_model(cfg, vocab_rows=vocab_rows)
+    batch = synthetic.make_batch(cfg, batch_size, seed=seed, vocab_rows=vocab_rows)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    def run(od):
+        P = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in sd.items()}
+        loss, logits, _, _ = O.encoder_step(P, batch, cfg["blocks"], cfg["heads"], operand_dtype=od)
+        loss.backward()
+        return dict(loss=loss.detach(), logits=[l.detach() for l in logits],
+                    grads={k: v.grad for k, v in P.items() if v.dtype.is_floating_point and v.grad is not None})
+
+    ref, emu = run(None), run(BF)
+    model = model.to(device)
+    b = {k: v.to(device) for k, v in batch.items()}
+    tr = train.EncoderTrainer(model, lr=1e-4, rowsparse=True)
+    tr.prepare(b)
+    tr.flat_grad.zero_()
+    for t_ in tr.tables:
+        t_._savqa_rowlog.clear()
+    loss = tr._forward_backward(b)
+    if str(device) != "cpu":
+        Fn.join_wgrad_streams()
+        torch.cuda.synchronize()
+    errs = {"loss": abs(float(loss) - float(ref["loss"])) / abs(float(ref["loss"]))}
+    assert errs["loss"] < 2e-3 + 3 * abs(float(emu["loss"]) - float(ref["loss"])) / abs(float(ref["loss"])), errs
+    with torch.no_grad():
+        logits = model.encoder_step(b["vis_fea"], b["vis_fea_mask"], b["q_ipt"], b["q_ipt_mask"], b["q_ipt_graph"], b["syb_ipt"],
+                                    b["macro_node_mask"], b["macro_graph_ipt"], True)
+    for name, got, r, e in zip(("logits_concat", "logits_vis", "logits_syb"), logits, ref["logits"], emu["logits"]):
+        errs[name] = check(f"headline: {name}", got, r, e, floor=1e-2, factor=3.0)  # SURVEY 8(c): <= 1e-2 end to end in bf16
+    names = {id(p): k for k, p in model.named_parameters()}
+    for p in tr.dense:
+        k = names[id(p)]
+        errs[k] = check(f"headline: grad {k}", p.grad, ref["grads"][k], emu["grads"][k], floor=floor, factor=factor)
+    # parameters outside the flat buffers must be exactly the ones the reference gives no (or an all-zero) gradient
+    dense = {names[id(p)] for p in tr.dense}
+    tables = {"att_vis_grid.syb_emb.weight", "att_syb.syb_emb.weight"}
+    for k, g_ in ref["grads"].items():
+        if k not in dense and k not in tables:
+            assert float(g_.abs().sum()) == 0.0, f"{k} has a reference gradient but is not in the trainer's flat buffers"
+    # row-sparse word-table gradients: (row id, row gradient) lists -> dense, vs the reference's dense table gradient
+    for t_, k in zip(tr.tables, ("att_vis_grid.syb_emb.weight", "att_syb.syb_emb.weight")):
+        dense_g = torch.zeros_like(t_.weight.data)
+        for idx, rows, scale, skip in t_._savqa_rowlog.pending:
+            ops.scatter_add_rows(dense_g, idx, rows, scale=scale, skip_row=skip)
+        errs[k] = check(f"headline: grad {k}", dense_g, ref["grads"][k], emu["grads"][k], floor=floor, factor=factor)
+        t_._savqa_rowlog.clear()
+    if verbose:
+        worst = sorted(((v, k) for k, v in errs.items()), reverse=True)[:8]
+        print("headline step parity, worst tensors:", [(k, f"{v:.2e}") for v, k in worst])
+    tr.release()
+    return errs
+
+
+def attention_direct_case(M, device, C, H, N, T, seed=0, p_edge=0.3):
+    """new_multihead_attention at the training step's sizes, DIRECTLY against O.attention (modules.py:236-311) on seeded random
+    inputs: output, attention probabilities, input and parameter gradients.  Padded tokens (zero rows), an edge-less query and
+    a query whose only edge is key-masked are included."""
+    case = f"direct_attn_c{C}_n{N}_t{T}_{seed}"
+    P0 = GS.make_params(case, GS.attention_shapes(C))
+    x = GS.randn(f"{case}/x", N, T, C)
+    x[:, T - 2:] = 0
+    x[0, 3] = 0
+    graph = GS.bernoulli(f"{case}/g", p_edge, N, T, T).float()
+    graph[:, 1] = 0                      # no edge at all
+    graph[:, 2] = 0
+    graph[:, 2, T - 1] = 1               # only edge is a key-masked (padded) token
+    dy = GS.randn(f"{case}/dy", N, T, C)
+    ref = _oracle_attention(P0, x, x, graph, H, dy, None, True)
+    emu = _oracle_attention(P0, x, x, graph, H, dy, BF, True)
+    m = M.new_multihead_attention(C, H, return_att=True)
+    set_params(m, P0)
+    m = m.to(device)
+    xx = x.clone().to(device).requires_grad_(True)
+    y, att = m(xx, xx, xx, graph.to(device))
+    errs = {"y": check(f"{case}: output", y, ref["y"], emu["y"]),
+            "att": check(f"{case}: attention probabilities", att, ref["att"], emu["att"])}
+    a4 = att.detach().cpu().view(H, N, T, T)
+    assert float(a4[:, :, 1].abs().sum()) == 0.0 and float(a4[:, :, 2].abs().sum()) == 0.0
+    (y * dy.to(device)).sum().backward()
+    zero_q = (x.abs().sum(-1) == 0)
+    errs["dx"] = check(f"{case}: d input", xx.grad, ref["dq"], emu["dq"], mask=zero_q)
+    ours = grads_of(m, P0.keys())
+    for k_ in P0:
+        errs[k_] = check(f"{case}: grad {k_}", ours[k_], ref[k_], emu[k_])
+    return errs
+
+
+def deferred_adam_case(ops, device, steps=12, rows=40, width=24, seed=0):
+    """savqa_adam_rows (deferred row-wise Adam) against DENSE torch.optim.Adam (main_itp_ddp_tar_super_node.py:206, 366) on a
+    small table whose rows come and go between steps: after flush the tables agree, and every row that a step reads is current
+    BEFORE the step reads it (what makes the forward pass see the dense optimizer's parameters)."""
+    g = torch.Generator().manual_seed(seed)
+    lr, b1, b2, eps = 1e-2, 0.9, 0.999, 1e-8
+    p0 = torch.randn(rows, width, generator=g)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=lr, betas=(b1, b2), eps=eps)
+    p = p0.clone().to(device)
+    grad, m, v = (torch.zeros(rows, width, device=device) for _ in range(3))
+    stamp = torch.zeros(rows, dtype=torch.int32, device=device)
+    dyn = torch.zeros(3, device=device)
+    worst_read = 0.0
+    for step in range(1, steps + 1):
+        n = int(torch.randint(1, 9, (1,), generator=g))
+        idx = torch.randint(0, rows, (n,), generator=g)
+        idx = torch.cat([idx, idx[:2]])  # duplicates inside one step
+        ops.adam_advance(dyn, lr, b1, b2)
+        ops.adam_rows(p, None, m, v, stamp, idx.to(device), lr, b1, b2, eps, step, dyn=dyn, apply=False)  # catch-up before the read
+        worst_read = max(worst_read, float((p[idx.to(device)].cpu() - ref.detach()[idx]).abs().max()))
+        rows_g = torch.randn(idx.numel(), width, generator=g)
+        dense = torch.zeros(rows, width)
+        dense.index_add_(0, idx, rows_g)
+        ref.grad = dense.clone()
+        opt.step()
+        ops.scatter_add_rows(grad, idx.to(device), rows_g.to(device))
+        ops.adam_rows(p, grad, m, v, stamp, idx.to(device), lr, b1, b2, eps, step, dyn=dyn, apply=True)
+        assert float(grad.abs().sum()) == 0.0  # consumed gradient rows are zeroed again
+    ops.adam_rows(p, None, m, v, stamp, None, lr, b1, b2, eps, steps + 1, dyn=None, apply=False)  # flush: every row through `steps`
+    err = float((p.cpu() - ref.detach()).abs().max())
+    assert worst_read < 5e-6 and err < 5e-6, (worst_read, err)
+    return err

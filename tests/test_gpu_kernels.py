@@ -497,3 +497,30 @@ def test_answer_loss_and_adam(ops):
     opt2.step()
     ops.adam_step(pd2, dev(g)[1:9998], m2, v2, 1e-3, 0.9, 0.999, 1e-8, 1)
     assert rel(pd2, pr2.detach()) < 1e-6
+
+
+def test_deferred_row_adam_equals_dense_adam(ops):
+    """Row-sparse word-table optimizer == the reference's dense torch.optim.Adam (rows replay the zero-gradient steps they
+    missed): tests/parity_cases.deferred_adam_case."""
+    import parity_cases as PC
+    for seed in range(3):
+        PC.deferred_adam_case(ops, "cuda", steps=15, seed=seed)
+    # a long absence takes the closed-form branch (> 256 missed steps): the parameter update of those steps is below fp32 resolution
+    rows, width = 4, 8
+    p = torch.randn(rows, width, device="cuda")
+    ref = p.clone().cpu().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-2)
+    grad, m, v = (torch.zeros(rows, width, device="cuda") for _ in range(3))
+    stamp = torch.zeros(rows, dtype=torch.int32, device="cuda")
+    g0 = torch.randn(rows, width)
+    idx = torch.arange(rows, device="cuda")
+    for step in (1, 400):
+        gd = g0 if step == 1 else 2 * g0
+        while opt.state and int(opt.state[ref]["step"]) < step - 1:
+            ref.grad = torch.zeros_like(ref)
+            opt.step()
+        ref.grad = gd.clone()
+        opt.step()
+        ops.scatter_add_rows(grad, idx, gd.cuda())
+        ops.adam_rows(p, grad, m, v, stamp, idx, 1e-2, 0.9, 0.999, 1e-8, step, apply=True)
+    assert float((p.cpu() - ref.detach()).abs().max()) < 1e-5

@@ -50,16 +50,20 @@ def _max_param_diff(m1, m2):
     return worst
 
 
-@pytest.mark.parametrize("rowsparse,steps", [(True, 1), (False, 2)])
+@pytest.mark.parametrize("rowsparse,steps", [(True, 3), (False, 2)])
 def test_bound_trainer_matches_autograd_adam(monkeypatch, rowsparse, steps):
     fake_ops.install(monkeypatch)
     from savqa_b200 import train
     cfg, model, b = _setup()
     ref = copy.deepcopy(model)
     lr = 1e-3
-    ref_losses = _reference_steps(ref, [b] * steps, lr)
+    # different batches per step: word rows come and go, so the row-sparse tables exercise the deferred (catch-up) Adam path
+    from savqa_b200 import synthetic
+    bs = [b] + [synthetic.make_batch(cfg, 4, seed=6 + i, vocab_rows=1200) for i in range(steps - 1)]
+    ref_losses = _reference_steps(ref, bs, lr)
     tr = train.EncoderTrainer(model, lr=lr, rowsparse=rowsparse)
-    losses = [float(tr.step(b)) for _ in range(steps)]
+    losses = [float(tr.step(x)) for x in bs]
+    tr.flush_tables()  # every word row up to date: the tables now hold what dense Adam holds
     # every attention / feed-forward / head pack that can be bound is bound, and its views alias the flat buffers
     att = model.att_vis_grid.enc_self_attention_0
     assert att._packs["qkv"].bound and att._packs["kv"].bound and att.normalization._sink.bound
@@ -146,3 +150,10 @@ def test_grad_reducer_launch_order_follows_the_backward_pass():
     order = [k for _, _, k in sorted(pending, key=lambda t: (t[0], t[1]))]
     assert order[0] == (0, "heads") and order[1:3] == [(a, "dec"), (b, "dec")]
     assert order[3:] == [(br, "enc", i) for i in range(5, -1, -1) for br in (a, b)]
+
+
+def test_deferred_row_adam_host_semantics(monkeypatch):
+    """The deferred row-wise Adam protocol (catch-up before the read, update after the backward, flush) equals dense
+    torch.optim.Adam -- here with the CPU stand-ins of the kernels; tests/test_gpu_kernels.py runs the same case on the B200."""
+    import parity_cases as PC
+    PC.deferred_adam_case(fake_ops, "cpu", steps=10)
