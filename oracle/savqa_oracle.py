@@ -19,12 +19,12 @@ Pinning: the reference has NO tests, golden vectors or fixtures of its own (SURV
 8(c)), so the oracle is pinned against the *live* reference modules, imported unmodified from
 /root/reference in the authoring container by oracle/make_golden.py, which commits seeded
 input/output vectors under tests/golden/.  tests/test_oracle_golden.py checks this file against
-those vectors (<= 2e-6 norm-rel in fp32, masks/gathers bit-exact) and
-tests/test_oracle_live_reference.py re-checks against the live reference whenever /root/reference
-is present.
+those vectors (<= 2e-6 norm-rel in fp32, masks/gathers bit-exact); re-running oracle/make_golden.py
+where /root/reference is present regenerates the fixtures bit for bit.
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
-this module.  The product package (structured-alignment-vqa_b200/savqa_b200) never does.
+Only tests/, __graft_entry__.smoke() and bench.py's baseline legs (cpu_baseline, --impl reference, and the
+stock-PyTorch-on-the-same-GPU comparator --impl stock-gpu, where these functions run on CUDA tensors through
+ATen / cuBLAS) may import this module.  The product package (structured-alignment-vqa_b200/savqa_b200) never does.
 
 Every function takes plain tensors and parameters keyed by the reference's state_dict names.
 `operand_dtype=torch.bfloat16` emulates "bf16 MMA operands, fp32 accumulate" (used only to calibrate
@@ -133,11 +133,11 @@ def attention(
     # key padding mask from the RAW key inputs: sign(|sum_c keys|) (modules.py:257-263)
     key_on = (keys.sum(-1) != 0)  # [N,Tk]
     key_on = key_on.repeat(num_heads, 1).unsqueeze(1)  # [H*N,1,Tk]
-    fill = torch.full((), KEY_MASK_FILL, dtype=S.dtype)
+    fill = torch.full((), KEY_MASK_FILL, dtype=S.dtype, device=S.device)
     S = torch.where(key_on, S, fill)
     if causality:  # modules.py:268-275
         tq, tk = S.shape[1], S.shape[2]
-        keep = torch.ones(tq, tk, dtype=torch.bool).tril()
+        keep = torch.ones(tq, tk, dtype=torch.bool, device=S.device).tril()
         S = torch.where(keep, S, fill)
 
     P = torch.softmax(S, dim=-1)  # modules.py:278 (max-subtracted over ALL keys)
@@ -194,13 +194,13 @@ def build_masks(
     B, V = first_mask.shape[0], first_mask.shape[1]
     Qn = q_mask.shape[1]
     T = V + Qn
-    graph_diag = torch.zeros(B, T, T, dtype=dtype)
+    graph_diag = torch.zeros(B, T, T, dtype=dtype, device=first_mask.device)
     graph_diag[:, V:, V:] = q_mask.to(dtype)
-    graph = torch.ones(B, T, T, dtype=dtype)
+    graph = torch.ones(B, T, T, dtype=dtype, device=first_mask.device)
     if first_graph is not None:
         graph[:, :V, :V] = first_graph.to(dtype)
     graph[:, V:, V:] = q_graph.to(dtype)
-    dec_mask = torch.zeros(B, 1, T, dtype=dtype)
+    dec_mask = torch.zeros(B, 1, T, dtype=dtype, device=first_mask.device)
     if dec_mask_on:
         # row sums of the block-diagonal mask; rows that are != 0 become 1 (AttModel_x3.py:113-116)
         dec_mask[:, 0, :V] = (first_mask.to(dtype).sum(-1) != 0).to(dtype)

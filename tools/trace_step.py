@@ -52,9 +52,9 @@ ks = [e for e in ev if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") an
 ks.sort(key=lambda e: e["ts"])
 print("gpu activities:", len(ks))
 if ks:
-    # split into replays at the host-to-device copy of the optimizer's per-step scalars (EncoderTrainer._set_dyn: the first
-    # activity of every replay)
-    starts = [i for i, e in enumerate(ks) if e.get("cat") == "gpu_memcpy" and "HtoD" in e["name"]]
+    # split into replays at the kernel that advances the optimizer's device-resident step counter (savqa_adam_advance: the
+    # first activity of every replay)
+    starts = [i for i, e in enumerate(ks) if "adam_advance_kernel" in e["name"]]
     lo = starts[1] if len(starts) >= 3 else 0
     hi = starts[2] if len(starts) >= 3 else len(ks)
     one = ks[lo:hi]
