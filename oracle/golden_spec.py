@@ -240,3 +240,39 @@ def branch_case(case: str, kind: str, B: int, V: int, Q: int, small_vocab: int =
 SMALL = dict(C=64, heads=4, blocks=6, maxlen=40, maxlen_q=12, maxlen_v=9, ncls=20, B=3, V=5, Q=4, M=7)
 # module-level goldens at the production width
 WIDE = dict(C=512, heads=8)
+
+
+# --------------------------------------------------------------------------------------------
+# MIL_NCE (AttModel_x3.py:285-443, only_obj=True)
+# --------------------------------------------------------------------------------------------
+def mil_nce_shapes(h: int) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Parameters the only_obj forward uses (R, bilinear, rel_mlp stay at their initial values: never read)."""
+    return [("syb_emb.weight", (407000, E_GLOVE)), ("marco_mlp.0.weight", (h, E_GLOVE)), ("marco_mlp.0.bias", (h,)),
+            ("syb_mlp.0.weight", (h, E_GLOVE)), ("syb_mlp.0.bias", (h,)), ("vis_mlp.0.weight", (h, F_REGION)), ("vis_mlp.0.bias", (h,)),
+            ("ipt_mlp.0.weight", (F_REGION, h)), ("ipt_mlp.0.bias", (F_REGION,))]
+
+
+MIL_CASES = {"mil_nce_h16_top2": dict(h=16, topN=2, B=3, V=5, M=7), "mil_nce_h64_top1": dict(h=64, topN=1, B=4, V=6, M=9),
+             "mil_nce_h128_top5": dict(h=128, topN=5, B=2, V=4, M=8)}
+
+
+def mil_nce_case(case: str, B: int, V: int, M: int, topN: int, small_vocab: int = SMALL_VOCAB):
+    """collate_fn-shaped MIL_NCE inputs (data_loader_itp_bbox_super_node_onlyobj.py:385-400): ragged object counts, distinct node
+    positions per object (-1 padding), PAD-like ids and a zero mask on padded objects."""
+    n_obj = randint(f"{case}/n_obj", max(1, V // 2), V + 1, B)
+    n_obj[0] = V
+    vis = rand(f"{case}/vis", B, V, F_REGION)
+    macro_ipt = randint(f"{case}/macro_ipt", 0, small_vocab - 1, B, M)
+    pos = randint(f"{case}/pos", 0, small_vocab - 1, B, V, topN)
+    neg = randint(f"{case}/neg", 0, small_vocab - 1, B, V, topN)
+    mask = torch.zeros(B, V, topN, dtype=torch.int32)
+    loc = torch.full((B, V), -1, dtype=torch.int64)
+    for b in range(B):
+        n = int(n_obj[b])
+        vis[b, n:] = 0
+        pos[b, n:] = small_vocab - 1
+        neg[b, n:] = small_vocab - 1
+        mask[b, :n] = 1
+        k = min(n, M)
+        loc[b, :k] = torch.randperm(M, generator=_gen(f"{case}/loc{b}"))[:k]
+    return dict(vis_fea=vis, macro_ipt=macro_ipt, macro_obj_loc=loc, pos=pos, neg=neg, mask=mask)

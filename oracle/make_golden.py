@@ -300,20 +300,59 @@ def token_goldens(M, out_dir):
         save(os.path.join(out_dir, f"{case}.npz"), y=y, dx=x.grad, checksum=GS.checksum({**P, "q": q}), **GS.pack_grads(case, g))
 
 
+def mil_nce_goldens(A, out_dir):
+    """The live reference's MIL_NCE (AttModel_x3.py:285-443, only_obj=True): outputs and gradients of every parameter it uses
+    for L = sum(out * w) + 3 * mil_nce_obj."""
+    glove = types.SimpleNamespace(vectors=torch.zeros(4, GS.E_GLOVE))
+    for case, c in GS.MIL_CASES.items():
+        P = GS.make_params(case, GS.mil_nce_shapes(c["h"]))
+        with torch.no_grad():
+            m = A.MIL_NCE(glove, c["h"], 0.0, 5, True)
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        for k, v in P.items():
+            if k == "syb_emb.weight":
+                sd[k][: GS.SMALL_VOCAB] = v
+            else:
+                assert sd[k].shape == v.shape, (k, sd[k].shape, v.shape)
+                sd[k] = v.clone()
+        m.load_state_dict(sd)
+        b = GS.mil_nce_case(case, c["B"], c["V"], c["M"], c["topN"])
+        e = torch.empty((c["B"], 0))
+        out, obj, rel = m(b["vis_fea"], b["macro_ipt"], b["macro_obj_loc"], b["pos"], b["neg"], b["mask"], e, e, e, e)
+        assert rel == 0
+        w = GS.randn(f"{case}/dout", *out.shape)
+        ((out * w).sum() + 3.0 * obj).backward()
+        named = dict(m.named_parameters())
+        grads = {}
+        for k in P:
+            g = named[k].grad
+            g = torch.zeros_like(named[k]) if g is None else g
+            if k == "syb_emb.weight":
+                assert float(g[GS.SMALL_VOCAB:].abs().sum()) == 0.0
+                g = g[: GS.SMALL_VOCAB]
+            grads[k] = g
+        save(os.path.join(out_dir, f"{case}.npz"), out=out, obj=obj, checksum=GS.checksum({**P, "vis": b["vis_fea"]}),
+             **GS.pack_grads(case, grads))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
-    ap.add_argument("--only", default="", help="'token': (re)generate only the one-token self-attention fixtures")
+    ap.add_argument("--only", default="", help="'token' / 'mil': (re)generate only the one-token self-attention / the MIL_NCE fixtures")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(1)  # bit-stable reductions while generating
     M, A = import_reference(args.ref)
-    if args.only != "token":
-        attention_goldens(M, args.out)
-        branch_goldens(M, A, args.out)
-    token_goldens(M, args.out)
+    if args.only == "mil":
+        mil_nce_goldens(A, args.out)
+    else:
+        if args.only != "token":
+            attention_goldens(M, args.out)
+            branch_goldens(M, A, args.out)
+            mil_nce_goldens(A, args.out)
+        token_goldens(M, args.out)
     with open(os.path.join(args.out, "MANIFEST.json"), "w") as f:
         json.dump({"torch": torch.__version__, "generator": "oracle/make_golden.py", "reference": "Peixixiong/Structured-Alignment-VQA",
                    "files": sorted(x for x in os.listdir(args.out) if x.endswith(".npz"))}, f, indent=1)

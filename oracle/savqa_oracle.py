@@ -325,6 +325,49 @@ def encoder_step(
     return loss, logits, fea_vis, fea_syb
 
 
+# --------------------------------------------------------------------------------------------
+# AttModel_x3.py:285-443  MIL_NCE (only_obj=True) and the full 16-argument step
+# --------------------------------------------------------------------------------------------
+def mil_nce(params: Params, vis_fea: Tensor, macro_ipt: Tensor, macro_obj_loc: Tensor, pos_ids: Tensor, neg_ids: Tensor,
+            obj_mask: Tensor, operand_dtype=None):
+    """MIL_NCE.forward with only_obj=True (AttModel_x3.py:339-379, 441-443).  `params` uses MIL_NCE's own key names.
+    Returns (macro_ipt_output [B,M,2048], mil_nce_obj scalar)."""
+    eps = 1e-6
+    table = params["syb_emb.weight"]
+    relu = torch.relu
+    nodes = relu(linear(table[macro_ipt], params["marco_mlp.0.weight"], params["marco_mlp.0.bias"], operand_dtype)).detach().clone()  # :352-354
+    pos = relu(linear(table[pos_ids], params["syb_mlp.0.weight"], params["syb_mlp.0.bias"], operand_dtype))    # [B,V,topN,h]  :356-357
+    neg = relu(linear(table[neg_ids], params["syb_mlp.0.weight"], params["syb_mlp.0.bias"], operand_dtype))    # :358-359
+    vis = relu(linear(vis_fea, params["vis_mlp.0.weight"], params["vis_mlp.0.bias"], operand_dtype))           # [B,V,h]  :361
+    m4 = obj_mask.unsqueeze(3).to(vis.dtype)
+    raw_pos = torch.matmul(_mm_operand(pos, operand_dtype), _mm_operand(vis, operand_dtype).unsqueeze(3))      # [B,V,topN,1]  :365
+    raw_neg = torch.matmul(_mm_operand(neg, operand_dtype), _mm_operand(vis, operand_dtype).unsqueeze(3))      # :366
+    s_pos = (m4 * raw_pos).clamp(min=eps)
+    s_neg = (m4 * raw_neg).clamp(min=eps)
+    floor = torch.zeros_like(s_neg).clamp(min=eps)
+    obj = torch.mean(torch.logsumexp(torch.cat((s_pos, floor), dim=1), dim=2)
+                     - torch.logsumexp(torch.cat((s_pos, s_neg), dim=1), dim=2))                               # :367
+    refined = torch.sum(torch.softmax(raw_pos, dim=2) * pos, dim=2)                                             # [B,V,h]  :372-374
+    b_idx, v_idx = (macro_obj_loc >= 0).nonzero(as_tuple=True)
+    nodes[b_idx, macro_obj_loc[b_idx, v_idx].long(), :] = refined[b_idx, v_idx, :]                              # :377-379
+    out = relu(linear(nodes, params["ipt_mlp.0.weight"], params["ipt_mlp.0.bias"], operand_dtype))              # :441
+    return out, obj
+
+
+def full_step(params: Params, batch: Dict[str, Tensor], num_blocks: int, num_heads: int, dec_mask_on: bool = True,
+              with_milnce_loss: bool = True, operand_dtype=None):
+    """One pass of the path as the train loop drives it WITH MIL_NCE (main...:321-345, 359-360; only_obj): the reference's
+    16-argument AttModel.forward (AttModel_x3.py:512-542) + the loss (+ mil_nce_loss = -mil_nce_obj when with_MILNCE_loss).
+    Returns (loss, (logits_concat, logits_vis, logits_syb), mil_nce_obj, new_macro_ipt)."""
+    syb_ipt, obj = mil_nce(sub(params, "MIL_NCE"), batch["vis_fea"], batch["macro_node_ipt"], batch["macro_obj_loc_ipt"],
+                           batch["micro_positive_obj_ipt"], batch["micro_negative_obj_ipt"], batch["micro_obj_mask"], operand_dtype)
+    b2 = dict(batch, syb_ipt=syb_ipt)
+    loss, logits, _, _ = encoder_step(params, b2, num_blocks, num_heads, dec_mask_on, operand_dtype)
+    if with_milnce_loss:
+        loss = loss - obj
+    return loss, logits, obj, syb_ipt
+
+
 def rel_err(a: Tensor, b: Tensor) -> float:
     """||a-b|| / ||b||  (the per-tensor parity metric of SURVEY.md 8(c))."""
     a = a.detach().double().reshape(-1)

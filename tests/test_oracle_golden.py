@@ -242,3 +242,23 @@ def test_g_weighted_softmax_identity():
     W = e / e.sum(-1, keepdim=True).clamp_min(1e-300)
     W[0, 0] = 0
     assert torch.allclose(W, W_ref, atol=1e-14)
+
+
+@pytest.mark.parametrize("case", sorted(GS.MIL_CASES))
+def test_mil_nce_oracle_vs_live_reference_golden(golden_dir, case):
+    """O.mil_nce (AttModel_x3.py:339-379, 441) against the live reference's MIL_NCE: output, mil_nce_obj and the gradients of every
+    parameter the only_obj forward uses (marco_mlp and the macro-node word rows get none: the `.detach()` at :354)."""
+    c = GS.MIL_CASES[case]
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    P0 = GS.make_params(case, GS.mil_nce_shapes(c["h"]))
+    assert abs(GS.checksum({**P0, "vis": GS.mil_nce_case(case, c["B"], c["V"], c["M"], c["topN"])["vis_fea"]}) - float(g["checksum"])) < 1e-6 * abs(float(g["checksum"]))
+    P = {k: v.clone().requires_grad_(True) for k, v in P0.items()}
+    b = GS.mil_nce_case(case, c["B"], c["V"], c["M"], c["topN"])
+    out, obj = O.mil_nce(P, b["vis_fea"], b["macro_ipt"], b["macro_obj_loc"], b["pos"], b["neg"], b["mask"])
+    assert O.rel_err(out, torch.from_numpy(g["out"])) < 2e-6
+    assert abs(float(obj) - float(g["obj"])) < 2e-6 * max(1.0, abs(float(g["obj"])))
+    w = GS.randn(f"{case}/dout", *out.shape)
+    ((out * w).sum() + 3.0 * obj).backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in P.items()}
+    GS.compare_grads(case, grads, g, 5e-6)
+    assert float(grads["marco_mlp.0.weight"].abs().sum()) == 0.0
