@@ -56,6 +56,17 @@ int savqa_build_masks(const void* first_mask, const void* q_mask, const void* q_
                       int in_is_float, int B, int V, int Q, int dec_mask_on,
                       float* graph_diag, float* graph, float* dec_mask, savqa_stream_t stream);
 
+/* ---- f2: the same masks from the loader's COMPACT hand-off ------------------------------------------------
+ * collate_fn's masks are prefix blocks (ones on [:n,:n]; data_loader_itp_bbox_super_node_onlyobj.py:355-358, 369-372, 412-414),
+ * so a length per sample carries them: first_len [B], q_len [B] (int32).  The 0/1 adjacency matrices travel bit-packed:
+ * first_graph_bits [B,V,ceil(V/32)] (NULL: visual branch, top-left block all ones), q_graph_bits [B,Q,ceil(Q/32)], bit j of
+ * word w of row r = edge r -> 32 w + j.  Outputs: graph_diag / graph / dec_mask exactly as savqa_build_masks writes them from
+ * the dense planes (bit for bit), plus -- when non-NULL -- the bit-packed forms [B,T,ceil(T/32)] of graph_diag and graph that
+ * the tcgen05 attention kernels read.  ~100 KB of input per step instead of ~30 MB of dense int32 planes. */
+int savqa_build_masks_compact(const int32_t* first_len, const int32_t* q_len, const uint32_t* first_graph_bits,
+                              const uint32_t* q_graph_bits, int B, int V, int Q, int dec_mask_on, float* graph_diag, float* graph,
+                              float* dec_mask, uint32_t* diag_bits, uint32_t* graph_bits, savqa_stream_t stream);
+
 /* bits[r, w] bit j = (graph[r, 32 w + j] != 0), zero past Tk, for r < rows, w < words_per_row (>= ceil(Tk / 32)).
  * Only meaningful for graphs whose entries are exactly 0 or 1 (the outputs of savqa_build_masks): the attention kernels
  * then read 4 bytes per 32 keys instead of 128. */
@@ -201,7 +212,25 @@ int savqa_answer_loss(const float* logits_concat, const float* logits_vis, const
                       int ncls, float epsilon, float grad_scale, float* loss, float* d_concat, float* d_vis, float* d_syb,
                       savqa_stream_t stream);
 
-/* ---- f3 (next): fused Adam over a flat fp32 parameter / gradient pair (torch.optim.Adam semantics,
+/* ---- f1: MIL_NCE object-word alignment head (AttModel_x3.py:285-443, only_obj=True) between its Linear layers -----------
+ * pn_h  bf16 [2*B*V*topN, ld_pn]: relu(syb_mlp(word rows)), the B*V*topN positive rows first, then the negative rows;
+ * vis_h bf16 [B*V, ld_vis]: relu(vis_mlp(vis_fea));  mask int32 [B,V,topN];  loc int64 [B,V] (node position of object v, < 0: none).
+ *   raw_pos[b,v,i] = <pos_h, vis_h>, raw_neg likewise                       (:365-366; written to raw[0 / 1][B*V*topN] for the backward)
+ *   mil_nce_obj    = sum_{b,v} [lse_i(eps) - lse_i(max(mask*raw_neg, eps))] / (2 B V)   (:367 -- the positive halves of the two
+ *                    concatenated logsumexp's are identical and cancel, in value and in gradient)          -> obj[0]
+ *   nodes[b, loc[b,v], :] = sum_i softmax_i(raw_pos)[i] * pos_h[b,v,i,:]    (:372-379; nodes bf16 [B*M, ld_nodes] holds
+ *                    relu(marco_mlp(.)) on entry, detached as at :354)
+ * term fp32 [B*V] is workspace.  topN <= 8, h even. */
+int savqa_mil_nce_fwd(const void* pn_h, int64_t ld_pn, const void* vis_h, int64_t ld_vis, const int32_t* mask, const int64_t* loc,
+                      void* nodes, int64_t ld_nodes, int B, int V, int M, int topN, int h, float* raw, float* term, float* obj,
+                      savqa_stream_t stream);
+/* Backward: d_nodes fp32 [B*M, ld_dn] (gradient of the node rows, may be NULL), d_obj device scalar (gradient of mil_nce_obj, may
+ * be NULL) -> ReLU-gated gradients of the pre-activations of syb_mlp (d_pn, layout of pn_h) and vis_mlp (d_vis), bf16. */
+int savqa_mil_nce_bwd(const void* pn_h, int64_t ld_pn, const void* vis_h, int64_t ld_vis, const int32_t* mask, const int64_t* loc,
+                      const float* raw, const float* d_nodes, int64_t ld_dn, const float* d_obj, int B, int V, int M, int topN, int h,
+                      void* d_pn, int64_t ld_dpn, void* d_vis, int64_t ld_dvis, savqa_stream_t stream);
+
+/* ---- f3: fused Adam over a flat fp32 parameter / gradient pair (torch.optim.Adam semantics,
  * main_itp_ddp_tar_super_node.py:206) and its row-sparse form for the word tables. ------------------------ */
 /* dyn (device, may be NULL) = {lr / (1 - beta1^step), sqrt(1 - beta2^step), step}: read at run time instead of the host
  * scalars, so that a captured CUDA graph follows the step counter. */

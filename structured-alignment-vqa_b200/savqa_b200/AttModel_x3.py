@@ -3,8 +3,8 @@ forward signatures, output shapes and state_dict keys; the graph-guided encoder 
 sm_100a kernels (modules.py of this package).
 
     AttModel_vis_grid  <- AttModel_x3.py:20-156      AttModel_syb <- :158-282      AttModel <- :471-542
-    MIL_NCE            <- :285-443  (OUT of the accelerated path, SURVEY.md 8(f1): restated with stock torch ops so
-                                     that a full AttModel step runs; only_obj=True only)
+    MIL_NCE            <- :285-443  (SURVEY.md 8(f1): gather + small GEMMs + one fused score kernel, forward and backward;
+                                     only_obj=True only)
     CompactBilinearPooling <- :444-469 (parameter holder only: torch.rfft no longer exists, `mcb=True` raises)
 
 Deliberate differences: no hard-coded `.cuda()` (inputs decide the device, which must be a B200); the per-sample
@@ -91,16 +91,22 @@ class _Branch(nn.Module):
             n = 2 * self.num_blocks * C
             pk.bind(fv.bf16(g[0]).view(n, C), fv.param(g[1]), fv.grad(g[0]).view(n, C), fv.grad(g[1]))
 
-    def _masks_aside(self, first_mask, q_mask, q_graph, first_graph, dec_on):
+    def _masks_aside(self, first_mask, q_mask, q_graph, first_graph, dec_on, compact=None):
         """Mask construction (AttModel_x3.py:103-122 / :229-247) depends on nothing the input MLPs produce: on a GPU it runs on a
-        helper stream next to them; the caller joins with the returned event before the first attention."""
-        if not first_mask.is_cuda:
-            return ops.build_masks(first_mask, q_mask, q_graph, first_graph, dec_on), None
+        helper stream next to them; the caller joins with the returned event before the first attention.  `compact` =
+        (first_len, q_len, q_graph_bits, first_graph_bits, V, Q): the loader's compact hand-off (collate.py) instead of dense planes."""
+        def build():
+            if compact is not None:
+                return ops.build_masks_compact(*compact, dec_on)
+            return ops.build_masks(first_mask, q_mask, q_graph, first_graph, dec_on)  # (+ the bit-packed forms of the two graphs)
+        probe = compact[0] if compact is not None else first_mask
+        if not probe.is_cuda:
+            return build(), None
         cur = torch.cuda.current_stream()
         aside = Fn.wgrad_stream_of(cur)
         aside.wait_stream(cur)
         with torch.cuda.stream(aside):
-            masks = ops.build_masks(first_mask, q_mask, q_graph, first_graph, dec_on)  # (+ the bit-packed forms of the two graphs)
+            masks = build()
             done = torch.cuda.Event()
             done.record(aside)
         for m in masks:
@@ -236,6 +242,18 @@ class AttModel_vis_grid(_Branch):
             torch.cuda.current_stream().wait_event(done)
         return self._encode_decode(x, graph_diag, graph, dec_mask)
 
+    def forward_compact(self, vis_fea, vis_len, q_fea, q_graph_bits, q_len, decMask):
+        """forward() on the loader's compact hand-off (collate.py): `vis_len` / `q_len` int32 [B] for the prefix-block masks, the
+        question graph bit-packed.  Same result as forward() on the dense planes, bit for bit."""
+        if vis_fea.dim() == 4:
+            vis_fea = vis_fea.reshape(-1, vis_fea.size(1) * vis_fea.size(2), vis_fea.size(3))
+        compact = (vis_len, q_len, q_graph_bits, None, vis_fea.shape[1], q_fea.shape[1])
+        (graph_diag, graph, dec_mask), done = self._masks_aside(None, None, None, None, decMask != False, compact)  # noqa: E712
+        x = self._input_stage(vis_fea, q_fea, self.syb_positional_encoding[0].lookup_table, self.dropout_rate)
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
+        return self._encode_decode(x, graph_diag, graph, dec_mask)
+
 
 class AttModel_syb(_Branch):
     def __init__(self, glove, hidden_size, maxlen, maxlen_q, num_blocks, num_heads, dropout_rate, num_classes):
@@ -267,11 +285,20 @@ class AttModel_syb(_Branch):
             torch.cuda.current_stream().wait_event(done)
         return self._encode_decode(x, graph_diag, graph, dec_mask)
 
+    def forward_compact(self, syb_ipt, macro_len, macro_graph_bits, q_fea, q_graph_bits, q_len, decMask):
+        """forward() on the loader's compact hand-off (collate.py); same result as forward() on the dense planes, bit for bit."""
+        compact = (macro_len, q_len, q_graph_bits, macro_graph_bits, syb_ipt.shape[1], q_fea.shape[1])
+        (graph_diag, graph, dec_mask), done = self._masks_aside(None, None, None, None, decMask != False, compact)  # noqa: E712
+        x = self._input_stage(syb_ipt, q_fea, self.syb_positional_encoding.lookup_table, 0.0)
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
+        return self._encode_decode(x, graph_diag, graph, dec_mask)
+
 
 class MIL_NCE(nn.Module):
-    """Object-word alignment head (AttModel_x3.py:285-443), restated with stock torch ops -- NOT part of the
-    accelerated path.  Produces `new_macro_ipt` [B,M,2048] for the symbolic branch and the
-    object MIL-NCE term.  Only the production `only_obj=True` configuration is implemented."""
+    """Object-word alignment head (AttModel_x3.py:285-443) on the sm_100a kernels (functional.MilNceFn): produces `new_macro_ipt`
+    [B,M,2048] for the symbolic branch and the object MIL-NCE term.  Only the production `only_obj=True` configuration is
+    implemented (the relation branch holds a Python loop over relations, :421-436, and is outside the scope)."""
 
     def __init__(self, glove, hidden_size, dropout_rate, num_relations, only_obj):
         super().__init__()
@@ -290,28 +317,22 @@ class MIL_NCE(nn.Module):
         self.softmax_bilinear = nn.Softmax(dim=0)
         self.bilinear = nn.Bilinear(hidden_size, hidden_size, num_relations, bias=False)
         self.ipt_mlp = nn.Sequential(nn.Linear(hidden_size, 2048), nn.ReLU(inplace=True))
+        self._pk = {k: WeightPack() for k in ("marco", "syb", "vis", "ipt")}
+        self._bf16_out = False  # AttModel.forward keeps new_macro_ipt in bf16 (the symbolic branch's first GEMM casts it anyway)
+
+    def _savqa_bind(self, fv):
+        Fn.bind_linear(self._pk["vis"], self.vis_mlp[0], fv)   # K = 2048
+        Fn.bind_linear(self._pk["ipt"], self.ipt_mlp[0], fv)   # K = hidden_size_mil; the K = 300 layers stay on the staging path
 
     def forward(self, vis_fea, macro_ipt, macro_obj_loc, micro_positive_obj, micro_negative_obj, micro_obj_mask,
                 micro_positive_rel, micro_negative_rel, micro_positive_rel_loc, micro_negative_rel_loc):
         if not self.only_obj:
             raise NotImplementedError("savqa_b200: the relation branch of MIL_NCE (only_obj=False) is outside the scope of this build")
-        eps = 1e-6
-        words = lambda ids: Fn.EmbeddingFn.apply(ids, self.syb_emb.weight, 1.0, -1)  # noqa: E731
-        nodes = self.marco_mlp(words(macro_ipt)).detach().clone()                 # [B,M,h]; detached at :354
-        pos = self.syb_mlp(words(micro_positive_obj))                             # [B,V,topN,h]
-        neg = self.syb_mlp(words(micro_negative_obj))
-        vis = self.vis_mlp(vis_fea).unsqueeze(3)                                  # [B,V,h,1]
-        m4 = micro_obj_mask.unsqueeze(3)
-        raw_pos = torch.matmul(pos, vis)                                          # [B,V,topN,1]
-        s_pos = (m4 * raw_pos).clamp(min=eps)
-        s_neg = (m4 * torch.matmul(neg, vis)).clamp(min=eps)
-        floor = torch.zeros_like(s_neg).clamp(min=eps)
-        mil_nce_obj = torch.mean(torch.logsumexp(torch.cat((s_pos, floor), dim=1), dim=2)
-                                 - torch.logsumexp(torch.cat((s_pos, s_neg), dim=1), dim=2))
-        refined = torch.sum(self.softmax(raw_pos) * pos, dim=2)                   # [B,V,h]
-        b_idx, v_idx = (macro_obj_loc >= 0).nonzero(as_tuple=True)
-        nodes[b_idx, macro_obj_loc[b_idx, v_idx].long(), :] = refined[b_idx, v_idx, :]
-        return self.ipt_mlp(nodes), mil_nce_obj, 0
+        out, obj = Fn.MilNceFn.apply(vis_fea, self.syb_emb.weight, self.marco_mlp[0].weight, self.marco_mlp[0].bias,
+                                     self.syb_mlp[0].weight, self.syb_mlp[0].bias, self.vis_mlp[0].weight, self.vis_mlp[0].bias,
+                                     self.ipt_mlp[0].weight, self.ipt_mlp[0].bias, macro_ipt, macro_obj_loc, micro_positive_obj,
+                                     micro_negative_obj, micro_obj_mask, self._pk, getattr(self.syb_emb, "_savqa_rowlog", None))
+        return (out if self._bf16_out else out.float()), obj, 0
 
 
 class CompactBilinearPooling(nn.Module):
@@ -348,6 +369,7 @@ class AttModel(nn.Module):
         self.att_vis_grid = AttModel_vis_grid(glove, hidden_size, maxlen, maxlen_q, num_blocks, num_heads, dropout_rate, maxlen_v, num_classes)
         self.att_syb = AttModel_syb(glove, hidden_size, maxlen, maxlen_q, num_blocks, num_heads, dropout_rate, num_classes)
         self.MIL_NCE = MIL_NCE(glove, hidden_size_mil, dropout_rate, num_relations, self.only_obj)
+        self.MIL_NCE._bf16_out = True
         self.cls = _head(hidden_size * 2, hidden_size, num_classes, dropout_rate)
         self.cls_vis = _head(hidden_size, hidden_size, num_classes, dropout_rate)
         self.cls_syb = _head(hidden_size, hidden_size, num_classes, dropout_rate)
@@ -401,34 +423,58 @@ class AttModel(nn.Module):
             lg.record_stream(main)
         return logits_concat, logits_vis, logits_syb
 
-    def encoder_step(self, vis_fea, vis_mask, q_ipt, q_mask, q_graph, syb_ipt, macro_mask, macro_graph, decMask=True):
-        """The accelerated path alone: both branch models + heads, with `syb_ipt` [B,M,2048] given (what MIL_NCE
-        hands to att_syb at AttModel_x3.py:530)."""
-        if not (getattr(self, "concurrent_branches", True) and vis_fea.is_cuda):
-            fea_vis_grid = self.att_vis_grid(vis_fea, vis_mask, q_ipt, q_graph, q_mask, decMask)
-            fea_syb = self.att_syb(syb_ipt, macro_mask, macro_graph, q_ipt, q_graph, q_mask, decMask)
+    def _two_branches(self, run_vis, run_syb, on_gpu):
+        """Runs the two branch models and the heads.  The branches are independent until the heads (AttModel_x3.py:529-531): on a
+        GPU the symbolic branch is forked onto a second stream so that its kernels (and, through autograd, their backward) overlap
+        the visual branch's -- the decoders' launch-bound M = B kernels of one branch hide under the encoder GEMMs of the other.
+        Inside a CUDA-graph capture this becomes two parallel branches of the graph."""
+        if not (getattr(self, "concurrent_branches", True) and on_gpu):
+            fea_vis_grid, fea_syb = run_vis(), run_syb()
             return self.answer_logits(Fn.bucket_mark(fea_vis_grid, (id(self), "heads")), Fn.bucket_mark(fea_syb, (id(self), "heads")))
-        # The two branch models are independent until the heads (AttModel_x3.py:529-531): fork the symbolic branch onto a
-        # second stream so that its kernels (and, through autograd, their backward) overlap the visual branch's -- the
-        # decoders' launch-bound M = B kernels of one branch hide under the encoder GEMMs of the other.  Inside a CUDA-graph
-        # capture this becomes two parallel branches of the graph.
         main = torch.cuda.current_stream()
-        side = _SIDE_STREAMS.get(vis_fea.device)
+        side = _SIDE_STREAMS.get(main.device)
         if side is None:
-            side = _SIDE_STREAMS[vis_fea.device] = torch.cuda.Stream(device=vis_fea.device)
+            side = _SIDE_STREAMS[main.device] = torch.cuda.Stream(device=main.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            fea_syb = self.att_syb(syb_ipt, macro_mask, macro_graph, q_ipt, q_graph, q_mask, decMask)
-        fea_vis_grid = self.att_vis_grid(vis_fea, vis_mask, q_ipt, q_graph, q_mask, decMask)
+            fea_syb = run_syb()
+        fea_vis_grid = run_vis()
         main.wait_stream(side)
         fea_syb.record_stream(main)
         return self.answer_logits(Fn.bucket_mark(fea_vis_grid, (id(self), "heads")), Fn.bucket_mark(fea_syb, (id(self), "heads")))
+
+    def encoder_step(self, vis_fea, vis_mask, q_ipt, q_mask, q_graph, syb_ipt, macro_mask, macro_graph, decMask=True):
+        """The two branch models + heads, with `syb_ipt` [B,M,2048] given (what MIL_NCE hands to att_syb at AttModel_x3.py:530)."""
+        return self._two_branches(lambda: self.att_vis_grid(vis_fea, vis_mask, q_ipt, q_graph, q_mask, decMask),
+                                  lambda: self.att_syb(syb_ipt, macro_mask, macro_graph, q_ipt, q_graph, q_mask, decMask), vis_fea.is_cuda)
+
+    def forward_compact(self, c, decMask=True, mcb=False):
+        """forward() on the loader's compact hand-off (collate.compact_batch): bf16 region features, per-sample lengths instead of
+        the prefix-block masks, bit-packed adjacency.  Returns what forward() returns on the dense batch, bit for bit (the masks the
+        kernels see are identical)."""
+        if mcb == True:  # noqa: E712
+            raise NotImplementedError("mcb=True needs torch.rfft (removed from PyTorch); the reference cannot run it either")
+        vis_fea = c["vis_fea"]
+        if vis_fea.dtype != torch.bfloat16:
+            vis_fea = _CastBf16.apply(vis_fea)
+        e = torch.empty((vis_fea.shape[0], 0), device=vis_fea.device)  # only_obj: main_itp_ddp_tar_super_node.py:290-308
+        new_macro_ipt, mil_nce_obj, mil_nce_rel = self.MIL_NCE(vis_fea, c["macro_node_ipt"], c["macro_obj_loc_ipt"], c["micro_positive_obj_ipt"],
+                                                               c["micro_negative_obj_ipt"], c["micro_obj_mask"], e, e, e, e)
+        logits = self._two_branches(
+            lambda: self.att_vis_grid.forward_compact(vis_fea, c["vis_len"], c["q_ipt"], c["q_graph_bits"], c["q_len"], decMask),
+            lambda: self.att_syb.forward_compact(new_macro_ipt, c["macro_len"], c["macro_graph_bits"], c["q_ipt"], c["q_graph_bits"], c["q_len"],
+                                                 decMask), vis_fea.is_cuda)
+        return (*logits, mil_nce_obj, mil_nce_rel)
 
     def forward(self, vis_fea, vis_mask, q_ipt, q_mask, q_graph, macro_ipt, macro_mask, macro_graph, macro_obj_loc,
                 micro_positive_obj, micro_negative_obj, micro_obj_mask, micro_positive_rel, micro_negative_rel,
                 micro_positive_rel_loc, micro_negative_rel_loc, decMask=True, mcb=False):
         if mcb == True:  # noqa: E712
             raise NotImplementedError("mcb=True needs torch.rfft (removed from PyTorch); the reference cannot run it either")
+        if vis_fea.dim() == 4:  # bs x gridx x gridy x fea_size
+            vis_fea = vis_fea.reshape(-1, vis_fea.size(1) * vis_fea.size(2), vis_fea.size(3))
+        if vis_fea.dtype != torch.bfloat16:
+            vis_fea = _CastBf16.apply(vis_fea)  # staged once: MIL_NCE's vis_mlp and the visual branch's syb_mlp2 both read it
         new_macro_ipt, mil_nce_obj, mil_nce_rel = self.MIL_NCE(vis_fea, macro_ipt, macro_obj_loc, micro_positive_obj,
                                                                micro_negative_obj, micro_obj_mask, micro_positive_rel,
                                                                micro_negative_rel, micro_positive_rel_loc, micro_negative_rel_loc)

@@ -51,6 +51,9 @@ SIGNATURES = {
     "savqa_device_check": [C.POINTER(C.c_int)],
     "savqa_launch_counts": [C.POINTER(i64), C.c_int],
     "savqa_build_masks": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp],
+    "savqa_build_masks_compact": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp],
+    "savqa_mil_nce_fwd": [vp, i64, vp, i64, vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp],
+    "savqa_mil_nce_bwd": [vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, i64, vp, i64, vp],
     "savqa_pack_graph_bits": [vp, i64, C.c_int, vp, C.c_int, vp],
     "savqa_gather_rows": [vp, i64, C.c_int, vp, i64, C.c_float, vp, i64, vp, i64, C.c_int, vp],
     "savqa_scatter_add_rows": [vp, i64, C.c_int, vp, i64, vp, i64, C.c_float, i64, vp],

@@ -824,6 +824,80 @@ class FeedForwardFn(Function):
 
 
 # ======================================================================================================
+# MIL_NCE  -- AttModel_x3.py:285-443 (only_obj=True)
+# ======================================================================================================
+class MilNceFn(Function):
+    """(new_macro_ipt [B,M,2048] bf16, mil_nce_obj) = MIL_NCE(vis_fea, word ids ...): one gather for the three id lists, the four
+    small Linear+ReLU layers on the tensor-core GEMM, the per-object score / logsumexp / softmax-refine / scatter stage in one
+    kernel (savqa_mil_nce_fwd), forward and backward.  marco_mlp and the macro-node word rows receive no gradient (`.detach()`
+    at AttModel_x3.py:354), exactly like the reference."""
+
+    @staticmethod
+    def forward(ctx, vis_fea, table, Wm, bm, Ws, bs, Wv, bv, Wi, bi, macro_ipt, loc, pos_ids, neg_ids, mask, packs, rowlog):
+        B, V = vis_fea.shape[0], vis_fea.shape[1]
+        M, topN, h, E, Fd = macro_ipt.shape[1], pos_ids.shape[2], Ws.shape[0], table.shape[1], vis_fea.shape[-1]
+        if h % 8 or topN > 8:
+            raise ValueError("savqa_b200: MIL_NCE needs hidden_size_mil % 8 == 0 and topN <= 8")
+        dev = vis_fea.device
+        vis_b = _as_bf16_rows(vis_fea, B * V, Fd)
+        ids_pn = torch.cat([pos_ids.reshape(-1), neg_ids.reshape(-1)])
+        _, x = ops.gather_rows(table.detach(), torch.cat([macro_ipt.reshape(-1), ids_pn]), want_f32=False, want_bf16=True)
+        xm, xpn = x[:B * M], x[B * M:]
+        pm, ps = packs["marco"].refresh([Wm], [bm]), packs["syb"].refresh([Ws], [bs])
+        pv, pi = packs["vis"].refresh([Wv], [bv]), packs["ipt"].refresh([Wi], [bi])
+        n = B * V * topN
+        nodes = torch.empty(B * M, h, device=dev, dtype=BF16)
+        ops.gemm(xm, pm.w, B * M, h, E, bias=pm.bias, relu=True, out_bf16=nodes)            # :352 (detached at :354)
+        pn_h = torch.empty(2 * n, h, device=dev, dtype=BF16)
+        ops.gemm(xpn, ps.w, 2 * n, h, E, bias=ps.bias, relu=True, out_bf16=pn_h)            # :356-359
+        vis_h = torch.empty(B * V, h, device=dev, dtype=BF16)
+        ops.gemm(vis_b, pv.w, B * V, h, Fd, bias=pv.bias, relu=True, out_bf16=vis_h)        # :361
+        mask_i = mask.reshape(-1).to(torch.int32).contiguous()
+        loc_l = loc.reshape(-1).to(torch.int64).contiguous()
+        raw, obj = ops.mil_nce_fwd(pn_h, vis_h, mask_i, loc_l, nodes, B, V, M, topN, h)     # :365-379
+        out = torch.empty(B * M, Wi.shape[0], device=dev, dtype=BF16)
+        ops.gemm(nodes, pi.w, B * M, Wi.shape[0], h, bias=pi.bias, relu=True, out_bf16=out)  # :441
+        ctx.packs, ctx.rowlog, ctx.dims, ctx.table_shape = packs, rowlog, (B, V, M, topN, h, E, Fd, Wi.shape[0]), table.shape
+        ctx.save_for_backward(xpn, vis_b, pn_h, vis_h, nodes, out, raw, mask_i, loc_l, ids_pn)
+        ctx.set_materialize_grads(False)
+        return out.view(B, M, Wi.shape[0]), obj.reshape(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out, d_obj):
+        xpn, vis_b, pn_h, vis_h, nodes, out, raw, mask_i, loc_l, ids_pn = ctx.saved_tensors
+        B, V, M, topN, h, E, Fd, Fo = ctx.dims
+        packs = ctx.packs
+        ps, pv, pi = packs["syb"], packs["vis"], packs["ipt"]
+        dev = out.device
+        if d_out is None and d_obj is None:
+            return (None,) * 17
+        d_nodes = dWi = dbi = None
+        if d_out is not None:
+            dpre = ops.relu_gate_bf16(d_out.reshape(B * M, Fo).contiguous(), out)
+            dbi = pi.bias_grad_buffer(Fo, dev)
+            dWi = pi.weight_grad(dpre, nodes, Fo, h, bias_grad=dbi)
+            d_nodes = torch.empty(B * M, h, device=dev, dtype=F32)
+            dgrad(dpre, pi, B * M, h, Fo, out_f32=d_nodes)
+        dobj = d_obj.reshape(1).float().contiguous() if d_obj is not None else None
+        d_pn, d_vis = ops.mil_nce_bwd(pn_h, vis_h, mask_i, loc_l, raw, d_nodes, dobj, B, V, M, topN, h)
+        dbs, dbv = ps.bias_grad_buffer(h, dev), pv.bias_grad_buffer(h, dev)
+        dWs = ps.weight_grad(d_pn, xpn, h, E, bias_grad=dbs)
+        dWv = pv.weight_grad(d_vis, vis_b, h, Fd, bias_grad=dbv)
+        dtable = None
+        if ctx.needs_input_grad[1]:
+            dx = torch.empty(2 * B * V * topN, E, device=dev, dtype=F32)
+            dgrad(d_pn, ps, 2 * B * V * topN, E, h, out_f32=dx)
+            if ctx.rowlog is not None:
+                ctx.rowlog.pending.append((ids_pn, dx, 1.0, -1))
+            else:
+                dtable = torch.zeros(ctx.table_shape, device=dev, dtype=F32)  # dense, like the reference
+                ops.scatter_add_rows(dtable, ids_pn, dx)
+        return (None, dtable, None, None, ps.out(dWs), ps.out(dbs), pv.out(dWv), pv.out(dbv), pi.out(dWi) if dWi is not None else None,
+                pi.out(dbi) if dbi is not None else None, None, None, None, None, None, None, None)
+
+
+# ======================================================================================================
 # three-head label-smoothed loss  -- main_itp_ddp_tar_super_node.py:335-345
 # ======================================================================================================
 class AnswerLossFn(Function):

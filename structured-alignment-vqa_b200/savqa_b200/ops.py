@@ -76,6 +76,65 @@ def build_masks(first_mask: Tensor, q_mask: Tensor, q_graph: Tensor, first_graph
     return graph_diag, graph, dec_mask
 
 
+def build_masks_compact(first_len: Tensor, q_len: Tensor, q_graph_bits: Tensor, first_graph_bits: Optional[Tensor], V: int, Q: int,
+                        dec_mask_on: bool):
+    """build_masks from the loader's compact hand-off (savqa_build_masks_compact): per-sample lengths (int32 [B]) instead of the
+    prefix-block masks, bit-packed adjacency (int32 [B,Q,ceil(Q/32)], [B,V,ceil(V/32)] | None) instead of int32 planes.  Same three
+    fp32 tensors as build_masks, bit for bit, with the graphs' bit-packed forms attached."""
+    for nm, t in (("first_len", first_len), ("q_len", q_len), ("q_graph_bits", q_graph_bits), ("first_graph_bits", first_graph_bits)):
+        _check(t, torch.int32, nm)
+        assert t is None or t.is_contiguous()
+    B = first_len.numel()
+    assert q_len.numel() == B and q_graph_bits.shape == (B, Q, (Q + 31) // 32)
+    assert first_graph_bits is None or first_graph_bits.shape == (B, V, (V + 31) // 32)
+    T = V + Q
+    dev = first_len.device
+    graph_diag = torch.empty(B, T, T, device=dev, dtype=F32)
+    graph = torch.empty(B, T, T, device=dev, dtype=F32)
+    dec_mask = torch.empty(B, 1, T, device=dev, dtype=F32)
+    wpr = (T + 31) // 32
+    dbits = torch.empty(B, T, wpr, device=dev, dtype=torch.int32)
+    gbits = torch.empty(B, T, wpr, device=dev, dtype=torch.int32)
+    call("savqa_build_masks_compact", ptr(first_len), ptr(q_len), ptr(first_graph_bits), ptr(q_graph_bits), B, V, Q, int(bool(dec_mask_on)),
+         ptr(graph_diag), ptr(graph), ptr(dec_mask), ptr(dbits), ptr(gbits))
+    graph_diag._savqa_bits = (dbits, graph_diag._version, graph_diag.data_ptr())
+    graph._savqa_bits = (gbits, graph._version, graph.data_ptr())
+    return graph_diag, graph, dec_mask
+
+
+def mil_nce_fwd(pn_h: Tensor, vis_h: Tensor, mask: Tensor, loc: Tensor, nodes: Tensor, B: int, V: int, M: int, topN: int, h: int):
+    """MIL_NCE between its Linear layers (savqa_mil_nce_fwd).  Overwrites the object rows of `nodes` (bf16 [B*M, >= h]) with the
+    refined object features; returns (raw fp32 [2, B*V*topN] for the backward, mil_nce_obj fp32 [1])."""
+    _check(pn_h, BF16, "pn_h")
+    _check(vis_h, BF16, "vis_h")
+    _check(nodes, BF16, "nodes")
+    _check(mask, torch.int32, "mask")
+    _check(loc, torch.int64, "loc")
+    assert pn_h.dim() == 2 and pn_h.shape[0] == 2 * B * V * topN and pn_h.shape[1] >= h and pn_h.stride(1) == 1
+    assert vis_h.dim() == 2 and vis_h.shape[0] == B * V and vis_h.shape[1] >= h and vis_h.stride(1) == 1
+    assert nodes.dim() == 2 and nodes.shape[0] == B * M and nodes.shape[1] >= h and nodes.stride(1) == 1
+    assert mask.is_contiguous() and mask.numel() == B * V * topN and loc.is_contiguous() and loc.numel() == B * V
+    raw = torch.empty(2, B * V * topN, device=pn_h.device, dtype=F32)
+    term = torch.empty(B * V, device=pn_h.device, dtype=F32)
+    obj = torch.empty(1, device=pn_h.device, dtype=F32)
+    call("savqa_mil_nce_fwd", ptr(pn_h), pn_h.stride(0), ptr(vis_h), vis_h.stride(0), ptr(mask), ptr(loc), ptr(nodes), nodes.stride(0), B, V, M,
+         topN, h, ptr(raw), ptr(term), ptr(obj))
+    return raw, obj
+
+
+def mil_nce_bwd(pn_h: Tensor, vis_h: Tensor, mask: Tensor, loc: Tensor, raw: Tensor, d_nodes: Optional[Tensor], d_obj: Optional[Tensor], B: int,
+                V: int, M: int, topN: int, h: int):
+    """Backward of mil_nce_fwd: returns the ReLU-gated pre-activation gradients (d_pn bf16 [2*B*V*topN, h], d_vis bf16 [B*V, h])."""
+    _check(d_nodes, F32, "d_nodes")
+    _check(d_obj, F32, "d_obj")
+    assert d_nodes is None or (d_nodes.dim() == 2 and d_nodes.shape[0] == B * M and d_nodes.shape[1] >= h and d_nodes.stride(1) == 1)
+    d_pn = torch.empty(2 * B * V * topN, h, device=pn_h.device, dtype=BF16)
+    d_vis = torch.empty(B * V, h, device=pn_h.device, dtype=BF16)
+    call("savqa_mil_nce_bwd", ptr(pn_h), pn_h.stride(0), ptr(vis_h), vis_h.stride(0), ptr(mask), ptr(loc), ptr(raw), ptr(d_nodes),
+         d_nodes.stride(0) if d_nodes is not None else 0, ptr(d_obj), B, V, M, topN, h, ptr(d_pn), h, ptr(d_vis), h)
+    return d_pn, d_vis
+
+
 def pack_graph_bits(graph: Tensor) -> Tensor:
     """int32 [N, Tq, ceil(Tk / 32)]: bit j of word w of a row = (graph[row, 32 w + j] != 0).  For 0/1 graphs only."""
     _check(graph, F32, "graph")

@@ -164,12 +164,23 @@ def bucket_key_of(model, name: str):
     return None
 
 
+#: inputs of one step, by input format
 STEP_KEYS = ("vis_fea", "vis_fea_mask", "q_ipt", "q_ipt_mask", "q_ipt_graph", "syb_ipt", "macro_node_mask", "macro_graph_ipt", "answer")
+FULL_KEYS = ("vis_fea", "vis_fea_mask", "q_ipt", "q_ipt_mask", "q_ipt_graph", "macro_node_ipt", "macro_node_mask", "macro_graph_ipt",
+             "macro_obj_loc_ipt", "micro_positive_obj_ipt", "micro_negative_obj_ipt", "micro_obj_mask", "answer")
+from .collate import COMPACT_KEYS  # noqa: E402  (full step on the loader's compact hand-off)
 
 
 class EncoderTrainer:
     def __init__(self, model: A.AttModel, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, rowsparse: bool = True,
-                 process_group=None, dec_mask: bool = True):
+                 process_group=None, dec_mask: bool = True, step: str = "encoder", with_milnce_loss: bool = True):
+        """step: "encoder" -- the two branch models + heads with `syb_ipt` given (AttModel.encoder_step);
+                 "full"    -- the train script's 16-argument AttModel.forward, MIL_NCE included, on collate_fn's dense batch
+                              (main_itp_ddp_tar_super_node.py:321-325), loss += -mil_nce_obj when with_milnce_loss (:359-360);
+                 "compact" -- the same full step on the loader's compact hand-off (collate.compact_batch)."""
+        assert step in ("encoder", "full", "compact")
+        self.step_kind, self.with_milnce_loss = step, with_milnce_loss
+        self.keys = {"encoder": STEP_KEYS, "full": FULL_KEYS, "compact": COMPACT_KEYS}[step]
         self.model = model
         self.lr, self.betas, self.eps = lr, betas, eps
         self.rowsparse = rowsparse
@@ -180,7 +191,7 @@ class EncoderTrainer:
         self.allreduce_chunks = 6
         self.overlap_allreduce = os.environ.get("SAVQA_OVERLAP_ALLREDUCE", "1") != "0"  # world > 1: see GradReducer
         self._debug_skip_allreduce = os.environ.get("SAVQA_DEBUG_SKIP_ALLREDUCE", "0") == "1"  # timing experiments only
-        self.tables = [model.att_vis_grid.syb_emb, model.att_syb.syb_emb]
+        self.tables = [model.att_vis_grid.syb_emb, model.att_syb.syb_emb] + ([model.MIL_NCE.syb_emb] if step != "encoder" else [])
         self.flat_param: Optional[torch.Tensor] = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.static: Optional[Dict[str, torch.Tensor]] = None
@@ -189,9 +200,21 @@ class EncoderTrainer:
 
     # ------------------------------------------------------------------------------------------------
     def _forward_backward(self, b: Dict[str, torch.Tensor]) -> torch.Tensor:
-        logits = self.model.encoder_step(b["vis_fea"], b["vis_fea_mask"], b["q_ipt"], b["q_ipt_mask"], b["q_ipt_graph"], b["syb_ipt"],
-                                         b["macro_node_mask"], b["macro_graph_ipt"], self.dec_mask)
+        mil_obj = None
+        if self.step_kind == "encoder":
+            logits = self.model.encoder_step(b["vis_fea"], b["vis_fea_mask"], b["q_ipt"], b["q_ipt_mask"], b["q_ipt_graph"], b["syb_ipt"],
+                                             b["macro_node_mask"], b["macro_graph_ipt"], self.dec_mask)
+        elif self.step_kind == "full":
+            e = torch.empty((b["vis_fea"].shape[0], 0), device=b["vis_fea"].device)  # only_obj: main...:290-308
+            *logits, mil_obj, _ = self.model(b["vis_fea"], b["vis_fea_mask"], b["q_ipt"], b["q_ipt_mask"], b["q_ipt_graph"], b["macro_node_ipt"],
+                                             b["macro_node_mask"], b["macro_graph_ipt"], b["macro_obj_loc_ipt"], b["micro_positive_obj_ipt"],
+                                             b["micro_negative_obj_ipt"], b["micro_obj_mask"], e, e, e, e, decMask=self.dec_mask, mcb=False)
+        else:
+            *logits, mil_obj, _ = self.model.forward_compact(b, decMask=self.dec_mask)
         loss = A.answer_loss(*logits, b["answer"])
+        if mil_obj is not None and self.with_milnce_loss:
+            loss = loss - mil_obj  # loss += mil_nce_loss, mil_nce_loss = -mil_nce_obj (main...:326-329, 359-360)
+        self.last_mil_obj = mil_obj.detach() if mil_obj is not None else None
         zs = getattr(self, "_zero_done", None)
         if zs is not None:  # the flat gradient buffer was being zeroed next to the forward pass (see _step_impl)
             torch.cuda.current_stream().wait_event(zs)
@@ -363,7 +386,10 @@ class EncoderTrainer:
 
     def _table_ids(self, b: Dict[str, torch.Tensor]):
         """Word ids each table is gathered with in a step (AttModel_x3.py:96, 216): the rows the forward pass will read."""
-        return [[b["q_ipt"]] for _ in self.tables]
+        ids = [[b["q_ipt"]], [b["q_ipt"]]]
+        if self.step_kind != "encoder":  # MIL_NCE reads the macro-node words too (they get no gradient, AttModel_x3.py:354)
+            ids.append([b["macro_node_ipt"], b["micro_positive_obj_ipt"], b["micro_negative_obj_ipt"]])
+        return ids
 
     def _catch_up_rows(self, b: Dict[str, torch.Tensor]) -> None:
         """Deferred Adam, part 1 (before the step's gathers): the rows this step reads replay the zero-gradient updates dense
@@ -390,6 +416,7 @@ class EncoderTrainer:
         b1, b2 = self.betas
         for t, st in zip(self.tables, self.row_state):
             log = t._savqa_rowlog
+            touched = []
             for idx, rows, scale, skip in log.pending:
                 if self.world > 1:
                     idx_all = torch.empty(self.world * idx.numel(), dtype=idx.dtype, device=idx.device)
@@ -398,8 +425,10 @@ class EncoderTrainer:
                     dist.all_gather_into_tensor(rows_all, rows, group=self.pg)
                     idx, rows, scale = idx_all, rows_all, scale / self.world
                 ops.scatter_add_rows(st["grad"], idx, rows, scale=scale, skip_row=skip)
-                ops.adam_rows(t.weight.data, st["grad"], st["m"], st["v"], st["stamp"], idx, self.lr, b1, b2, self.eps,
-                              max(self.step_count, 1), dyn=self.dyn, apply=True)
+                touched.append(idx.reshape(-1))
+            if touched:  # ONE update per table and step, after every gradient list has been accumulated (a row is claimed once per step)
+                ops.adam_rows(t.weight.data, st["grad"], st["m"], st["v"], st["stamp"], touched[0] if len(touched) == 1 else torch.cat(touched),
+                              self.lr, b1, b2, self.eps, max(self.step_count, 1), dyn=self.dyn, apply=True)
             log.clear()
 
     def _step_impl(self, b: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -445,7 +474,7 @@ class EncoderTrainer:
         """Captures the whole step into a CUDA graph over static input buffers."""
         if self.flat_param is None:
             self.prepare(batch)
-        self.static = {k: batch[k].clone() for k in STEP_KEYS}
+        self.static = {k: batch[k].clone() for k in self.keys}
         Fn.FORCE_RESTAGE = True  # the bf16 weight staging must be part of the replayed graph
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -464,7 +493,7 @@ class EncoderTrainer:
         """Copies a (pinned host or device) batch into the graph's static input buffers."""
         ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream())
         with ctx:
-            for k in STEP_KEYS:
+            for k in self.keys:
                 self.static[k].copy_(batch[k], non_blocking=True)
 
     # ---- double-buffered host -> device input path (the loader hand-off of SURVEY.md 8(f2)) ---------------------
@@ -481,14 +510,14 @@ class EncoderTrainer:
         cs = self._copy_stream
         cs.wait_event(self._staging_free)  # the previous commit() has consumed the staging buffers
         with torch.cuda.stream(cs):
-            for k in STEP_KEYS:
+            for k in self.keys:
                 self.staging[k].copy_(batch[k], non_blocking=True)
             self._staged.record(cs)
 
     def commit(self) -> None:
         cur = torch.cuda.current_stream()
         cur.wait_event(self._staged)
-        for k in STEP_KEYS:
+        for k in self.keys:
             self.static[k].copy_(self.staging[k], non_blocking=True)
         self._staging_free.record(cur)
 

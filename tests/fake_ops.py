@@ -37,6 +37,57 @@ def build_masks(first_mask, q_mask, q_graph, first_graph, dec_mask_on):
     return gd, g, dm
 
 
+def build_masks_compact(first_len, q_len, q_graph_bits, first_graph_bits, V, Q, dec_mask_on):
+    from savqa_b200 import collate
+
+    def block(n, N):
+        valid = torch.arange(N)[None, :] < n[:, None].long()
+        return (valid[:, :, None] & valid[:, None, :]).to(torch.int32)
+    fg = collate.unpack_adjacency(first_graph_bits, V) if first_graph_bits is not None else None
+    return build_masks(block(first_len, V), block(q_len, Q), collate.unpack_adjacency(q_graph_bits, Q), fg, dec_mask_on)
+
+
+def mil_nce_fwd(pn_h, vis_h, mask, loc, nodes, B, V, M, topN, h):
+    """savqa_mil_nce_fwd restated (AttModel_x3.py:365-379): per-object scores, mil_nce_obj, softmax-refined object rows into nodes."""
+    n = B * V * topN
+    pos, neg, vis = pn_h[:n, :h].float().view(B * V, topN, h), pn_h[n:, :h].float().view(B * V, topN, h), vis_h[:, :h].float()
+    rp, rn = (pos * vis[:, None]).sum(-1), (neg * vis[:, None]).sum(-1)
+    sn = (mask.view(B * V, topN).float() * rn).clamp(min=1e-6)
+    term = (1e-6 + torch.log(torch.tensor(float(topN)))) - torch.logsumexp(sn, 1)
+    obj = (term.sum() / (2.0 * B * V)).reshape(1)
+    refined = (torch.softmax(rp, 1)[:, :, None] * pos).sum(1)
+    lo = loc.view(B * V)
+    ok = (lo >= 0) & (lo < M)
+    rows = (torch.arange(B * V) // V) * M + lo
+    nodes[rows[ok], :h] = refined[ok].to(BF16)
+    return torch.stack([rp.reshape(-1), rn.reshape(-1)]), obj
+
+
+def mil_nce_bwd(pn_h, vis_h, mask, loc, raw, d_nodes, d_obj, B, V, M, topN, h):
+    """savqa_mil_nce_bwd restated with the kernel's explicit formulas (not autograd)."""
+    n = B * V * topN
+    pos, neg, vis = pn_h[:n, :h].float().view(B * V, topN, h), pn_h[n:, :h].float().view(B * V, topN, h), vis_h[:, :h].float()
+    rp, rn = raw[0].view(B * V, topN), raw[1].view(B * V, topN)
+    mk = mask.view(B * V, topN).float()
+    g = float(d_obj) / (2.0 * B * V) if d_obj is not None else 0.0
+    mrn = mk * rn
+    q = torch.softmax(mrn.clamp(min=1e-6), 1)
+    dn = -g * q * torch.where(mrn >= 1e-6, mk, torch.zeros_like(mk))
+    p = torch.softmax(rp, 1)
+    lo = loc.view(B * V)
+    ok = (lo >= 0) & (lo < M)
+    dr = torch.zeros(B * V, h)
+    if d_nodes is not None:
+        rows = (torch.arange(B * V) // V) * M + lo
+        dr[ok] = d_nodes[rows[ok], :h]
+    dp = (dr[:, None] * pos).sum(-1)
+    draw = p * (dp - (p * dp).sum(1, keepdim=True))
+    dpos = (p[:, :, None] * dr[:, None] + draw[:, :, None] * vis[:, None]) * (pos > 0)
+    dneg = (dn[:, :, None] * vis[:, None]) * (neg > 0)
+    dvis = ((draw[:, :, None] * pos).sum(1) + (dn[:, :, None] * neg).sum(1)) * (vis > 0)
+    return torch.cat([dpos.reshape(n, h), dneg.reshape(n, h)]).to(BF16), dvis.to(BF16)
+
+
 def gather_rows(table, idx, scale=1.0, want_f32=True, want_bf16=False):
     out = table[idx.reshape(-1)]
     if scale != 1.0:

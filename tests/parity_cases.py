@@ -334,3 +334,72 @@ def deferred_adam_case(ops, device, steps=12, rows=40, width=24, seed=0):
     err = float((p.cpu() - ref.detach()).abs().max())
     assert worst_read < 5e-6 and err < 5e-6, (worst_read, err)
     return err
+
+
+def mil_nce_module_case(A, golden_dir, device, case):
+    """Our MIL_NCE module (functional.MilNceFn: gather + tensor-core GEMMs + savqa_mil_nce_fwd/bwd) against the golden vectors of
+    the live reference's MIL_NCE (AttModel_x3.py:285-443, only_obj) and the oracle: new_macro_ipt, mil_nce_obj, and the gradients
+    of every parameter the forward uses for L = sum(out * w) + 3 * mil_nce_obj."""
+    import types
+    c = GS.MIL_CASES[case]
+    g = load(golden_dir, case)
+    P0 = GS.make_params(case, GS.mil_nce_shapes(c["h"]))
+    b = GS.mil_nce_case(case, c["B"], c["V"], c["M"], c["topN"])
+    w = GS.randn(f"{case}/dout", c["B"], c["M"], GS.F_REGION)
+
+    def run(od):
+        P = {k: v.clone().requires_grad_(True) for k, v in P0.items()}
+        out, obj = O.mil_nce(P, b["vis_fea"], b["macro_ipt"], b["macro_obj_loc"], b["pos"], b["neg"], b["mask"], operand_dtype=od)
+        ((out * w).sum() + 3.0 * obj).backward()
+        return dict(out=out.detach(), obj=obj.detach(), **{k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in P.items()})
+
+    ref, emu = run(None), run(BF)
+    assert O.rel_err(ref["out"], t(g["out"])) < 2e-6 and abs(float(ref["obj"]) - float(g["obj"])) < 2e-6 * max(1.0, abs(float(g["obj"])))
+    saved = A.VOCAB_ROWS
+    A.VOCAB_ROWS = GS.SMALL_VOCAB
+    try:
+        m = A.MIL_NCE(types.SimpleNamespace(vectors=torch.zeros(4, GS.E_GLOVE)), c["h"], 0.0, 5, True)
+    finally:
+        A.VOCAB_ROWS = saved
+    missing = m.load_state_dict({k: v.clone() for k, v in P0.items()}, strict=False)
+    assert set(missing.missing_keys) == {"R", "rel_mlp.0.weight", "rel_mlp.0.bias", "rel_mlp.2.weight", "rel_mlp.2.bias", "bilinear.weight"}
+    m = m.to(device)
+    dv = lambda x: x.to(device)  # noqa: E731
+    e = torch.empty((c["B"], 0), device=device)
+    out, obj, rel = m(dv(b["vis_fea"]), dv(b["macro_ipt"]), dv(b["macro_obj_loc"]), dv(b["pos"]), dv(b["neg"]), dv(b["mask"]), e, e, e, e)
+    assert out.shape == (c["B"], c["M"], GS.F_REGION) and out.dtype == torch.float32 and rel == 0
+    errs = {"out": check(f"{case}: new_macro_ipt", out, t(g["out"]), emu["out"])}
+    errs["obj"] = abs(float(obj) - float(ref["obj"])) / max(1.0, abs(float(ref["obj"])))
+    assert errs["obj"] < 3e-3 + 3 * abs(float(emu["obj"]) - float(ref["obj"])) / max(1.0, abs(float(ref["obj"]))), errs
+    ((out * w.to(device)).sum() + 3.0 * obj).backward()
+    named = dict(m.named_parameters())
+    for k in P0:
+        got = named[k].grad
+        if float(ref[k].abs().sum()) == 0.0:  # marco_mlp: `.detach()` at AttModel_x3.py:354
+            assert got is None or float(got.abs().sum()) == 0.0, k
+            continue
+        errs[k] = check(f"{case}: grad {k}", got, ref[k], emu[k], floor=2e-2, factor=6.0)
+    return errs
+
+
+def compact_equals_dense_case(device, batch_size=6, cfg=None, vocab_rows=3000, train_mode=False):
+    """AttModel.forward_compact on collate.compact_batch(batch) returns what AttModel.forward returns on the dense collate_fn batch
+    whose features were rounded to bf16, BIT FOR BIT (the masks the kernels see are identical: savqa_build_masks_compact vs
+    savqa_build_masks)."""
+    from savqa_b200 import collate, synthetic
+    cfg = cfg or dict(synthetic.GQA_SHAPED, V=12, Q=8, M=20, ncls=64)
+    model = synthetic.build_model(cfg, vocab_rows=vocab_rows).to(device)
+    model.train(train_mode)
+    b = synthetic.make_batch(cfg, batch_size, seed=9, vocab_rows=vocab_rows)
+    c = collate.compact_batch(b)
+    dense = {k: v.to(device) for k, v in collate.expand_batch(c).items()}
+    comp = {k: v.to(device) for k, v in c.items()}
+    e = torch.empty((batch_size, 0), device=device)
+    with torch.no_grad():
+        ref = model(dense["vis_fea"], dense["vis_fea_mask"], dense["q_ipt"], dense["q_ipt_mask"], dense["q_ipt_graph"], dense["macro_node_ipt"],
+                    dense["macro_node_mask"], dense["macro_graph_ipt"], dense["macro_obj_loc_ipt"], dense["micro_positive_obj_ipt"],
+                    dense["micro_negative_obj_ipt"], dense["micro_obj_mask"], e, e, e, e, decMask=True, mcb=False)
+        got = model.forward_compact(comp, decMask=True)
+    for a_, b_ in zip(got[:4], ref[:4]):
+        assert torch.equal(a_, b_)
+    return got

@@ -153,3 +153,31 @@ def test_product_fails_loudly_without_gpu():
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         x = torch.randn(2, 3, 64)
         a(x, x, x, torch.ones(2, 3, 3))
+
+
+@pytest.mark.parametrize("case", ["mil_nce_h16_top2", "mil_nce_h64_top1", "mil_nce_h128_top5"])
+def test_mil_nce_wiring_vs_golden(monkeypatch, golden_dir, case):
+    """functional.MilNceFn (forward and hand-written backward) with the kernels replaced by their CPU restatements, against the
+    live reference's MIL_NCE golden and the oracle."""
+    fake_ops.install(monkeypatch)
+    from savqa_b200 import AttModel_x3 as A
+    errs = PC.mil_nce_module_case(A, golden_dir, "cpu", case)
+    assert errs["out"] < 1e-2
+
+
+def test_compact_hand_off_equals_dense(monkeypatch):
+    """collate.compact_batch -> AttModel.forward_compact == AttModel.forward on the dense batch, bit for bit; the compact batch is
+    ~8x smaller than the dense one."""
+    fake_ops.install(monkeypatch)
+    from savqa_b200 import collate, synthetic
+    PC.compact_equals_dense_case("cpu")
+    b = synthetic.make_batch(synthetic.GQA_SHAPED, 4, seed=1, vocab_rows=2000)
+    c = collate.compact_batch(b)
+    nbytes = lambda d, keys: sum(d[k].numel() * d[k].element_size() for k in keys)  # noqa: E731
+    from savqa_b200 import train
+    assert nbytes(c, collate.COMPACT_KEYS) * 2.5 < nbytes(b, train.FULL_KEYS)
+    bad = dict(b)
+    bad["vis_fea_mask"] = b["vis_fea_mask"].clone()
+    bad["vis_fea_mask"][0, 0, 1] = 0
+    with pytest.raises(ValueError):
+        collate.compact_batch(bad)

@@ -157,3 +157,42 @@ def test_deferred_row_adam_host_semantics(monkeypatch):
     torch.optim.Adam -- here with the CPU stand-ins of the kernels; tests/test_gpu_kernels.py runs the same case on the B200."""
     import parity_cases as PC
     PC.deferred_adam_case(fake_ops, "cpu", steps=10)
+
+
+@pytest.mark.parametrize("kind", ["full", "compact"])
+def test_full_step_trainer_matches_autograd_adam(monkeypatch, kind):
+    """The train script's whole step -- 16-argument AttModel.forward with MIL_NCE, loss + (-mil_nce_obj), backward, Adam
+    (main_itp_ddp_tar_super_node.py:321-366) -- through the bound trainer (three row-sparse word tables, MIL_NCE's Linear layers in
+    the flat buffers), from collate_fn's dense batch and from the compact hand-off: same losses / parameters as plain autograd over
+    the unbound modules + dense torch.optim.Adam."""
+    fake_ops.install(monkeypatch)
+    from savqa_b200 import AttModel_x3 as A, collate, synthetic, train
+    cfg, model, b0 = _setup()
+    bs = [collate.expand_batch(collate.compact_batch(x)) for x in
+          [b0] + [synthetic.make_batch(cfg, 4, seed=16 + i, vocab_rows=1200) for i in range(2)]]  # bf16-representable features
+    ref = copy.deepcopy(model)
+    lr = 1e-3
+    opt, ref_losses = None, []
+    for b in bs:
+        ref.zero_grad(set_to_none=True)
+        e = torch.empty((4, 0))
+        lc, lv, ls, obj, _ = ref(b["vis_fea"], b["vis_fea_mask"], b["q_ipt"], b["q_ipt_mask"], b["q_ipt_graph"], b["macro_node_ipt"],
+                                 b["macro_node_mask"], b["macro_graph_ipt"], b["macro_obj_loc_ipt"], b["micro_positive_obj_ipt"],
+                                 b["micro_negative_obj_ipt"], b["micro_obj_mask"], e, e, e, e, decMask=True, mcb=False)
+        loss = A.answer_loss(lc, lv, ls, b["answer"]) - obj
+        loss.backward()
+        if opt is None:
+            # eps well above the rounding noise of the gradients: with the default 1e-8 a 1-ulp parameter difference (deferred vs
+            # dense Adam differ in the order of a few fp32 operations) flips the sign-like update of noise-level gradients
+            opt = torch.optim.Adam([p for p in ref.parameters() if p.grad is not None], lr=lr, eps=1e-2)
+        opt.step()
+        ref_losses.append(float(loss))
+    tr = train.EncoderTrainer(model, lr=lr, eps=1e-2, rowsparse=True, step=kind)
+    feed = bs if kind == "full" else [collate.compact_batch(x) for x in bs]
+    losses = [float(tr.step(x)) for x in feed]
+    tr.flush_tables()
+    assert len(tr.tables) == 3 and model.MIL_NCE._pk["vis"].bound and model.MIL_NCE._pk["ipt"].bound
+    assert losses == pytest.approx(ref_losses, rel=2e-5)
+    assert _max_param_diff(model, ref) < 2e-5
+    assert model.MIL_NCE.marco_mlp[0].weight.grad is None  # detached at AttModel_x3.py:354: never in the flat buffers
+    tr.release()
