@@ -240,7 +240,7 @@ def cpu_reference_run(cfg, steps, warmup, batch_size, threads=None, optimizer=Tr
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     model = synthetic.build_model(cfg, vocab_rows=20000)  # gather / row-update cost is row-count independent; keeps host RAM small
-    params = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and not k.startswith(("mcb.", "MIL_NCE.", "cls_mcb.")))
+    params = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and not k.startswith(("mcb.", "cls_mcb.")))
               for k, v in model.state_dict().items()}
     batch = synthetic.make_batch(cfg, batch_size, seed=0, vocab_rows=20000)
     times = []
@@ -249,7 +249,7 @@ def cpu_reference_run(cfg, steps, warmup, batch_size, threads=None, optimizer=Tr
         t0 = time.perf_counter()
         for p in params.values():
             p.grad = None
-        loss, _, _, _ = O.encoder_step(params, batch, cfg["blocks"], cfg["heads"])
+        loss, _, _, _ = O.full_step(params, batch, cfg["blocks"], cfg["heads"])  # 16-argument forward incl. MIL_NCE + loss (main...:321-360)
         loss.backward()
         if optimizer:
             if opt is None:
@@ -271,7 +271,7 @@ def stock_gpu_run(cfg, batch_size, steps, warmup, mode, dev, vocab_rows=None):
     from oracle import savqa_oracle as O
     from savqa_b200 import synthetic
     model = synthetic.build_model(cfg, vocab_rows=vocab_rows)
-    params = {k: v.detach().to(dev).requires_grad_(v.dtype.is_floating_point and not k.startswith(("mcb.", "MIL_NCE.", "cls_mcb.")))
+    params = {k: v.detach().to(dev).requires_grad_(v.dtype.is_floating_point and not k.startswith(("mcb.", "cls_mcb.")))
               for k, v in model.state_dict().items()}
     del model
     batch = {k: v.to(dev) for k, v in synthetic.make_batch(cfg, batch_size, seed=0, vocab_rows=vocab_rows).items()}
@@ -284,7 +284,7 @@ def stock_gpu_run(cfg, batch_size, steps, warmup, mode, dev, vocab_rows=None):
         for p in params.values():
             p.grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
-            loss, _, _, _ = O.encoder_step(params, batch, cfg["blocks"], cfg["heads"])
+            loss, _, _, _ = O.full_step(params, batch, cfg["blocks"], cfg["heads"])
         loss.backward()
         if opt is None:
             opt = torch.optim.Adam([p for p in params.values() if p.grad is not None], lr=1e-4)
@@ -299,9 +299,16 @@ def stock_gpu_run(cfg, batch_size, steps, warmup, mode, dev, vocab_rows=None):
 
 
 def train_config(args, world):
-    return {"workload": "configs[2]/[3]: AttModel_x3 encoder training step (fwd+bwd+classifier heads+loss+Adam), GQA-shaped synthetic "
-                        "batch, V=36 regions + Q=20 tokens (T=56) visual branch, M=108 nodes + Q=20 (T=128) symbolic branch, hidden 512, "
-                        "8 heads, 6+6 blocks, 1845 classes, decMask=True, dropout 0",
+    what = {"compact": "the train script's WHOLE step: 16-argument AttModel.forward (MIL_NCE -> symbolic node features, both branch models, "
+                       "heads), loss + MIL-NCE term, backward, Adam; inputs = the loader's compact hand-off (bf16 region features, lengths, "
+                       "bit-packed adjacency)",
+            "full": "the train script's WHOLE step (16-argument AttModel.forward incl. MIL_NCE, loss + MIL-NCE term, backward, Adam); inputs = "
+                    "collate_fn's dense fp32 / int32 batch",
+            "encoder": "encoder step with MIL_NCE's output `syb_ipt` [B,M,2048] fp32 shipped from the host (round-1 workload)"}[args.step]
+    return {"workload": f"configs[2]/[3]: AttModel_x3 training step -- {what}; GQA-shaped synthetic batch, V=36 regions + Q=20 tokens (T=56) "
+                        "visual branch, M=108 nodes + Q=20 (T=128) symbolic branch, hidden 512, 8 heads, 6+6 blocks, hidden_size_mil 64, "
+                        "topN 1, 1845 classes, decMask=True, dropout 0",
+            "step": args.step,
             "per_gpu_batch": args.batch, "global_batch": args.batch * max(world, 1), "parallelism": f"dp{max(world, 1)}",
             "l2": "activations per step (~2 GB) exceed the 126 MB L2; no explicit flush",
             "word_tables": "dense flat buffers (dense gradients + dense Adam)" if args.dense_tables else
@@ -316,10 +323,16 @@ def run_training(args, rank, world, local_rank, dev, peaks, sampler, dense_table
     cfg = synthetic.GQA_SHAPED
     model = synthetic.build_model(cfg, seed=0).to(dev)
     model.train()
-    host_batches = [synthetic.make_batch(cfg, args.batch, seed=100 + rank * 16 + i, pin=True) for i in range(2)]
-    host_batches = [{k: b[k] for k in train.STEP_KEYS} for b in host_batches]
+    from savqa_b200 import collate
+    keys = {"encoder": train.STEP_KEYS, "full": train.FULL_KEYS, "compact": train.COMPACT_KEYS}[args.step]
+    host_batches = []
+    for i in range(2):
+        b = synthetic.make_batch(cfg, args.batch, seed=100 + rank * 16 + i)
+        if args.step == "compact":
+            b = collate.compact_batch(b)  # what a collate_fn replacement emits
+        host_batches.append({k: b[k].contiguous().pin_memory() for k in keys})
     dev_batch = {k: v.to(dev) for k, v in host_batches[0].items()}
-    trainer = train.EncoderTrainer(model, lr=1e-4, rowsparse=not dense_tables)
+    trainer = train.EncoderTrainer(model, lr=1e-4, rowsparse=not dense_tables, step=args.step)
     trainer.prepare(dev_batch)
 
     def barrier():
@@ -412,9 +425,13 @@ def run_inference(args, rank, world, dev, peaks, steps, warmup):
     cfg = synthetic.CFG2
     B = args.infer_batch
     model = synthetic.build_model(cfg, seed=0).to(dev).eval()
-    host = [{k: b[k] for k in infer.ENCODER_KEYS} for b in (synthetic.make_batch(cfg, B, seed=300 + rank * 16 + i, pin=True) for i in range(2))]
+    from savqa_b200 import collate
+    host = []
+    for i in range(2):
+        b = collate.compact_batch(synthetic.make_batch(cfg, B, seed=300 + rank * 16 + i))
+        host.append({k: b[k].contiguous().pin_memory() for k in infer.COMPACT_KEYS})
     dev_batch = {k: v.to(dev) for k, v in host[0].items()}
-    runner = infer.InferenceRunner(model, dec_mask=True, full=False)
+    runner = infer.InferenceRunner(model, dec_mask=True, full=True, keys=infer.COMPACT_KEYS)
     runner.capture(dev_batch)
 
     def barrier():
@@ -454,7 +471,7 @@ def run_inference(args, rank, world, dev, peaks, steps, warmup):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(tt[0]), float(tt[1])
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-    flops = synthetic.step_flops(cfg, B, backward=False)
+    flops = synthetic.step_flops(cfg, B, backward=False, full=True)
     res = dict(ms=ms, e2e_ms=e2e_ms, h2d=h2d, d2h=B * cfg["ncls"] * 4, flops=flops, launches=runner.launches_per_batch, batch=B,
                finite=bool(torch.isfinite(out[0]).all()))
     runner.graph = None
@@ -493,6 +510,9 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="samples per GPU (training)")
     ap.add_argument("--infer-batch", type=int, default=256, help="samples per GPU (inference, BASELINE configs[1])")
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"])
+    ap.add_argument("--step", default="compact", choices=["compact", "full", "encoder"],
+                    help="compact: whole step (MIL_NCE included) from the compact loader hand-off; full: same from collate_fn's dense batch; "
+                         "encoder: round-1 workload (syb_ipt shipped from the host)")
     ap.add_argument("--dense-tables", action="store_true", help="word tables in the dense flat buffers: dense gradients + dense Adam")
     ap.add_argument("--stock-dtype", default="both", choices=["fp32", "bf16", "both"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -570,7 +590,8 @@ def main():
             line = {"metric": METRIC_INFER, "value": r["batch"] * world * args.steps / (r["ms"] / 1e3), "unit": UNIT, "n_gpus": world,
                     "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per, "higher_is_better": True, "scaling": "weak",
                     "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                    "config": {"workload": "configs[1]: AttModel_x3 inference (both branch models + heads, no grad), batch 256 per GPU, V=100 regions "
+                    "config": {"workload": "configs[1]: AttModel_x3 inference (16-argument forward: MIL_NCE + both branch models + heads, no grad; compact "
+                                           "loader hand-off), batch 256 per GPU, V=100 regions "
                                            "(T=120), M=279 symbolic nodes (T=299), 2048-d features, hidden 512, 8 heads, 6+6 blocks, decMask=True",
                                "per_gpu_batch": r["batch"], "global_batch": r["batch"] * world, "parallelism": f"batch-sharded x{world}, no collective",
                                "l2": "inputs per batch (~0.5 GB) exceed the 126 MB L2; no explicit flush"},
@@ -593,7 +614,7 @@ def main():
     extras = not args.no_extras and world == 1  # comparators and secondary lines: single-GPU run only (N > 1 ranks would idle in NCCL)
     line = None
     if rank == 0:
-        flops = synthetic.step_flops(cfg, args.batch, backward=True)
+        flops = synthetic.step_flops(cfg, args.batch, backward=True, full=args.step != "encoder")
         achieved = flops / (ms_per_step / 1e3) / 1e12
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -636,7 +657,7 @@ def main():
                 v, sec, threads = cpu_reference_run(cfg, 3, 1, args.cpu_sample)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                         "sample": f"{args.cpu_sample}-sample GQA-shaped batch (the GPU step's batch), mean of 3 fwd+bwd+Adam encoder "
-                                                  f"steps after one warm-up (oracle port, torch CPU fp32, {sec:.2f} s per step)"}
+                                                  f"steps (16-argument forward incl. MIL_NCE) after one warm-up (oracle port, torch CPU fp32, {sec:.2f} s per step)"}
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     if rank == 0:

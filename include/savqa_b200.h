@@ -254,8 +254,9 @@ int savqa_adam_advance(float* dyn, float lr, float beta1, float beta2, savqa_str
  *               are zeroed again, so the table never needs a 488 MB memset);
  *   apply == 0: nothing more -- the catch-up through step - 1, run BEFORE the step's gathers read the rows; idx == NULL brings
  *               every row of the table up to date (before a checkpoint or an evaluation pass).
- * step is read from dyn[2] when dyn != NULL.  Replays longer than 256 steps apply the oldest part in closed form to the moments
- * only (their parameter updates are below fp32 resolution). */
+ * step is read from dyn[2] when dyn != NULL.  The replay of a row stops as soon as a zero-gradient step leaves every element unchanged
+ * (the updates shrink by ~beta1 / sqrt(beta2) per step: from there on dense Adam's are lost in fp32 rounding too), at the latest
+ * after 256 steps; the remaining decay of the moments is applied in closed form. */
 int savqa_adam_rows(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int32_t* row_stamp, int64_t table_rows, int width,
                     const int64_t* idx, int64_t n_idx, float lr, float beta1, float beta2, float eps, int step, const float* dyn,
                     int apply, savqa_stream_t stream);

@@ -364,9 +364,12 @@ __global__ void adam_advance_kernel(float* __restrict__ dyn, float lr, float b1,
 // replayed with a zero gradient, exactly what the dense optimizer did to it in the meantime (m *= b1, v *= b2,
 // p -= lr_s m / (sqrt(v) / sqrt(bc2_s) + eps)) -- and then (apply != 0) takes its step-t update with the accumulated gradient,
 // which is zeroed again.  apply == 0 is the catch-up alone (through step t - 1), run before the step's gathers read the row.
-// The replay is cut after kReplayMax steps (the update has decayed by (b1 / sqrt(b2))^k < 1e-11 by then; the remaining decay of
-// the moments is applied in closed form).  idx == nullptr: every row of the table (flush before a checkpoint / evaluation).
+// The update of a zero-gradient step shrinks by ~b1 / sqrt(b2) per step, so the replay stops as soon as one step leaves every
+// element of the row (chunk) unchanged -- from then on dense Adam's updates are lost in fp32 rounding as well -- and at the
+// latest after kReplayMax steps; the remaining decay of the moments is applied in closed form.
+// idx == nullptr: every row of the table (flush before a checkpoint / evaluation).
 constexpr int kReplayMax = 256;
+constexpr int kRowChunk = 10;  // elements per lane held in registers during a replay: 320 columns per pass (word rows: 300)
 
 __global__ void adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                  int* __restrict__ stamp, long table_rows, int width, const int64_t* __restrict__ idx, long n_idx, float lr,
@@ -387,34 +390,70 @@ __global__ void adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, f
     const long base = row * static_cast<long>(width);
     // steps old+1 .. last_zero see a zero gradient; step `target` sees g when apply
     const int last_zero = apply ? target - 1 : target;
-    int first = old + 1;
-    float decay_m = 1.0f, decay_v = 1.0f;
-    if (old == 0) {
-      first = last_zero + 1;  // never touched: moments are zero, nothing to replay
-    } else if (last_zero - first + 1 > kReplayMax) {
-      const int skip = last_zero - first + 1 - kReplayMax;  // oldest missed steps: update below fp32 resolution, decay in closed form
-      decay_m = static_cast<float>(pow(static_cast<double>(b1), static_cast<double>(skip)));
-      decay_v = static_cast<float>(pow(static_cast<double>(b2), static_cast<double>(skip)));
-      first += skip;
+    const int first = (old == 0) ? last_zero + 1 : old + 1;  // never touched: moments are zero, nothing to replay
+    const int replay_to = (last_zero - first + 1 > kReplayMax) ? first + kReplayMax - 1 : last_zero;
+    float step_apply = 0.0f, bc2_apply = 1.0f;
+    if (apply) {
+      const double sd = static_cast<double>(target);
+      step_apply = dyn ? dyn[0] : static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), sd)));
+      bc2_apply = dyn ? dyn[1] : static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), sd)));
     }
-    for (int c = lane; c < width; c += 32) {
-      float pi = p[base + c], mi = m[base + c] * decay_m, vi = v[base + c] * decay_v;
-      for (int s = first; s <= last_zero; ++s) {
-        const double sd = static_cast<double>(s);
-        const float step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), sd)));
-        const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), sd)));
-        adam_one(pi, 0.0f, mi, vi, b1, b2, eps, step_size, bc2_sqrt);
+    for (int c0 = 0; c0 < width; c0 += 32 * kRowChunk) {
+      float pi[kRowChunk], mi[kRowChunk], vi[kRowChunk];
+#pragma unroll
+      for (int j = 0; j < kRowChunk; ++j) {
+        const int c = c0 + j * 32 + lane;
+        const bool ok = c < width;
+        pi[j] = ok ? p[base + c] : 0.0f;
+        mi[j] = ok ? m[base + c] : 0.0f;
+        vi[j] = ok ? v[base + c] : 0.0f;
       }
-      if (apply) {
-        const double sd = static_cast<double>(target);
-        const float step_size = dyn ? dyn[0] : static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), sd)));
-        const float bc2_sqrt = dyn ? dyn[1] : static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), sd)));
-        adam_one(pi, g[base + c], mi, vi, b1, b2, eps, step_size, bc2_sqrt);
-        g[base + c] = 0.0f;
+      int s_done = first - 1;  // last zero-gradient step applied to this chunk
+      bool live = first <= replay_to;
+      for (int s0 = first; live && s0 <= replay_to; s0 += 32) {
+        // per-step scalars of steps s0 .. s0+31, one per lane (the same double-precision formulas as adam_advance_kernel)
+        const double sd = static_cast<double>(s0 + lane);
+        const float ss_l = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), sd)));
+        const float bc_l = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), sd)));
+        for (int k = 0; k < 32 && s0 + k <= replay_to; ++k) {
+          const float ss = __shfl_sync(0xffffffffu, ss_l, k);
+          const float bc = __shfl_sync(0xffffffffu, bc_l, k);
+          bool changed = false;
+#pragma unroll
+          for (int j = 0; j < kRowChunk; ++j) {
+            const float before = pi[j];
+            adam_one(pi[j], 0.0f, mi[j], vi[j], b1, b2, eps, ss, bc);
+            changed = changed || (pi[j] != before);
+          }
+          s_done = s0 + k;
+          if (!__any_sync(0xffffffffu, changed)) {  // every later zero-gradient update is smaller still: lost in rounding too
+            live = false;
+            break;
+          }
+        }
       }
-      p[base + c] = pi;
-      m[base + c] = mi;
-      v[base + c] = vi;
+      if (s_done < last_zero && old != 0) {
+        const double rest = static_cast<double>(last_zero - s_done);
+        const float dm = static_cast<float>(pow(static_cast<double>(b1), rest));
+        const float dv = static_cast<float>(pow(static_cast<double>(b2), rest));
+#pragma unroll
+        for (int j = 0; j < kRowChunk; ++j) {
+          mi[j] *= dm;
+          vi[j] *= dv;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kRowChunk; ++j) {
+        const int c = c0 + j * 32 + lane;
+        if (c >= width) continue;
+        if (apply) {
+          adam_one(pi[j], g[base + c], mi[j], vi[j], b1, b2, eps, step_apply, bc2_apply);
+          g[base + c] = 0.0f;
+        }
+        p[base + c] = pi[j];
+        m[base + c] = mi[j];
+        v[base + c] = vi[j];
+      }
     }
   }
 }

@@ -23,12 +23,17 @@ from . import AttModel_x3 as A
 ENCODER_KEYS = ("vis_fea", "vis_fea_mask", "q_ipt", "q_ipt_mask", "q_ipt_graph", "syb_ipt", "macro_node_mask", "macro_graph_ipt")
 FULL_KEYS = ("vis_fea", "vis_fea_mask", "q_ipt", "q_ipt_mask", "q_ipt_graph", "macro_node_ipt", "macro_node_mask", "macro_graph_ipt",
              "macro_obj_loc_ipt", "micro_positive_obj_ipt", "micro_negative_obj_ipt", "micro_obj_mask")
+COMPACT_KEYS = ("vis_fea", "vis_len", "q_ipt", "q_len", "q_graph_bits", "macro_node_ipt", "macro_len", "macro_graph_bits",
+                "macro_obj_loc_ipt", "micro_positive_obj_ipt", "micro_negative_obj_ipt", "micro_obj_mask")
 
 
 def forward_batch(model: A.AttModel, b: Dict[str, torch.Tensor], dec_mask: bool = True, full: Optional[bool] = None):
     """(logits_concat, logits_vis, logits_syb, mil_nce_obj | None) of one collate_fn-shaped batch.  full=True runs the reference's
     16-argument AttModel.forward (MIL_NCE produces the symbolic node features, AttModel_x3.py:525-530); full=False takes
     `syb_ipt` [B,M,2048] as given (the encoder path alone)."""
+    if "vis_len" in b:  # the loader's compact hand-off (collate.compact_batch)
+        lc, lv, ls, mil_obj, _ = model.forward_compact(b, decMask=dec_mask)
+        return lc, lv, ls, mil_obj
     if full is None:
         full = "syb_ipt" not in b
     if full:

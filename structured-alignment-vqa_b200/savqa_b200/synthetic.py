@@ -115,9 +115,18 @@ def branch_flops(cfg: Dict, T: int, with_heads: bool = False) -> float:
     return float(f)
 
 
-def step_flops(cfg: Dict, batch_size: int, backward: bool = True) -> float:
-    """fwd (+ bwd = 2x fwd) FLOPs of the encoder step: both branches + the three classifier heads."""
+def mil_nce_flops(cfg: Dict) -> float:
+    """Algorithmic forward FLOPs of MIL_NCE (only_obj) for one sample: marco_mlp, syb_mlp on the positive and negative words,
+    vis_mlp, the object-word scores and the refinement, ipt_mlp (AttModel_x3.py:352-379, 441)."""
+    E, F_, h, V, M, n = 300, 2048, cfg["hidden_mil"], cfg["V"], cfg["M"], cfg["topN"]
+    return float(2 * E * h * M + 2 * E * h * 2 * V * n + 2 * F_ * h * V + 3 * 2 * V * n * h + 2 * h * F_ * M)
+
+
+def step_flops(cfg: Dict, batch_size: int, backward: bool = True, full: bool = False) -> float:
+    """fwd (+ bwd = 2x fwd) FLOPs of the step: both branches + the three classifier heads (+ MIL_NCE when `full`)."""
     C, ncls = cfg["hidden"], cfg["ncls"]
     per = branch_flops(cfg, cfg["V"] + cfg["Q"]) + branch_flops(cfg, cfg["M"] + cfg["Q"])
     per += 2 * (2 * C * C + 2 * C * ncls) + (4 * C * C + 2 * C * ncls)
+    if full:
+        per += mil_nce_flops(cfg)
     return per * batch_size * (3.0 if backward else 1.0)

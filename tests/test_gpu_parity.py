@@ -184,6 +184,120 @@ def test_tcgen05_attention_vs_oracle_direct(M, T):
     print(T, {k: f"{v:.2e}" for k, v in errs.items()})
 
 
+@pytest.mark.parametrize("case", ["mil_nce_h16_top2", "mil_nce_h64_top1", "mil_nce_h128_top5"])
+def test_mil_nce_vs_golden(A, golden_dir, case):
+    """MIL_NCE on the kernels (AttModel_x3.py:285-443, only_obj) vs the live reference's golden vectors and the oracle: output,
+    mil_nce_obj, every parameter gradient."""
+    errs = PC.mil_nce_module_case(A, golden_dir, "cuda", case)
+    print(case, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["out"] < 1e-2
+
+
+def test_mil_nce_production_shape_vs_oracle(A):
+    """The launcher's production MIL_NCE (hidden_size_mil 1024, topN 5, submit.py:96-98) at B = 16, V = 36, M = 108 vs the oracle."""
+    import types
+    from savqa_b200 import synthetic
+    cfg = dict(synthetic.GQA_SHAPED, hidden_mil=1024, topN=5)
+    b = synthetic.make_batch(cfg, 16, seed=4, vocab_rows=3000)
+    saved = A.VOCAB_ROWS
+    A.VOCAB_ROWS = 3000
+    try:
+        torch.manual_seed(0)
+        m = A.MIL_NCE(types.SimpleNamespace(vectors=torch.randn(100, 300)), 1024, 0.0, 5, True)
+    finally:
+        A.VOCAB_ROWS = saved
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ref_out, ref_obj = O.mil_nce(P, b["vis_fea"], b["macro_node_ipt"], b["macro_obj_loc_ipt"], b["micro_positive_obj_ipt"],
+                                 b["micro_negative_obj_ipt"], b["micro_obj_mask"])
+    emu_out, emu_obj = O.mil_nce(P, b["vis_fea"], b["macro_node_ipt"], b["macro_obj_loc_ipt"], b["micro_positive_obj_ipt"],
+                                 b["micro_negative_obj_ipt"], b["micro_obj_mask"], operand_dtype=torch.bfloat16)
+    m = m.cuda()
+    e = torch.empty((16, 0), device="cuda")
+    out, obj, _ = m(b["vis_fea"].cuda(), b["macro_node_ipt"].cuda(), b["macro_obj_loc_ipt"].cuda(), b["micro_positive_obj_ipt"].cuda(),
+                    b["micro_negative_obj_ipt"].cuda(), b["micro_obj_mask"].cuda(), e, e, e, e)
+    import parity_util
+    parity_util.check("mil_nce production shape: new_macro_ipt", out, ref_out, emu_out)
+    assert abs(float(obj) - float(ref_obj)) < 3e-3 * max(1.0, abs(float(ref_obj))) + 3 * abs(float(emu_obj) - float(ref_obj))
+
+
+def test_compact_hand_off_bit_identical_and_trainer_steps(A):
+    """(i) AttModel.forward_compact (lengths + bit-packed adjacency + bf16 features, savqa_build_masks_compact) == AttModel.forward
+    on collate_fn's dense planes, bit for bit, at a small and at the GQA shape; (ii) the bound trainer's full step from the
+    compact hand-off == from the dense batch (same loss sequence, eager and replayed graph)."""
+    import copy
+    from savqa_b200 import collate, synthetic, train
+    PC.compact_equals_dense_case("cuda")
+    PC.compact_equals_dense_case("cuda", batch_size=32, cfg=dict(synthetic.GQA_SHAPED, ncls=128), vocab_rows=5000)
+    cfg = dict(synthetic.GQA_SHAPED, V=12, Q=8, M=20, ncls=64)
+    model = synthetic.build_model(cfg, vocab_rows=3000).cuda()
+    c_host = collate.compact_batch(synthetic.make_batch(cfg, 8, seed=2, vocab_rows=3000))
+    comp = {k: v.cuda() for k, v in c_host.items()}
+    dense = {k: v.cuda() for k, v in collate.expand_batch(c_host).items()}
+    m1, m2, m3 = copy.deepcopy(model), copy.deepcopy(model), copy.deepcopy(model)
+    t_dense = train.EncoderTrainer(m1, lr=1e-4, step="full")
+    t_comp = train.EncoderTrainer(m2, lr=1e-4, step="compact")
+    t_graph = train.EncoderTrainer(m3, lr=1e-4, step="compact")
+    l_dense = [float(t_dense.step(dense)) for _ in range(4)]
+    l_comp = [float(t_comp.step(comp)) for _ in range(4)]
+    assert l_dense == l_comp, (l_dense, l_comp)  # identical masks and features -> identical kernels on identical operands
+    t_graph.capture(comp, warmup=2)
+    l_graph = [float(t_graph.replay()) for _ in range(2)]
+    assert abs(l_graph[0] - l_comp[2]) < 2e-3 * abs(l_comp[2]) and abs(l_graph[1] - l_comp[3]) < 2e-3 * abs(l_comp[3]), (l_comp, l_graph)
+    assert l_comp[3] < l_comp[0]
+    assert len(t_comp.tables) == 3
+
+
+def test_full_step_headline_size_vs_oracle(A):
+    """The WHOLE train-script step at B = 128 (16-argument forward with MIL_NCE from the compact hand-off, loss - mil_nce_obj,
+    backward) through the bound trainer vs O.full_step(...).backward(): loss, mil_nce_obj, logits, MIL_NCE's gradients."""
+    from savqa_b200 import collate, functional as Fn, synthetic, train
+    cfg = synthetic.GQA_SHAPED
+    V = 5000
+    model = synthetic.build_model(cfg, vocab_rows=V)
+    c_host = collate.compact_batch(synthetic.make_batch(cfg, 128, seed=21, vocab_rows=V))
+    dense = collate.expand_batch(c_host)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    def run(od):
+        P = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in sd.items()}
+        loss, logits, obj, _ = O.full_step(P, dense, cfg["blocks"], cfg["heads"], operand_dtype=od)
+        loss.backward()
+        return dict(loss=loss.detach(), obj=obj.detach(), logits=[l.detach() for l in logits],
+                    grads={k: v.grad for k, v in P.items() if v.dtype.is_floating_point and v.grad is not None})
+
+    ref, emu = run(None), run(torch.bfloat16)
+    model = model.cuda()
+    comp = {k: v.cuda() for k, v in c_host.items()}
+    tr = train.EncoderTrainer(model, lr=1e-4, step="compact")
+    tr.prepare(comp)
+    tr.flat_grad.zero_()
+    for t_ in tr.tables:
+        t_._savqa_rowlog.clear()
+    loss = tr._forward_backward(comp)
+    Fn.join_wgrad_streams()
+    torch.cuda.synchronize()
+    import parity_util
+    assert abs(float(loss) - float(ref["loss"])) < (2e-3 + 3 * abs(float(emu["loss"] - ref["loss"])) / abs(float(ref["loss"]))) * abs(float(ref["loss"]))
+    assert abs(float(tr.last_mil_obj) - float(ref["obj"])) < 3e-3 * max(1.0, abs(float(ref["obj"]))) + 3 * abs(float(emu["obj"] - ref["obj"]))
+    names = {id(p): k for k, p in model.named_parameters()}
+    seen = set()
+    for p in tr.dense:
+        k = names[id(p)]
+        if k.startswith("MIL_NCE."):
+            seen.add(k)
+            parity_util.check(f"full step: grad {k}", p.grad, ref["grads"][k], emu["grads"][k], floor=2e-2, factor=6.0)
+    assert seen == {"MIL_NCE.vis_mlp.0.weight", "MIL_NCE.vis_mlp.0.bias", "MIL_NCE.ipt_mlp.0.weight", "MIL_NCE.ipt_mlp.0.bias",
+                    "MIL_NCE.syb_mlp.0.weight", "MIL_NCE.syb_mlp.0.bias"}, seen
+    mil_table = tr.tables[2]
+    dense_g = torch.zeros_like(mil_table.weight.data)
+    from savqa_b200 import ops
+    for idx, rows, scale, skip in mil_table._savqa_rowlog.pending:
+        ops.scatter_add_rows(dense_g, idx, rows, scale=scale, skip_row=skip)
+    parity_util.check("full step: grad MIL_NCE.syb_emb.weight", dense_g, ref["grads"]["MIL_NCE.syb_emb.weight"],
+                      emu["grads"]["MIL_NCE.syb_emb.weight"], floor=2e-2, factor=6.0)
+    tr.release()
+
+
 def test_trainer_bound_gradients_match_autograd_and_graph_replay(A):
     """train.EncoderTrainer: the backward kernels that accumulate straight into the flat gradient buffer (bound weight
     packs, fused bias-gradient column sums, MN-major dgrad) give the gradients plain autograd gives through the unbound

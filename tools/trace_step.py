@@ -28,9 +28,10 @@ if world > 1:  # under torchrun: every rank runs the step, rank 0 records its ow
 cfg = synthetic.GQA_SHAPED
 model = synthetic.build_model(cfg, seed=0).to(dev)
 model.train()
-b = synthetic.make_batch(cfg, args.batch, seed=100 + rank * 16, pin=True)
-dev_batch = {k: b[k].to(dev) for k in train.STEP_KEYS}
-trainer = train.EncoderTrainer(model, lr=1e-4, rowsparse=True)
+from savqa_b200 import collate  # noqa: E402
+b = collate.compact_batch(synthetic.make_batch(cfg, args.batch, seed=100 + rank * 16))
+dev_batch = {k: b[k].to(dev) for k in train.COMPACT_KEYS}
+trainer = train.EncoderTrainer(model, lr=1e-4, rowsparse=True, step="compact")
 trainer.prepare(dev_batch)
 trainer.capture(dev_batch, warmup=2)
 for _ in range(5):
