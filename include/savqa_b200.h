@@ -29,7 +29,7 @@ extern "C" {
 #define SAVQA_ERR_CUDA 2
 #define SAVQA_ERR_UNSUPPORTED 3
 
-#define SAVQA_ABI_VERSION 3
+#define SAVQA_ABI_VERSION 4
 
 typedef void* savqa_stream_t; /* cudaStream_t */
 
@@ -104,9 +104,11 @@ int savqa_colsum_bf16(const void* x_bf16, int64_t ld, int64_t rows, int cols, fl
 
 /* ---- a6: residual + layer_normalization (modules.py:62-65; residuals at :304, :439) ------------------
  * pre = x (+ res);  y = gamma * (pre - mean) / (std_unbiased + eps) + beta.
- * Optional outputs: pre (saved for backward), y_bf16, on[r] = (sum_c y[r,c] != 0). */
+ * Optional outputs: pre (saved for backward), y_bf16, on[r] = (sum_c y[r,c] != 0), stats[r] = {mean, sigma} (what a fused
+ * dgrad + LayerNorm-backward epilogue reads, savqa_gemm_rowln mode 2). */
 int savqa_residual_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float eps,
-                                 int64_t rows, int C, float* pre, float* y, void* y_bf16, float* on, savqa_stream_t stream);
+                                 int64_t rows, int C, float* pre, float* y, void* y_bf16, float* on, float* stats,
+                                 savqa_stream_t stream);
 /* dx = LN'(pre)[dy] (+ dres_in);  dgamma/dbeta are ACCUMULATED (+=).  sigma == 0 rows follow autograd:
  * dx = (g - mean g) / eps.  dx_bf16 optional.  dxsum (optional, fp32 [C]) += sum_rows dx: the bias gradient of the
  * Linear whose output fed this LayerNorm (feedforward.conv2, modules.py:429, 439). */
@@ -158,6 +160,38 @@ typedef struct savqa_gemm_problem {
 
 int savqa_gemm_bf16_grouped(const savqa_gemm_problem_t* problems, int count, int a_mn_major, int b_mn_major, int N, int split_k,
                             savqa_stream_t stream);
+
+/* ---- a9: cluster GEMM with a row-wise (LayerNorm) epilogue for the decoder's M = B-row chain (AttModel_x3.py:141-154) ----
+ * acc[m,n] = sum_k A[m,k] B[n,k] (B K-major [N, ldb], or MN-major [K, ldb] when b_mn_major: a dgrad reads the weight that way).
+ * A thread-block cluster computes a [128 x N] block, one 64-column slab per CTA; row reductions cross the CTAs through
+ * distributed shared memory (csrc/rowln_tcgen05.cu).
+ *   mode 0: v = gate?(relu?(acc + bias)) + res                            -> y (fp32) and / or y_bf16           (N % 64 == 0)
+ *   mode 1: a = relu?(acc + bias) [-> act_bf16; the fp32 path continues from the ROUNDED value]; pre = a * rowscale[m] + res[m,n];
+ *           y = gamma (pre - mean) / (sigma_unbiased + eps) + beta          -> pre, y, y_bf16, on[m] = (sum_n y != 0), stats[m] = {mean, sigma}
+ *           replaces Linear(+ReLU) -> (* query mask) -> + residual -> layer_normalization (modules.py:62-65, 304-307, 439-447)
+ *   mode 2: dy = acc + res; dx = d layer_normalization(pre)[dy] using stats    -> y = dx (fp32), y_bf16, dxg_bf16 = (gate_bf16 > 0) ? dx * rowscale : 0,
+ *           dgamma[n] += sum_m dy c / s, dbeta[n] += sum_m dy, dxsum[n] += sum_m dx  (atomics)
+ * modes 1 / 2 need N in {64, 128, 256, 512} (cluster of N / 64 CTAs).  Unused pointers are NULL. */
+typedef struct savqa_rowln_args {
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb; int b_mn_major;
+  int M, N, K, mode, relu;
+  const float* bias;
+  const float* rowscale;
+  const float* res; int64_t ld_res;
+  const void* gate_bf16; int64_t ld_gate;
+  const float* gamma; const float* beta; float eps;
+  void* act_bf16; int64_t ld_act;
+  float* pre; int64_t ld_pre;          /* mode 1: output; mode 2: input */
+  float* y; int64_t ld_y;
+  void* y_bf16; int64_t ld_yb;
+  float* on;
+  float* stats;                        /* [M, 2]; mode 1: output (optional); mode 2: input */
+  void* dxg_bf16; int64_t ld_dxg;
+  float* dgamma; float* dbeta; float* dxsum;
+} savqa_rowln_args_t;
+
+int savqa_gemm_rowln(const savqa_rowln_args_t* args, savqa_stream_t stream);
 
 /* Scheduling hint for the calling thread's NEXT savqa_gemm_bf16* launches: the persistent CTA-pair kernel takes at most `sms`
  * SMs (0 = all).  The training step sets it around the GEMMs it puts on side streams (weight gradients, the decoder's K/V

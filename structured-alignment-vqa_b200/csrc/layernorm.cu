@@ -16,7 +16,8 @@ template <int NV>  // NV float4 per lane, C == NV * 128
 __global__ void __launch_bounds__(256, SAVQA_LN_FWD_BLOCKS) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                          long rows, float* __restrict__ pre, float* __restrict__ y,
-                                                         __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ on) {
+                                                         __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ on,
+                                                         float* __restrict__ stats) {
   constexpr int C = NV * 128;
   pdl_trigger();
   pdl_wait();
@@ -51,6 +52,10 @@ __global__ void __launch_bounds__(256, SAVQA_LN_FWD_BLOCKS) ln_fwd_vec_kernel(co
     }
     const float sigma = sqrtf(warp_sum(q) * (1.0f / (C - 1)));
     const float inv = 1.0f / (sigma + eps);
+    if (stats && lane == 0) {
+      stats[2 * r] = mean;
+      stats[2 * r + 1] = sigma;
+    }
     float ys = 0.0f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -73,7 +78,8 @@ __global__ void __launch_bounds__(256, SAVQA_LN_FWD_BLOCKS) ln_fwd_vec_kernel(co
 // generic width (e.g. C = 64 in the small golden model): one warp per row, three L1-resident passes
 __global__ void ln_fwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, float eps, long rows, int C, float* __restrict__ pre,
-                                      float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ on) {
+                                      float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ on,
+                                      float* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const long warp0 = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
   const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
@@ -89,6 +95,10 @@ __global__ void ln_fwd_generic_kernel(const float* __restrict__ x, const float* 
     }
     const float sigma = sqrtf(warp_sum(q) / (C - 1));
     const float inv = 1.0f / (sigma + eps);
+    if (stats && lane == 0) {
+      stats[2 * r] = mean;
+      stats[2 * r + 1] = sigma;
+    }
     float ys = 0.0f;
     for (int c = lane; c < C; c += 32) {
       const float p = x[r * C + c] + (res ? res[r * C + c] : 0.0f);
@@ -251,7 +261,8 @@ inline bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) ==
 using namespace savqa;
 
 extern "C" int savqa_residual_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float eps,
-                                            int64_t rows, int C, float* pre, float* y, void* y_bf16, float* on, savqa_stream_t stream_) {
+                                            int64_t rows, int C, float* pre, float* y, void* y_bf16, float* on, float* stats,
+                                            savqa_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (rows == 0) return SAVQA_OK;
   SAVQA_REQUIRE(x && gamma && beta && y && C >= 2, "savqa_residual_layernorm_fwd: bad argument");
@@ -261,12 +272,12 @@ extern "C" int savqa_residual_layernorm_fwd(const float* x, const float* res, co
   const int grid = ln_grid(rows, 8);
   if (vec) {
     switch (C / 128) {
-#define LN_CASE(NV) case NV: SAVQA_CHECK_CUDA(launch_kernel(true, ln_fwd_vec_kernel<NV>, dim3(grid), dim3(256), 0, stream, x, res, gamma, beta, eps, static_cast<long>(rows), pre, y, yb, on)); break;
+#define LN_CASE(NV) case NV: SAVQA_CHECK_CUDA(launch_kernel(true, ln_fwd_vec_kernel<NV>, dim3(grid), dim3(256), 0, stream, x, res, gamma, beta, eps, static_cast<long>(rows), pre, y, yb, on, stats)); break;
       LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
 #undef LN_CASE
     }
   } else {
-    ln_fwd_generic_kernel<<<grid, 256, 0, stream>>>(x, res, gamma, beta, eps, rows, C, pre, y, yb, on);
+    ln_fwd_generic_kernel<<<grid, 256, 0, stream>>>(x, res, gamma, beta, eps, rows, C, pre, y, yb, on, stats);
   }
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;

@@ -149,11 +149,42 @@ class _Branch(nn.Module):
         dec = self.dec_emb.lookup_table[2] * (C ** 0.5) + self.dec_positional_encoding.lookup_table[0]
         dec = dec.reshape(1, 1, C).expand(B, 1, C).contiguous()
         dec = self.dec_dropout(dec)
+        if self._fused_decoder_ok(dec, memory):
+            layers = [(getattr(self, 'dec_self_attention_%d' % i), getattr(self, 'dec_vanilla_attention_%d' % i),
+                       getattr(self, 'dec_feed_forward_%d' % i)) for i in range(self.num_blocks)]
+            y, yb, on = Fn.DecoderFn.apply(dec, memory, dec_mask, dict(layers=layers, heads=self.num_heads,
+                                                                       kv_holder=getattr(memory, "_savqa_kv_holder", None)))
+            y._savqa_side = Fn.Side(y, yb, on)
+            return y
         for i in range(self.num_blocks):
             dec = getattr(self, 'dec_self_attention_%d' % i)(dec, dec, dec)
             dec = getattr(self, 'dec_vanilla_attention_%d' % i)(dec, memory, memory, dec_mask)
             dec = getattr(self, 'dec_feed_forward_%d' % i)(dec)
         return dec
+
+    def _fused_decoder_ok(self, dec, memory) -> bool:
+        """Whether the decoder runs as functional.DecoderFn (fused cluster GEMM + LayerNorm launches): a shape the row-wise epilogue
+        takes, no active dropout, and -- when gradients are needed -- the trainer's bound packs with the fused K/V block."""
+        C = self.hidden_size
+        if not (Fn.FUSED_DECODER and self.num_blocks > 0 and dec.is_cuda == memory.is_cuda and ops.rowln_fits(dec.shape[0], C, C)
+                and C % self.num_heads == 0 and (4 * C) % 64 == 0):
+            return False
+        if not dec.is_cuda and not getattr(ops.gemm_rowln, "__module__", "").endswith("fake_ops"):
+            return False
+        if self.training and (self.dec_dropout.p > 0):
+            return False
+        ff0 = self.dec_feed_forward_0
+        if ff0.num_units[0] % 64 or ff0.num_units[1] != C:
+            return False
+        if torch.is_grad_enabled() and (dec.requires_grad or memory.requires_grad):
+            holder = getattr(memory, "_savqa_kv_holder", None)
+            bound = all(getattr(self, 'dec_self_attention_%d' % i)._packs["v"].bound and getattr(self, 'dec_vanilla_attention_%d' % i)._packs["q"].bound
+                        and getattr(self, 'dec_vanilla_attention_%d' % i)._packs["kv"].bound
+                        and getattr(self, 'dec_feed_forward_%d' % i)._packs["w1"].bound and getattr(self, 'dec_feed_forward_%d' % i)._packs["w2"].bound
+                        and getattr(self, 'dec_self_attention_%d' % i).normalization._sink.bound
+                        for i in range(self.num_blocks))
+            return bool(bound and holder is not None and holder.kv_all is not None)
+        return True
 
     def _join_memory(self, x):
         """Training on a B200 with bound weight packs: routes the cross-attention K/V projections of the encoder output (and
@@ -458,13 +489,21 @@ class AttModel(nn.Module):
         if vis_fea.dtype != torch.bfloat16:
             vis_fea = _CastBf16.apply(vis_fea)
         e = torch.empty((vis_fea.shape[0], 0), device=vis_fea.device)  # only_obj: main_itp_ddp_tar_super_node.py:290-308
-        new_macro_ipt, mil_nce_obj, mil_nce_rel = self.MIL_NCE(vis_fea, c["macro_node_ipt"], c["macro_obj_loc_ipt"], c["micro_positive_obj_ipt"],
-                                                               c["micro_negative_obj_ipt"], c["micro_obj_mask"], e, e, e, e)
+        mil = {}
+
+        def run_syb():
+            # MIL_NCE feeds only the symbolic branch (AttModel_x3.py:525, 530): it runs at the head of that branch's stream, forward and
+            # -- through autograd -- backward, next to the visual branch instead of in front of both
+            new_macro_ipt, mil["obj"], mil["rel"] = self.MIL_NCE(vis_fea, c["macro_node_ipt"], c["macro_obj_loc_ipt"], c["micro_positive_obj_ipt"],
+                                                                 c["micro_negative_obj_ipt"], c["micro_obj_mask"], e, e, e, e)
+            return self.att_syb.forward_compact(new_macro_ipt, c["macro_len"], c["macro_graph_bits"], c["q_ipt"], c["q_graph_bits"], c["q_len"],
+                                                decMask)
         logits = self._two_branches(
             lambda: self.att_vis_grid.forward_compact(vis_fea, c["vis_len"], c["q_ipt"], c["q_graph_bits"], c["q_len"], decMask),
-            lambda: self.att_syb.forward_compact(new_macro_ipt, c["macro_len"], c["macro_graph_bits"], c["q_ipt"], c["q_graph_bits"], c["q_len"],
-                                                 decMask), vis_fea.is_cuda)
-        return (*logits, mil_nce_obj, mil_nce_rel)
+            run_syb, vis_fea.is_cuda)
+        if vis_fea.is_cuda and isinstance(mil["obj"], torch.Tensor):
+            mil["obj"].record_stream(torch.cuda.current_stream())
+        return (*logits, mil["obj"], mil["rel"])
 
     def forward(self, vis_fea, vis_mask, q_ipt, q_mask, q_graph, macro_ipt, macro_mask, macro_graph, macro_obj_loc,
                 micro_positive_obj, micro_negative_obj, micro_obj_mask, micro_positive_rel, micro_negative_rel,
@@ -475,12 +514,18 @@ class AttModel(nn.Module):
             vis_fea = vis_fea.reshape(-1, vis_fea.size(1) * vis_fea.size(2), vis_fea.size(3))
         if vis_fea.dtype != torch.bfloat16:
             vis_fea = _CastBf16.apply(vis_fea)  # staged once: MIL_NCE's vis_mlp and the visual branch's syb_mlp2 both read it
-        new_macro_ipt, mil_nce_obj, mil_nce_rel = self.MIL_NCE(vis_fea, macro_ipt, macro_obj_loc, micro_positive_obj,
-                                                               micro_negative_obj, micro_obj_mask, micro_positive_rel,
-                                                               micro_negative_rel, micro_positive_rel_loc, micro_negative_rel_loc)
-        logits_concat, logits_vis, logits_syb = self.encoder_step(vis_fea, vis_mask, q_ipt, q_mask, q_graph, new_macro_ipt,
-                                                                  macro_mask, macro_graph, decMask)
-        return logits_concat, logits_vis, logits_syb, mil_nce_obj, mil_nce_rel
+        mil = {}
+
+        def run_syb():  # MIL_NCE at the head of the symbolic branch's stream (it feeds only that branch, AttModel_x3.py:525, 530)
+            new_macro_ipt, mil["obj"], mil["rel"] = self.MIL_NCE(vis_fea, macro_ipt, macro_obj_loc, micro_positive_obj, micro_negative_obj,
+                                                                 micro_obj_mask, micro_positive_rel, micro_negative_rel,
+                                                                 micro_positive_rel_loc, micro_negative_rel_loc)
+            return self.att_syb(new_macro_ipt, macro_mask, macro_graph, q_ipt, q_graph, q_mask, decMask)
+        logits_concat, logits_vis, logits_syb = self._two_branches(
+            lambda: self.att_vis_grid(vis_fea, vis_mask, q_ipt, q_graph, q_mask, decMask), run_syb, vis_fea.is_cuda)
+        if vis_fea.is_cuda and isinstance(mil["obj"], torch.Tensor):
+            mil["obj"].record_stream(torch.cuda.current_stream())
+        return logits_concat, logits_vis, logits_syb, mil["obj"], mil["rel"]
 
 
 def answer_loss(logits_concat, logits_vis, logits_syb, answer, epsilon=0.1):

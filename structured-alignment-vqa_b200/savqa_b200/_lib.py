@@ -44,6 +44,16 @@ class AttnArgs(C.Structure):
                 ("graph_bits", vp), ("bits_n_stride", i64), ("bits_q_stride", i64), ("stats", vp)]
 
 
+class RowLnArgs(C.Structure):
+    """savqa_rowln_args_t"""
+    _fields_ = [("A", vp), ("lda", i64), ("B", vp), ("ldb", i64), ("b_mn_major", C.c_int),
+                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("mode", C.c_int), ("relu", C.c_int),
+                ("bias", vp), ("rowscale", vp), ("res", vp), ("ld_res", i64), ("gate_bf16", vp), ("ld_gate", i64),
+                ("gamma", vp), ("beta", vp), ("eps", C.c_float),
+                ("act_bf16", vp), ("ld_act", i64), ("pre", vp), ("ld_pre", i64), ("y", vp), ("ld_y", i64), ("y_bf16", vp), ("ld_yb", i64),
+                ("on", vp), ("stats", vp), ("dxg_bf16", vp), ("ld_dxg", i64), ("dgamma", vp), ("dbeta", vp), ("dxsum", vp)]
+
+
 #: every symbol include/savqa_b200.h declares: name -> argtypes (restype is int unless noted)
 SIGNATURES = {
     "savqa_abi_version": [],
@@ -62,10 +72,11 @@ SIGNATURES = {
     "savqa_row_nonzero": [vp, i64, i64, C.c_int, vp, vp, i64, vp],
     "savqa_relu_gate_bf16": [vp, C.c_int, i64, vp, i64, vp, i64, i64, C.c_int, vp],
     "savqa_colsum_bf16": [vp, i64, i64, C.c_int, vp, vp],
-    "savqa_residual_layernorm_fwd": [vp, vp, vp, vp, C.c_float, i64, C.c_int, vp, vp, vp, vp, vp],
+    "savqa_residual_layernorm_fwd": [vp, vp, vp, vp, C.c_float, i64, C.c_int, vp, vp, vp, vp, vp, vp],
     "savqa_layernorm_bwd": [vp, vp, vp, C.c_float, i64, C.c_int, vp, vp, vp, vp, vp, vp, vp],
     "savqa_gemm_bf16": [vp, i64, C.c_int, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(GemmEpilogue), C.c_int, vp],
     "savqa_gemm_bf16_grouped": [C.POINTER(GemmProblem), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "savqa_gemm_rowln": [C.POINTER(RowLnArgs), vp],
     "savqa_set_gemm_sm_limit": [C.c_int],
     "savqa_graph_attn_fwd": [C.POINTER(AttnArgs), vp],
     "savqa_graph_attn_bwd": [C.POINTER(AttnArgs), vp],

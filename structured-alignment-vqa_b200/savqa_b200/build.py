@@ -16,7 +16,7 @@ ROOT = os.path.dirname(PKG_DIR)  # structured-alignment-vqa_b200/
 CSRC = os.path.join(ROOT, "csrc")
 LIB_DIR = os.path.join(ROOT, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsavqa_b200.so")
-SOURCES = ["api.cu", "elementwise.cu", "milnce.cu", "layernorm.cu", "gemm_tcgen05.cu", "gemm2_tcgen05.cu", "attn_simt.cu", "attn_tcgen05.cu", "attn_bwd_tcgen05.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "milnce.cu", "layernorm.cu", "gemm_tcgen05.cu", "gemm2_tcgen05.cu", "rowln_tcgen05.cu", "attn_simt.cu", "attn_tcgen05.cu", "attn_bwd_tcgen05.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 

@@ -765,6 +765,160 @@ class TokenSelfAttentionFn(Function):
 
 
 # ======================================================================================================
+# the decoder chain  -- AttModel_x3.py:141-154
+# ======================================================================================================
+#: the decoder's L x (one-token self-attention, one-query cross-attention, feedforward) chain on fused cluster GEMM + LayerNorm
+#: launches (savqa_gemm_rowln); SAVQA_FUSED_DECODER=0 keeps the per-module chain (A/B comparison, fallback for other shapes)
+FUSED_DECODER = os.environ.get("SAVQA_FUSED_DECODER", "1") != "0"
+
+
+class DecoderFn(Function):
+    """The whole decoder of one branch model as ONE autograd node.  Every layer is a chain of M = B-row kernels whose length is
+    the sum of their latencies; here each Linear -> (mask) -> residual -> LayerNorm group is one cluster launch whose CTAs exchange
+    the row statistics through distributed shared memory (csrc/rowln_tcgen05.cu), and in the backward pass every dgrad GEMM
+    carries the LayerNorm backward (and the ReLU gate of the layer in front of it) in its epilogue:
+
+        forward, per layer:   [Wv + mask + res + LN] -> [Wq] -> one-query attention -> res + LN -> [W1] -> [W2 + res + LN]     (6 launches, was 9)
+        backward, per layer:  [W2^T, gate] -> [W1^T + res + LN'] -> attention' -> [Wq^T + res + LN' + gate] -> [Wv^T + res + LN'] (6, was 12)
+
+    Weight gradients go to the side stream as before (WeightPack.weight_grad).  Training needs the trainer's bound packs (gradients
+    are accumulated straight into the flat buffers) and the fused K/V block of the encoder output (MemoryHolder); inference takes
+    any packs."""
+
+    @staticmethod
+    def forward(ctx, x0, memory, dec_mask, cfg):
+        layers, H = cfg["layers"], cfg["heads"]
+        B, C = x0.shape[0], x0.shape[-1]
+        N, T = memory.shape[0], memory.shape[1]
+        Mk, d = N * T, C // H
+        dev = x0.device
+        x = x0.reshape(B, C)
+        x = x if x.is_contiguous() else x.contiguous()
+        x_on, xb = ops.row_nonzero(x)
+        ms = Side.of(memory)
+        if ms is not None and ms.bf16 is not None and ms.on is not None:
+            mem_b, mem_on = ms.bf16.reshape(Mk, C), ms.on
+        else:
+            mem_on, mem_b = ops.row_nonzero(memory.reshape(Mk, C) if memory.is_contiguous() else memory.contiguous().reshape(Mk, C))
+        holder = cfg.get("kv_holder")
+        fused_kv = holder is not None and holder.kv_all is not None
+        if fused_kv and x0.is_cuda:
+            torch.cuda.current_stream().wait_event(holder.kv_done)
+        g = dec_mask if dec_mask.dtype == F32 else dec_mask.float()
+        g = g if g.is_contiguous() else g.contiguous()
+        f32 = lambda *shape: torch.empty(*shape, device=dev, dtype=F32)    # noqa: E731
+        b16 = lambda *shape: torch.empty(*shape, device=dev, dtype=BF16)   # noqa: E731
+        saved = []
+        for i, (sa, ca, ff) in enumerate(layers):
+            n1, n2, n3 = sa.normalization, ca.normalization, ff.normalization
+            pv = sa._packs["v"].refresh([sa.V_proj[0].weight], [sa.V_proj[0].bias])
+            pq = ca._packs["q"].refresh([ca.Q_proj[0].weight], [ca.Q_proj[0].bias])
+            p1 = ff._packs["w1"].refresh([ff.conv1[0].weight], [ff.conv1[0].bias])
+            p2 = ff._packs["w2"].refresh([ff.conv2.weight], [ff.conv2.bias])
+            Hd = p1.w.shape[0]
+            # self-attention over one token: y1 = LN(relu(x Wv^T + bv) * query_mask + x)      (modules.py:119-207 with a single key)
+            vb, pre1, y1, y1b, on1, st1 = b16(B, C), f32(B, C), f32(B, C), b16(B, C), f32(B), f32(B, 2)
+            ops.gemm_rowln(xb, pv.w, B, C, C, 1, bias=pv.bias, relu=True, rowscale=x_on, res=x, gamma=n1.gamma.detach(), beta=n1.beta.detach(),
+                           eps=n1.epsilon, act_bf16=vb, pre=pre1, y=y1, y_bf16=y1b, on=on1, stats=st1)
+            # cross-attention: one query per sample over the encoder output                    (modules.py:236-311, Tq = 1)
+            q = b16(B, C)
+            ops.gemm_rowln(y1b, pq.w, B, C, C, 0, bias=pq.bias, relu=True, y_bf16=q)
+            if fused_kv:
+                kv = holder.kv_all[:, 2 * C * i:2 * C * (i + 1)]
+            else:
+                pkv = ca._packs["kv"].refresh([ca.K_proj[0].weight, ca.V_proj[0].weight], [ca.K_proj[0].bias, ca.V_proj[0].bias])
+                kv = b16(Mk, 2 * C)
+                ops.gemm(mem_b, pkv.w, Mk, 2 * C, C, bias=pkv.bias, relu=True, out_bf16=kv)
+            k, v = kv[:, :C], kv[:, C:]
+            o, _ = ops.graph_attention_fwd(q, k, v, g, mem_on, on1, N, H, 1, T, d, False, 1, False, 1)
+            st2 = f32(B, 2)
+            y2, pre2, y2b, on2 = ops.layernorm_fwd(o, y1, n2.gamma.detach(), n2.beta.detach(), n2.epsilon, save_pre=True, want_bf16=True,
+                                                   want_on=True, stats=st2)
+            # feedforward: y3 = LN(relu(y2 W1^T + b1) W2^T + b2 + y2)                           (modules.py:432-447)
+            h = b16(B, Hd)
+            ops.gemm_rowln(y2b, p1.w, B, Hd, C, 0, bias=p1.bias, relu=True, y_bf16=h)
+            pre3, y3, y3b, on3, st3 = f32(B, C), f32(B, C), b16(B, C), f32(B), f32(B, 2)
+            ops.gemm_rowln(h, p2.w, B, C, Hd, 1, bias=p2.bias, res=y2, gamma=n3.gamma.detach(), beta=n3.beta.detach(), eps=n3.epsilon,
+                           pre=pre3, y=y3, y_bf16=y3b, on=on3, stats=st3)
+            saved.append(dict(xb=xb, x_on=x_on, vb=vb, pre1=pre1, st1=st1, y1b=y1b, on1=on1, q=q, k=k, v=v, pre2=pre2, st2=st2, y2b=y2b,
+                              h=h, pre3=pre3, st3=st3))
+            x, xb, x_on = y3, y3b, on3
+        ctx.cfg, ctx.saved_layers, ctx.dims = cfg, saved, (B, C, N, T, H, d)
+        ctx.g, ctx.mem_on, ctx.fused_kv = g, mem_on, fused_kv
+        ctx.mark_non_differentiable(xb, x_on)
+        ctx.set_materialize_grads(False)
+        return x.reshape(B, 1, C), xb.reshape(B, 1, C), x_on
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, *_unused):
+        if dy is None:
+            return None, None, None, None
+        cfg, saved = ctx.cfg, ctx.saved_layers
+        layers = cfg["layers"]
+        B, C, N, T, H, d = ctx.dims
+        Mk = N * T
+        dev = dy.device
+        holder = cfg.get("kv_holder")
+        assert ctx.fused_kv and holder is not None, "savqa_b200: the fused decoder's backward needs the trainer's bound K/V block"
+        f32 = lambda *shape: torch.empty(*shape, device=dev, dtype=F32)    # noqa: E731
+        b16 = lambda *shape: torch.empty(*shape, device=dev, dtype=BF16)   # noqa: E731
+        L = len(layers)
+        # LayerNorm backward of the top layer's feedforward: its input gradient comes from the heads, not from one of our GEMMs
+        ff = layers[L - 1][2]
+        n3, p2 = ff.normalization, ff._packs["w2"]
+        dg, db = n3._sink.buffers(n3.gamma)
+        dy2 = dy.reshape(B, C)
+        dz, dzb = ops.layernorm_bwd(dy2 if dy2.is_contiguous() else dy2.contiguous(), saved[L - 1]["pre3"], n3.gamma.detach(), n3.epsilon, dg, db,
+                                    want_bf16=True, dxsum=p2.bias_grad_buffer(C, dev))
+        dx0 = None
+        for i in range(L - 1, -1, -1):
+            s = saved[i]
+            sa, ca, ff = layers[i]
+            n1, n2 = sa.normalization, ca.normalization
+            pv, pq, pkv, p1, p2 = sa._packs["v"], ca._packs["q"], ca._packs["kv"], ff._packs["w1"], ff._packs["w2"]
+            Hd = p1.w.shape[0]
+            # feedforward: dh = (dz W2) * [h > 0];  d y2 = dh W1 + dz, and straight on through the cross-attention's LayerNorm
+            p2.weight_grad(dzb, s["h"], C, Hd)
+            dh = b16(B, Hd)
+            ops.gemm_rowln(dzb, p2.w, B, Hd, C, 0, b_mn=True, gate=s["h"], y_bf16=dh)
+            p1.weight_grad(dh, s["y2b"], Hd, C, bias_grad=p1.bias_grad_buffer(Hd, dev))
+            dg2, db2 = n2._sink.buffers(n2.gamma)
+            dpre2 = f32(B, C)
+            ops.gemm_rowln(dh, p1.w, B, C, Hd, 2, b_mn=True, res=dz, pre=s["pre2"], stats=s["st2"], gamma=n2.gamma.detach(), eps=n2.epsilon,
+                           y=dpre2, dgamma=dg2, dbeta=db2)
+            # cross-attention core (one query): ReLU-gated dq, this layer's slice of the fused K/V gradient, the projections' bias gradients
+            if holder.dkv_all is None:
+                holder.dkv_all = b16(Mk, holder.pack_all.w.shape[0])
+            dkv = holder.dkv_all[:, 2 * C * i:2 * C * (i + 1)]
+            dq = b16(B, C)
+            dbkv = pkv.bias_grad_buffer(2 * C, dev)
+            ops.graph_attention_bwd(s["q"], s["k"], s["v"], ctx.g, ctx.mem_on, s["on1"], N, H, 1, T, d, False, 1, dpre2, dq, dkv[:, :C], dkv[:, C:],
+                                    dbq=pq.bias_grad_buffer(C, dev), dbk=dbkv[:C], dbv=dbkv[C:])
+            pq.weight_grad(dq, s["y1b"], C, C)
+            # d y1 = dq Wq + dpre2 -> the self-attention's LayerNorm backward -> dvb = (dpre1 * query_mask) * [vb > 0]
+            dg1, db1 = n1._sink.buffers(n1.gamma)
+            dpre1, dvb = f32(B, C), b16(B, C)
+            ops.gemm_rowln(dq, pq.w, B, C, C, 2, b_mn=True, res=dpre2, pre=s["pre1"], stats=s["st1"], gamma=n1.gamma.detach(), eps=n1.epsilon,
+                           y=dpre1, dxg_bf16=dvb, gate=s["vb"], rowscale=s["x_on"], dgamma=dg1, dbeta=db1)
+            pv.weight_grad(dvb, s["xb"], C, C, bias_grad=pv.bias_grad_buffer(C, dev))
+            # d x = dvb Wv + dpre1: the gradient of the layer below's output -> its feedforward LayerNorm backward in the same launch
+            if i > 0:
+                ffp = layers[i - 1][2]
+                n3p, p2p = ffp.normalization, ffp._packs["w2"]
+                dg3, db3 = n3p._sink.buffers(n3p.gamma)
+                dz, dzb = f32(B, C), b16(B, C)
+                ops.gemm_rowln(dvb, pv.w, B, C, C, 2, b_mn=True, res=dpre1, pre=saved[i - 1]["pre3"], stats=saved[i - 1]["st3"],
+                               gamma=n3p.gamma.detach(), eps=n3p.epsilon, y=dz, y_bf16=dzb, dgamma=dg3, dbeta=db3,
+                               dxsum=p2p.bias_grad_buffer(C, dev))
+            else:
+                dx0 = f32(B, C)
+                ops.gemm_rowln(dvb, pv.w, B, C, C, 0, b_mn=True, res=dpre1, y=dx0)
+        ctx.saved_layers = None
+        return dx0.reshape(B, 1, C), None, None, None
+
+
+# ======================================================================================================
 # feedforward  -- modules.py:405-447
 # ======================================================================================================
 class FeedForwardFn(Function):

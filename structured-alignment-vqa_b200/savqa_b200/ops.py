@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import AttnArgs, GemmEpilogue, GemmProblem, call, ptr
+from ._lib import AttnArgs, GemmEpilogue, GemmProblem, RowLnArgs, call, ptr
 
 Tensor = torch.Tensor
 BF16 = torch.bfloat16
@@ -248,8 +248,9 @@ def colsum_bf16(x: Tensor, out: Tensor) -> None:
 
 
 def layernorm_fwd(x: Tensor, res: Optional[Tensor], gamma: Tensor, beta: Tensor, eps: float, save_pre: bool, want_bf16: bool,
-                  want_on: bool):
-    """y = LN(x + res) (modules.py:62-65).  Returns (y, pre | None, y_bf16 | None, on | None)."""
+                  want_on: bool, stats: Optional[Tensor] = None):
+    """y = LN(x + res) (modules.py:62-65).  Returns (y, pre | None, y_bf16 | None, on | None); `stats` (fp32 [rows, 2], optional)
+    receives {mean, sigma} of every row."""
     for nm, t in (("x", x), ("res", res), ("gamma", gamma), ("beta", beta)):
         _check(t, F32, nm)
     assert x.is_contiguous() and (res is None or (res.is_contiguous() and res.shape == x.shape))
@@ -259,7 +260,10 @@ def layernorm_fwd(x: Tensor, res: Optional[Tensor], gamma: Tensor, beta: Tensor,
     pre = torch.empty_like(x) if save_pre else None
     yb = torch.empty(x.shape, device=x.device, dtype=BF16) if want_bf16 else None
     on = torch.empty(rows, device=x.device, dtype=F32) if want_on else None
-    call("savqa_residual_layernorm_fwd", ptr(x), ptr(res), ptr(gamma), ptr(beta), float(eps), rows, C_, ptr(pre), ptr(y), ptr(yb), ptr(on))
+    _check(stats, F32, "stats")
+    assert stats is None or (stats.is_contiguous() and stats.numel() >= 2 * rows)
+    call("savqa_residual_layernorm_fwd", ptr(x), ptr(res), ptr(gamma), ptr(beta), float(eps), rows, C_, ptr(pre), ptr(y), ptr(yb), ptr(on),
+         ptr(stats))
     return y, pre, yb, on
 
 
@@ -333,6 +337,59 @@ def _fill_epilogue(e, M, N, bias, res, rowtab, rowtab_period, gate, relu, alpha,
     if colsum is not None:
         assert colsum.is_contiguous() and colsum.numel() >= N and split_k == 1
         e.colsum = ptr(colsum)
+
+
+def rowln_fits(M: int, N: int, K: int) -> bool:
+    """Shapes savqa_gemm_rowln's row-wise (LayerNorm) modes take: one cluster of N / 64 <= 8 CTAs per 128-row block."""
+    return N in (64, 128, 256, 512) and K % 8 == 0 and M >= 1
+
+
+def gemm_rowln(a: Tensor, b: Tensor, M: int, N: int, K: int, mode: int, *, b_mn: bool = False, bias: Optional[Tensor] = None,
+               relu: bool = False, rowscale: Optional[Tensor] = None, res: Optional[Tensor] = None, gate: Optional[Tensor] = None,
+               gamma: Optional[Tensor] = None, beta: Optional[Tensor] = None, eps: float = 1e-8, act_bf16: Optional[Tensor] = None,
+               pre: Optional[Tensor] = None, y: Optional[Tensor] = None, y_bf16: Optional[Tensor] = None, on: Optional[Tensor] = None,
+               stats: Optional[Tensor] = None, dxg_bf16: Optional[Tensor] = None, dgamma: Optional[Tensor] = None,
+               dbeta: Optional[Tensor] = None, dxsum: Optional[Tensor] = None) -> None:
+    """Cluster GEMM with a row-wise epilogue (savqa_gemm_rowln): mode 0 plain, 1 Linear -> (* rowscale) -> + res -> LayerNorm,
+    2 dgrad -> + res -> LayerNorm backward.  All matrices are 2-D views with a contiguous last dimension."""
+    _check(a, BF16, "A")
+    _check(b, BF16, "B")
+    for nm, t in (("bias", bias), ("rowscale", rowscale), ("res", res), ("gamma", gamma), ("beta", beta), ("pre", pre), ("y", y), ("on", on),
+                  ("stats", stats), ("dgamma", dgamma), ("dbeta", dbeta), ("dxsum", dxsum)):
+        _check(t, F32, nm)
+    for nm, t in (("gate", gate), ("act_bf16", act_bf16), ("y_bf16", y_bf16), ("dxg_bf16", dxg_bf16)):
+        _check(t, BF16, nm)
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1 and a.shape[0] >= M and a.shape[1] >= K
+    assert (b.shape[0] >= K and b.shape[1] >= N) if b_mn else (b.shape[0] >= N and b.shape[1] >= K)
+    g = RowLnArgs()
+    g.A, g.lda, g.B, g.ldb, g.b_mn_major = ptr(a), a.stride(0), ptr(b), b.stride(0), int(b_mn)
+    g.M, g.N, g.K, g.mode, g.relu = M, N, K, int(mode), int(relu)
+    g.bias, g.rowscale, g.gamma, g.beta, g.eps = ptr(bias), ptr(rowscale), ptr(gamma), ptr(beta), float(eps)
+    g.on, g.stats, g.dgamma, g.dbeta, g.dxsum = ptr(on), ptr(stats), ptr(dgamma), ptr(dbeta), ptr(dxsum)
+    for t in (bias, gamma, beta, dgamma, dbeta, dxsum):
+        assert t is None or (t.is_contiguous() and t.numel() >= N)
+    for t in (rowscale, on):
+        assert t is None or (t.is_contiguous() and t.numel() >= M)
+    assert stats is None or (stats.is_contiguous() and stats.numel() >= 2 * M)
+
+    def mat(t, nm):
+        assert t.dim() == 2 and t.stride(1) == 1 and t.shape[0] >= M and t.shape[1] >= N, nm
+        return ptr(t), t.stride(0)
+    if res is not None:
+        g.res, g.ld_res = mat(res, "res")
+    if gate is not None:
+        g.gate_bf16, g.ld_gate = mat(gate, "gate")
+    if act_bf16 is not None:
+        g.act_bf16, g.ld_act = mat(act_bf16, "act_bf16")
+    if pre is not None:
+        g.pre, g.ld_pre = mat(pre, "pre")
+    if y is not None:
+        g.y, g.ld_y = mat(y, "y")
+    if y_bf16 is not None:
+        g.y_bf16, g.ld_yb = mat(y_bf16, "y_bf16")
+    if dxg_bf16 is not None:
+        g.dxg_bf16, g.ld_dxg = mat(dxg_bf16, "dxg_bf16")
+    call("savqa_gemm_rowln", C.byref(g))
 
 
 @contextlib.contextmanager

@@ -143,13 +143,15 @@ def colsum_bf16(x, out):
     out += x.float().sum(0)[: out.numel()]
 
 
-def layernorm_fwd(x, res, gamma, beta, eps, save_pre, want_bf16, want_on):
+def layernorm_fwd(x, res, gamma, beta, eps, save_pre, want_bf16, want_on, stats=None):
     pre = x if res is None else x + res
     C = pre.shape[-1]
     mean = pre.mean(-1, keepdim=True)
     c = pre - mean
     sigma = torch.sqrt((c * c).sum(-1, keepdim=True) / (C - 1))
     y = gamma * c / (sigma + eps) + beta
+    if stats is not None:
+        stats.view(-1, 2)[:mean.numel()] = torch.cat([mean.reshape(-1, 1), sigma.reshape(-1, 1)], 1)
     return y, (pre.clone() if save_pre else None), (y.to(BF16) if want_bf16 else None), ((y.reshape(-1, C).sum(-1) != 0).float() if want_on else None)
 
 
@@ -201,6 +203,75 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, bias=None, res=None, rowtab=N
         out_bf16[:M, :N] = v.to(BF16)
     if colsum is not None:
         colsum[:N] += v.sum(0)
+
+
+def rowln_fits(M, N, K):
+    return N in (64, 128, 256, 512) and K % 8 == 0 and M >= 1
+
+
+def gemm_rowln(a, b, M, N, K, mode, *, b_mn=False, bias=None, relu=False, rowscale=None, res=None, gate=None, gamma=None, beta=None,
+               eps=1e-8, act_bf16=None, pre=None, y=None, y_bf16=None, on=None, stats=None, dxg_bf16=None, dgamma=None, dbeta=None,
+               dxsum=None):
+    """savqa_gemm_rowln restated: bf16 operands, fp32 accumulate, the three epilogue modes with the kernel's explicit formulas."""
+    A = a[:M, :K].float()
+    W = b[:K, :N].float().t() if b_mn else b[:N, :K].float()
+    acc = A @ W.t()
+    if mode != 2:
+        v = acc + (bias[:N] if bias is not None else 0.0)
+        if relu:
+            v = v.clamp(min=0)
+        if gate is not None:
+            v = torch.where(gate[:M, :N].float() > 0, v, torch.zeros_like(v))
+        if act_bf16 is not None:
+            act_bf16[:M, :N] = v.to(BF16)
+            v = act_bf16[:M, :N].float()
+        if mode == 0:
+            if res is not None:
+                v = v + res[:M, :N]
+            if y is not None:
+                y[:M, :N] = v
+            if y_bf16 is not None:
+                y_bf16[:M, :N] = v.to(BF16)
+            return
+        if rowscale is not None:
+            v = v * rowscale[:M, None]
+        if res is not None:
+            v = v + res[:M, :N]
+        if pre is not None:
+            pre[:M, :N] = v
+        mean = v.mean(-1, keepdim=True)
+        sigma = ((v - mean) ** 2).sum(-1, keepdim=True).div(N - 1).sqrt()
+        out = gamma[:N] * (v - mean) / (sigma + eps) + beta[:N]
+        if y is not None:
+            y[:M, :N] = out
+        if y_bf16 is not None:
+            y_bf16[:M, :N] = out.to(BF16)
+        if on is not None:
+            on[:M] = (out.sum(-1) != 0).float()
+        if stats is not None:
+            stats.view(-1, 2)[:M] = torch.cat([mean, sigma], 1)
+        return
+    dy = acc + (res[:M, :N] if res is not None else 0.0)
+    st = stats.view(-1, 2)[:M]
+    mean, sigma = st[:, :1], st[:, 1:2]
+    c = pre[:M, :N] - mean
+    s_ = sigma + eps
+    if dbeta is not None:
+        dbeta[:N] += dy.sum(0)
+    if dgamma is not None:
+        dgamma[:N] += (dy * c / s_).sum(0)
+    g = dy * gamma[:N]
+    k2 = torch.where(sigma > 0, (g * c).sum(-1, keepdim=True) / ((N - 1) * sigma * s_ * s_), torch.zeros_like(sigma))
+    dx = (g - g.mean(-1, keepdim=True)) / s_ - c * k2
+    if dxsum is not None:
+        dxsum[:N] += dx.sum(0)
+    if y is not None:
+        y[:M, :N] = dx
+    if y_bf16 is not None:
+        y_bf16[:M, :N] = dx.to(BF16)
+    if dxg_bf16 is not None:
+        t = dx * (rowscale[:M, None] if rowscale is not None else 1.0)
+        dxg_bf16[:M, :N] = torch.where(gate[:M, :N].float() > 0, t, torch.zeros_like(t)).to(BF16)
 
 
 def tc_attention_bwd_fits(d, Tq, Tk):

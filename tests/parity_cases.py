@@ -283,12 +283,19 @@ def attention_direct_case(M, device, C, H, N, T, seed=0, p_edge=0.3):
     dy = GS.randn(f"{case}/dy", N, T, C)
     ref = _oracle_attention(P0, x, x, graph, H, dy, None, True)
     emu = _oracle_attention(P0, x, x, graph, H, dy, BF, True)
-    m = M.new_multihead_attention(C, H, return_att=True)
+    # probabilities from a return_att module (forward only); output and gradients from the module as the training step builds it
+    # (return_att=False: forward statistics kept for the one-pass shared-tile backward kernel)
+    m_att = M.new_multihead_attention(C, H, return_att=True)
+    set_params(m_att, P0)
+    m_att = m_att.to(device)
+    with torch.no_grad():
+        y_att, att = m_att(x.to(device), x.to(device), x.to(device), graph.to(device))
+    m = M.new_multihead_attention(C, H)
     set_params(m, P0)
     m = m.to(device)
     xx = x.clone().to(device).requires_grad_(True)
-    y, att = m(xx, xx, xx, graph.to(device))
-    errs = {"y": check(f"{case}: output", y, ref["y"], emu["y"]),
+    y = m(xx, xx, xx, graph.to(device))
+    errs = {"y": check(f"{case}: output", y, ref["y"], emu["y"]), "y_att": check(f"{case}: output (return_att)", y_att, ref["y"], emu["y"]),
             "att": check(f"{case}: attention probabilities", att, ref["att"], emu["att"])}
     a4 = att.detach().cpu().view(H, N, T, T)
     assert float(a4[:, :, 1].abs().sum()) == 0.0 and float(a4[:, :, 2].abs().sum()) == 0.0

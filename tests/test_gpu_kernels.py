@@ -524,3 +524,68 @@ def test_deferred_row_adam_equals_dense_adam(ops):
         ops.scatter_add_rows(grad, idx, gd.cuda())
         ops.adam_rows(p, grad, m, v, stamp, idx, 1e-2, 0.9, 0.999, 1e-8, step, apply=True)
     assert float((p.cpu() - ref.detach()).abs().max()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ cluster GEMM + row-wise epilogue
+@pytest.mark.parametrize("M,N,K,b_mn", [(128, 512, 512, False), (128, 512, 2048, False), (100, 512, 512, True), (128, 256, 192, False),
+                                        (77, 64, 64, False), (256, 512, 512, True), (300, 128, 2048, True)])
+def test_gemm_rowln_layernorm_modes(ops, M, N, K, b_mn):
+    """savqa_gemm_rowln modes 1 (Linear -> mask -> residual -> LayerNorm) and 2 (dgrad -> residual -> LayerNorm backward -> ReLU gate)
+    against the fp32 restatement of the same formulas (tests/fake_ops.py), incl. ragged row counts, clusters of 1 / 2 / 4 / 8 CTAs,
+    several 128-row blocks, K-major and MN-major weights."""
+    import fake_ops as F
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(BF)
+    w = (torch.randn(K, N, generator=g) if b_mn else torch.randn(N, K, generator=g)).mul(K ** -0.5).to(BF)
+    bias, rowscale = torch.randn(N, generator=g) * 0.1, (torch.rand(M, generator=g) < 0.8).float()
+    res, gamma, beta = torch.randn(M, N, generator=g), torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.1
+    res[3] = 0
+    rowscale[3] = 0  # an all-zero LayerNorm input row when the bias is masked too: exercised below through rowscale = 0, res = 0
+    outs = lambda dev: dict(act_bf16=torch.zeros(M, N, dtype=BF, device=dev), pre=torch.zeros(M, N, device=dev), y=torch.zeros(M, N, device=dev),  # noqa: E731
+                            y_bf16=torch.zeros(M, N, dtype=BF, device=dev), on=torch.zeros(M, device=dev), stats=torch.zeros(M, 2, device=dev))
+    ref, got = outs("cpu"), outs("cuda")
+    F.gemm_rowln(a, w, M, N, K, 1, b_mn=b_mn, bias=bias, relu=True, rowscale=rowscale, res=res, gamma=gamma, beta=beta, eps=1e-8, **ref)
+    ops.gemm_rowln(dev(a), dev(w), M, N, K, 1, b_mn=b_mn, bias=dev(bias), relu=True, rowscale=dev(rowscale), res=dev(res), gamma=dev(gamma),
+                   beta=dev(beta), eps=1e-8, **got)
+    assert torch.equal(got["act_bf16"].cpu(), ref["act_bf16"]) or rel(got["act_bf16"].float(), ref["act_bf16"].float()) < 2e-3
+    assert rel(got["pre"], ref["pre"]) < 2e-3 and rel(got["y"], ref["y"]) < 3e-3 and rel(got["stats"], ref["stats"]) < 2e-3
+    assert torch.equal(got["on"].cpu(), ref["on"])
+    assert torch.equal(got["y"][3].cpu(), beta)  # constant (zero) LayerNorm input row -> exactly beta
+    assert rel(got["y_bf16"].float(), got["y"].to(BF).float()) < 1e-6
+    # mode 2 on the kernel's own forward outputs
+    dy_a = (torch.randn(M, K, generator=g) * 0.3).to(BF)
+    res2 = torch.randn(M, N, generator=g)
+    gate = (torch.randn(M, N, generator=g)).to(BF)
+    pre_d, stats_d = got["pre"].clone(), got["stats"].clone()
+    o2 = lambda dev: dict(y=torch.zeros(M, N, device=dev), y_bf16=torch.zeros(M, N, dtype=BF, device=dev), dxg_bf16=torch.zeros(M, N, dtype=BF, device=dev),  # noqa: E731
+                          dgamma=torch.zeros(N, device=dev), dbeta=torch.zeros(N, device=dev), dxsum=torch.zeros(N, device=dev))
+    r2, g2 = o2("cpu"), o2("cuda")
+    F.gemm_rowln(dy_a, w, M, N, K, 2, b_mn=b_mn, res=res2, pre=pre_d.cpu(), stats=stats_d.cpu(), gamma=gamma, eps=1e-8, gate=gate,
+                 rowscale=rowscale, **r2)
+    ops.gemm_rowln(dev(dy_a), dev(w), M, N, K, 2, b_mn=b_mn, res=dev(res2), pre=pre_d, stats=stats_d, gamma=dev(gamma), eps=1e-8, gate=dev(gate),
+                   rowscale=dev(rowscale), **g2)
+    live = torch.ones(M, dtype=torch.bool)
+    live[3] = False  # the sigma == 0 row carries 1 / eps = 1e8-scaled values: compared apart
+    assert rel(g2["y"].cpu()[live], r2["y"][live]) < 2e-3
+    assert rel(g2["y"].cpu()[3], r2["y"][3]) < 2e-3
+    assert rel(g2["dxg_bf16"].float().cpu()[live], r2["dxg_bf16"].float()[live]) < 6e-3
+    for k_ in ("dbeta", "dgamma"):
+        assert rel(g2[k_], r2[k_]) < 2e-3, k_
+    # plain mode with a ReLU gate and a residual (the feedforward's dgrad)
+    yp_r, yp_g = torch.zeros(M, N, dtype=BF), torch.zeros(M, N, dtype=BF, device="cuda")
+    F.gemm_rowln(dy_a, w, M, N, K, 0, b_mn=b_mn, gate=gate, y_bf16=yp_r)
+    ops.gemm_rowln(dev(dy_a), dev(w), M, N, K, 0, b_mn=b_mn, gate=dev(gate), y_bf16=yp_g)
+    assert rel(yp_g.float(), yp_r.float()) < 3e-3
+
+
+def test_gemm_rowln_plain_wide(ops):
+    """Plain mode at the decoder's conv1 shape (N = 2048: 32 independent CTAs) with bias + ReLU, fp32 and bf16 outputs."""
+    import fake_ops as F
+    M, N, K = 128, 2048, 512
+    g = torch.Generator().manual_seed(5)
+    a, w, bias = (torch.randn(M, K, generator=g) * 0.5).to(BF), (torch.randn(N, K, generator=g) * K ** -0.5).to(BF), torch.randn(N, generator=g) * 0.1
+    yr, ybr = torch.zeros(M, N), torch.zeros(M, N, dtype=BF)
+    yg, ybg = torch.zeros(M, N, device="cuda"), torch.zeros(M, N, dtype=BF, device="cuda")
+    F.gemm_rowln(a, w, M, N, K, 0, bias=bias, relu=True, y=yr, y_bf16=ybr)
+    ops.gemm_rowln(dev(a), dev(w), M, N, K, 0, bias=dev(bias), relu=True, y=yg, y_bf16=ybg)
+    assert rel(yg, yr) < 2e-3 and rel(ybg.float(), ybr.float()) < 3e-3

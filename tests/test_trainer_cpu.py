@@ -196,3 +196,66 @@ def test_full_step_trainer_matches_autograd_adam(monkeypatch, kind):
     assert _max_param_diff(model, ref) < 2e-5
     assert model.MIL_NCE.marco_mlp[0].weight.grad is None  # detached at AttModel_x3.py:354: never in the flat buffers
     tr.release()
+
+
+def test_fused_decoder_matches_per_module_chain(monkeypatch):
+    """functional.DecoderFn (the decoder as fused GEMM + LayerNorm launches, forward and hand-written backward) against the
+    per-module chain (TokenSelfAttentionFn -> GraphAttentionFn -> FeedForwardFn per layer, itself pinned to the oracle): output,
+    gradient of the start token, every decoder parameter gradient in the flat buffer, and d(memory) through the fused K/V block."""
+    fake_ops.install(monkeypatch)
+    from savqa_b200 import functional as Fn, ops, synthetic, train
+    cfg, model, b = _setup(batch=5)
+    tr = train.EncoderTrainer(model, lr=1e-3)
+    tr.prepare(b)  # binds the packs / LayerNorm sinks to the flat buffers
+    br = model.att_syb
+    C, L, H = br.hidden_size, br.num_blocks, br.num_heads
+    B, T = 5, 9
+    g = torch.Generator().manual_seed(3)
+    mem0 = torch.randn(B, T, C, generator=g)
+    mem0[1, T - 2:] = 0  # padded memory tokens (key-masked)
+    dec_mask = (torch.rand(B, 1, T, generator=g) < 0.8).float()
+    dec_mask[:, 0, 0] = 1
+    dout = torch.randn(B, 1, C, generator=g)
+    x0 = (br.dec_emb.lookup_table[2] * (C ** 0.5) + br.dec_positional_encoding.lookup_table[0]).detach().reshape(1, 1, C).expand(B, 1, C).contiguous()
+    layers = [(getattr(br, 'dec_self_attention_%d' % i), getattr(br, 'dec_vanilla_attention_%d' % i), getattr(br, 'dec_feed_forward_%d' % i))
+              for i in range(L)]
+
+    def run(fused):
+        tr.flat_grad.zero_()
+        x = x0.clone().requires_grad_(True)
+        mem = mem0.clone().requires_grad_(True)
+        if fused:
+            pall = br._pk["kv_all"]
+            on, mb = ops.row_nonzero(mem.detach().reshape(B * T, C))
+            kv_all = torch.empty(B * T, 2 * L * C, dtype=torch.bfloat16)
+            ops.gemm(mb, pall.w, B * T, 2 * L * C, C, bias=pall.bias, relu=True, out_bf16=kv_all)
+            h = Fn.MemoryHolder()
+            h.kv_all, h.pack_all, h.mem_bf16, h.shape = kv_all, pall, mb, mem.shape
+            memj = Fn.MemoryJoinFn.apply(mem, h)
+            memj._savqa_side = Fn.Side(memj, mb, on)
+            y, _, _ = Fn.DecoderFn.apply(x, memj, dec_mask, dict(layers=layers, heads=H, kv_holder=h))
+        else:
+            y = x
+            for sa, ca, ff in layers:
+                y = ff(ca(sa(y, y, y), mem, mem, dec_mask))
+        (y * dout).sum().backward()
+        return y.detach(), x.grad.clone(), mem.grad.clone(), tr.flat_grad.clone()
+
+    monkeypatch.setattr(Fn, "WGRAD_SIDE_STREAM", False)
+    y1, dx1, dm1, fg1 = run(True)
+    y0, dx0, dm0, fg0 = run(False)
+    rel = lambda a_, b_: float((a_ - b_).norm() / (b_.norm() + 1e-30))  # noqa: E731
+    assert rel(y1, y0) < 1e-5, rel(y1, y0)
+    assert rel(dx1, dx0) < 2e-3 and rel(dm1, dm0) < 2e-3, (rel(dx1, dx0), rel(dm1, dm0))
+    names = {id(p): k for k, p in model.named_parameters()}
+    off = tr.views._off
+    for p in tr.dense:
+        k = names[id(p)]
+        if k.startswith("att_syb.dec_") and not k.startswith(("att_syb.dec_emb", "att_syb.dec_pos")):
+            o, n = off[id(p)]
+            a_, b_ = fg1[o:o + n], fg0[o:o + n]
+            if float(b_.abs().sum()) == 0.0:
+                assert float(a_.abs().sum()) == 0.0, k
+            else:
+                assert rel(a_, b_) < 5e-3, (k, rel(a_, b_))
+    tr.release()
