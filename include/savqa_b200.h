@@ -95,10 +95,14 @@ int savqa_cast_transpose_bf16(const float* src, int64_t ld_src, void* dst_bf16, 
  * sign(abs(sum(x,-1))) of modules.py:257,289.  Optionally also writes a bf16 copy of x. */
 int savqa_row_nonzero(const float* x, int64_t ld, int64_t rows, int cols, float* on, void* x_bf16, int64_t ld_bf16,
                       savqa_stream_t stream);
-/* out_bf16[r,c] = (act_bf16[r,c] > 0) ? dy[r,c] : 0   -- ReLU backward staged as the bf16 GEMM operand.
- * dy is fp32 when dy_is_f32 != 0, bf16 otherwise. */
+/* out_bf16[r,c] = (act_bf16[r,c] > 0) ? dy[src(r),c] : 0   -- ReLU backward staged as the bf16 GEMM operand.
+ * dy is fp32 when dy_is_f32 != 0, bf16 otherwise.  src(r) = (r / group_rows) * group_stride + r % group_rows lets the rows of dy sit
+ * in equally spaced groups inside a larger matrix (the node rows of every sample inside d x_in [B, T, 2048], AttModel_x3.py:218-219);
+ * group_rows <= 0: src(r) = r. */
 int savqa_relu_gate_bf16(const void* dy, int dy_is_f32, int64_t ld_dy, const void* act_bf16, int64_t ld_act, void* out_bf16,
-                         int64_t ld_out, int64_t rows, int cols, savqa_stream_t stream);
+                         int64_t ld_out, int64_t rows, int cols, int64_t group_rows, int64_t group_stride, savqa_stream_t stream);
+/* Zero fill by at most max_blocks (<= 0: 8 per SM) persistent blocks: a background fill that does not hold the block scheduler. */
+int savqa_fill_zero(void* p, int64_t bytes, int max_blocks, savqa_stream_t stream);
 /* out[c] += sum_r x_bf16[r, c]  (bias gradients). */
 int savqa_colsum_bf16(const void* x_bf16, int64_t ld, int64_t rows, int cols, float* out, savqa_stream_t stream);
 

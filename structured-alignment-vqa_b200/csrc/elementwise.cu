@@ -159,17 +159,66 @@ __global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, long l
   }
 }
 
+// out[r, :] = (act[r, :] > 0) ? dy[src(r), :] : 0 in bf16, with src(r) = (r / group_rows) * group_stride + r % group_rows: the rows of
+// dy may sit in groups inside a larger tensor (the node rows of every sample inside d[B, T, 2048]) -- no contiguous copy first.
+// Eight columns per thread (16-byte accesses) when the pointers / pitches allow it.
 template <typename TDy>
 __global__ void relu_gate_kernel(const TDy* __restrict__ dy, long ld_dy, const __nv_bfloat16* __restrict__ act, long ld_act,
-                                 __nv_bfloat16* __restrict__ out, long ld_out, long rows, int cols) {
+                                 __nv_bfloat16* __restrict__ out, long ld_out, long rows, int cols, long group_rows, long group_stride,
+                                 int vec) {
+  if (vec) {
+    const int cv = cols >> 3;
+    const long total = rows * cv;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+      const long r = i / cv;
+      const int c = static_cast<int>(i - r * cv) << 3;
+      const long sr = (r / group_rows) * group_stride + (r % group_rows);
+      const uint4 a4 = __ldg(reinterpret_cast<const uint4*>(act + r * ld_act + c));
+      float g[8];
+      if constexpr (sizeof(TDy) == 4) {
+        const float4 lo = __ldcs(reinterpret_cast<const float4*>(dy + sr * ld_dy + c));
+        const float4 hi = __ldcs(reinterpret_cast<const float4*>(dy + sr * ld_dy + c) + 1);
+        g[0] = lo.x; g[1] = lo.y; g[2] = lo.z; g[3] = lo.w; g[4] = hi.x; g[5] = hi.y; g[6] = hi.z; g[7] = hi.w;
+      } else {
+        const uint4 d4 = __ldcs(reinterpret_cast<const uint4*>(dy + sr * ld_dy + c));
+        const uint32_t w[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_bf16x2(w[q]);
+          g[2 * q] = f.x;
+          g[2 * q + 1] = f.y;
+        }
+      }
+      const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = unpack_bf16x2(aw[q]);
+        o[q] = pack_bf16x2(f.x > 0.0f ? g[2 * q] : 0.0f, f.y > 0.0f ? g[2 * q + 1] : 0.0f);
+      }
+      *reinterpret_cast<uint4*>(out + r * ld_out + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    return;
+  }
   const long total = rows * cols;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const long r = i / cols;
     const int c = static_cast<int>(i % cols);
-    const float g = static_cast<float>(dy[r * ld_dy + c]);
+    const long sr = (r / group_rows) * group_stride + (r % group_rows);
+    const float g = static_cast<float>(dy[sr * ld_dy + c]);
     const float a = __bfloat162float(act[r * ld_act + c]);
     out[r * ld_out + c] = __float2bfloat16_rn(a > 0.0f ? g : 0.0f);
   }
+}
+
+// Zero fill with a BOUNDED grid: a kernel of tens of thousands of blocks keeps the block scheduler from dispatching the kernels
+// other streams launch behind it until its last wave (seen in the step trace: the 356 MB gradient zero-fill "next to" the forward
+// pass delayed it by its full 50 us); a few persistent blocks trickle through HBM underneath them instead.
+__global__ void __launch_bounds__(256) fill_zero_kernel(uint4* __restrict__ p, long n16, uint8_t* __restrict__ tail, long n_tail) {
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n16; i += static_cast<long>(gridDim.x) * blockDim.x) p[i] = z;
+  if (blockIdx.x == 0)
+    for (long i = threadIdx.x; i < n_tail; i += blockDim.x) tail[i] = 0;
 }
 
 // One warp per row: fp32 row sum (the reference's sum(x,-1)), on = (sum != 0); optional bf16 copy of the row.
@@ -203,47 +252,59 @@ __global__ void row_nonzero_kernel(const float* __restrict__ x, long ld, long ro
 
 // out[c] += sum_r x[r,c].  Block = 32 x 8 threads over a 64-column strip (bf16x2 per thread), rows strided over
 // blockIdx.y; one atomicAdd per column per block.
-__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long ld, long rows, int cols, float* __restrict__ out) {
-  __shared__ float part[8][64];
-  const int c = blockIdx.x * 64 + threadIdx.x * 2;
-  float a0 = 0.0f, a1 = 0.0f;
-  if (c < cols) {
-    const bool pair = (c + 1 < cols) && (ld % 2 == 0);
-    long r = static_cast<long>(blockIdx.y) * blockDim.y + threadIdx.y;
-    const long stride = static_cast<long>(gridDim.y) * blockDim.y;
-    if (pair) {  // four rows in flight per thread: the kernel is a pure stream, its loads must not wait for each other
-      float b0 = 0.0f, b1 = 0.0f, c0 = 0.0f, c1 = 0.0f, d0 = 0.0f, d1 = 0.0f;
-      for (; r + 3 * stride < rows; r += 4 * stride) {
-        const uint32_t u0 = *reinterpret_cast<const uint32_t*>(x + r * ld + c);
-        const uint32_t u1 = *reinterpret_cast<const uint32_t*>(x + (r + stride) * ld + c);
-        const uint32_t u2 = *reinterpret_cast<const uint32_t*>(x + (r + 2 * stride) * ld + c);
-        const uint32_t u3 = *reinterpret_cast<const uint32_t*>(x + (r + 3 * stride) * ld + c);
-        const float2 f0 = unpack_bf16x2(u0), f1 = unpack_bf16x2(u1), f2 = unpack_bf16x2(u2), f3 = unpack_bf16x2(u3);
-        a0 += f0.x; a1 += f0.y; b0 += f1.x; b1 += f1.y; c0 += f2.x; c1 += f2.y; d0 += f3.x; d1 += f3.y;
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long ld, long rows, int cols, float* __restrict__ out,
+                                                          int vec) {
+  // block = 8 warps over one 256-column strip: lane l owns columns [8 l, 8 l + 8) (one 16-byte load per row), every warp strides
+  // over the rows with four loads in flight; the eight warps' partial sums meet in shared memory, one atomic per column per block
+  __shared__ float part[8][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+  long r = static_cast<long>(blockIdx.y) * 8 + w;
+  const long stride = static_cast<long>(gridDim.y) * 8;
+  if (vec && c + 8 <= cols) {
+    for (; r + 3 * stride < rows; r += 4 * stride) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldcs(reinterpret_cast<const uint4*>(x + (r + k * stride) * ld + c));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t q[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(q[j]);
+          acc[2 * j] += f.x;
+          acc[2 * j + 1] += f.y;
+        }
       }
-      a0 = (a0 + b0) + (c0 + d0);
-      a1 = (a1 + b1) + (c1 + d1);
     }
     for (; r < rows; r += stride) {
-      if (pair) {
-        const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
-        a0 += f.x;
-        a1 += f.y;
-      } else {
-        a0 += __bfloat162float(x[r * ld + c]);
-        if (c + 1 < cols) a1 += __bfloat162float(x[r * ld + c + 1]);
+      const uint4 u = __ldcs(reinterpret_cast<const uint4*>(x + r * ld + c));
+      const uint32_t q[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(q[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
       }
     }
+  } else {
+    for (; r < rows; r += stride)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c + j < cols) acc[j] += __bfloat162float(x[r * ld + c + j]);
   }
-  part[threadIdx.y][threadIdx.x * 2] = a0;
-  part[threadIdx.y][threadIdx.x * 2 + 1] = a1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[w][lane * 8 + j] = acc[j];
   __syncthreads();
-  if (threadIdx.y == 0) {
-    for (int k = 0; k < 2; ++k) {
-      float s = 0.0f;
-      for (int j = 0; j < 8; ++j) s += part[j][threadIdx.x * 2 + k];
-      if (c + k < cols) atomicAdd(out + c + k, s);
-    }
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col < cols) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += part[j][threadIdx.x];
+    atomicAdd(out + col, sum);
   }
 }
 
@@ -387,6 +448,7 @@ __global__ void adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, f
     if (lane == 0) old = atomicMax(stamp + row, target);
     old = __shfl_sync(0xffffffffu, old, 0);
     if (old >= target) continue;  // another occurrence of this row took it (or it is already current)
+    if (old == 0 && !apply) continue;  // never touched: moments are zero, no update to replay, nothing to rewrite
     const long base = row * static_cast<long>(width);
     // steps old+1 .. last_zero see a zero gradient; step `target` sees g when apply
     const int last_zero = apply ? target - 1 : target;
@@ -565,18 +627,39 @@ extern "C" int savqa_row_nonzero(const float* x, int64_t ld, int64_t rows, int c
 }
 
 extern "C" int savqa_relu_gate_bf16(const void* dy, int dy_is_f32, int64_t ld_dy, const void* act, int64_t ld_act, void* out, int64_t ld_out,
-                                    int64_t rows, int cols, savqa_stream_t stream_) {
+                                    int64_t rows, int cols, int64_t group_rows, int64_t group_stride, savqa_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (rows == 0 || cols == 0) return SAVQA_OK;
   SAVQA_REQUIRE(dy && act && out && ld_dy >= cols && ld_act >= cols && ld_out >= cols, "savqa_relu_gate_bf16: bad argument");
-  const int grid = grid_for(rows * cols, 256);
+  if (group_rows <= 0) {
+    group_rows = rows;
+    group_stride = rows;
+  }
+  SAVQA_REQUIRE(group_stride >= group_rows, "savqa_relu_gate_bf16: group_stride < group_rows");
+  auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const int vec = (cols % 8 == 0 && ld_act % 8 == 0 && ld_out % 8 == 0 && ld_dy % (dy_is_f32 ? 4 : 8) == 0 && a16(dy) && a16(act) && a16(out)) ? 1 : 0;
+  const int grid = grid_for(vec ? rows * (cols / 8) : rows * cols, 256);
   if (dy_is_f32)
     relu_gate_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(dy), ld_dy, static_cast<const __nv_bfloat16*>(act), ld_act,
-                                                      static_cast<__nv_bfloat16*>(out), ld_out, rows, cols);
+                                                      static_cast<__nv_bfloat16*>(out), ld_out, rows, cols, group_rows, group_stride, vec);
   else
     relu_gate_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy,
                                                               static_cast<const __nv_bfloat16*>(act), ld_act,
-                                                              static_cast<__nv_bfloat16*>(out), ld_out, rows, cols);
+                                                              static_cast<__nv_bfloat16*>(out), ld_out, rows, cols, group_rows, group_stride, vec);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_fill_zero(void* p, int64_t bytes, int max_blocks, savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (bytes == 0) return SAVQA_OK;
+  SAVQA_REQUIRE(p && bytes > 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0, "savqa_fill_zero: needs a 16-byte aligned buffer");
+  const long n16 = bytes / 16;
+  long blocks = (n16 + 255) / 256;
+  const long cap = max_blocks > 0 ? max_blocks : static_cast<long>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  fill_zero_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<uint4*>(p), n16, static_cast<uint8_t*>(p) + n16 * 16, bytes - n16 * 16);
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;
 }
@@ -588,13 +671,13 @@ extern "C" int savqa_colsum_bf16(const void* x, int64_t ld, int64_t rows, int co
 int savqa::colsum_bf16(const void* x, int64_t ld, int64_t rows, int cols, float* out, cudaStream_t stream) {
   if (rows == 0 || cols == 0) return SAVQA_OK;
   SAVQA_REQUIRE(x && out && ld >= cols, "savqa_colsum_bf16: bad argument");
-  const int strips = (cols + 63) / 64;
-  long by = (rows + 63) / 64;
+  const int strips = (cols + 255) / 256;
+  long by = (rows + 31) / 32;  // >= 4 rows per warp
   const long cap = (static_cast<long>(sm_count()) * 4 + strips - 1) / strips;
   if (by > cap) by = cap;
   if (by < 1) by = 1;
-  colsum_bf16_kernel<<<dim3(strips, static_cast<unsigned>(by)), dim3(32, 8), 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, rows,
-                                                                                           cols, out);
+  const int vec = (ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
+  colsum_bf16_kernel<<<dim3(strips, static_cast<unsigned>(by)), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, cols, out, vec);
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;
 }

@@ -70,7 +70,8 @@ SIGNATURES = {
     "savqa_cast_bf16": [vp, i64, vp, i64, i64, C.c_int, C.c_int, vp],
     "savqa_cast_transpose_bf16": [vp, i64, vp, i64, i64, C.c_int, C.c_int, vp],
     "savqa_row_nonzero": [vp, i64, i64, C.c_int, vp, vp, i64, vp],
-    "savqa_relu_gate_bf16": [vp, C.c_int, i64, vp, i64, vp, i64, i64, C.c_int, vp],
+    "savqa_relu_gate_bf16": [vp, C.c_int, i64, vp, i64, vp, i64, i64, C.c_int, i64, i64, vp],
+    "savqa_fill_zero": [vp, i64, C.c_int, vp],
     "savqa_colsum_bf16": [vp, i64, i64, C.c_int, vp, vp],
     "savqa_residual_layernorm_fwd": [vp, vp, vp, vp, C.c_float, i64, C.c_int, vp, vp, vp, vp, vp, vp],
     "savqa_layernorm_bwd": [vp, vp, vp, C.c_float, i64, C.c_int, vp, vp, vp, vp, vp, vp, vp],

@@ -252,6 +252,19 @@ class NormSink:
 _NO_SINK = NormSink()
 
 
+def _grouped_rows(t: Tensor):
+    """A [B, R, W] slice of a larger row-major tensor (stride (S * W, W, 1), S >= R: what torch.cat's backward hands out) seen as the
+    2-D matrix it lives in: (matrix [(B - 1) S + R, W], R, S) for the kernels that address rows in equally spaced groups -- or None."""
+    if t.dim() != 3 or not t.is_cuda:
+        return None
+    B, R, W = t.shape
+    sb, sr, sw = t.stride()
+    if sw != 1 or sr != W or sb % W or sb < R * W or (t.data_ptr() % 16) or t.dtype not in (F32, BF16):
+        return None
+    S = sb // W
+    return torch.as_strided(t, ((B - 1) * S + R, W), (W, 1)), R, S
+
+
 def _as_bf16_rows(x: Tensor, M: int, K: int) -> Tensor:
     """[M, pad8(K)] bf16 staging of an activation (cast kernel for fp32, view for bf16)."""
     if x.dtype == BF16:
@@ -294,10 +307,13 @@ class LinearFn(Function):
         xb, act = ctx.saved_tensors
         pack: WeightPack = ctx.pack
         M, N, K = ctx.dims
-        dy2 = dy.reshape(M, N)
-        if not dy2.is_contiguous():
+        grp = _grouped_rows(dy) if (ctx.relu and not dy.is_contiguous()) else None
+        dy2 = dy.reshape(M, N) if grp is None else None
+        if dy2 is not None and not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        if ctx.relu:
+        if grp is not None:  # a slice of a concatenated gradient (the question rows of d x_in): gated where it lies, no copy first
+            dyb = ops.relu_gate_bf16(grp[0], act, group_rows=grp[1], group_stride=grp[2])
+        elif ctx.relu:
             dyb = ops.relu_gate_bf16(dy2, act)
         elif dy2.dtype == BF16:
             dyb = dy2
@@ -1028,7 +1044,13 @@ class MilNceFn(Function):
             return (None,) * 17
         d_nodes = dWi = dbi = None
         if d_out is not None:
-            dpre = ops.relu_gate_bf16(d_out.reshape(B * M, Fo).contiguous(), out)
+            # d_out usually is the node-row part of d x_in [B, T, 2048] (the symbolic branch concatenates the question rows behind
+            # the nodes, AttModel_x3.py:218-219): gate it where it lies instead of copying it out first
+            grp = _grouped_rows(d_out)
+            if grp is not None:
+                dpre = ops.relu_gate_bf16(grp[0], out, group_rows=grp[1], group_stride=grp[2])
+            else:
+                dpre = ops.relu_gate_bf16(d_out.reshape(B * M, Fo).contiguous(), out)
             dbi = pi.bias_grad_buffer(Fo, dev)
             dWi = pi.weight_grad(dpre, nodes, Fo, h, bias_grad=dbi)
             d_nodes = torch.empty(B * M, h, device=dev, dtype=F32)

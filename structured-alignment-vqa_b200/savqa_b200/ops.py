@@ -223,19 +223,32 @@ def row_nonzero(x: Tensor, want_bf16: bool = True):
     return on, xb
 
 
-def relu_gate_bf16(dy: Tensor, act: Tensor) -> Tensor:
-    """bf16 (act > 0 ? dy : 0); dy fp32 or bf16, act bf16 -- the staged A operand of dgrad / wgrad behind a ReLU."""
+def relu_gate_bf16(dy: Tensor, act: Tensor, group_rows: int = 0, group_stride: int = 0) -> Tensor:
+    """bf16 (act > 0 ? dy : 0); dy fp32 or bf16, act bf16 -- the staged A operand of dgrad / wgrad behind a ReLU.
+    group_rows > 0: dy is the [*, ld] matrix that holds the wanted rows in groups of `group_rows` every `group_stride` rows."""
     _check(act, BF16, "act")
     if dy.dtype not in (F32, BF16) or not dy.is_cuda:
         raise TypeError("savqa_b200: `dy` must be a CUDA fp32 or bf16 tensor")
-    rows, cols, ld = _rows2d(dy)
     arows, acols, ald = _rows2d(act)
+    if group_rows > 0:
+        assert dy.dim() == 2 and dy.stride(1) == 1
+        rows, cols, ld = arows, dy.shape[1], dy.stride(0)
+        assert rows % group_rows == 0 and dy.shape[0] >= (rows // group_rows - 1) * group_stride + group_rows
+    else:
+        rows, cols, ld = _rows2d(dy)
     assert arows == rows and acols >= cols
     out = torch.empty(rows, pad8(cols), device=dy.device, dtype=BF16)
     if pad8(cols) != cols:
         out.zero_()
-    call("savqa_relu_gate_bf16", ptr(dy), int(dy.dtype == F32), ld, ptr(act), ald, ptr(out), out.stride(0), rows, cols)
+    call("savqa_relu_gate_bf16", ptr(dy), int(dy.dtype == F32), ld, ptr(act), ald, ptr(out), out.stride(0), rows, cols, int(group_rows),
+         int(group_stride))
     return out
+
+
+def fill_zero(t: Tensor, max_blocks: int = 0) -> None:
+    """t.zero_() by a bounded number of persistent blocks (savqa_fill_zero): a background fill under other streams' kernels."""
+    assert t.is_cuda and t.is_contiguous()
+    call("savqa_fill_zero", ptr(t), t.numel() * t.element_size(), int(max_blocks))
 
 
 def colsum_bf16(x: Tensor, out: Tensor) -> None:

@@ -442,7 +442,7 @@ class EncoderTrainer:
                 self._zero_stream = torch.cuda.Stream()
             self._zero_stream.wait_stream(cur)
             with torch.cuda.stream(self._zero_stream):
-                self.flat_grad.zero_()
+                ops.fill_zero(self.flat_grad, max_blocks=96)  # a background trickle: does not hold the block scheduler (see the kernel)
                 self._zero_done = torch.cuda.Event()
                 self._zero_done.record(self._zero_stream)
         else:

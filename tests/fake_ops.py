@@ -132,7 +132,15 @@ def row_nonzero(x, want_bf16=True):
     return on, xb
 
 
-def relu_gate_bf16(dy, act):
+def fill_zero(t, max_blocks=0):
+    t.zero_()
+
+
+def relu_gate_bf16(dy, act, group_rows=0, group_stride=0):
+    if group_rows > 0:
+        rows = act.shape[0]
+        r = torch.arange(rows)
+        dy = dy[(r // group_rows) * group_stride + (r % group_rows)]
     rows, cols = dy.shape
     out = torch.zeros(rows, pad8(cols), dtype=BF16)
     out[:, :cols] = torch.where(act[:, :cols].float() > 0, dy.float(), torch.zeros(())).to(BF16)

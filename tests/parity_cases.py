@@ -294,7 +294,9 @@ def attention_direct_case(M, device, C, H, N, T, seed=0, p_edge=0.3):
     set_params(m, P0)
     m = m.to(device)
     xx = x.clone().to(device).requires_grad_(True)
-    y = m(xx, xx, xx, graph.to(device))
+    from savqa_b200 import ops as _ops
+    gd = _ops.attach_graph_bits(graph.to(device))  # a 0/1 graph as AttModel_x3's mask builder hands it over: with its bit-packed form
+    y = m(xx, xx, xx, gd)
     errs = {"y": check(f"{case}: output", y, ref["y"], emu["y"]), "y_att": check(f"{case}: output (return_att)", y_att, ref["y"], emu["y"]),
             "att": check(f"{case}: attention probabilities", att, ref["att"], emu["att"])}
     a4 = att.detach().cpu().view(H, N, T, T)

@@ -589,3 +589,14 @@ def test_gemm_rowln_plain_wide(ops):
     F.gemm_rowln(a, w, M, N, K, 0, bias=bias, relu=True, y=yr, y_bf16=ybr)
     ops.gemm_rowln(dev(a), dev(w), M, N, K, 0, bias=dev(bias), relu=True, y=yg, y_bf16=ybg)
     assert rel(yg, yr) < 2e-3 and rel(ybg.float(), ybr.float()) < 3e-3
+
+
+def test_layernorm_forward_statistics(ops):
+    """The optional {mean, sigma} output of savqa_residual_layernorm_fwd (what the fused dgrad + LayerNorm-backward epilogue reads)."""
+    for rows, C in ((37, 512), (19, 64)):
+        x, res = GS.randn(f"lnst/x{C}", rows, C), GS.randn(f"lnst/r{C}", rows, C)
+        gamma, beta = GS.rand(f"lnst/g{C}", C, lo=0.8, hi=1.2), GS.randn(f"lnst/b{C}", C)
+        stats = torch.zeros(rows, 2, device="cuda")
+        ops.layernorm_fwd(dev(x), dev(res), dev(gamma), dev(beta), 1e-8, True, True, True, stats=stats)
+        pre = x + res
+        assert rel(stats[:, 0], pre.mean(-1)) < 1e-5 and rel(stats[:, 1], pre.std(-1)) < 1e-5
