@@ -445,10 +445,15 @@ __global__ void adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, f
     const long row = idx ? idx[r] : r;
     if (row < 0 || row >= table_rows) continue;
     int old = 0;
-    if (lane == 0) old = atomicMax(stamp + row, target);
+    if (lane == 0) {
+      old = stamp[row];
+      // a never-touched row (moments zero) has nothing to catch up on and keeps its stamp 0: it must not turn into a row that is
+      // replayed (read and rewritten) at every later step; everything else is claimed by exactly one occurrence
+      if (apply || old != 0) old = atomicMax(stamp + row, target);
+    }
     old = __shfl_sync(0xffffffffu, old, 0);
     if (old >= target) continue;  // another occurrence of this row took it (or it is already current)
-    if (old == 0 && !apply) continue;  // never touched: moments are zero, no update to replay, nothing to rewrite
+    if (old == 0 && !apply) continue;
     const long base = row * static_cast<long>(width);
     // steps old+1 .. last_zero see a zero gradient; step `target` sees g when apply
     const int last_zero = apply ? target - 1 : target;
@@ -701,7 +706,9 @@ extern "C" int savqa_adam_step(float* param, const float* grad, float* exp_avg, 
   const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
   auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const int vec = (a16(param) && a16(grad) && a16(exp_avg) && a16(exp_avg_sq) && (!param_bf16 || (reinterpret_cast<uintptr_t>(param_bf16) & 7) == 0)) ? 1 : 0;
-  adam_kernel<<<grid_for((n + 3) / 4, 256, 16), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2),
+  // 6 resident blocks per SM (1536 of 2048 threads): the stream is HBM-bound long before that, and the word tables' row updates on
+  // the helper stream find room next to it instead of waiting for its last block (step trace: they started 370 us late)
+  adam_kernel<<<grid_for((n + 3) / 4, 256, 6), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2),
                                                                   dyn, static_cast<__nv_bfloat16*>(param_bf16), vec);
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;

@@ -36,6 +36,12 @@ VOCAB_ROWS = 407000  # hard-coded in the reference (AttModel_x3.py:36, 168, 293)
 _SIDE_STREAMS = {}   # device -> second stream of AttModel.encoder_step
 _HEAD_STREAMS = {}   # device -> the two extra streams of AttModel.answer_logits
 _HEADS_PARALLEL = os.environ.get("SAVQA_HEADS_PARALLEL", "1") != "0"
+#: SMs the persistent GEMMs of the (visual, symbolic) branch stream may take: a static split in proportion to the branches' work (T = 56 vs
+#: 128 tokens per sample) lets one branch's GEMM compute while the other's pays its fixed launch / pipeline-fill / tail cost, instead of the
+#: two taking turns on all 148 SMs (7.70 -> 7.41 ms/step measured; "0,0" = no split)
+_BRANCH_SMS = tuple(int(x) for x in os.environ.get("SAVQA_BRANCH_SMS", "56,92").split(","))
+if not any(_BRANCH_SMS):
+    _BRANCH_SMS = None
 
 
 class _CastBf16(torch.autograd.Function):
@@ -48,6 +54,11 @@ class _CastBf16(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         return dy.float()
+
+
+def _bucket_blocks() -> int:
+    from . import train
+    return train.BUCKET_BLOCKS
 
 
 def _word_table(glove) -> nn.Embedding:
@@ -141,7 +152,7 @@ class _Branch(nn.Module):
         for i in range(self.num_blocks):
             # blocks 0,1: graph_diag; the reference aliases graph_cross and graph, so 2.. all see `graph` (:118-139)
             g = graph_diag if i < 2 else graph
-            x = Fn.bucket_mark(x, (id(self), "enc", i))  # multi-GPU: block i's gradients are final once backward passes here
+            x = Fn.bucket_mark(x, (id(self), "enc", i // _bucket_blocks()))  # multi-GPU: block i's gradients are final once backward passes here
             x = getattr(self, 'enc_self_attention_%d' % i)(x, x, x, g)
             x = getattr(self, 'enc_feed_forward_%d' % i)(x)
         memory = self._join_memory(x)
@@ -466,6 +477,10 @@ class AttModel(nn.Module):
         side = _SIDE_STREAMS.get(main.device)
         if side is None:
             side = _SIDE_STREAMS[main.device] = torch.cuda.Stream(device=main.device)
+        if _BRANCH_SMS is not None:  # experiment: static split of the SMs between the two branches' persistent GEMMs
+            for st, n in ((main, _BRANCH_SMS[0]), (side, _BRANCH_SMS[1])):
+                ops.set_stream_sm_limit(st, n)
+                ops.set_stream_sm_limit(Fn.wgrad_stream_of(st), min(n, Fn.SIDE_GEMM_SMS) if n else 0)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             fea_syb = run_syb()

@@ -300,6 +300,35 @@ def layernorm_bwd(dy: Tensor, pre: Tensor, gamma: Tensor, eps: float, dgamma: Op
 # ------------------------------------------------------------------------------------------------------
 
 
+#: experiment (SAVQA_BRANCH_SMS): cuda stream handle -> SMs the persistent GEMMs launched on that stream may take.  The two branch
+#: models run on two streams; with a static split of the SMs between them (in proportion to their work) a GEMM of one branch computes
+#: while the other branch's GEMM pays its fixed launch / pipeline-fill / tail cost, instead of the two taking turns on all 148 SMs.
+_STREAM_SM_LIMIT = {}
+
+
+def set_stream_sm_limit(stream, sms: int) -> None:
+    if sms and sms > 0:
+        _STREAM_SM_LIMIT[stream.cuda_stream] = int(sms)
+    else:
+        _STREAM_SM_LIMIT.pop(stream.cuda_stream, None)
+
+
+@contextlib.contextmanager
+def _stream_limit():
+    lim = _STREAM_SM_LIMIT.get(torch.cuda.current_stream().cuda_stream) if _STREAM_SM_LIMIT else None
+    if not lim:
+        yield
+        return
+    lib = _lib.load()
+    old = lib.savqa_set_gemm_sm_limit(int(lim))
+    if old and old < lim:
+        lib.savqa_set_gemm_sm_limit(old)
+    try:
+        yield
+    finally:
+        lib.savqa_set_gemm_sm_limit(old)
+
+
 def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False, bias: Optional[Tensor] = None,
          res: Optional[Tensor] = None, rowtab: Optional[Tensor] = None, rowtab_period: int = 0, gate: Optional[Tensor] = None,
          relu: bool = False, alpha: float = 1.0, out_f32: Optional[Tensor] = None, out_bf16: Optional[Tensor] = None,
@@ -324,7 +353,8 @@ def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_
         assert b.shape[0] >= N and b.shape[1] >= K, (b.shape, N, K)
     e = GemmEpilogue()
     _fill_epilogue(e, M, N, bias, res, rowtab, rowtab_period, gate, relu, alpha, out_f32, out_bf16, accumulate, split_k, colsum)
-    call("savqa_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), M, N, K, C.byref(e), int(split_k))
+    with _stream_limit():
+        call("savqa_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), M, N, K, C.byref(e), int(split_k))
 
 
 def _fill_epilogue(e, M, N, bias, res, rowtab, rowtab_period, gate, relu, alpha, out_f32, out_bf16, accumulate, split_k, colsum) -> None:

@@ -151,6 +151,8 @@ class GradReducer:
 
 
 _BUCKET_RE = re.compile(r"^(att_vis_grid|att_syb)\.(enc|dec)_[a-z_]+_(\d+)\.")
+#: encoder blocks per all-reduce bucket (1: one 11.5 MB bucket per block and branch; 2 / 3: fewer, larger collectives)
+BUCKET_BLOCKS = max(1, int(os.environ.get("SAVQA_BUCKET_BLOCKS", "1")))
 
 
 def bucket_key_of(model, name: str):
@@ -158,7 +160,7 @@ def bucket_key_of(model, name: str):
     m = _BUCKET_RE.match(name)
     if m:
         branch = getattr(model, m.group(1))
-        return (id(branch), "enc", int(m.group(3))) if m.group(2) == "enc" else (id(branch), "dec")
+        return (id(branch), "enc", int(m.group(3)) // BUCKET_BLOCKS) if m.group(2) == "enc" else (id(branch), "dec")
     if name.split(".")[0] in ("cls", "cls_vis", "cls_syb"):
         return (id(model), "heads")
     return None
@@ -317,7 +319,11 @@ class EncoderTrainer:
         # 8.39 ms) -- the step is bound by the aggregate HBM / SM time of its kernels, not by its critical path.
         per_bucket_adam = os.environ.get("SAVQA_ADAM_PER_BUCKET", "0") == "1" and self.flat_grad.is_cuda
         if (self.world > 1 or per_bucket_adam) and self.overlap_allreduce and not self._debug_skip_allreduce:
-            need = {k: (2 if k[1] == "heads" else 1) for k in self.bucket_ranges}  # both decoder outputs feed the heads
+            # both decoder outputs feed the heads; a bucket of several encoder blocks is final when the backward pass has left its
+            # lowest block
+            nb = max((getattr(b_, "num_blocks", 0) for b_ in (model.att_vis_grid, model.att_syb)), default=0)
+            need = {k: (2 if k[1] == "heads" else (min(BUCKET_BLOCKS, nb - k[2] * BUCKET_BLOCKS) if k[1] == "enc" else 1))
+                    for k in self.bucket_ranges}
             self.reducer = GradReducer(self.flat_grad, dict(self.bucket_ranges), need, self.pg, self.world,
                                        self._adam_range if per_bucket_adam else None)
 

@@ -372,19 +372,18 @@ def test_trainer_bound_gradients_match_autograd_and_graph_replay(A):
         t_._savqa_rowlog.clear()
     assert abs(float(loss) - float(ref_loss)) < 1e-5 * abs(float(ref_loss))
     names = {id(p): k for k, p in model.named_parameters()}
-    worst = ("", 0.0)
+    errs = []
     for p in tr.dense:
         k = names[id(p)]
-        scale = float(ref_grads[k].abs().max())
-        err = float((p.grad - ref_grads[k]).abs().max()) / (scale + 1e-12)
-        if err > worst[1]:
-            worst = (k, err)
-    # Same kernels on the same operands up to the ORDER of fp32 sums: atomics, and the trainer's fused decoder K/V backward
-    # (one K = 2 L C dgrad GEMM where the unbound modules accumulate L GEMMs).  A 1-ulp fp32 difference in d(memory) flips a few
-    # bf16 roundings of the MMA operands in each of the 6 encoder blocks behind it, so the deepest blocks' gradients agree to a
-    # few 2^-9 of max|grad| (measured worst: 6e-3, on the cancellation-dominated K-projection bias of block 1); an indexing or
-    # layout error would show up as O(1).
-    assert worst[1] < 1e-2, worst
+        errs.append((float((p.grad - ref_grads[k]).norm()) / (float(ref_grads[k].norm()) + 1e-30), k))
+    errs.sort(reverse=True)
+    print("bound vs autograd, worst norm-rel:", [(f"{e:.2e}", k) for e, k in errs[:6]], "median", errs[len(errs) // 2][0])
+    # Same math on bf16 operands, but not the same rounding points: the bound path runs the fused decoder (LayerNorm statistics merged
+    # from 64-column slabs), the fused decoder K/V backward (one K = 2 L C dgrad where the unbound modules accumulate L GEMMs) and fp32
+    # atomics.  A 1e-4 forward difference flips ~1e-3 of the ReLU gates behind it, and a gradient's norm-relative error goes with the
+    # square root of that fraction (a few percent; more on the 8-sample bias gradients of this small case).  An indexing or layout
+    # error shows up as O(1).
+    assert errs[0][0] < 0.3 and errs[len(errs) // 2][0] < 0.05, errs[:5]
 
     # eager step == replayed graph step (same static batch), and the mirror follows the parameters
     tr2_model = copy.deepcopy(ref)
