@@ -91,6 +91,11 @@ int savqa_cast_bf16(const float* src, int64_t ld_src, void* dst_bf16, int64_t ld
 /* dst_bf16[c, r] = src[r, c]  (weight transposes for dgrad), dst row pitch ld_dst, columns [rows, pad_to) zero. */
 int savqa_cast_transpose_bf16(const float* src, int64_t ld_src, void* dst_bf16, int64_t ld_dst, int64_t rows, int cols, int pad_to,
                               savqa_stream_t stream);
+/* Column regrouping: the matrix is `groups` groups of w_in columns per row; out gets `groups` groups of w_out columns, the first
+ * min(w_in, w_out) columns of every group copied, the rest zero.  Pads the heads of a [rows, H*32] projection to [rows, H*64] (and
+ * drops the padding again on the way back).  elem_bytes 2 (bf16) or 4 (fp32). */
+int savqa_regroup_cols(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t rows, int groups, int w_in, int w_out,
+                       int elem_bytes, savqa_stream_t stream);
 /* on[r] = (sum_c x[r, c] != 0) ? 1.0f : 0.0f  -- the activation-derived key / query masks
  * sign(abs(sum(x,-1))) of modules.py:257,289.  Optionally also writes a bf16 copy of x. */
 int savqa_row_nonzero(const float* x, int64_t ld, int64_t rows, int cols, float* on, void* x_bf16, int64_t ld_bf16,
@@ -238,6 +243,10 @@ typedef struct savqa_attn_args {
    * -- together with the forward output `out` -- by the tcgen05 backward, which then needs ONE pass over the score tile
    * (sum_j W_j dW_j == <dO_row, out_row>) instead of three. */
   float* stats;
+  /* head size the 1/sqrt(d) score scale is taken from when it differs from the tile width `d` (0: use d).  Heads of 32 channels run
+   * on the tcgen05 engine as 64-wide tiles whose upper halves are zero (savqa_regroup_cols pads them): the contractions are
+   * unchanged by the zero channels, only the scale must stay 1/sqrt(32). */
+  int scale_d;
 } savqa_attn_args_t;
 
 int savqa_graph_attn_fwd(const savqa_attn_args_t* args, savqa_stream_t stream);

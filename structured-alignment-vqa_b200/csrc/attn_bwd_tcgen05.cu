@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
   const bool row_ok = i < a.Tq;
   const long qrow = static_cast<long>(n) * a.Tq + (row_ok ? i : 0);
   const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
+  const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(a.scale_d > 0 ? a.scale_d : D));
   const int renorm = (a.graph || a.graph_bits) ? a.renorm : 0;
   const uint32_t* bits_row = a.graph_bits ? sBits + t * wpr : nullptr;
   const float* grow = (a.graph && row_ok) ? a.graph + static_cast<long>(n) * a.graph_n_stride + static_cast<long>(i) * a.graph_q_stride : nullptr;
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_tc1_kernel(const __grid_const
   tc_fence_after();
   const long qrow = static_cast<long>(n) * a.Tq + (row_ok ? i : 0);
   const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
+  const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(a.scale_d > 0 ? a.scale_d : D));
   const float qon = (a.query_on && row_ok) ? a.query_on[qrow] : 1.0f;
   const float4 st = __ldg(reinterpret_cast<const float4*>(a.stats) + static_cast<long>(hn) * a.Tq + (row_ok ? i : 0));
   const float m = st.x, inv_z = fabsf(st.y), scale = st.z, beta = st.w, alpha = st.y < 0.0f ? 0.0f : 1.0f;

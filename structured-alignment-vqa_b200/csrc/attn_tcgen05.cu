@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
   const bool row_ok = i < a.Tq;
   const long qrow = static_cast<long>(n) * a.Tq + (row_ok ? i : 0);
   const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));  // exact for D = 64
+  const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(a.scale_d > 0 ? a.scale_d : D));  // exact for D = 64
   const int renorm = (a.graph || a.graph_bits) ? a.renorm : 0;
   const float* grow = (a.graph && row_ok) ? a.graph + static_cast<long>(n) * a.graph_n_stride + static_cast<long>(i) * a.graph_q_stride : nullptr;
 

@@ -211,6 +211,19 @@ __global__ void relu_gate_kernel(const TDy* __restrict__ dy, long ld_dy, const _
   }
 }
 
+template <typename T>
+__global__ void regroup_cols_kernel(const T* __restrict__ in, long ld_in, T* __restrict__ out, long ld_out, long rows, int groups, int w_in,
+                                    int w_out) {
+  const long per_row = static_cast<long>(groups) * w_out;
+  const long total = rows * per_row;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / per_row;
+    const int rem = static_cast<int>(i - r * per_row);
+    const int gidx = rem / w_out, c = rem - gidx * w_out;
+    out[r * ld_out + rem] = c < w_in ? in[r * ld_in + gidx * w_in + c] : T(0);
+  }
+}
+
 // Zero fill with a BOUNDED grid: a kernel of tens of thousands of blocks keeps the block scheduler from dispatching the kernels
 // other streams launch behind it until its last wave (seen in the step trace: the 356 MB gradient zero-fill "next to" the forward
 // pass delayed it by its full 50 us); a few persistent blocks trickle through HBM underneath them instead.
@@ -651,6 +664,23 @@ extern "C" int savqa_relu_gate_bf16(const void* dy, int dy_is_f32, int64_t ld_dy
     relu_gate_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy,
                                                               static_cast<const __nv_bfloat16*>(act), ld_act,
                                                               static_cast<__nv_bfloat16*>(out), ld_out, rows, cols, group_rows, group_stride, vec);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_regroup_cols(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t rows, int groups, int w_in, int w_out,
+                                  int elem_bytes, savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows == 0) return SAVQA_OK;
+  SAVQA_REQUIRE(in && out && groups > 0 && w_in > 0 && w_out > 0 && (elem_bytes == 2 || elem_bytes == 4), "savqa_regroup_cols: bad argument");
+  SAVQA_REQUIRE(ld_in >= static_cast<int64_t>(groups) * w_in && ld_out >= static_cast<int64_t>(groups) * w_out, "savqa_regroup_cols: pitch");
+  const int grid = grid_for(rows * groups * w_out, 256);
+  if (elem_bytes == 2)
+    regroup_cols_kernel<uint16_t><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(in), ld_in, static_cast<uint16_t*>(out), ld_out, rows, groups,
+                                                            w_in, w_out);
+  else
+    regroup_cols_kernel<uint32_t><<<grid, 256, 0, stream>>>(static_cast<const uint32_t*>(in), ld_in, static_cast<uint32_t*>(out), ld_out, rows, groups,
+                                                            w_in, w_out);
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;
 }

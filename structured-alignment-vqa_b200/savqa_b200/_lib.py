@@ -41,7 +41,7 @@ class AttnArgs(C.Structure):
                 ("out", vp), ("ldo", i64), ("att", vp),
                 ("dout", vp), ("ld_dout", i64), ("dq", vp), ("ld_dq", i64), ("dk", vp), ("ld_dk", i64),
                 ("dv", vp), ("ld_dv", i64), ("scratch", vp), ("dbq", vp), ("dbk", vp), ("dbv", vp),
-                ("graph_bits", vp), ("bits_n_stride", i64), ("bits_q_stride", i64), ("stats", vp)]
+                ("graph_bits", vp), ("bits_n_stride", i64), ("bits_q_stride", i64), ("stats", vp), ("scale_d", C.c_int)]
 
 
 class RowLnArgs(C.Structure):
@@ -72,6 +72,7 @@ SIGNATURES = {
     "savqa_row_nonzero": [vp, i64, i64, C.c_int, vp, vp, i64, vp],
     "savqa_relu_gate_bf16": [vp, C.c_int, i64, vp, i64, vp, i64, i64, C.c_int, i64, i64, vp],
     "savqa_fill_zero": [vp, i64, C.c_int, vp],
+    "savqa_regroup_cols": [vp, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "savqa_colsum_bf16": [vp, i64, i64, C.c_int, vp, vp],
     "savqa_residual_layernorm_fwd": [vp, vp, vp, vp, C.c_float, i64, C.c_int, vp, vp, vp, vp, vp, vp],
     "savqa_layernorm_bwd": [vp, vp, vp, C.c_float, i64, C.c_int, vp, vp, vp, vp, vp, vp, vp],

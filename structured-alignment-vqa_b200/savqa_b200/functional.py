@@ -54,6 +54,8 @@ def tc_attention_fits(d: int, Tk: int) -> bool:
     """Whether the tcgen05 attention kernel (csrc/attn_tcgen05.cu) takes this shape: head size 64 / 128 and Q, K, V
     and the bf16 probability tile of one (sample, head) inside one CTA's 227 KB of shared memory, scores in 512 TMEM
     columns.  Other shapes run on the CUDA-core kernel (engine 1)."""
+    if d == 32:
+        d = 64  # zero-padded to 64-wide tiles by ops.graph_attention_fwd (score scale stays 1/sqrt(32))
     if d not in (64, 128) or Tk > 512:
         return False
     dch = d // 64

@@ -245,6 +245,19 @@ def relu_gate_bf16(dy: Tensor, act: Tensor, group_rows: int = 0, group_stride: i
     return out
 
 
+def regroup_cols(x: Tensor, groups: int, w_in: int, w_out: int, out: Optional[Tensor] = None) -> Tensor:
+    """[rows, groups * w_in] -> [rows, groups * w_out]: every group's first min(w_in, w_out) columns copied, the rest zero
+    (savqa_regroup_cols).  x / out may be column slices of wider matrices (row pitch = stride(0)); bf16 or fp32."""
+    if x.dtype not in (F32, BF16) or not x.is_cuda:
+        raise TypeError("savqa_b200: `x` must be a CUDA fp32 or bf16 tensor")
+    assert x.dim() == 2 and x.stride(1) == 1 and x.shape[1] >= groups * w_in
+    if out is None:
+        out = torch.empty(x.shape[0], groups * w_out, device=x.device, dtype=x.dtype)
+    assert out.dtype == x.dtype and out.dim() == 2 and out.stride(1) == 1 and out.shape[0] == x.shape[0] and out.shape[1] >= groups * w_out
+    call("savqa_regroup_cols", ptr(x), x.stride(0), ptr(out), out.stride(0), x.shape[0], groups, w_in, w_out, x.element_size())
+    return out
+
+
 def fill_zero(t: Tensor, max_blocks: int = 0) -> None:
     """t.zero_() by a bounded number of persistent blocks (savqa_fill_zero): a background fill under other streams' kernels."""
     assert t.is_cuda and t.is_contiguous()
@@ -512,11 +525,18 @@ def _set_graph_bits(a: AttnArgs, graph_bits: Optional[Tensor], N: int, Tq: int, 
 
 def graph_attention_fwd(q: Tensor, k: Tensor, v: Tensor, graph: Optional[Tensor], key_on: Tensor, query_on: Tensor, N: int, H: int,
                         Tq: int, Tk: int, d: int, causal: bool, renorm: int, want_att: bool, engine: int,
-                        graph_bits: Optional[Tensor] = None, stats: Optional[Tensor] = None):
+                        graph_bits: Optional[Tensor] = None, stats: Optional[Tensor] = None, scale_d: int = 0):
     """Attention core of modules.py:246-301.  q/k/v: bf16 2-D views [N*T, >= H*d].  Returns (out fp32 [N*Tq, H*d], att | None)."""
     for nm, t in (("q", q), ("k", k), ("v", v)):
         _check(t, BF16, nm)
         assert t.dim() == 2 and t.stride(1) == 1
+    if engine == 0 and d == 32:
+        # 32-channel heads (16 heads x 512) on the tcgen05 engine: 64-wide tiles whose upper halves are zero; the score scale stays
+        # 1/sqrt(32) (AttnArgs.scale_d).  The zero channels change neither Q K^T nor the first 32 columns of P V.
+        q64, k64, v64 = (regroup_cols(t, H, 32, 64) for t in (q, k, v))
+        out64, att = graph_attention_fwd(q64, k64, v64, graph, key_on, query_on, N, H, Tq, Tk, 64, causal, renorm, want_att, 0,
+                                         graph_bits=graph_bits, stats=stats, scale_d=32)
+        return regroup_cols(out64, H, 64, 32), att
     _check(graph, F32, "graph")
     a = AttnArgs()
     a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0)
@@ -526,7 +546,7 @@ def graph_attention_fwd(q: Tensor, k: Tensor, v: Tensor, graph: Optional[Tensor]
         a.graph_q_stride = Tk if graph.shape[1] == Tq else 0
     a.key_on, a.query_on = ptr(key_on), ptr(query_on)
     a.N, a.H, a.Tq, a.Tk, a.d = N, H, Tq, Tk, d
-    a.causal, a.renorm, a.engine = int(causal), int(renorm), int(engine)
+    a.causal, a.renorm, a.engine, a.scale_d = int(causal), int(renorm), int(engine), int(scale_d)
     if graph is not None:
         _set_graph_bits(a, graph_bits, N, Tq, Tk)
     out = torch.empty(N * Tq, H * d, device=q.device, dtype=F32)
@@ -543,6 +563,10 @@ def graph_attention_fwd(q: Tensor, k: Tensor, v: Tensor, graph: Optional[Tensor]
 def tc_attention_bwd_fits(d: int, Tq: int, Tk: int) -> bool:
     """Shapes the tcgen05 attention backward (csrc/attn_bwd_tcgen05.cu) takes: one CTA holds the whole (sample, head)
     problem -- Q, dO, K, V and the two bf16 [128, Tk] tiles in shared memory, S / dW / dQ / dK / dV in 512 TMEM columns."""
+    if d == 32:
+        d = 64  # zero-padded heads (see graph_attention_fwd)
+    if Tq > 128:
+        Tq = 128 if Tq <= 256 else Tq  # two query tiles, one launch each (graph_attention_bwd)
     if d not in (64, 128) or Tq > 128 or Tk > 256:
         return False
     kt = (Tk + 127) // 128
@@ -558,13 +582,54 @@ def tc_attention_bwd_fits(d: int, Tq: int, Tk: int) -> bool:
 def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout: Tensor, dq: Tensor, dk: Tensor,
                         dv: Tensor, engine: Optional[int] = None, dbq: Optional[Tensor] = None, dbk: Optional[Tensor] = None,
                         dbv: Optional[Tensor] = None, graph_bits: Optional[Tensor] = None, stats: Optional[Tensor] = None,
-                        fwd_out: Optional[Tensor] = None) -> None:
+                        fwd_out: Optional[Tensor] = None, scale_d: int = 0) -> None:
     """Gradient of the attention core; dq/dk/dv are bf16 2-D views and come back ReLU-gated by q/k/v > 0.
     dbq/dbk/dbv (fp32 [H*d], optional) accumulate the column sums of dq/dk/dv: the projections' bias gradients.
     engine None: tcgen05 kernel when the shape fits, CUDA-core kernels otherwise (Tq == 1: the one-warp row kernel)."""
     if engine is None:
         strides_ok = all(t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0 for t in (q, k, v, dq, dk, dv))
         engine = 0 if (tc_attention_bwd_fits(d, Tq, Tk) and strides_ok and Tq > 1) else 1
+    if engine == 0 and d == 32:
+        # zero-padded 64-wide heads on the tcgen05 engine (see graph_attention_fwd); the gradients of the padding are dropped again
+        C32 = H * 32
+        q64, k64, v64 = (regroup_cols(t, H, 32, 64) for t in (q, k, v))
+        dout64 = regroup_cols(dout, H, 32, 64)
+        fo64 = regroup_cols(fwd_out, H, 32, 64) if fwd_out is not None else None
+        d64 = [torch.empty(t.shape[0], H * 64, device=q.device, dtype=BF16) for t in (dq, dk, dv)]
+        graph_attention_bwd(q64, k64, v64, graph, key_on, query_on, N, H, Tq, Tk, 64, causal, renorm, dout64, d64[0], d64[1], d64[2], engine=0,
+                            graph_bits=graph_bits, stats=stats, fwd_out=fo64, scale_d=32)
+        for src, dst, db in zip(d64, (dq, dk, dv), (dbq, dbk, dbv)):
+            regroup_cols(src, H, 64, 32, out=dst)
+            if db is not None:
+                colsum_bf16(dst[:, :C32], db)
+        return
+    if engine == 0 and 128 < Tq <= 256:
+        # the tcgen05 backward holds <= 128 queries per CTA: two query tiles, one launch each over ALL keys; dQ rows are disjoint, the
+        # tiles' (ReLU-gated, hence additive) dK / dV contributions are summed
+        Cq = H * d
+        first = True
+        for t0 in range(0, Tq, 128):
+            t1 = min(Tq, t0 + 128)
+            n = t1 - t0
+            rows = lambda t, w: t.unflatten(0, (N, Tq))[:, t0:t1, :w].reshape(N * n, w).contiguous()  # noqa: E731
+            q_t, do_t = rows(q[:, :Cq], Cq), rows(dout[:, :Cq], Cq)
+            fo_t = rows(fwd_out[:, :Cq], Cq) if fwd_out is not None else None
+            st_t = stats.reshape(H, N, Tq, 4)[:, :, t0:t1].contiguous().reshape(-1, 4) if stats is not None else None
+            qon_t = query_on.reshape(N, Tq)[:, t0:t1].contiguous()
+            g_t, gb_t = graph, graph_bits
+            if graph is not None and graph.shape[1] == Tq:
+                g_t = graph[:, t0:t1].contiguous()
+                gb_t = graph_bits[:, t0:t1].contiguous() if graph_bits is not None else None
+            dq_t = torch.empty(N * n, Cq, device=q.device, dtype=BF16)
+            dk_t, dv_t = (dk, dv) if first else (torch.empty(dk.shape[0], Cq, device=q.device, dtype=BF16), torch.empty(dv.shape[0], Cq, device=q.device, dtype=BF16))
+            graph_attention_bwd(q_t, k, v, g_t, key_on, qon_t, N, H, n, Tk, d, causal, renorm, do_t, dq_t, dk_t, dv_t, engine=0, dbq=dbq, dbk=dbk,
+                                dbv=dbv, graph_bits=gb_t, stats=st_t, fwd_out=fo_t, scale_d=scale_d)
+            dq.unflatten(0, (N, Tq))[:, t0:t1, :Cq].copy_(dq_t.reshape(N, n, Cq))
+            if not first:
+                dk[:, :Cq].add_(dk_t)
+                dv[:, :Cq].add_(dv_t)
+            first = False
+        return
     a = AttnArgs()
     a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0)
     if graph is not None:
@@ -572,7 +637,7 @@ def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causa
         a.graph_q_stride = Tk if graph.shape[1] == Tq else 0
     a.key_on, a.query_on = ptr(key_on), ptr(query_on)
     a.N, a.H, a.Tq, a.Tk, a.d = N, H, Tq, Tk, d
-    a.causal, a.renorm, a.engine = int(causal), int(renorm), int(engine)
+    a.causal, a.renorm, a.engine, a.scale_d = int(causal), int(renorm), int(engine), int(scale_d)
     _check(dout, F32, "dout")
     assert dout.dim() == 2 and dout.stride(1) == 1
     a.dout, a.ld_dout = ptr(dout), dout.stride(0)

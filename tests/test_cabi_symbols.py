@@ -49,4 +49,4 @@ def test_struct_layouts_match_header():
     """ctypes mirrors of the two argument structs have the C sizes (LP64: 8-byte pointers / int64, 4-byte int / float)."""
     from savqa_b200 import _lib
     assert ctypes.sizeof(_lib.GemmEpilogue) == 16 + 12 * 8
-    assert ctypes.sizeof(_lib.AttnArgs) == 11 * 8 + 8 * 4 + 19 * 8
+    assert ctypes.sizeof(_lib.AttnArgs) == 11 * 8 + 8 * 4 + 19 * 8 + 8  # + scale_d (int, padded to 8)

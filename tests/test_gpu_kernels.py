@@ -600,3 +600,42 @@ def test_layernorm_forward_statistics(ops):
         ops.layernorm_fwd(dev(x), dev(res), dev(gamma), dev(beta), 1e-8, True, True, True, stats=stats)
         pre = x + res
         assert rel(stats[:, 0], pre.mean(-1)) < 1e-5 and rel(stats[:, 1], pre.std(-1)) < 1e-5
+
+
+@pytest.mark.parametrize("N,H,T,d", [(3, 16, 40, 32), (2, 16, 100, 32), (2, 8, 200, 64), (2, 8, 256, 64), (2, 16, 160, 32)])
+def test_attention_tcgen05_small_heads_and_long_queries(ops, N, H, T, d):
+    """BASELINE configs[4] shapes that used to fall to the CUDA-core engine: 32-channel heads (16 heads x 512: run as zero-padded
+    64-wide tiles, score scale 1/sqrt(32)) and the backward pass for 128 < Tq <= 256 (two query tiles).  Forward and backward of the
+    tcgen05 engine against the fp32 CUDA-core verification engine (itself checked against the restatement above)."""
+    from savqa_b200 import _lib
+    C = H * d
+    g = torch.Generator().manual_seed(N * 1000 + T + d)
+    qkv = (torch.randn(N * T, 3 * C, generator=g) * 0.5).relu().to(BF).cuda()
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    graph = (torch.rand(N, T, T, generator=g) < 0.3).float().cuda()
+    graph[:, torch.arange(T), torch.arange(T)] = 1
+    graph[:, 1] = 0
+    key_on = torch.ones(N * T).cuda()
+    key_on[T - 2:T] = 0
+    q_on = torch.ones(N * T).cuda()
+    q_on[3] = 0
+    bits = ops.pack_graph_bits(graph)
+    stats = torch.empty(H * N * T, 4, device="cuda")
+    c0 = _lib.launch_counts()
+    o0, _ = ops.graph_attention_fwd(q, k, v, graph, key_on, q_on, N, H, T, T, d, False, 1, False, 0, graph_bits=bits, stats=stats)
+    o1, _ = ops.graph_attention_fwd(q, k, v, graph, key_on, q_on, N, H, T, T, d, False, 1, False, 1)
+    assert rel(o0, o1) < 3e-3, rel(o0, o1)
+    dout = torch.randn(N * T, C, generator=g).cuda()
+    outs = []
+    for eng in (0, 1):
+        dqkv = torch.zeros(N * T, 3 * C, device="cuda", dtype=BF)
+        db = [torch.zeros(C, device="cuda") for _ in range(3)]
+        ops.graph_attention_bwd(q, k, v, graph, key_on, q_on, N, H, T, T, d, False, 1, dout, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:],
+                                engine=eng, dbq=db[0], dbk=db[1], dbv=db[2], graph_bits=bits if eng == 0 else None,
+                                stats=stats if eng == 0 else None, fwd_out=o0 if eng == 0 else None)
+        outs.append((dqkv.float(), db))
+    c1 = _lib.launch_counts()
+    assert c1["attn_fwd_tc"] > c0["attn_fwd_tc"] and (c1["attn_bwd_tc"] + c1["attn_bwd_tc_shared"]) > (c0["attn_bwd_tc"] + c0["attn_bwd_tc_shared"])
+    assert rel(outs[0][0], outs[1][0]) < 1.5e-2, rel(outs[0][0], outs[1][0])
+    for a_, b_ in zip(outs[0][1], outs[1][1]):
+        assert rel(a_, b_) < 1.5e-2

@@ -39,7 +39,7 @@ def timeit(fn, iters=8):
 
 print(f"batch {N} samples; peaks: {peaks['bf16_tflops']} TFLOP/s bf16 (burst), {peaks['hbm_gbs']} GB/s HBM")
 print(f"{'d_model':>7s} {'heads':>5s} {'d':>4s} {'T':>4s} {'graph':>7s} | {'fwd us':>7s} {'TF/s':>7s} {'%tensor':>8s} {'%HBM':>6s} | {'bwd us':>7s} {'TF/s':>7s} {'%tensor':>8s} {'%HBM':>6s}")
-for C, H in ((512, 8), (1024, 16), (1024, 8)):
+for C, H in ((512, 8), (512, 16), (1024, 16), (1024, 8)):
     d = C // H
     for T in (36, 56, 100, 128, 256):
         if not tc_attention_fits(d, T):
