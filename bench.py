@@ -307,7 +307,7 @@ def train_config(args, world):
             "encoder": "encoder step with MIL_NCE's output `syb_ipt` [B,M,2048] fp32 shipped from the host (round-1 workload)"}[args.step]
     return {"workload": f"configs[2]/[3]: AttModel_x3 training step -- {what}; GQA-shaped synthetic batch, V=36 regions + Q=20 tokens (T=56) "
                         "visual branch, M=108 nodes + Q=20 (T=128) symbolic branch, hidden 512, 8 heads, 6+6 blocks, hidden_size_mil 64, "
-                        "topN 1, 1845 classes, decMask=True, dropout 0",
+                        f"topN 1, 1845 classes, decMask=True, dropout {args.dropout:g}",
             "step": args.step,
             "per_gpu_batch": args.batch, "global_batch": args.batch * max(world, 1), "parallelism": f"dp{max(world, 1)}",
             "l2": "activations per step (~2 GB) exceed the 126 MB L2; no explicit flush",
@@ -321,7 +321,7 @@ def run_training(args, rank, world, local_rank, dev, peaks, sampler, dense_table
     import torch.distributed as dist
     from savqa_b200 import synthetic, train
     cfg = synthetic.GQA_SHAPED
-    model = synthetic.build_model(cfg, seed=0).to(dev)
+    model = synthetic.build_model(cfg, seed=0, dropout=args.dropout).to(dev)
     model.train()
     from savqa_b200 import collate
     keys = {"encoder": train.STEP_KEYS, "full": train.FULL_KEYS, "compact": train.COMPACT_KEYS}[args.step]
@@ -513,6 +513,7 @@ def main():
     ap.add_argument("--step", default="compact", choices=["compact", "full", "encoder"],
                     help="compact: whole step (MIL_NCE included) from the compact loader hand-off; full: same from collate_fn's dense batch; "
                          "encoder: round-1 workload (syb_ipt shipped from the host)")
+    ap.add_argument("--dropout", type=float, default=0.0, help="dropout_rate of the model (the launcher's production value is 0.5, submit.py:72-104)")
     ap.add_argument("--dense-tables", action="store_true", help="word tables in the dense flat buffers: dense gradients + dense Adam")
     ap.add_argument("--stock-dtype", default="both", choices=["fp32", "bf16", "both"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

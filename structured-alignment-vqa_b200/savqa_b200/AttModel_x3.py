@@ -182,8 +182,7 @@ class _Branch(nn.Module):
             return False
         if not dec.is_cuda and not getattr(ops.gemm_rowln, "__module__", "").endswith("fake_ops"):
             return False
-        if self.training and (self.dec_dropout.p > 0):
-            return False
+        # (dec_dropout acts on the start token BEFORE the decoder stack, AttModel_x3.py:147: it does not stand in the way of the fusion)
         ff0 = self.dec_feed_forward_0
         if ff0.num_units[0] % 64 or ff0.num_units[1] != C:
             return False

@@ -35,7 +35,7 @@ def forward_batch(model: A.AttModel, b: Dict[str, torch.Tensor], dec_mask: bool 
         lc, lv, ls, mil_obj, _ = model.forward_compact(b, decMask=dec_mask)
         return lc, lv, ls, mil_obj
     if full is None:
-        full = "syb_ipt" not in b
+        full = "micro_positive_obj_ipt" in b  # MIL_NCE's inputs are there: the reference's whole forward
     if full:
         e = b.get("micro_positive_rel_ipt")
         if e is None:

@@ -181,3 +181,30 @@ def test_compact_hand_off_equals_dense(monkeypatch):
     bad["vis_fea_mask"][0, 0, 1] = 0
     with pytest.raises(ValueError):
         collate.compact_batch(bad)
+
+
+def test_evaluate_loop_matches_reference_eval(monkeypatch):
+    """infer.evaluate == the reference's eval() for --model_v 3 (main_itp_ddp_tar_super_node.py:60-142): batch-size-weighted mean of the
+    label-smoothed 3-head loss (+ the MIL-NCE term), accuracy over the samples whose answer id is not 0 -- here against the oracle's
+    full_step on the same batches, from collate_fn's dense batches and from the compact hand-off."""
+    fake_ops.install(monkeypatch)
+    from savqa_b200 import collate, infer, synthetic
+    cfg = synthetic.TINY
+    model = synthetic.build_model(cfg, vocab_rows=1200)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    dense = [collate.expand_batch(collate.compact_batch(synthetic.make_batch(cfg, n, seed=40 + n, vocab_rows=1200))) for n in (4, 6)]
+    dense[0]["answer"][0] = 0  # never counted as correct (main...:125)
+    tot = cnt = correct = 0.0
+    for b in dense:
+        with torch.no_grad():
+            loss, logits, obj, _ = O.full_step(sd, b, cfg["blocks"], cfg["heads"], with_milnce_loss=True)
+        lsm = sum(torch.log_softmax(l, -1) for l in logits) / 3
+        pred = lsm.argmax(1)
+        n = b["answer"].shape[0]
+        tot += float(loss) * n
+        cnt += n
+        correct += float(((pred == b["answer"]) & (b["answer"] != 0)).sum())
+    for batches in (dense, [collate.compact_batch(b) for b in dense]):
+        loss, ok, n = infer.evaluate(model, batches, dec_mask=True, with_milnce_loss=True)
+        assert n == cnt and abs(loss - tot / cnt) < 5e-3 * abs(tot / cnt), (loss, tot / cnt)
+        assert abs(ok - correct) <= 1  # bf16 operands may flip one near-tie argmax
