@@ -124,8 +124,10 @@ __global__ void __launch_bounds__(128 * RS) attn_bwd_tc_kernel(const __grid_cons
   const int t = tid & 127;       // query row / TMEM lane of this thread
   const int half = tid >> 7;     // which half of the columns it works on
   const int warp = t >> 5;       // TMEM lane quadrant
-  const int hn = blockIdx.x;
-  const int h = hn / a.N, n = hn % a.N;
+  // CTA order: the H heads of one sample are neighbours, so that the CTAs in flight together read the SAME rows of the fused
+  // [q | k | v] projection (3 KB per token, 128 B of it per head and operand): one DRAM page serves all of them
+  const int n = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int hn = h * a.N + n;  // the reference's head-major batch index (layout of `att` and of the row statistics)
   const int kc2 = p.kc;  // 64-key chunks of the dS / W' tiles that are written; the MMAs read whole 128-key tiles, so with an odd
                          // count the last tile's second chunk is whatever follows in shared memory (finite bf16 data of the next
                          // region): it only feeds dK / dV rows >= Tk, which are never stored
@@ -552,8 +554,10 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_tc1_kernel(const __grid_const
   const int t = tid & 127;       // query row / key row / TMEM lane of this thread
   const int half = tid >> 7;     // which 64 key columns (row pass) / which 32 head columns (epilogue) it works on
   const int warp = t >> 5;       // TMEM lane quadrant
-  const int hn = blockIdx.x;
-  const int h = hn / a.N, n = hn % a.N;
+  // CTA order: the H heads of one sample are neighbours, so that the CTAs in flight together read the SAME rows of the fused
+  // [q | k | v] projection (3 KB per token, 128 B of it per head and operand): one DRAM page serves all of them
+  const int n = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int hn = h * a.N + n;  // the reference's head-major batch index (layout of `att` and of the row statistics)
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int kc = p.kc;                           // 64-key chunks of the tile (1 or 2); each thread owns kc 32-column chunks of its row

@@ -343,9 +343,11 @@ __global__ void __launch_bounds__(kRowWarps * 32) attn_row1_fwd_kernel(const sav
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* wbuf = reinterpret_cast<float*>(smem) + warp * (a.Tk + d);  // [Tk] W', then [d] q
   float* sq = wbuf + a.Tk;
-  const long hn = static_cast<long>(blockIdx.x) * kRowWarps + warp;
-  if (hn >= static_cast<long>(a.N) * a.H) return;
-  const int h = static_cast<int>(hn / a.N), n = static_cast<int>(hn % a.N);
+  const long wi = static_cast<long>(blockIdx.x) * kRowWarps + warp;  // work item: the H heads of one sample are neighbours, so that the CTAs / warps that
+                                                       // run together read the same K / V rows (one DRAM page per key row)
+  if (wi >= static_cast<long>(a.N) * a.H) return;
+  const int n = static_cast<int>(wi / a.H), h = static_cast<int>(wi % a.H);
+  const long hn = static_cast<long>(h) * a.N + n;  // the reference's head-major batch index (layout of `att`)
   const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q) + static_cast<long>(n) * a.ldq + h * d;
   for (int c = lane; c < d; c += 32) sq[c] = __bfloat162float(Q[c]);
   __syncwarp();
@@ -386,9 +388,11 @@ __global__ void __launch_bounds__(kRowWarps * 32) attn_row1_bwd_kernel(const sav
   float* wbuf = dsbuf + a.Tk;
   float* sq = wbuf + a.Tk;
   float* sg = sq + d;
-  const long hn = static_cast<long>(blockIdx.x) * kRowWarps + warp;
-  if (hn >= static_cast<long>(a.N) * a.H) return;
-  const int h = static_cast<int>(hn / a.N), n = static_cast<int>(hn % a.N);
+  const long wi = static_cast<long>(blockIdx.x) * kRowWarps + warp;  // work item: the H heads of one sample are neighbours, so that the CTAs / warps that
+                                                       // run together read the same K / V rows (one DRAM page per key row)
+  if (wi >= static_cast<long>(a.N) * a.H) return;
+  const int n = static_cast<int>(wi / a.H), h = static_cast<int>(wi % a.H);
+  const long hn = static_cast<long>(h) * a.N + n;  // the reference's head-major batch index (layout of `att`)
   const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q) + static_cast<long>(n) * a.ldq + h * d;
   const float* dO = a.dout + static_cast<long>(n) * a.ld_dout + h * d;
   for (int c = lane; c < d; c += 32) {
@@ -508,9 +512,11 @@ __global__ void __launch_bounds__(kPieceWarps * 32) attn_row1_fwd_piece_kernel(c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sS = reinterpret_cast<float*>(smem) + warp * (a.Tk + d);  // [Tk] scores, then W'; [d] q
   float* sq = sS + a.Tk;
-  const long hn = static_cast<long>(blockIdx.x) * kPieceWarps + warp;
-  if (hn >= static_cast<long>(a.N) * a.H) return;
-  const int h = static_cast<int>(hn / a.N), n = static_cast<int>(hn % a.N);
+  const long wi = static_cast<long>(blockIdx.x) * kPieceWarps + warp;  // work item: the H heads of one sample are neighbours, so that the CTAs / warps that
+                                                       // run together read the same K / V rows (one DRAM page per key row)
+  if (wi >= static_cast<long>(a.N) * a.H) return;
+  const int n = static_cast<int>(wi / a.H), h = static_cast<int>(wi % a.H);
+  const long hn = static_cast<long>(h) * a.N + n;  // the reference's head-major batch index (layout of `att`)
   const int pc = lane % P, ks = lane / P;
   const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q) + static_cast<long>(n) * a.ldq + h * d;
   for (int c = lane; c < d; c += 32) sq[c] = __bfloat162float(Q[c]);
@@ -590,9 +596,11 @@ __global__ void __launch_bounds__(kPieceWarps * 32) attn_row1_bwd_piece_kernel(c
   float* sD = sS + a.Tk;
   float* sq = sD + a.Tk;
   float* sg = sq + d;
-  const long hn = static_cast<long>(blockIdx.x) * kPieceWarps + warp;
-  if (hn >= static_cast<long>(a.N) * a.H) return;
-  const int h = static_cast<int>(hn / a.N), n = static_cast<int>(hn % a.N);
+  const long wi = static_cast<long>(blockIdx.x) * kPieceWarps + warp;  // work item: the H heads of one sample are neighbours, so that the CTAs / warps that
+                                                       // run together read the same K / V rows (one DRAM page per key row)
+  if (wi >= static_cast<long>(a.N) * a.H) return;
+  const int n = static_cast<int>(wi / a.H), h = static_cast<int>(wi % a.H);
+  const long hn = static_cast<long>(h) * a.N + n;  // the reference's head-major batch index (layout of `att`)
   const int pc = lane % P, ks = lane / P;
   const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q) + static_cast<long>(n) * a.ldq + h * d;
   const float* dO = a.dout + static_cast<long>(n) * a.ld_dout + h * d;
@@ -780,8 +788,10 @@ __global__ void __launch_bounds__(kSplitWarps * 32) attn_row1_fwd_split_kernel(c
   float* sW = sS + a.Tk;                       // [Tk] W' = W * query mask
   float* sq = sW + a.Tk;                       // [d]  q
   float* sO = sq + d;                          // [kSplitWarps][d] partial outputs
-  const long hn = blockIdx.x;
-  const int h = static_cast<int>(hn / a.N), n = static_cast<int>(hn % a.N);
+  const long wi = blockIdx.x;  // work item: the H heads of one sample are neighbours, so that the CTAs / warps that
+                                                       // run together read the same K / V rows (one DRAM page per key row)
+  const int n = static_cast<int>(wi / a.H), h = static_cast<int>(wi % a.H);
+  const long hn = static_cast<long>(h) * a.N + n;  // the reference's head-major batch index (layout of `att`)
   const int pc = lane % P, ks = lane / P;
   const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q) + static_cast<long>(n) * a.ldq + h * d;
   for (int c = threadIdx.x; c < d; c += blockDim.x) sq[c] = __bfloat162float(Q[c]);
@@ -883,8 +893,10 @@ __global__ void __launch_bounds__(kSplitWarps * 32, 4) attn_row1_bwd_split_kerne
   float* sq = sW + a.Tk;                       // [d]  q
   float* sg = sq + d;                          // [d]  dO
   float* sP = sg + d;                          // [kSplitWarps][3][d] partial dQ, bias-gradient sums of dK, dV
-  const long hn = blockIdx.x;
-  const int h = static_cast<int>(hn / a.N), n = static_cast<int>(hn % a.N);
+  const long wi = blockIdx.x;  // work item: the H heads of one sample are neighbours, so that the CTAs / warps that
+                                                       // run together read the same K / V rows (one DRAM page per key row)
+  const int n = static_cast<int>(wi / a.H), h = static_cast<int>(wi % a.H);
+  const long hn = static_cast<long>(h) * a.N + n;  // the reference's head-major batch index (layout of `att`)
   const int pc = lane % P, ks = lane / P;
   const __nv_bfloat16* Q = static_cast<const __nv_bfloat16*>(a.q) + static_cast<long>(n) * a.ldq + h * d;
   const float* dO = a.dout + static_cast<long>(n) * a.ld_dout + h * d;

@@ -54,8 +54,10 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
   pdl_trigger();
   const savqa_attn_args_t& a = p.a;
   const int t = threadIdx.x, warp = t >> 5;
-  const int hn = blockIdx.x;
-  const int h = hn / a.N, n = hn % a.N;
+  // CTA order: the H heads of one sample are neighbours, so that the CTAs in flight together read the SAME rows of the fused
+  // [q | k | v] projection (3 KB per token, 128 B of it per head and operand): one DRAM page serves all of them
+  const int n = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int hn = h * a.N + n;  // the reference's head-major batch index (layout of `att` and of the row statistics)
   const int q0 = blockIdx.y * 128;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
