@@ -355,7 +355,12 @@ class RowGradLog:
     the trainer exchanges / scatters / applies them (savqa_scatter_add_rows + savqa_adam_rows)."""
 
     def __init__(self):
-        self.pending = []  # list of (flat_idx int64 [n], rows fp32 [n, width], scale)
+        self.pending = []  # list of (flat_idx int64 [n], rows fp32 [n, width], scale, skip_row)
+        #: trainer hooks: before_read(ids) runs right before a gather reads the table (deferred Adam: the rows are caught up on the
+        #: stream that is about to read them); on_grad() right after a gradient list was appended (the update can start while the rest
+        #: of the backward pass runs)
+        self.before_read = None
+        self.on_grad = None
 
     def clear(self):
         self.pending.clear()
@@ -365,6 +370,8 @@ class EmbeddingFn(Function):
     @staticmethod
     def forward(ctx, idx, table, scale: float, skip_row: int, rowlog: Optional[RowGradLog] = None):
         flat = idx.reshape(-1)
+        if rowlog is not None and rowlog.before_read is not None:
+            rowlog.before_read(flat)
         out, _ = ops.gather_rows(table.detach(), flat, scale=scale, want_f32=True)
         ctx.save_for_backward(flat)
         ctx.table_shape, ctx.scale, ctx.skip_row, ctx.rowlog = table.shape, scale, skip_row, rowlog
@@ -378,6 +385,8 @@ class EmbeddingFn(Function):
         d2 = d2 if d2.is_contiguous() else d2.contiguous()
         if ctx.rowlog is not None:
             ctx.rowlog.pending.append((flat, d2, ctx.scale, ctx.skip_row))
+            if ctx.rowlog.on_grad is not None:
+                ctx.rowlog.on_grad()
             return None, None, None, None, None
         dtable = torch.zeros(ctx.table_shape, device=dy.device, dtype=F32)  # dense, like the reference
         ops.scatter_add_rows(dtable, flat, d2, scale=ctx.scale, skip_row=ctx.skip_row)
@@ -1013,7 +1022,10 @@ class MilNceFn(Function):
         dev = vis_fea.device
         vis_b = _as_bf16_rows(vis_fea, B * V, Fd)
         ids_pn = torch.cat([pos_ids.reshape(-1), neg_ids.reshape(-1)])
-        _, x = ops.gather_rows(table.detach(), torch.cat([macro_ipt.reshape(-1), ids_pn]), want_f32=False, want_bf16=True)
+        ids_all = torch.cat([macro_ipt.reshape(-1), ids_pn])
+        if rowlog is not None and rowlog.before_read is not None:
+            rowlog.before_read(ids_all)
+        _, x = ops.gather_rows(table.detach(), ids_all, want_f32=False, want_bf16=True)
         xm, xpn = x[:B * M], x[B * M:]
         pm, ps = packs["marco"].refresh([Wm], [bm]), packs["syb"].refresh([Ws], [bs])
         pv, pi = packs["vis"].refresh([Wv], [bv]), packs["ipt"].refresh([Wi], [bi])
@@ -1068,6 +1080,8 @@ class MilNceFn(Function):
             dgrad(d_pn, ps, 2 * B * V * topN, E, h, out_f32=dx)
             if ctx.rowlog is not None:
                 ctx.rowlog.pending.append((ids_pn, dx, 1.0, -1))
+                if ctx.rowlog.on_grad is not None:
+                    ctx.rowlog.on_grad()
             else:
                 dtable = torch.zeros(ctx.table_shape, device=dev, dtype=F32)  # dense, like the reference
                 ops.scatter_add_rows(dtable, ids_pn, dx)

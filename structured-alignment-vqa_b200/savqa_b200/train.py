@@ -195,6 +195,7 @@ class EncoderTrainer:
         self._debug_skip_allreduce = os.environ.get("SAVQA_DEBUG_SKIP_ALLREDUCE", "0") == "1"  # timing experiments only
         self.tables = [model.att_vis_grid.syb_emb, model.att_syb.syb_emb] + ([model.MIL_NCE.syb_emb] if step != "encoder" else [])
         self.flat_param: Optional[torch.Tensor] = None
+        self.row_state = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.static: Optional[Dict[str, torch.Tensor]] = None
         self.static_loss: Optional[torch.Tensor] = None
@@ -312,6 +313,14 @@ class EncoderTrainer:
         # every step (ops.adam_advance, part of the captured graph), so a host that queues steps ahead of the GPU cannot hand a
         # step the scalars -- or the row stamp of savqa_adam_rows -- of another one
         self.dyn = torch.zeros(3, device=dev)
+        if self.rowsparse:
+            import functools
+            for i, t in enumerate(self.tables):
+                # deferred Adam, part 1: rows are caught up right before the gather that reads them, on that gather's stream
+                t._savqa_rowlog.before_read = functools.partial(self._catch_up_ids, i)
+                # part 2 on one GPU: a table's update starts as soon as its gradient rows exist (on the branch's helper stream, under the
+                # rest of the backward pass); with several ranks the row lists are exchanged after the bucket all-reduces (_apply_rows)
+                t._savqa_rowlog.on_grad = functools.partial(self._apply_table_now, i) if self.world == 1 else None
         Fn.WEIGHT_EPOCH += 1
         self.reducer = None
         # Per-bucket Adam under the backward pass (GradReducer.apply_fn) is implemented but OFF: measured on B200 it moves the
@@ -390,21 +399,52 @@ class EncoderTrainer:
         ops.adam_step(self.flat_param[lo:hi], self.flat_grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.lr, b1, b2,
                       self.eps, max(self.step_count, 1), dyn=self.dyn, param_bf16=self.flat_bf16[lo:hi])
 
-    def _table_ids(self, b: Dict[str, torch.Tensor]):
-        """Word ids each table is gathered with in a step (AttModel_x3.py:96, 216): the rows the forward pass will read."""
-        ids = [[b["q_ipt"]], [b["q_ipt"]]]
-        if self.step_kind != "encoder":  # MIL_NCE reads the macro-node words too (they get no gradient, AttModel_x3.py:354)
-            ids.append([b["macro_node_ipt"], b["micro_positive_obj_ipt"], b["micro_negative_obj_ipt"]])
-        return ids
-
-    def _catch_up_rows(self, b: Dict[str, torch.Tensor]) -> None:
-        """Deferred Adam, part 1 (before the step's gathers): the rows this step reads replay the zero-gradient updates dense
+    def _catch_up_ids(self, i: int, ids: torch.Tensor) -> None:
+        """Deferred Adam, part 1 (RowGradLog.before_read): the rows a gather is about to read replay the zero-gradient updates dense
         Adam applied to them while they were absent from the batches (savqa_adam_rows, apply=0)."""
         b1, b2 = self.betas
-        for t, st, id_list in zip(self.tables, self.row_state, self._table_ids(b)):
-            for ids in id_list:
-                ops.adam_rows(t.weight.data, None, st["m"], st["v"], st["stamp"], ids.reshape(-1), self.lr, b1, b2, self.eps,
-                              max(self.step_count, 1), dyn=self.dyn, apply=False)
+        st = self.row_state[i]
+        ops.adam_rows(self.tables[i].weight.data, None, st["m"], st["v"], st["stamp"], ids.reshape(-1), self.lr, b1, b2, self.eps,
+                      max(self.step_count, 1), dyn=self.dyn, apply=False)
+
+    def _apply_table(self, i: int) -> None:
+        """Deferred Adam, part 2 for one table: its (row id, row gradient) lists -> (all-gather over the ranks) -> scatter-add -> this
+        step's update of the touched rows (rows that only another rank read are caught up here first)."""
+        b1, b2 = self.betas
+        t, st = self.tables[i], self.row_state[i]
+        log = t._savqa_rowlog
+        touched = []
+        for idx, rows, scale, skip in log.pending:
+            if self.world > 1:
+                idx_all = torch.empty(self.world * idx.numel(), dtype=idx.dtype, device=idx.device)
+                rows_all = torch.empty(self.world * rows.shape[0], rows.shape[1], dtype=rows.dtype, device=rows.device)
+                dist.all_gather_into_tensor(idx_all, idx, group=self.pg)
+                dist.all_gather_into_tensor(rows_all, rows, group=self.pg)
+                idx, rows, scale = idx_all, rows_all, scale / self.world
+            ops.scatter_add_rows(st["grad"], idx, rows, scale=scale, skip_row=skip)
+            touched.append(idx.reshape(-1))
+        if touched:  # ONE update per table and step, after every gradient list has been accumulated (a row is claimed once per step)
+            ops.adam_rows(t.weight.data, st["grad"], st["m"], st["v"], st["stamp"], touched[0] if len(touched) == 1 else torch.cat(touched),
+                          self.lr, b1, b2, self.eps, max(self.step_count, 1), dyn=self.dyn, apply=True)
+        log.clear()
+
+    def _apply_table_now(self, i: int) -> None:
+        """RowGradLog.on_grad (one GPU): launch table i's update on the helper stream of the stream its gradient was produced on."""
+        if self.row_state is None:
+            return
+        if not self.flat_param.is_cuda:
+            self._apply_table(i)
+            return
+        cur = torch.cuda.current_stream()
+        aside = Fn.wgrad_stream_of(cur)
+        aside.wait_stream(cur)
+        if aside not in Fn._WGRAD_DIRTY:
+            Fn._WGRAD_DIRTY.append(aside)  # joined with the weight-gradient streams before the optimizer (join_wgrad_streams)
+        for idx, rows, _, _ in self.tables[i]._savqa_rowlog.pending:
+            idx.record_stream(aside)
+            rows.record_stream(aside)
+        with torch.cuda.stream(aside):
+            self._apply_table(i)
 
     def flush_tables(self) -> None:
         """Brings EVERY row of the word tables up to date with the current step (before state_dict() / evaluation): after it the
@@ -417,30 +457,13 @@ class EncoderTrainer:
                           dyn=None, apply=False)
 
     def _apply_rows(self) -> None:
-        """Deferred Adam, part 2: (row id, row gradient) lists -> scatter-add -> this step's update of the touched rows (rows that
-        another rank read are caught up here first)."""
-        b1, b2 = self.betas
-        for t, st in zip(self.tables, self.row_state):
-            log = t._savqa_rowlog
-            touched = []
-            for idx, rows, scale, skip in log.pending:
-                if self.world > 1:
-                    idx_all = torch.empty(self.world * idx.numel(), dtype=idx.dtype, device=idx.device)
-                    rows_all = torch.empty(self.world * rows.shape[0], rows.shape[1], dtype=rows.dtype, device=rows.device)
-                    dist.all_gather_into_tensor(idx_all, idx, group=self.pg)
-                    dist.all_gather_into_tensor(rows_all, rows, group=self.pg)
-                    idx, rows, scale = idx_all, rows_all, scale / self.world
-                ops.scatter_add_rows(st["grad"], idx, rows, scale=scale, skip_row=skip)
-                touched.append(idx.reshape(-1))
-            if touched:  # ONE update per table and step, after every gradient list has been accumulated (a row is claimed once per step)
-                ops.adam_rows(t.weight.data, st["grad"], st["m"], st["v"], st["stamp"], touched[0] if len(touched) == 1 else torch.cat(touched),
-                              self.lr, b1, b2, self.eps, max(self.step_count, 1), dyn=self.dyn, apply=True)
-            log.clear()
+        """Updates of the tables whose gradient lists are still pending (every table when there are several ranks)."""
+        for i in range(len(self.tables)):
+            if self.tables[i]._savqa_rowlog.pending:
+                self._apply_table(i)
 
     def _step_impl(self, b: Dict[str, torch.Tensor]) -> torch.Tensor:
         ops.adam_advance(self.dyn, self.lr, self.betas[0], self.betas[1])  # step += 1 on the device; read by the Adam kernels below
-        if self.rowsparse:
-            self._catch_up_rows(b)
         if self.flat_grad.is_cuda:
             # 356 MB of zeros (48 us at HBM speed) that nothing reads before the backward pass: on a helper stream, next to the forward
             cur = torch.cuda.current_stream()

@@ -232,6 +232,7 @@ def headline_step_case(device, batch_size=128, vocab_rows=5000, seed=11, floor=2
     tr.flat_grad.zero_()
     for t_ in tr.tables:
         t_._savqa_rowlog.clear()
+        t_._savqa_rowlog.on_grad = None  # keep the (row id, row gradient) lists for the comparison below instead of applying them
     loss = tr._forward_backward(b)
     if str(device) != "cpu":
         Fn.join_wgrad_streams()

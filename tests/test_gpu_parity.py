@@ -276,6 +276,7 @@ def test_full_step_headline_size_vs_oracle(A):
     tr.flat_grad.zero_()
     for t_ in tr.tables:
         t_._savqa_rowlog.clear()
+        t_._savqa_rowlog.on_grad = None  # keep the (row id, row gradient) lists for the comparison below instead of applying them
     loss = tr._forward_backward(comp)
     Fn.join_wgrad_streams()
     torch.cuda.synchronize()
