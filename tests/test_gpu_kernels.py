@@ -639,3 +639,40 @@ def test_attention_tcgen05_small_heads_and_long_queries(ops, N, H, T, d):
     assert rel(outs[0][0], outs[1][0]) < 1.5e-2, rel(outs[0][0], outs[1][0])
     for a_, b_ in zip(outs[0][1], outs[1][1]):
         assert rel(a_, b_) < 1.5e-2
+
+
+def test_two_host_threads_share_the_library(ops):
+    """Two host threads launching through the C ABI at the same time (own streams, different per-thread SM limits, the shared
+    TMA-descriptor cache behind its mutex): results identical to the single-threaded ones."""
+    import threading
+    M, N, K = 1024, 512, 512
+    g = torch.Generator().manual_seed(0)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(BF).cuda()
+    ws = [(torch.randn(N, K, generator=g) * K ** -0.5).to(BF).cuda() for _ in range(2)]
+    ref = []
+    for w in ws:
+        o = torch.empty(M, N, device="cuda")
+        ops.gemm(a, w, M, N, K, out_f32=o)
+        ref.append(o.clone())
+    torch.cuda.synchronize()
+    outs, errs = [None, None], []
+
+    def work(i):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st), ops.gemm_sm_limit(32 if i == 0 else 100):
+                for _ in range(40):
+                    o = torch.empty(M, N, device="cuda")
+                    ops.gemm(a, ws[i], M, N, K, out_f32=o)
+                    x = torch.randn(64 + i, 512, device="cuda")
+                    ops.layernorm_fwd(x, None, torch.ones(512, device="cuda"), torch.zeros(512, device="cuda"), 1e-8, False, False, False)
+                outs[i] = o
+            st.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for o, r in zip(outs, ref):
+        assert torch.equal(o, r)
