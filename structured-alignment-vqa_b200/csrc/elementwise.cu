@@ -211,6 +211,20 @@ __global__ void relu_gate_kernel(const TDy* __restrict__ dy, long ld_dy, const _
   }
 }
 
+// 16 bytes per thread (the group widths and pitches are multiples of 16 bytes): a vector either lies inside a group's copied part
+// or inside its zero part.
+__global__ void regroup_cols_vec_kernel(const uint4* __restrict__ in, long ld_in16, uint4* __restrict__ out, long ld_out16, long rows, int groups,
+                                        int w_in16, int w_out16) {
+  const long per_row = static_cast<long>(groups) * w_out16;
+  const long total = rows * per_row;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / per_row;
+    const int rem = static_cast<int>(i - r * per_row);
+    const int gidx = rem / w_out16, c = rem - gidx * w_out16;
+    out[r * ld_out16 + rem] = c < w_in16 ? __ldg(in + r * ld_in16 + gidx * w_in16 + c) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 template <typename T>
 __global__ void regroup_cols_kernel(const T* __restrict__ in, long ld_in, T* __restrict__ out, long ld_out, long rows, int groups, int w_in,
                                     int w_out) {
@@ -674,6 +688,14 @@ extern "C" int savqa_regroup_cols(const void* in, int64_t ld_in, void* out, int6
   if (rows == 0) return SAVQA_OK;
   SAVQA_REQUIRE(in && out && groups > 0 && w_in > 0 && w_out > 0 && (elem_bytes == 2 || elem_bytes == 4), "savqa_regroup_cols: bad argument");
   SAVQA_REQUIRE(ld_in >= static_cast<int64_t>(groups) * w_in && ld_out >= static_cast<int64_t>(groups) * w_out, "savqa_regroup_cols: pitch");
+  const int per16 = 16 / elem_bytes;
+  if (w_in % per16 == 0 && w_out % per16 == 0 && ld_in % per16 == 0 && ld_out % per16 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    regroup_cols_vec_kernel<<<grid_for(rows * groups * (w_out / per16), 256), 256, 0, stream>>>(
+        static_cast<const uint4*>(in), ld_in / per16, static_cast<uint4*>(out), ld_out / per16, rows, groups, w_in / per16, w_out / per16);
+    SAVQA_CHECK_CUDA(cudaGetLastError());
+    return SAVQA_OK;
+  }
   const int grid = grid_for(rows * groups * w_out, 256);
   if (elem_bytes == 2)
     regroup_cols_kernel<uint16_t><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(in), ld_in, static_cast<uint16_t*>(out), ld_out, rows, groups,

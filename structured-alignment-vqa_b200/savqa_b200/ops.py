@@ -560,13 +560,9 @@ def graph_attention_fwd(q: Tensor, k: Tensor, v: Tensor, graph: Optional[Tensor]
     return out, att
 
 
-def tc_attention_bwd_fits(d: int, Tq: int, Tk: int) -> bool:
-    """Shapes the tcgen05 attention backward (csrc/attn_bwd_tcgen05.cu) takes: one CTA holds the whole (sample, head)
-    problem -- Q, dO, K, V and the two bf16 [128, Tk] tiles in shared memory, S / dW / dQ / dK / dV in 512 TMEM columns."""
-    if d == 32:
-        d = 64  # zero-padded heads (see graph_attention_fwd)
-    if Tq > 128:
-        Tq = 128 if Tq <= 256 else Tq  # two query tiles, one launch each (graph_attention_bwd)
+def _bwd_one_cta_fits(d: int, Tq: int, Tk: int) -> bool:
+    """One CTA of csrc/attn_bwd_tcgen05.cu holds the whole (sample, head) problem: Q, dO, K, V and the two bf16 [128, Tk] tiles in
+    shared memory, S / dW / dQ / dK / dV in 512 TMEM columns."""
     if d not in (64, 128) or Tq > 128 or Tk > 256:
         return False
     kt = (Tk + 127) // 128
@@ -577,6 +573,17 @@ def tc_attention_bwd_fits(d: int, Tq: int, Tk: int) -> bool:
     dch = d // 64
     smem = 1024 + 2 * dch * 16384 + 2 * dch * tk16 * 128 + 2 * ((tk16 + 63) // 64) * 16384 + Tk * 4 + 16 + 128 * ((Tk + 31) // 32) * 4
     return smem + 64 <= 227 * 1024
+
+
+def tc_attention_bwd_fits(d: int, Tq: int, Tk: int) -> bool:
+    """Shapes the tcgen05 attention backward takes: directly when one CTA holds the (sample, head) problem, otherwise as (query tile,
+    key tile) pairs of <= 128 x 128 on the forward's row statistics (graph_attention_bwd); 32-channel heads as zero-padded 64-wide
+    tiles."""
+    if d == 32:
+        d = 64
+    if d not in (64, 128):
+        return False
+    return _bwd_one_cta_fits(d, Tq, Tk) or (Tq <= 512 and Tk <= 512 and _bwd_one_cta_fits(d, min(Tq, 128), min(Tk, 128)))
 
 
 def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causal, renorm, dout: Tensor, dq: Tensor, dk: Tensor,
@@ -603,32 +610,55 @@ def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causa
             if db is not None:
                 colsum_bf16(dst[:, :C32], db)
         return
-    if engine == 0 and 128 < Tq <= 256:
-        # the tcgen05 backward holds <= 128 queries per CTA: two query tiles, one launch each over ALL keys; dQ rows are disjoint, the
-        # tiles' (ReLU-gated, hence additive) dK / dV contributions are summed
+    if engine == 0 and (Tq > 128 or not _bwd_one_cta_fits(d, Tq, Tk)):
+        # The tcgen05 backward holds one (<= 128 query) x (all keys) problem per CTA.  Larger problems are TILED here: with the forward's
+        # row statistics {m, 1/Z, scale, beta} and t = <dO, O> every (query tile, key tile) pair is independent -- W' and dS of a tile
+        # need nothing from the other key tiles -- so each pair is one launch on contiguous copies of its rows; dQ sums over the key
+        # tiles, dK / dV over the query tiles (the ReLU gates are per element, so the tiles' gated contributions are additive).
+        assert stats is not None and fwd_out is not None and not causal, "tiled tcgen05 backward needs the forward statistics"
         Cq = H * d
-        first = True
-        for t0 in range(0, Tq, 128):
-            t1 = min(Tq, t0 + 128)
+        qt = [(t0, min(Tq, t0 + 128)) for t0 in range(0, Tq, 128)]
+        if _bwd_one_cta_fits(d, min(Tq, 128), Tk):
+            kstep = Tk
+        else:  # balanced key tiles that start on 32-key (bit-word) boundaries
+            nk = (Tk + 127) // 128
+            kstep = ((Tk + nk - 1) // nk + 31) // 32 * 32
+        kt = [(s0, min(Tk, s0 + kstep)) for s0 in range(0, Tk, kstep)]
+        rows = lambda t, T, t0, t1, w: t.unflatten(0, (N, T))[:, t0:t1, :w].reshape(N * (t1 - t0), w).contiguous()  # noqa: E731
+        dq3, dk3, dv3 = dq.unflatten(0, (N, Tq)), dk.unflatten(0, (N, Tk)), dv.unflatten(0, (N, Tk))
+        st4 = stats.reshape(H, N, Tq, 4)
+        for qi, (t0, t1) in enumerate(qt):
             n = t1 - t0
-            rows = lambda t, w: t.unflatten(0, (N, Tq))[:, t0:t1, :w].reshape(N * n, w).contiguous()  # noqa: E731
-            q_t, do_t = rows(q[:, :Cq], Cq), rows(dout[:, :Cq], Cq)
-            fo_t = rows(fwd_out[:, :Cq], Cq) if fwd_out is not None else None
-            st_t = stats.reshape(H, N, Tq, 4)[:, :, t0:t1].contiguous().reshape(-1, 4) if stats is not None else None
+            q_t, do_t, fo_t = rows(q, Tq, t0, t1, Cq), rows(dout, Tq, t0, t1, Cq), rows(fwd_out, Tq, t0, t1, Cq)
+            st_t = st4[:, :, t0:t1].contiguous().reshape(-1, 4)
             qon_t = query_on.reshape(N, Tq)[:, t0:t1].contiguous()
-            g_t, gb_t = graph, graph_bits
-            if graph is not None and graph.shape[1] == Tq:
-                g_t = graph[:, t0:t1].contiguous()
-                gb_t = graph_bits[:, t0:t1].contiguous() if graph_bits is not None else None
-            dq_t = torch.empty(N * n, Cq, device=q.device, dtype=BF16)
-            dk_t, dv_t = (dk, dv) if first else (torch.empty(dk.shape[0], Cq, device=q.device, dtype=BF16), torch.empty(dv.shape[0], Cq, device=q.device, dtype=BF16))
-            graph_attention_bwd(q_t, k, v, g_t, key_on, qon_t, N, H, n, Tk, d, causal, renorm, do_t, dq_t, dk_t, dv_t, engine=0, dbq=dbq, dbk=dbk,
-                                dbv=dbv, graph_bits=gb_t, stats=st_t, fwd_out=fo_t, scale_d=scale_d)
-            dq.unflatten(0, (N, Tq))[:, t0:t1, :Cq].copy_(dq_t.reshape(N, n, Cq))
-            if not first:
-                dk[:, :Cq].add_(dk_t)
-                dv[:, :Cq].add_(dv_t)
-            first = False
+            dq_acc = None
+            for ki, (s0, s1) in enumerate(kt):
+                m = s1 - s0
+                whole = (m == Tk)
+                k_t, v_t = (k, v) if whole else (rows(k, Tk, s0, s1, Cq), rows(v, Tk, s0, s1, Cq))
+                kon_t = key_on if whole else key_on.reshape(N, Tk)[:, s0:s1].contiguous()
+                g_t, gb_t = graph, graph_bits
+                if graph is not None:
+                    gq = slice(t0, t1) if graph.shape[1] == Tq else slice(None)
+                    g_t = graph[:, gq, s0:s1].contiguous()
+                    gb_t = graph_bits[:, gq, s0 // 32:(s1 + 31) // 32].contiguous() if graph_bits is not None else None
+                dq_t = torch.empty(N * n, Cq, device=q.device, dtype=BF16)
+                dk_t, dv_t = torch.empty(N * m, Cq, device=q.device, dtype=BF16), torch.empty(N * m, Cq, device=q.device, dtype=BF16)
+                graph_attention_bwd(q_t, k_t, v_t, g_t, kon_t, qon_t, N, H, n, m, d, False, renorm, do_t, dq_t, dk_t, dv_t, engine=0,
+                                    graph_bits=gb_t, stats=st_t, fwd_out=fo_t, scale_d=scale_d or d)
+                dq_acc = dq_t if dq_acc is None else dq_acc.add_(dq_t)
+                tgt_k, tgt_v = dk3[:, s0:s1, :Cq], dv3[:, s0:s1, :Cq]
+                if qi == 0:
+                    tgt_k.copy_(dk_t.reshape(N, m, Cq))
+                    tgt_v.copy_(dv_t.reshape(N, m, Cq))
+                else:
+                    tgt_k.add_(dk_t.reshape(N, m, Cq))
+                    tgt_v.add_(dv_t.reshape(N, m, Cq))
+            dq3[:, t0:t1, :Cq].copy_(dq_acc.reshape(N, n, Cq))
+        for g_, db in ((dq, dbq), (dk, dbk), (dv, dbv)):
+            if db is not None:
+                colsum_bf16(g_[:, :Cq], db)
         return
     a = AttnArgs()
     a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0)

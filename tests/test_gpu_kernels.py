@@ -602,7 +602,8 @@ def test_layernorm_forward_statistics(ops):
         assert rel(stats[:, 0], pre.mean(-1)) < 1e-5 and rel(stats[:, 1], pre.std(-1)) < 1e-5
 
 
-@pytest.mark.parametrize("N,H,T,d", [(3, 16, 40, 32), (2, 16, 100, 32), (2, 8, 200, 64), (2, 8, 256, 64), (2, 16, 160, 32)])
+@pytest.mark.parametrize("N,H,T,d", [(3, 16, 40, 32), (2, 16, 100, 32), (2, 8, 200, 64), (2, 8, 256, 64), (2, 16, 160, 32), (2, 16, 256, 32),
+                                     (2, 8, 299, 64), (2, 4, 256, 128)])
 def test_attention_tcgen05_small_heads_and_long_queries(ops, N, H, T, d):
     """BASELINE configs[4] shapes that used to fall to the CUDA-core engine: 32-channel heads (16 heads x 512: run as zero-padded
     64-wide tiles, score scale 1/sqrt(32)) and the backward pass for 128 < Tq <= 256 (two query tiles).  Forward and backward of the

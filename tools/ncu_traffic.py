@@ -3,6 +3,7 @@
 kernel (profiles/r2_ncu_hbm_kernels.txt) and (ii) profiles/r2_ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per
 launch, which bench.py reports as `roofline.traffic`.  usage: python tools/ncu_traffic.py gpurun_out/prof_hbm_r2.ncu-rep"""
 import csv
+import re
 import io
 import json
 import os
@@ -48,7 +49,8 @@ for r in data:
     vals = {k: num(r, k) for k in want if k in col}
     rd, wr, us = vals.get("dram__bytes_read.sum"), vals.get("dram__bytes_write.sum"), vals.get("gpu__time_duration.sum")
     tot = (rd or 0) + (wr or 0)
-    out_lines.append(f"{name[:70]:70s} {us:8.1f} us  dram read {rd / 1e6:8.1f} MB  write {wr / 1e6:8.1f} MB  = {tot / us / 1e3:7.1f} GB/s under ncu  "
+    short = re.sub(r"^.*::", "", name.split("(")[0])
+    out_lines.append(f"{short[:44]:44s} {us:8.1f} us  dram read {rd / 1e6:8.1f} MB  write {wr / 1e6:8.1f} MB  = {tot / us / 1e3:7.1f} GB/s under ncu  "
                      f"algorithmic {ALGO[key] / 1e6:7.1f} MB ({tot / ALGO[key]:.2f}x)  dram% {vals.get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')}  "
                      f"L2% {vals.get('lts__throughput.avg.pct_of_peak_sustained_elapsed')}  sm% {vals.get('sm__throughput.avg.pct_of_peak_sustained_elapsed')}  "
                      f"tensor% {vals.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')}  regs {vals.get('launch__registers_per_thread')}")
