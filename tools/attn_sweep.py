@@ -66,6 +66,8 @@ for C, H in ((512, 8), (512, 16), (1024, 16), (1024, 8)):
                 us_b = timeit(bwd)
                 bf_, bb = 10.0 * N * H * T * T * d, M * 3 * C * 2 * 2 + N * T * T / 8 + 2 * M * C * 4
                 row += f" {us_b:7.1f} {bf_ / us_b / 1e6:7.1f} {100 * bf_ / us_b / 1e6 / peaks['bf16_tflops']:7.2f}% {100 * bb / us_b / 1e3 / peaks['hbm_gbs']:5.1f}%"
+                if not ops._bwd_one_cta_fits(64 if d == 32 else d, T, T):
+                    row += "  (tiled: query x key tiles of <= 128 on the forward statistics)"
             else:
                 row += "   (backward: CUDA-core engine for this shape)"
             print(row, flush=True)

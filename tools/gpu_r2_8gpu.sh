@@ -12,7 +12,7 @@ import json
 d=json.load(open('gpurun_out/r2_bench_8gpu_$name.json')); print('$name', {k: round(d[k],3) for k in ('value','ms_per_step','loss')}, 'e2e', round(d['e2e']['value']), d.get('ranks',{}).get('param_checksums_equal'))" 2>&1 | tail -1
 }
 run default SAVQA_X=1
-run reserve12 SAVQA_BRANCH_SMS=52,84 NCCL_MAX_CTAS=12
+run reserve12 SAVQA_BRANCH_SMS=52,84 NCCL_MAX_CTAS=12 NCCL_MAX_NCHANNELS=12
 run buckets3 SAVQA_BUCKET_BLOCKS=3
 run simple NCCL_PROTO=Simple
 timeout -k 10 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29523 tools/trace_step.py > gpurun_out/r2_trace_8gpu.log 2>&1
