@@ -523,6 +523,22 @@ def _set_graph_bits(a: AttnArgs, graph_bits: Optional[Tensor], N: int, Tq: int, 
     a.bits_q_stride = wpr if graph_bits.shape[1] == Tq else 0
 
 
+def _adjacent(a: Tensor, b: Tensor, c: Tensor, width: int) -> bool:
+    """a | b | c are consecutive `width`-column blocks of one row-major matrix (the fused [M, 3C] projection layout)."""
+    es = a.element_size()
+    return (a.shape[0] == b.shape[0] == c.shape[0] and a.stride(0) == b.stride(0) == c.stride(0) and a.stride(0) >= 3 * width
+            and b.data_ptr() == a.data_ptr() + width * es and c.data_ptr() == b.data_ptr() + width * es)
+
+
+def _pad_heads_qkv(q: Tensor, k: Tensor, v: Tensor, H: int):
+    """32-channel heads -> zero-padded 64-wide heads; one launch when q | k | v are the column blocks of one fused projection."""
+    if _adjacent(q, k, v, H * 32):
+        fused = torch.as_strided(q, (q.shape[0], 3 * H * 32), (q.stride(0), 1))
+        out = regroup_cols(fused, 3 * H, 32, 64)
+        return out[:, :H * 64], out[:, H * 64:2 * H * 64], out[:, 2 * H * 64:]
+    return tuple(regroup_cols(t, H, 32, 64) for t in (q, k, v))
+
+
 def graph_attention_fwd(q: Tensor, k: Tensor, v: Tensor, graph: Optional[Tensor], key_on: Tensor, query_on: Tensor, N: int, H: int,
                         Tq: int, Tk: int, d: int, causal: bool, renorm: int, want_att: bool, engine: int,
                         graph_bits: Optional[Tensor] = None, stats: Optional[Tensor] = None, scale_d: int = 0):
@@ -533,7 +549,7 @@ def graph_attention_fwd(q: Tensor, k: Tensor, v: Tensor, graph: Optional[Tensor]
     if engine == 0 and d == 32:
         # 32-channel heads (16 heads x 512) on the tcgen05 engine: 64-wide tiles whose upper halves are zero; the score scale stays
         # 1/sqrt(32) (AttnArgs.scale_d).  The zero channels change neither Q K^T nor the first 32 columns of P V.
-        q64, k64, v64 = (regroup_cols(t, H, 32, 64) for t in (q, k, v))
+        q64, k64, v64 = _pad_heads_qkv(q, k, v, H)
         out64, att = graph_attention_fwd(q64, k64, v64, graph, key_on, query_on, N, H, Tq, Tk, 64, causal, renorm, want_att, 0,
                                          graph_bits=graph_bits, stats=stats, scale_d=32)
         return regroup_cols(out64, H, 64, 32), att
@@ -599,14 +615,22 @@ def graph_attention_bwd(q, k, v, graph, key_on, query_on, N, H, Tq, Tk, d, causa
     if engine == 0 and d == 32:
         # zero-padded 64-wide heads on the tcgen05 engine (see graph_attention_fwd); the gradients of the padding are dropped again
         C32 = H * 32
-        q64, k64, v64 = (regroup_cols(t, H, 32, 64) for t in (q, k, v))
+        q64, k64, v64 = _pad_heads_qkv(q, k, v, H)
         dout64 = regroup_cols(dout, H, 32, 64)
         fo64 = regroup_cols(fwd_out, H, 32, 64) if fwd_out is not None else None
-        d64 = [torch.empty(t.shape[0], H * 64, device=q.device, dtype=BF16) for t in (dq, dk, dv)]
+        fused = _adjacent(dq, dk, dv, C32)
+        if fused:  # dq | dk | dv are the three column blocks of one [M, 3C] gradient: one padded buffer, one launch back
+            all64 = torch.empty(dq.shape[0], 3 * H * 64, device=q.device, dtype=BF16)
+            d64 = [all64[:, i * H * 64:(i + 1) * H * 64] for i in range(3)]
+        else:
+            d64 = [torch.empty(t.shape[0], H * 64, device=q.device, dtype=BF16) for t in (dq, dk, dv)]
         graph_attention_bwd(q64, k64, v64, graph, key_on, query_on, N, H, Tq, Tk, 64, causal, renorm, dout64, d64[0], d64[1], d64[2], engine=0,
                             graph_bits=graph_bits, stats=stats, fwd_out=fo64, scale_d=32)
+        if fused:
+            regroup_cols(all64, 3 * H, 64, 32, out=torch.as_strided(dq, (dq.shape[0], 3 * C32), (dq.stride(0), 1)))
         for src, dst, db in zip(d64, (dq, dk, dv), (dbq, dbk, dbv)):
-            regroup_cols(src, H, 64, 32, out=dst)
+            if not fused:
+                regroup_cols(src, H, 64, 32, out=dst)
             if db is not None:
                 colsum_bf16(dst[:, :C32], db)
         return
