@@ -223,7 +223,14 @@ class _Branch(nn.Module):
             kv_all = torch.empty(Mk, n, device=x.device, dtype=torch.bfloat16)
             h.side.wait_event(h.ready)
             with torch.cuda.stream(h.side), Fn.ops.gemm_sm_limit(Fn.SIDE_GEMM_SMS):
-                Fn.ops.gemm(mem_bf16, pall.w, Mk, n, C, bias=pall.bias, relu=True, out_bf16=kv_all)
+                if self.num_blocks > 1 and Fn.FUSED_DECODER:
+                    # layer 0's slice first, in a launch of its own: the decoder's first cross-attention waits for 1/L of the work
+                    Fn.ops.gemm(mem_bf16, pall.w[:2 * C], Mk, 2 * C, C, bias=pall.bias[:2 * C], relu=True, out_bf16=kv_all[:, :2 * C])
+                    h.kv_done0 = torch.cuda.Event()
+                    h.kv_done0.record(h.side)
+                    Fn.ops.gemm(mem_bf16, pall.w[2 * C:], Mk, n - 2 * C, C, bias=pall.bias[2 * C:], relu=True, out_bf16=kv_all[:, 2 * C:])
+                else:
+                    Fn.ops.gemm(mem_bf16, pall.w, Mk, n, C, bias=pall.bias, relu=True, out_bf16=kv_all)
             kv_all.record_stream(h.side)
             mem_bf16.record_stream(h.side)
             h.kv_done = torch.cuda.Event()

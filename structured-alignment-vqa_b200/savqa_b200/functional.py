@@ -469,7 +469,11 @@ class MemoryHolder:
         self.side: Optional["torch.cuda.Stream"] = None
         # fused form (the branch model's [2 L C, C] K/V block is bound): ONE projection GEMM for all L layers ...
         self.kv_all: Optional[Tensor] = None              # bf16 [N*T, 2 L C]: layer i reads columns [2 C i, 2 C (i + 1))
-        self.kv_done: Optional["torch.cuda.Event"] = None
+        self.kv_done: Optional["torch.cuda.Event"] = None   # the whole block is projected
+        self.kv_done0: Optional["torch.cuda.Event"] = None  # layer 0's slice is (it is projected first, by a launch of its own: the
+        #                                                     decoder's first cross-attention then waits ~20 us instead of ~100)
+        self.dmem_rest: Optional[Tensor] = None             # d(memory) of layers 1..L-1, launched under the decoder's last layer (backward)
+        self.rest_done: Optional["torch.cuda.Event"] = None
         self.pack_all: Optional[WeightPack] = None
         self.mem_bf16: Optional[Tensor] = None
         self.dkv_all: Optional[Tensor] = None             # ... and one dgrad (K = 2 L C) + one wgrad once every layer has written its slice
@@ -497,7 +501,17 @@ class MemoryJoinFn(Function):
             Mk, n = dkv.shape
             C = pk.w.shape[1]
             d = torch.empty(Mk, C, device=dkv.device, dtype=F32)
-            ops.gemm(dkv, pk.w, Mk, C, n, b_mn=True, res=None if g is None else g.reshape(Mk, C), out_f32=d)
+            res = None if g is None else g.reshape(Mk, C)
+            if h.dmem_rest is not None:
+                # layers 1..L-1 were contracted on the side stream while the decoder's backward was still in its last layer
+                # (DecoderFn.backward): only layer 0's K = 2C slice is left on the critical path
+                torch.cuda.current_stream().wait_event(h.rest_done)
+                if res is not None:
+                    h.dmem_rest.add_(res)
+                ops.gemm(dkv[:, :2 * C], pk.w[:2 * C], Mk, C, 2 * C, b_mn=True, res=h.dmem_rest, out_f32=d)
+                h.dmem_rest = None
+            else:
+                ops.gemm(dkv, pk.w, Mk, C, n, b_mn=True, res=res, out_f32=d)
             pk.weight_grad(dkv, h.mem_bf16, n, C)
             g = d.reshape(ctx_shape(h))
             h.dkv_all = h.kv_all = None
@@ -829,8 +843,6 @@ class DecoderFn(Function):
             mem_on, mem_b = ops.row_nonzero(memory.reshape(Mk, C) if memory.is_contiguous() else memory.contiguous().reshape(Mk, C))
         holder = cfg.get("kv_holder")
         fused_kv = holder is not None and holder.kv_all is not None
-        if fused_kv and x0.is_cuda:
-            torch.cuda.current_stream().wait_event(holder.kv_done)
         g = dec_mask if dec_mask.dtype == F32 else dec_mask.float()
         g = g if g.is_contiguous() else g.contiguous()
         f32 = lambda *shape: torch.empty(*shape, device=dev, dtype=F32)    # noqa: E731
@@ -851,6 +863,9 @@ class DecoderFn(Function):
             q = b16(B, C)
             ops.gemm_rowln(y1b, pq.w, B, C, C, 0, bias=pq.bias, relu=True, y_bf16=q)
             if fused_kv:
+                if x0.is_cuda and i <= 1:  # layer 0's K/V slice is projected first; the other layers' in a second launch
+                    ev = holder.kv_done0 if (i == 0 and holder.kv_done0 is not None) else holder.kv_done
+                    torch.cuda.current_stream().wait_event(ev)
                 kv = holder.kv_all[:, 2 * C * i:2 * C * (i + 1)]
             else:
                 pkv = ca._packs["kv"].refresh([ca.K_proj[0].weight, ca.V_proj[0].weight], [ca.K_proj[0].bias, ca.V_proj[0].bias])
@@ -923,6 +938,21 @@ class DecoderFn(Function):
             ops.graph_attention_bwd(s["q"], s["k"], s["v"], ctx.g, ctx.mem_on, s["on1"], N, H, 1, T, d, False, 1, dpre2, dq, dkv[:, :C], dkv[:, C:],
                                     dbq=pq.bias_grad_buffer(C, dev), dbk=dbkv[:C], dbv=dbkv[C:])
             pq.weight_grad(dq, s["y1b"], C, C)
+            if i == 1 and L > 1 and dev.type == "cuda" and WGRAD_SIDE_STREAM:
+                # every layer but 0 has written its slice of the fused K/V gradient: contract them now (K = 2 (L - 1) C) on the side
+                # stream, under the rest of the chain; MemoryJoinFn.backward adds layer 0's slice
+                cur = torch.cuda.current_stream()
+                side = wgrad_stream_of(cur)
+                side.wait_stream(cur)
+                if side not in _WGRAD_DIRTY:
+                    _WGRAD_DIRTY.append(side)
+                pall, dall = holder.pack_all, holder.dkv_all
+                with torch.cuda.stream(side), ops.gemm_sm_limit(SIDE_GEMM_SMS):
+                    holder.dmem_rest = torch.empty(Mk, C, device=dev, dtype=F32)
+                    ops.gemm(dall[:, 2 * C:], pall.w[2 * C:], Mk, C, dall.shape[1] - 2 * C, b_mn=True, out_f32=holder.dmem_rest)
+                    holder.rest_done = torch.cuda.Event()
+                    holder.rest_done.record(side)
+                holder.dmem_rest.record_stream(cur)
             # d y1 = dq Wq + dpre2 -> the self-attention's LayerNorm backward -> dvb = (dpre1 * query_mask) * [vb > 0]
             dg1, db1 = n1._sink.buffers(n1.gamma)
             dpre1, dvb = f32(B, C), b16(B, C)
