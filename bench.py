@@ -400,12 +400,15 @@ def run_training(args, rank, world, local_rank, dev, peaks, sampler, dense_table
         tt = torch.tensor([ms, e2e_ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(tt[0]), float(tt[1])
-        chk = torch.stack([trainer.flat_param.double().sum(), trainer.flat_param.double().abs().sum(),
-                           torch.tensor(loss_val, device=dev, dtype=torch.float64)])
+        trainer.flush_tables()  # outside the timed region: every table row current, so the tables can be compared as a whole
+        tabs = [t.weight.data.view(torch.int32).sum(dtype=torch.int64).double() for t in trainer.tables]  # exact checksum of the bits
+        chk = torch.stack([trainer.flat_param.double().sum(), trainer.flat_param.double().abs().sum()] + tabs +
+                          [torch.tensor(loss_val, device=dev, dtype=torch.float64)])
         got = [torch.zeros_like(chk) for _ in range(world)]
         dist.all_gather(got, chk)
-        ranks = {"loss": [float(g[2]) for g in got], "param_checksum": [float(g[0]) for g in got],
-                 "param_checksums_equal": all(bool(torch.equal(got[0][:2], g[:2])) for g in got)}
+        ranks = {"loss": [float(g[-1]) for g in got], "param_checksum": [float(g[0]) for g in got],
+                 "table_checksums": [[float(x) for x in g[2:-1]] for g in got],
+                 "param_checksums_equal": all(bool(torch.equal(got[0][:-1], g[:-1])) for g in got)}
         assert ranks["param_checksums_equal"], f"ranks diverged: {ranks}"
     res = dict(ms=ms, e2e_ms=e2e_ms, loss=loss_val, h2d=h2d, launches_per_step=launches_per_step, ranks=ranks)
     trainer.graph = None

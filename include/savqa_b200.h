@@ -29,7 +29,7 @@ extern "C" {
 #define SAVQA_ERR_CUDA 2
 #define SAVQA_ERR_UNSUPPORTED 3
 
-#define SAVQA_ABI_VERSION 4
+#define SAVQA_ABI_VERSION 5
 
 typedef void* savqa_stream_t; /* cudaStream_t */
 
@@ -83,6 +83,13 @@ int savqa_gather_rows(const float* table, int64_t table_rows, int width, const i
  * F.embedding: modules.py:34-41).  dense fp32 table gradient, atomics. */
 int savqa_scatter_add_rows(float* dtable, int64_t table_rows, int width, const int64_t* idx, int64_t n_idx, const float* dout,
                            int64_t ld_dout, float scale, int64_t skip_row, savqa_stream_t stream);
+/* The same accumulation into a signed Q15.48 fixed-point table (acc[idx[r], c] += round(dout[r, c] * scale * 2^48), 64-bit integer
+ * atomics): integer addition is associative, so every data-parallel replica that accumulates the same gathered lists ends with the
+ * same bits whatever order its atomics ran in -- what DDP's all-reduce of the dense embedding gradient guarantees in the reference
+ * (main_itp_ddp_tar_super_node.py:404).  Resolution 3.6e-15, range +-32768 (saturating per addend); a NaN addend counts as 0.
+ * savqa_adam_rows consumes the table with grad_q48 = 1. */
+int savqa_scatter_add_rows_q48(int64_t* acc, int64_t table_rows, int width, const int64_t* idx, int64_t n_idx, const float* dout,
+                               int64_t ld_dout, float scale, int64_t skip_row, savqa_stream_t stream);
 
 /* ---- staging casts --------------------------------------------------------------------------------- */
 /* dst_bf16[r, c] = src[r, c] for c < cols, 0 for cols <= c < pad_to. */
@@ -297,16 +304,17 @@ int savqa_adam_advance(float* dyn, float lr, float beta1, float beta2, savqa_str
  * exactly once per call even if it occurs several times: the steps it missed since row_stamp are replayed with a zero gradient
  * (m *= beta1, v *= beta2, p -= lr_s m / (sqrt(v) / sqrt(1 - beta2^s) + eps): what dense Adam does to a row that is absent from a
  * batch), then
- *   apply != 0: the step-`step` update with grad (the dense fp32 table savqa_scatter_add_rows accumulated into; consumed rows
- *               are zeroed again, so the table never needs a 488 MB memset);
+ *   apply != 0: the step-`step` update with grad (the dense table savqa_scatter_add_rows accumulated into as float, grad_q48 = 0,
+ *               or savqa_scatter_add_rows_q48 as int64 fixed point, grad_q48 = 1; consumed rows are zeroed again, so the table
+ *               never needs a memset);
  *   apply == 0: nothing more -- the catch-up through step - 1, run BEFORE the step's gathers read the rows; idx == NULL brings
  *               every row of the table up to date (before a checkpoint or an evaluation pass).
  * step is read from dyn[2] when dyn != NULL.  The replay of a row stops as soon as a zero-gradient step leaves every element unchanged
  * (the updates shrink by ~beta1 / sqrt(beta2) per step: from there on dense Adam's are lost in fp32 rounding too), at the latest
  * after 256 steps; the remaining decay of the moments is applied in closed form. */
-int savqa_adam_rows(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int32_t* row_stamp, int64_t table_rows, int width,
-                    const int64_t* idx, int64_t n_idx, float lr, float beta1, float beta2, float eps, int step, const float* dyn,
-                    int apply, savqa_stream_t stream);
+int savqa_adam_rows(float* param, void* grad, int grad_q48, float* exp_avg, float* exp_avg_sq, int32_t* row_stamp, int64_t table_rows,
+                    int width, const int64_t* idx, int64_t n_idx, float lr, float beta1, float beta2, float eps, int step,
+                    const float* dyn, int apply, savqa_stream_t stream);
 
 #ifdef __cplusplus
 }

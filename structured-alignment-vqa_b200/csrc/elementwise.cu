@@ -118,6 +118,35 @@ __global__ void scatter_add_rows_kernel(float* __restrict__ dtable, long table_r
   }
 }
 
+// Row gradients of a data-parallel step: every rank accumulates the SAME gathered (row id, gradient row) lists, and the replicas must
+// stay bit-identical although the order of the atomics is not. Integer addition is associative, float addition is not: the accumulator
+// is a signed Q15.48 fixed-point table (resolution 2^-48 = 3.6e-15, range +-32768; a float scaled by a power of two is exact, so the
+// only rounding is the one to 2^-48). savqa_adam_rows reads it back (grad_q48 = 1).
+constexpr float kQ48 = 281474976710656.0f;          // 2^48
+constexpr float kQ48Inv = 1.0f / 281474976710656.0f;
+
+__global__ void scatter_add_rows_q48_kernel(long long* __restrict__ acc, long table_rows, int width, const int64_t* __restrict__ idx,
+                                            long n_idx, const float* __restrict__ dout, long ld_dout, float scale, long skip_row) {
+  const int lane = threadIdx.x & 31;
+  const long warp0 = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+  const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+  for (long r = warp0; r < n_idx; r += nwarps) {
+    const long dst = idx[r];
+    if (dst < 0 || dst >= table_rows || dst == skip_row) continue;
+    unsigned long long* trow = reinterpret_cast<unsigned long long*>(acc) + dst * static_cast<long>(width);
+    const float* g = dout + r * ld_dout;
+    for (int c = lane; c < width; c += 32) {
+      const long long q = __float2ll_rn(g[c] * scale * kQ48);  // saturates; two's complement wrap-around makes the unsigned add signed
+      if (q != 0) atomicAdd(trow + c, static_cast<unsigned long long>(q));
+    }
+  }
+}
+
+__device__ __forceinline__ float load_row_grad(const float* g, long i) { return g[i]; }
+__device__ __forceinline__ float load_row_grad(const long long* g, long i) { return __ll2float_rn(g[i]) * kQ48Inv; }
+__device__ __forceinline__ void clear_row_grad(float* g, long i) { g[i] = 0.0f; }
+__device__ __forceinline__ void clear_row_grad(long long* g, long i) { g[i] = 0; }
+
 // ------------------------------------------------------------------------------------------------------
 // staging casts
 // ------------------------------------------------------------------------------------------------------
@@ -459,7 +488,8 @@ __global__ void adam_advance_kernel(float* __restrict__ dyn, float lr, float b1,
 constexpr int kReplayMax = 256;
 constexpr int kRowChunk = 10;  // elements per lane held in registers during a replay: 320 columns per pass (word rows: 300)
 
-__global__ void adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+template <typename G>
+__global__ void adam_rows_kernel(float* __restrict__ p, G* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                  int* __restrict__ stamp, long table_rows, int width, const int64_t* __restrict__ idx, long n_idx, float lr,
                                  float b1, float b2, float eps, int step, const float* __restrict__ dyn, int apply) {
   if (dyn) step = static_cast<int>(dyn[2]);
@@ -541,8 +571,8 @@ __global__ void adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, f
         const int c = c0 + j * 32 + lane;
         if (c >= width) continue;
         if (apply) {
-          adam_one(pi[j], g[base + c], mi[j], vi[j], b1, b2, eps, step_apply, bc2_apply);
-          g[base + c] = 0.0f;
+          adam_one(pi[j], load_row_grad(g, base + c), mi[j], vi[j], b1, b2, eps, step_apply, bc2_apply);
+          clear_row_grad(g, base + c);
         }
         p[base + c] = pi[j];
         m[base + c] = mi[j];
@@ -619,6 +649,17 @@ extern "C" int savqa_scatter_add_rows(float* dtable, int64_t table_rows, int wid
   SAVQA_REQUIRE(dtable && idx && dout && width > 0 && ld_dout >= width, "savqa_scatter_add_rows: bad argument");
   scatter_add_rows_kernel<<<grid_for(n_idx * 32, 256), 256, 0, stream>>>(dtable, table_rows, width, idx, n_idx, dout, ld_dout, scale,
                                                                           skip_row);
+  SAVQA_CHECK_CUDA(cudaGetLastError());
+  return SAVQA_OK;
+}
+
+extern "C" int savqa_scatter_add_rows_q48(int64_t* acc, int64_t table_rows, int width, const int64_t* idx, int64_t n_idx,
+                                          const float* dout, int64_t ld_dout, float scale, int64_t skip_row, savqa_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_idx == 0) return SAVQA_OK;
+  SAVQA_REQUIRE(acc && idx && dout && width > 0 && ld_dout >= width, "savqa_scatter_add_rows_q48: bad argument");
+  scatter_add_rows_q48_kernel<<<grid_for(n_idx * 32, 256), 256, 0, stream>>>(reinterpret_cast<long long*>(acc), table_rows, width, idx,
+                                                                              n_idx, dout, ld_dout, scale, skip_row);
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;
 }
@@ -774,16 +815,22 @@ extern "C" int savqa_adam_advance(float* dyn, float lr, float beta1, float beta2
   return SAVQA_OK;
 }
 
-extern "C" int savqa_adam_rows(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int32_t* row_stamp, int64_t table_rows,
-                               int width, const int64_t* idx, int64_t n_idx, float lr, float beta1, float beta2, float eps, int step,
-                               const float* dyn, int apply, savqa_stream_t stream_) {
+extern "C" int savqa_adam_rows(float* param, void* grad, int grad_q48, float* exp_avg, float* exp_avg_sq, int32_t* row_stamp,
+                               int64_t table_rows, int width, const int64_t* idx, int64_t n_idx, float lr, float beta1, float beta2,
+                               float eps, int step, const float* dyn, int apply, savqa_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (idx == nullptr) n_idx = table_rows;
   if (n_idx == 0) return SAVQA_OK;
   SAVQA_REQUIRE(param && exp_avg && exp_avg_sq && row_stamp && width > 0 && step >= 1 && (grad || !apply), "savqa_adam_rows: bad argument");
   SAVQA_REQUIRE(idx || !apply, "savqa_adam_rows: the whole-table form is the catch-up alone (apply == 0)");
-  adam_rows_kernel<<<grid_for(n_idx * 32, 256), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, row_stamp, table_rows, width, idx, n_idx,
-                                                                   lr, beta1, beta2, eps, step, dyn, apply);
+  if (grad_q48)
+    adam_rows_kernel<long long><<<grid_for(n_idx * 32, 256), 256, 0, stream>>>(param, static_cast<long long*>(grad), exp_avg, exp_avg_sq,
+                                                                                row_stamp, table_rows, width, idx, n_idx, lr, beta1, beta2,
+                                                                                eps, step, dyn, apply);
+  else
+    adam_rows_kernel<float><<<grid_for(n_idx * 32, 256), 256, 0, stream>>>(param, static_cast<float*>(grad), exp_avg, exp_avg_sq, row_stamp,
+                                                                            table_rows, width, idx, n_idx, lr, beta1, beta2, eps, step, dyn,
+                                                                            apply);
   SAVQA_CHECK_CUDA(cudaGetLastError());
   return SAVQA_OK;
 }

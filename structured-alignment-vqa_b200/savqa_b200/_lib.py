@@ -67,6 +67,7 @@ SIGNATURES = {
     "savqa_pack_graph_bits": [vp, i64, C.c_int, vp, C.c_int, vp],
     "savqa_gather_rows": [vp, i64, C.c_int, vp, i64, C.c_float, vp, i64, vp, i64, C.c_int, vp],
     "savqa_scatter_add_rows": [vp, i64, C.c_int, vp, i64, vp, i64, C.c_float, i64, vp],
+    "savqa_scatter_add_rows_q48": [vp, i64, C.c_int, vp, i64, vp, i64, C.c_float, i64, vp],
     "savqa_cast_bf16": [vp, i64, vp, i64, i64, C.c_int, C.c_int, vp],
     "savqa_cast_transpose_bf16": [vp, i64, vp, i64, i64, C.c_int, C.c_int, vp],
     "savqa_row_nonzero": [vp, i64, i64, C.c_int, vp, vp, i64, vp],
@@ -83,7 +84,7 @@ SIGNATURES = {
     "savqa_graph_attn_fwd": [C.POINTER(AttnArgs), vp],
     "savqa_graph_attn_bwd": [C.POINTER(AttnArgs), vp],
     "savqa_answer_loss": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp, vp],
-    "savqa_adam_rows": [vp, vp, vp, vp, vp, i64, C.c_int, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, C.c_int, vp],
+    "savqa_adam_rows": [vp, vp, C.c_int, vp, vp, vp, i64, C.c_int, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, C.c_int, vp],
     "savqa_adam_advance": [vp, C.c_float, C.c_float, C.c_float, vp],
     "savqa_adam_step": [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, vp],
 }

@@ -173,14 +173,21 @@ def gather_rows(table: Tensor, idx: Tensor, scale: float = 1.0, want_f32: bool =
     return out32, out16
 
 
+Q48 = float(2 ** 48)  # scale of the fixed-point row-gradient accumulator (savqa_scatter_add_rows_q48)
+
+
 def scatter_add_rows(dtable: Tensor, idx: Tensor, dout: Tensor, scale: float = 1.0, skip_row: int = -1) -> None:
-    _check(dtable, F32, "dtable")
+    """dtable[idx[r]] += dout[r] * scale.  A float32 dtable takes float atomics (savqa_scatter_add_rows); an int64 dtable is the Q15.48
+    fixed-point accumulator whose result does not depend on the order of the atomics (savqa_scatter_add_rows_q48) -- the form the
+    trainer uses, so that data-parallel replicas stay bit-identical."""
+    assert dtable.dtype in (F32, torch.int64), f"dtable: float32 or int64 (Q15.48) expected, got {dtable.dtype}"
     _check(idx, torch.int64, "idx")
     _check(dout, F32, "dout")
     idx = idx.contiguous()
     rows, width, ld = _rows2d(dout)
     assert rows == idx.numel() and width == dtable.shape[1] and dtable.is_contiguous()
-    call("savqa_scatter_add_rows", ptr(dtable), dtable.shape[0], width, ptr(idx), rows, ptr(dout), ld, float(scale), int(skip_row))
+    fn = "savqa_scatter_add_rows" if dtable.dtype == F32 else "savqa_scatter_add_rows_q48"
+    call(fn, ptr(dtable), dtable.shape[0], width, ptr(idx), rows, ptr(dout), ld, float(scale), int(skip_row))
 
 
 def cast_bf16(src: Tensor, out: Optional[Tensor] = None, pad_to: Optional[int] = None) -> Tensor:
@@ -753,12 +760,16 @@ def adam_rows(param: Tensor, grad: Optional[Tensor], exp_avg: Tensor, exp_avg_sq
     """Row-sparse Adam with dense-Adam semantics (savqa_adam_rows): rows named in idx (each once) first replay the zero-gradient
     steps they missed, then -- apply=True -- take this step's update (their gradient rows are zeroed).  apply=False is the
     catch-up alone (through step - 1); idx=None then covers the whole table."""
-    for nm, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+    for nm, t in (("param", param), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
         _check(t, F32, nm)
+    q48 = grad is not None and grad.dtype == torch.int64  # the fixed-point accumulator of scatter_add_rows
+    if not q48:
+        _check(grad, F32, "grad")
+    for t in (param, grad, exp_avg, exp_avg_sq):
         assert t is None or (t.is_contiguous() and t.shape == param.shape)
     _check(row_stamp, torch.int32, "row_stamp")
     _check(idx, torch.int64, "idx")
     assert idx is not None or not apply
     idx = idx.contiguous() if idx is not None else None
-    call("savqa_adam_rows", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(row_stamp), param.shape[0], param.shape[1], ptr(idx),
+    call("savqa_adam_rows", ptr(param), ptr(grad), int(q48), ptr(exp_avg), ptr(exp_avg_sq), ptr(row_stamp), param.shape[0], param.shape[1], ptr(idx),
          idx.numel() if idx is not None else 0, lr, beta1, beta2, eps, int(step), ptr(dyn), int(bool(apply)))

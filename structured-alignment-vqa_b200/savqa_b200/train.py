@@ -307,7 +307,7 @@ class EncoderTrainer:
             for t in self.tables:
                 w = t.weight
                 w.grad = None
-                self.row_state.append(dict(grad=torch.zeros_like(w), m=torch.zeros_like(w), v=torch.zeros_like(w),
+                self.row_state.append(dict(grad=torch.zeros(w.shape, dtype=torch.int64, device=w.device), m=torch.zeros_like(w), v=torch.zeros_like(w),
                                            stamp=torch.zeros(w.shape[0], dtype=torch.int32, device=dev)))
         # {lr / (1 - b1^s), sqrt(1 - b2^s), s}: the step counter lives on the DEVICE and is advanced by a kernel at the head of
         # every step (ops.adam_advance, part of the captured graph), so a host that queues steps ahead of the GPU cannot hand a

@@ -5,8 +5,8 @@
   (i)  ranks that were built from DIFFERENT seeds hold bit-identical parameters after prepare() (rank 0's, what
        DistributedDataParallel's constructor does, main_itp_ddp_tar_super_node.py:203) and stay bit-identical after k steps
        (dense flat buffer AND the row-sparse word tables with their lazy row-wise Adam);
-  (ii) N ranks x B samples give the gradients of ONE rank x N*B samples (the concatenated batch) up to the order of fp32 sums,
-       and the post-Adam parameters follow.
+  (ii) at step 1 (identical parameters) N ranks x B samples give the gradients of ONE rank x N*B samples (the concatenated batch)
+       up to the order of fp32 sums, and the post-Adam parameters follow.
 tests/test_gpu_parity.py::test_dp_two_ranks_on_hardware launches this when the box has >= 2 GPUs."""
 import argparse
 import json
@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"])
     ap.add_argument("--dense-tables", action="store_true")
+    ap.add_argument("--step", default="full", choices=["encoder", "full"])
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -36,52 +37,74 @@ def main():
     solo = dist.new_group([0])  # every rank calls it; rank 0 uses it as a world-1 "group" for the single-process comparison
     from savqa_b200 import synthetic, train
     cfg = dict(synthetic.GQA_SHAPED, ncls=256)
-    V = 4000
-    keys = train.STEP_KEYS
+    V = 4000  # a small vocabulary: most word rows occur many times per step and on both ranks (the duplicate-row path of the tables)
+    keys = train.STEP_KEYS if args.step == "encoder" else train.FULL_KEYS
     batches = [synthetic.make_batch(cfg, args.batch, seed=100 + r, vocab_rows=V) for r in range(world)]
     mine = {k: batches[rank][k].to(dev) for k in keys}
+    lr = 1e-3
 
     model = synthetic.build_model(cfg, vocab_rows=V, seed=rank).to(dev)  # different weights per rank until prepare() broadcasts
-    tr = train.EncoderTrainer(model, lr=1e-3, rowsparse=not args.dense_tables)
+    tr = train.EncoderTrainer(model, lr=lr, rowsparse=not args.dense_tables, step=args.step)
     tr.prepare(mine)
-    result = {"world": world, "mode": args.mode, "rowsparse": not args.dense_tables}
+    result = {"world": world, "mode": args.mode, "step": args.step, "rowsparse": not args.dense_tables}
 
     def all_equal(t):
         got = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(got, t.contiguous())
         return all(torch.equal(got[0], g) for g in got[1:])
 
-    result["params_equal_after_prepare"] = all_equal(tr.flat_param) and all(all_equal(t.weight.data) for t in tr.tables)
+    def replicas_equal():
+        return {"flat": all_equal(tr.flat_param), "tables": [all_equal(t.weight.data) for t in tr.tables]}
+
+    eq0 = replicas_equal()
+    result["params_equal_after_prepare"] = eq0["flat"] and all(eq0["tables"])
+    # ---- step 1 (eager in both modes): identical parameters on both sides, so the gradients can be compared tightly
     if args.mode == "graph":
-        tr.capture(mine, warmup=1)  # one eager step
-        first_grad = None
-        losses = [float(tr.replay()) for _ in range(args.steps - 1)]
+        tr.capture(mine, warmup=1)
+        losses = [None]
     else:
-        losses = [float(tr.step(mine)) for _ in range(args.steps)]
+        losses = [float(tr.step(mine))]
     torch.cuda.synchronize()
-    result["params_equal_after_steps"] = all_equal(tr.flat_param) and all(all_equal(t.weight.data) for t in tr.tables)
+    grad_dp = tr.flat_grad.clone()  # all-reduced (AVG) gradients of step 1
+    param_dp = tr.flat_param.clone()
+    tables_dp = [t.weight.data.clone() for t in tr.tables]
+    # ---- steps 2..k: the replicas must stay bit-identical (dense flat buffer AND the deferred row-wise Adam of the word tables)
+    for _ in range(args.steps - 1):
+        losses.append(float(tr.replay() if args.mode == "graph" else tr.step(mine)))
+    tr.flush_tables()
+    torch.cuda.synchronize()
+    eq1 = replicas_equal()
+    result["replicas_after_steps"] = eq1
+    result["params_equal_after_steps"] = eq1["flat"] and all(eq1["tables"])
     result["mirror_tracks_params"] = bool(torch.equal(tr.flat_bf16, tr.flat_param.to(torch.bfloat16)))
-    grad_dp = tr.flat_grad.clone()  # all-reduced (AVG) gradients of the LAST step
 
     ok = True
-    if rank == 0:
+    if rank == 0 and args.step == "full":
+        # MIL-NCE draws its negatives from the other samples of the rank's OWN batch (AttModel_x3.py:24-63, as under the reference's
+        # DDP): 2 x B is not one batch of 2B there, so (ii) is checked on the encoder step and (i) on both
+        ok = result["params_equal_after_prepare"] and result["params_equal_after_steps"] and result["mirror_tracks_params"]
+        result.update(ok=ok, steps=args.steps, losses=losses, single_rank_comparison="skipped: MIL-NCE negatives are per-rank")
+        print("DP_CHECK " + json.dumps(result), flush=True)
+    elif rank == 0:
         ref_model = synthetic.build_model(cfg, vocab_rows=V, seed=0).to(dev)
         cat = {k: torch.cat([b[k] for b in batches], 0).to(dev) for k in keys}
-        ref = train.EncoderTrainer(ref_model, lr=1e-3, rowsparse=not args.dense_tables, process_group=solo)
+        ref = train.EncoderTrainer(ref_model, lr=lr, rowsparse=not args.dense_tables, process_group=solo, step=args.step)
         assert ref.world == 1
-        for _ in range(args.steps):
-            ref.step(cat)
+        ref.step(cat)
         torch.cuda.synchronize()
         assert ref.flat_param.numel() == tr.flat_param.numel()
         gerr = float((grad_dp - ref.flat_grad).norm() / ref.flat_grad.norm())
-        perr = float((tr.flat_param - ref.flat_param).abs().max())
-        terr = max(float((a.weight.data - b.weight.data).abs().max()) for a, b in zip(tr.tables, ref.tables))
-        result.update(grad_rel_err_vs_single_rank=gerr, param_max_abs_diff=perr, table_max_abs_diff=terr, lr=1e-3, steps=args.steps,
-                      losses=losses)
-        # same kernels on the same operands up to the order of fp32 sums (per-rank partial sums, atomics) and the bf16 roundings
-        # those reorderings flip after the first update; Adam moves a parameter by at most ~lr per step
+        perr = float((param_dp - ref.flat_param).abs().max())
+        pmean = float((param_dp - ref.flat_param).abs().mean())
+        terr = max(float((a - b.weight.data).abs().max()) for a, b in zip(tables_dp, ref.tables))
+        result.update(grad_rel_err_vs_single_rank=gerr, param_max_abs_diff=perr, param_mean_abs_diff=pmean, table_max_abs_diff=terr,
+                      lr=lr, steps=args.steps, losses=losses)
+        # Step 1 runs the same kernels on the same operands; what differs is the order of the fp32 sums (per-rank partial sums then
+        # the all-reduce, split-K and scatter atomics) and the 1/B factor folded into dY before its bf16 rounding (a power of two:
+        # the same mantissas).  Adam's first update is lr * g / (|g| + eps): a gradient element near zero may flip its sign, so
+        # single parameters may differ by up to 2 lr while the mean difference stays far below lr.
         ok = (result["params_equal_after_prepare"] and result["params_equal_after_steps"] and result["mirror_tracks_params"]
-              and gerr < 5e-2 and perr <= 2.5 * 1e-3 * args.steps and terr <= 2.5 * 1e-3 * args.steps)
+              and gerr < 5e-3 and perr <= 2.01 * lr and pmean < 0.05 * lr and terr <= 2.01 * lr)
         result["ok"] = ok
         print("DP_CHECK " + json.dumps(result), flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)

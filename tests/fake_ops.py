@@ -102,7 +102,10 @@ def gather_rows(table, idx, scale=1.0, want_f32=True, want_bf16=False):
 def scatter_add_rows(dtable, idx, dout, scale=1.0, skip_row=-1):
     idx = idx.reshape(-1)
     keep = idx != skip_row
-    dtable.index_add_(0, idx[keep], dout.reshape(idx.numel(), -1)[keep] * scale)
+    add = dout.reshape(idx.numel(), -1)[keep] * scale
+    if dtable.dtype == torch.int64:  # the Q15.48 fixed-point accumulator (savqa_scatter_add_rows_q48)
+        add = torch.round(add.double() * float(2 ** 48)).to(torch.int64)
+    dtable.index_add_(0, idx[keep], add)
 
 
 def cast_bf16(src, out=None, pad_to=None):
@@ -454,6 +457,8 @@ def adam_rows(param, grad, exp_avg, exp_avg_sq, row_stamp, idx, lr, beta1, beta2
                 param[r] -= (lr / bc1) * exp_avg[r] / (exp_avg_sq[r].sqrt() / (bc2 ** 0.5) + eps)
         if apply:
             g = grad[r]
+            if grad.dtype == torch.int64:
+                g = g.to(torch.float32) * (1.0 / float(2 ** 48))
             exp_avg[r] = beta1 * exp_avg[r] + (1 - beta1) * g
             exp_avg_sq[r] = beta2 * exp_avg_sq[r] + (1 - beta2) * g * g
             bc1, bc2 = 1 - beta1 ** target, 1 - beta2 ** target

@@ -321,7 +321,8 @@ def deferred_adam_case(ops, device, steps=12, rows=40, width=24, seed=0):
     ref = p0.clone().requires_grad_(True)
     opt = torch.optim.Adam([ref], lr=lr, betas=(b1, b2), eps=eps)
     p = p0.clone().to(device)
-    grad, m, v = (torch.zeros(rows, width, device=device) for _ in range(3))
+    m, v = (torch.zeros(rows, width, device=device) for _ in range(2))
+    grad = torch.zeros(rows, width, dtype=torch.int64, device=device)  # the trainer's Q15.48 accumulator (order-independent sums)
     stamp = torch.zeros(rows, dtype=torch.int32, device=device)
     dyn = torch.zeros(3, device=device)
     worst_read = 0.0

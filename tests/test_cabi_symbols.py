@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} declared in include/savqa_b200.h but not exported by {lib_path}"
     lib.savqa_abi_version.restype = ctypes.c_int
-    assert lib.savqa_abi_version() == 4
+    assert lib.savqa_abi_version() == 5
 
 
 def test_python_binding_covers_the_header(lib_path):

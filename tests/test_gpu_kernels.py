@@ -65,6 +65,19 @@ def test_gather_scatter(ops):
     ref.index_add_(0, flat[keep], dout[keep])
     assert rel(dt, ref) < 1e-6
     assert float(dt[999].abs().sum()) == 0.0
+    # the fixed-point accumulator: heavily duplicated rows, two runs -> the same bits (what keeps data-parallel replicas identical),
+    # and the value of the float64 sum to 2^-48 per addend
+    hot = torch.randint(0, 7, (4000,), generator=torch.Generator().manual_seed(3))
+    hot[::50] = 999
+    big = GS.randn("gk/dout_hot", 4000, 300) * 1e-3
+    q = [torch.zeros(1000, 300, dtype=torch.int64, device="cuda") for _ in range(2)]
+    for t in q:
+        ops.scatter_add_rows(t, dev(hot), dev(big), scale=0.5, skip_row=999)
+    assert torch.equal(q[0], q[1])
+    ref64 = torch.zeros(1000, 300, dtype=torch.float64)
+    ref64.index_add_(0, hot[hot != 999], (big * 0.5).double()[hot != 999])
+    assert float((q[0].cpu().double() / ops.Q48 - ref64).abs().max()) < 4000 * 2.0 ** -48
+    assert int(q[0][999].abs().sum()) == 0
     # empty input is a no-op
     ops.gather_rows(dev(table), torch.zeros(0, dtype=torch.int64, device="cuda"))
 

@@ -434,8 +434,8 @@ def test_cfg2_inference_full_size_vs_oracle_and_batch_sharding(A):
         assert torch.equal(a_, b_[128:256])
 
 
-@pytest.mark.parametrize("mode", ["graph", "eager"])
-def test_dp_two_ranks_on_hardware(mode):
+@pytest.mark.parametrize("mode,step", [("graph", "encoder"), ("eager", "encoder"), ("graph", "full")])
+def test_dp_two_ranks_on_hardware(mode, step):
     """2 ranks x B samples over NCCL == 1 rank x 2B samples, ranks bit-identical after k steps (tests/dp_check.py under torchrun).
     Needs two GPUs: skipped on the driver's 1-GPU test box, run with `gpurun --gpus 2` (profiles/r2_dp_check.txt)."""
     import os
@@ -445,7 +445,7 @@ def test_dp_two_ranks_on_hardware(mode):
         pytest.skip("needs 2 GPUs")
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29531", os.path.join(here, "dp_check.py"), "--mode", mode]
+           "--master-port", "29531", os.path.join(here, "dp_check.py"), "--mode", mode, "--step", step]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0 and "DP_CHECK" in r.stdout
