@@ -503,7 +503,28 @@ def leave(world):
     os._exit(0)
 
 
+_REAL_STDOUT = None
+
+
+def _own_stdout() -> None:
+    """stdout carries exactly ONE line, the JSON result: everything libraries write to file descriptor 1 (NCCL prints its version
+    banner there) goes to stderr instead; emit() writes the result to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _own_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -550,7 +571,7 @@ def main():
                                  "sample": f"{n}-sample GQA-shaped batch per step, full fwd+bwd of the encoder step + torch.optim.Adam "
                                            "(oracle port, torch CPU fp32, 20000-row word tables)"},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch.distributed as dist
@@ -574,7 +595,7 @@ def main():
                 "dtype": "f32 / bf16-autocast", "data": "synthetic", "config": dict(config, word_tables="dense (reference semantics)"),
                 "modes": res, "note": "restated reference path (oracle/savqa_oracle.py) on CUDA tensors: stock ATen / cuBLAS kernels, dense "
                                       "407000-row table gradients, torch.optim.Adam"}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------------------------------ our arm (B200)
@@ -606,7 +627,7 @@ def main():
                     "step_roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                                       "frac": achieved / peaks["tf_sustained"],
                                       "note": f"algorithmic dense-equivalent forward FLOPs {r['flops'] / 1e12:.3f} TFLOP/batch/GPU over the CUDA-event time"}}
-            print(json.dumps(line), flush=True)
+            emit(line)
         leave(world)
         return
 
@@ -665,7 +686,7 @@ def main():
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     leave(world)
 
 

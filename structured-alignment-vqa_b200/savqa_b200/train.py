@@ -188,6 +188,16 @@ class EncoderTrainer:
         self.rowsparse = rowsparse
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        # The word tables' row lists travel on a communicator of their own (NCCL): collectives of ONE communicator run in launch
+        # order, so on the gradient communicator a table's all-gathers would queue behind every bucket all-reduce that was launched
+        # before them -- on this one they overlap the rest of the backward pass and the last buckets.  (A caller-supplied subgroup,
+        # gloo, or SAVQA_TABLE_COMM=0: the gradient group is used.)
+        self.table_pg = process_group
+        if (self.world > 1 and process_group is None and dist.get_backend() == "nccl"
+                and os.environ.get("SAVQA_TABLE_COMM", "1") != "0"):
+            self.table_pg = dist.new_group(backend="nccl")
+        self._table_streams: Dict[int, "torch.cuda.Stream"] = {}
+        self._table_busy = []
         self.dec_mask = dec_mask
         self.step_count = 0
         self.allreduce_chunks = 6
@@ -318,9 +328,10 @@ class EncoderTrainer:
             for i, t in enumerate(self.tables):
                 # deferred Adam, part 1: rows are caught up right before the gather that reads them, on that gather's stream
                 t._savqa_rowlog.before_read = functools.partial(self._catch_up_ids, i)
-                # part 2 on one GPU: a table's update starts as soon as its gradient rows exist (on the branch's helper stream, under the
-                # rest of the backward pass); with several ranks the row lists are exchanged after the bucket all-reduces (_apply_rows)
-                t._savqa_rowlog.on_grad = functools.partial(self._apply_table_now, i) if self.world == 1 else None
+                # part 2: a table's exchange (several ranks: all-gather of its row lists) and update start as soon as its gradient rows
+                # exist, on a helper stream, under the rest of the backward pass
+                eager = self.world == 1 or (dev.type == "cuda" and os.environ.get("SAVQA_TABLES_EAGER", "1") != "0")
+                t._savqa_rowlog.on_grad = functools.partial(self._apply_table_now, i) if eager else None
         Fn.WEIGHT_EPOCH += 1
         self.reducer = None
         # Per-bucket Adam under the backward pass (GradReducer.apply_fn) is implemented but OFF: measured on B200 it moves the
@@ -393,6 +404,9 @@ class EncoderTrainer:
             self._apply_rows()
         elif rows_done:
             torch.cuda.current_stream().wait_stream(self._rows_stream)
+        for s_ in self._table_busy:  # tables whose exchange + update started inside the backward pass (several ranks)
+            torch.cuda.current_stream().wait_stream(s_)
+        self._table_busy = []
 
     def _adam_range(self, lo: int, hi: int) -> None:
         b1, b2 = self.betas
@@ -418,8 +432,8 @@ class EncoderTrainer:
             if self.world > 1:
                 idx_all = torch.empty(self.world * idx.numel(), dtype=idx.dtype, device=idx.device)
                 rows_all = torch.empty(self.world * rows.shape[0], rows.shape[1], dtype=rows.dtype, device=rows.device)
-                dist.all_gather_into_tensor(idx_all, idx, group=self.pg)
-                dist.all_gather_into_tensor(rows_all, rows, group=self.pg)
+                dist.all_gather_into_tensor(idx_all, idx, group=self.table_pg)
+                dist.all_gather_into_tensor(rows_all, rows, group=self.table_pg)
                 idx, rows, scale = idx_all, rows_all, scale / self.world
             ops.scatter_add_rows(st["grad"], idx, rows, scale=scale, skip_row=skip)
             touched.append(idx.reshape(-1))
@@ -436,10 +450,19 @@ class EncoderTrainer:
             self._apply_table(i)
             return
         cur = torch.cuda.current_stream()
-        aside = Fn.wgrad_stream_of(cur)
-        aside.wait_stream(cur)
-        if aside not in Fn._WGRAD_DIRTY:
-            Fn._WGRAD_DIRTY.append(aside)  # joined with the weight-gradient streams before the optimizer (join_wgrad_streams)
+        if self.world == 1:
+            aside = Fn.wgrad_stream_of(cur)
+            aside.wait_stream(cur)
+            if aside not in Fn._WGRAD_DIRTY:
+                Fn._WGRAD_DIRTY.append(aside)  # joined with the weight-gradient streams before the optimizer (join_wgrad_streams)
+        else:
+            # a stream per table: the exchange of one table must not queue behind the update of another, and the optimizer's
+            # all-reduces must not wait for it either (joined at the very end of the step, _exchange_and_apply)
+            aside = self._table_streams.get(i)
+            if aside is None:
+                aside = self._table_streams[i] = torch.cuda.Stream()
+            aside.wait_stream(cur)
+            self._table_busy.append(aside)
         for idx, rows, _, _ in self.tables[i]._savqa_rowlog.pending:
             idx.record_stream(aside)
             rows.record_stream(aside)

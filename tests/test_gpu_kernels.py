@@ -519,6 +519,10 @@ def test_deferred_row_adam_equals_dense_adam(ops):
     import parity_cases as PC
     for seed in range(3):
         PC.deferred_adam_case(ops, "cuda", steps=15, seed=seed)
+    # the word rows' width (three 16-byte groups per lane, the last one ragged), a width the 16-byte kernel does not take (scalar
+    # kernel), one that needs all three groups
+    for width in (300, 10, 384):
+        PC.deferred_adam_case(ops, "cuda", steps=12, rows=24, width=width, seed=7)
     # a long absence takes the closed-form branch (> 256 missed steps): the parameter update of those steps is below fp32 resolution
     rows, width = 4, 8
     p = torch.randn(rows, width, device="cuda")
