@@ -525,6 +525,8 @@ def emit(line: dict) -> None:
 
 def main():
     _own_stdout()
+    if int(os.environ.get("WORLD_SIZE", "1") or 1) > 1:  # see savqa_b200/__init__.py; here too, ahead of any CUDA call of this process
+        os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

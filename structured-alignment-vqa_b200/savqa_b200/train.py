@@ -152,7 +152,9 @@ class GradReducer:
 
 _BUCKET_RE = re.compile(r"^(att_vis_grid|att_syb)\.(enc|dec)_[a-z_]+_(\d+)\.")
 #: encoder blocks per all-reduce bucket (1: one 11.5 MB bucket per block and branch; 2 / 3: fewer, larger collectives)
-BUCKET_BLOCKS = max(1, int(os.environ.get("SAVQA_BUCKET_BLOCKS", "1")))
+# 3 encoder blocks per bucket (35 MB of fp32 gradients): measured on 8 B200 against 1 / 2 blocks per bucket (8.27 vs 8.38 ms/step) --
+# fewer, larger all-reduces spend less of the backward pass in NCCL's latency-bound regime (profiles/r2_bench_8gpu_variants.txt)
+BUCKET_BLOCKS = max(1, int(os.environ.get("SAVQA_BUCKET_BLOCKS", "3")))
 
 
 def bucket_key_of(model, name: str):
