@@ -124,6 +124,7 @@ def dominant_kernel_roofline(batch, cfg, peaks, iters=10):
     from savqa_b200 import ops
     C, Hd = cfg["hidden"], 4 * cfg["hidden"]
     BF = torch.bfloat16
+    ops.clear_stream_sm_limits()  # the training leg left this stream with the visual branch's share of the SMs (56 of 148)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     total_flops = total_us = 0.0
     n_launch = 0

@@ -333,6 +333,12 @@ def set_stream_sm_limit(stream, sms: int) -> None:
         _STREAM_SM_LIMIT.pop(stream.cuda_stream, None)
 
 
+def clear_stream_sm_limits() -> None:
+    """Forgets every per-stream SM budget (the branch models set theirs again at their next forward): for code that times a
+    GEMM alone on a stream a model has run on."""
+    _STREAM_SM_LIMIT.clear()
+
+
 @contextlib.contextmanager
 def _stream_limit():
     lim = _STREAM_SM_LIMIT.get(torch.cuda.current_stream().cuda_stream) if _STREAM_SM_LIMIT else None
