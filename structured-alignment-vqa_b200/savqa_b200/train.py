@@ -37,9 +37,12 @@ class GradReducer:
     the compute and weight-gradient streams that feed it, and overlaps the remaining backward.  finish() reduces whatever
     was not reported and hands back the (range, work) list for the optimizer to follow."""
 
-    def __init__(self, flat_grad: torch.Tensor, buckets, need, group, world: int = 2, apply_fn=None):
+    def __init__(self, flat_grad: torch.Tensor, buckets, need, group, world: int = 2, apply_fn=None, merged: bool = False):
         self.flat_grad, self.buckets, self.need, self.group = flat_grad, buckets, need, group
         self.world = world
+        # merged (one GPU): ONE optimizer launch over all reported buckets, behind the last of them -- it then runs next to the input
+        # stages' / MIL_NCE's backward and the word-table updates (a chain of small kernels on a nearly idle GPU) instead of after them
+        self.merged = merged and apply_fn is not None and flat_grad.is_cuda
         # apply_fn(lo, hi): the optimizer update of flat range [lo, hi).  Under graph capture it is launched per bucket, right
         # behind the bucket's all-reduce (world 1: behind its last gradient kernel) on a stream of its own, so that the
         # HBM-bound Adam kernel runs under the rest of the backward pass instead of after it.  Safe: once a bucket's gradients
@@ -79,7 +82,7 @@ class GradReducer:
         w = Fn._WGRAD_STREAMS.get((cur.device_index, cur.cuda_stream))
         # the heads run on streams of their own (AttModel.answer_logits): their bucket waits for every weight-gradient stream in use
         extra = [s_ for s_ in Fn._WGRAD_DIRTY if s_ is not w] if key[1] == "heads" else []
-        if torch.cuda.is_current_stream_capturing():
+        if self.merged or torch.cuda.is_current_stream_capturing():
             # Inside a graph capture the HOST order of the launches is irrelevant to when the kernels run -- but collectives of
             # one communicator execute in launch order, and autograd walks the whole visual branch before the symbolic one: launched
             # from here, every symbolic-branch bucket would queue behind the visual branch's LAST bucket (seen in the 2-GPU kernel
@@ -105,8 +108,21 @@ class GradReducer:
             return None
         return dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
 
-    def _launch_pending(self) -> None:
+    def _launch_pending(self) -> bool:
         r, a = self.launch_stream, self.apply_stream
+        if self.merged and self.pending:
+            lo_all, hi_all = min(p_[2] for p_ in self.pending), max(p_[3] for p_ in self.pending)
+            covered = sorted((p_[2], p_[3]) for p_ in self.pending)
+            if all(covered[i][1] >= covered[i + 1][0] for i in range(len(covered) - 1)):  # the buckets tile one range of the buffer
+                for p_ in self.pending:
+                    for ev in p_[4]:
+                        a.wait_event(ev)
+                with torch.cuda.stream(a):
+                    self.apply_fn(lo_all, hi_all)
+                self.works.append((lo_all, hi_all, None, True))
+                self.pending = []
+                return False  # the launch stream took no part (under graph capture it must not be waited for then)
+        used = bool(self.pending)
         for _, _, lo, hi, evs in sorted(self.pending, key=lambda t: (t[0], t[1])):
             for ev in evs:
                 r.wait_event(ev)
@@ -124,13 +140,14 @@ class GradReducer:
                 applied = True
             self.works.append((lo, hi, work, applied))
         self.pending = []
+        return used
 
     def finish(self, chunks: int):
         """All-reduces the ranges no bucket report covered (in `chunks` pieces so that the optimizer can follow one piece
         behind) and returns every (lo, hi, work | None, already_applied) in launch order."""
         if self.launch_stream is not None:
-            self._launch_pending()
-            torch.cuda.current_stream().wait_stream(self.launch_stream)
+            if self._launch_pending():
+                torch.cuda.current_stream().wait_stream(self.launch_stream)
         covered = sorted(self.buckets[k] for k in self.done)
         gaps, pos, n = [], 0, self.flat_grad.numel()
         for lo, hi in covered:
@@ -340,14 +357,17 @@ class EncoderTrainer:
         # 0.44 ms of Adam under the backward and the backward slows down by as much (1 GPU: 7.65 -> 7.65 ms; 2 GPUs: 8.07 ->
         # 8.39 ms) -- the step is bound by the aggregate HBM / SM time of its kernels, not by its critical path.
         per_bucket_adam = os.environ.get("SAVQA_ADAM_PER_BUCKET", "0") == "1" and self.flat_grad.is_cuda
-        if (self.world > 1 or per_bucket_adam) and self.overlap_allreduce and not self._debug_skip_allreduce:
+        # One GPU: the Adam of everything but the input stages / MIL_NCE (96 % of the parameters) is launched ONCE, behind the last
+        # encoder block's gradients -- next to the chain of small kernels that ends the backward pass, not after it
+        early_adam = self.world == 1 and self.flat_grad.is_cuda and os.environ.get("SAVQA_EARLY_ADAM", "1") != "0" and not per_bucket_adam
+        if (self.world > 1 or per_bucket_adam or early_adam) and self.overlap_allreduce and not self._debug_skip_allreduce:
             # both decoder outputs feed the heads; a bucket of several encoder blocks is final when the backward pass has left its
             # lowest block
             nb = max((getattr(b_, "num_blocks", 0) for b_ in (model.att_vis_grid, model.att_syb)), default=0)
             need = {k: (2 if k[1] == "heads" else (min(BUCKET_BLOCKS, nb - k[2] * BUCKET_BLOCKS) if k[1] == "enc" else 1))
                     for k in self.bucket_ranges}
             self.reducer = GradReducer(self.flat_grad, dict(self.bucket_ranges), need, self.pg, self.world,
-                                       self._adam_range if per_bucket_adam else None)
+                                       self._adam_range if (per_bucket_adam or early_adam) else None, merged=early_adam)
 
     def sync_mirror(self) -> None:
         """Re-derives the bf16 mirror from the fp32 parameters (after prepare(), or after load_state_dict wrote into them)."""
