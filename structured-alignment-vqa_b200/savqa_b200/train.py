@@ -122,7 +122,6 @@ class GradReducer:
                 self.works.append((lo_all, hi_all, None, True))
                 self.pending = []
                 return False  # the launch stream took no part (under graph capture it must not be waited for then)
-        used = bool(self.pending)
         for _, _, lo, hi, evs in sorted(self.pending, key=lambda t: (t[0], t[1])):
             for ev in evs:
                 r.wait_event(ev)
@@ -140,7 +139,7 @@ class GradReducer:
                 applied = True
             self.works.append((lo, hi, work, applied))
         self.pending = []
-        return used
+        return True
 
     def finish(self, chunks: int):
         """All-reduces the ranges no bucket report covered (in `chunks` pieces so that the optimizer can follow one piece

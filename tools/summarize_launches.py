@@ -16,8 +16,11 @@ for r in rd:
     rows.append((int(r["ID"]), r["Kernel Name"], ns))
 # one step = from one gather_rows launch pair to the next adam_kernel
 names = [n for _, n, _ in rows]
+adv = [i for i, n in enumerate(names) if "adam_advance_kernel" in n]
 adam = [i for i, n in enumerate(names) if "adam_kernel" in n]
-if len(adam) >= 2:
+if len(adv) >= 2:  # round 2: the device-side step counter's kernel opens every step
+    lo, hi = adv[-2], adv[-1]
+elif len(adam) >= 2:
     lo, hi = adam[0] + 1, adam[1] + 1
     # include row-adam launches that follow the dense adam
     while hi < len(names) and ("adam_rows" in names[hi] or "scatter_add" in names[hi]):
