@@ -530,7 +530,7 @@ def main():
         os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "stock-gpu"])
     ap.add_argument("--workload", default="train", choices=["train", "inference"])
