@@ -14,8 +14,8 @@
 //   mode 2 (LN bwd):  dy = acc + res;  dx = LN'(pre)[dy] (formula of csrc/layernorm.cu)    -> dx, dx_bf16, dxg_bf16 = gate(dx * rowscale),
 //                     dgamma += sum_r dy c / s, dbeta += sum_r dy, dxsum += sum_r dx        (a dgrad GEMM that feeds a LayerNorm backward)
 //
-// Per CTA: warp 0 = TMA producer, warp 1 = TMEM allocator + tcgen05.mma issuer (M = 128, N = 64), warps 2..5 = epilogue (one
-// thread per output row, its 64 accumulator columns in registers).  A [128 x K] is streamed in 64-column k-blocks by every CTA
+// Per CTA: warp 0 = TMA producer, warp 1 = TMEM allocator + tcgen05.mma issuer (M = 128, N = 64), warps 2..9 = epilogue (one
+// thread per output row and 32-column half of the slab, its accumulator columns in registers).  A [128 x K] is streamed in 64-column k-blocks by every CTA
 // (L2-resident: the previous link wrote it), B is the CTA's own [64 x K] slab of the weights.
 #include "common.cuh"
 
@@ -26,13 +26,15 @@ constexpr int BM = 128;
 constexpr int BN = 64;   // columns per CTA
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int EC = 32;   // columns per epilogue thread (two epilogue warps per TMEM lane quadrant)
+constexpr int kThreads = 320;
 constexpr int kStages = 8;
 constexpr int kMaxCluster = 8;
 constexpr int kABytes = BM * BK * 2;
 constexpr int kBBytes = BN * BK * 2;
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kPartBytes = 2 * kMaxCluster * BM * 8;  // two exchange rounds x ranks x rows x {float, float}
+constexpr int kMaxSlab = 2 * kMaxCluster;             // 32-column partials per output row
+constexpr int kPartBytes = 2 * kMaxSlab * BM * 8;     // two exchange rounds x slabs x rows x {float, float}
 constexpr int kSmemBytes = kStages * kStageBytes + kPartBytes + 1024;
 
 struct RowLnParams {
@@ -44,10 +46,16 @@ __device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float x,
   asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(x), "f"(y) : "memory");
 }
 
-// every CTA of the cluster receives this thread's pair at part[round][my_rank][row]
-__device__ __forceinline__ void share_pair(float2* part, int round, uint32_t my_rank, int cluster, int row, float x, float y) {
-  const uint32_t local = smem_u32(part + (round * kMaxCluster + static_cast<int>(my_rank)) * BM + row);
+// every CTA of the cluster receives this thread's pair at part[round][slab][row]
+__device__ __forceinline__ void share_pair(float2* part, int round, int slab, int cluster, int row, float x, float y) {
+  const uint32_t local = smem_u32(part + (round * kMaxSlab + slab) * BM + row);
   for (int r = 0; r < cluster; ++r) st_cluster_f32x2(mapa_shared(local, static_cast<uint32_t>(r)), x, y);
+}
+
+// this thread's pair -> part[round][slab][row] of every CTA of the cluster (or of this CTA alone when nothing is exchanged)
+__device__ __forceinline__ void put_pair(float2* part, bool exchange, int round, int slab, int cluster, int row, float x, float y) {
+  if (exchange) share_pair(part, round, slab, cluster, row, x, y);
+  else part[(round * kMaxSlab + slab) * BM + row] = make_float2(x, y);
 }
 
 template <bool B_MN>
@@ -132,46 +140,53 @@ rowln_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   __syncwarp();  // lanes 1..31 of the two single-thread role warps wait for their lane 0: the barriers below are warp-aligned
 
-  // ===================== epilogue (warps 2..5) interleaved with the cluster barriers every warp takes =====================
+  // ===================== epilogue (warps 2..9) interleaved with the cluster barriers every warp takes =====================
+  // Two warps per TMEM lane quadrant, each thread one output row and EC = 32 of the CTA's 64 columns: the row epilogue is
+  // straight-line code that every thread runs once (instruction fetch is its first stall reason, profiles/r2_ncu_rowln.txt) --
+  // half the columns per thread is half the code, and the two halves run side by side.  A row's statistics are merged from
+  // 2 * cluster partials of 32 columns each (slab index 2 * rank + half), in slab order, by every thread that needs them.
   const bool epi = warp >= 2;
   const int quad = warp & 3;
+  const int half = epi ? ((warp - 2) >> 2) : 0;
   const int row = quad * 32 + lane;           // row of the 128-row block this thread owns (epilogue warps)
   const long grow = static_cast<long>(m_blk) * BM + row;
   const bool row_ok = epi && grow < p.M;
-  float v[BN];
-  float c_[BN];                                // mode 2: pre - mean
+  const int nc0 = n0 + EC * half;             // first global column of this thread
+  const int slab = 2 * static_cast<int>(my_rank) + half;
+  const int nslab = 2 * p.cluster;
+  float v[EC];
+  float c_[EC];                                // mode 2: pre - mean
   float mean = 0.0f, sigma = 0.0f, inv = 0.0f;
   if (epi) {
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-#pragma unroll
-    for (int h = 0; h < BN / 32; ++h) {
+    {
       uint32_t r[32];
       __syncwarp();
-      tmem_ld_32x32(t_row + 32 * h, r);
+      tmem_ld_32x32(t_row + EC * half, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[32 * h + j] = __uint_as_float(r[j]);
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
     }
     tc_fence_before();
     if (a.mode != 2) {
       // ---- forward value: relu?(acc + bias), optional bf16 activation output, gate, row scale, residual ----
       if (a.bias) {
 #pragma unroll
-        for (int j = 0; j < BN; j += 4) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + j));
+        for (int j = 0; j < EC; j += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + nc0 + j));
           v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
         }
       }
       if (a.relu) {
 #pragma unroll
-        for (int j = 0; j < BN; ++j) v[j] = fmaxf(v[j], 0.0f);
+        for (int j = 0; j < EC; ++j) v[j] = fmaxf(v[j], 0.0f);
       }
       if (a.gate_bf16 && row_ok) {
-        const uint4* g4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.gate_bf16) + grow * a.ld_gate + n0);
+        const uint4* g4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.gate_bf16) + grow * a.ld_gate + nc0);
 #pragma unroll
-        for (int j = 0; j < BN / 8; ++j) {
+        for (int j = 0; j < EC / 8; ++j) {
           const uint4 g = __ldg(g4 + j);
           const uint32_t w[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
@@ -185,9 +200,9 @@ rowln_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (a.act_bf16) {
         // the bf16 activation the next GEMM / the backward reads; the fp32 path continues from its ROUNDED value (what the unfused
         // path does: relu output staged in bf16, then multiplied by the query mask, functional.TokenSelfAttentionFn)
-        uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.act_bf16) + grow * a.ld_act + n0);
+        uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.act_bf16) + grow * a.ld_act + nc0);
 #pragma unroll
-        for (int j = 0; j < BN / 8; ++j) {
+        for (int j = 0; j < EC / 8; ++j) {
           const uint4 pk = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
           if (row_ok) o4[j] = pk;
@@ -204,53 +219,52 @@ rowln_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (a.rowscale) {
           const float rs = row_ok ? __ldg(a.rowscale + grow) : 0.0f;
 #pragma unroll
-          for (int j = 0; j < BN; ++j) v[j] *= rs;
+          for (int j = 0; j < EC; ++j) v[j] *= rs;
         }
         if (a.res && row_ok) {
 #pragma unroll
-          for (int j = 0; j < BN; j += 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(a.res + grow * a.ld_res + n0 + j));
+          for (int j = 0; j < EC; j += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(a.res + grow * a.ld_res + nc0 + j));
             v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
           }
         }
         if (!row_ok) {
 #pragma unroll
-          for (int j = 0; j < BN; ++j) v[j] = 0.0f;
+          for (int j = 0; j < EC; ++j) v[j] = 0.0f;
         }
         if (a.pre && row_ok) {
 #pragma unroll
-          for (int j = 0; j < BN; j += 4)
-            *reinterpret_cast<float4*>(a.pre + grow * a.ld_pre + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < EC; j += 4)
+            *reinterpret_cast<float4*>(a.pre + grow * a.ld_pre + nc0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
         // slab statistics: (sum, M2 about the slab mean) -> exact pairwise merge over the cluster (Chan et al.)
         float s = 0.0f;
 #pragma unroll
-        for (int j = 0; j < BN; ++j) s += v[j];
-        const float ml = s * (1.0f / BN);
+        for (int j = 0; j < EC; ++j) s += v[j];
+        const float ml = s * (1.0f / EC);
         float m2 = 0.0f;
 #pragma unroll
-        for (int j = 0; j < BN; ++j) m2 = fmaf(v[j] - ml, v[j] - ml, m2);
-        if (exchange) share_pair(part, 0, my_rank, p.cluster, row, s, m2);
-        else part[row] = make_float2(s, m2);
+        for (int j = 0; j < EC; ++j) m2 = fmaf(v[j] - ml, v[j] - ml, m2);
+        put_pair(part, exchange, 0, slab, p.cluster, row, s, m2);
       } else {
         // ---- plain epilogue: (+ residual) store ----
         if (a.res && row_ok) {
 #pragma unroll
-          for (int j = 0; j < BN; j += 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(a.res + grow * a.ld_res + n0 + j));
+          for (int j = 0; j < EC; j += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(a.res + grow * a.ld_res + nc0 + j));
             v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
           }
         }
         if (row_ok) {
           if (a.y) {
 #pragma unroll
-            for (int j = 0; j < BN; j += 4)
-              *reinterpret_cast<float4*>(a.y + grow * a.ld_y + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < EC; j += 4)
+              *reinterpret_cast<float4*>(a.y + grow * a.ld_y + nc0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
           if (a.y_bf16) {
-            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.y_bf16) + grow * a.ld_yb + n0);
+            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.y_bf16) + grow * a.ld_yb + nc0);
 #pragma unroll
-            for (int j = 0; j < BN / 8; ++j)
+            for (int j = 0; j < EC / 8; ++j)
               o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
           }
@@ -260,8 +274,8 @@ rowln_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // ---- mode 2: dy = acc + res; g = dy * gamma; c = pre - mean (statistics saved by the forward) ----
       if (a.res && row_ok) {
 #pragma unroll
-        for (int j = 0; j < BN; j += 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(a.res + grow * a.ld_res + n0 + j));
+        for (int j = 0; j < EC; j += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(a.res + grow * a.ld_res + nc0 + j));
           v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
         }
       }
@@ -272,44 +286,43 @@ rowln_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       inv = 1.0f / (sigma + a.eps);
       float sg = 0.0f, dot = 0.0f;
 #pragma unroll
-      for (int j = 0; j < BN; j += 4) {
+      for (int j = 0; j < EC; j += 4) {
         float4 pr = make_float4(mean, mean, mean, mean);
-        if (row_ok) pr = __ldg(reinterpret_cast<const float4*>(a.pre + grow * a.ld_pre + n0 + j));
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + n0 + j));
+        if (row_ok) pr = __ldg(reinterpret_cast<const float4*>(a.pre + grow * a.ld_pre + nc0 + j));
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + nc0 + j));
         c_[j] = pr.x - mean; c_[j + 1] = pr.y - mean; c_[j + 2] = pr.z - mean; c_[j + 3] = pr.w - mean;
         if (!row_ok) { v[j] = 0.0f; v[j + 1] = 0.0f; v[j + 2] = 0.0f; v[j + 3] = 0.0f; }
         const float g0 = v[j] * gm.x, g1 = v[j + 1] * gm.y, g2 = v[j + 2] * gm.z, g3 = v[j + 3] * gm.w;
         sg += (g0 + g1) + (g2 + g3);
         dot = fmaf(g0, c_[j], fmaf(g1, c_[j + 1], fmaf(g2, c_[j + 2], fmaf(g3, c_[j + 3], dot))));
       }
-      if (exchange) share_pair(part, 0, my_rank, p.cluster, row, sg, dot);
-      else part[row] = make_float2(sg, dot);
+      put_pair(part, exchange, 0, slab, p.cluster, row, sg, dot);
     }
   }
   if (a.mode == 0) {
-    // nothing crosses CTAs in plain mode
+    // nothing crosses CTAs (or warps) in plain mode
   } else {
     __syncwarp();
     if (exchange) cluster_sync_all(); else __syncthreads();
     float ysum = 0.0f;
     if (epi) {
       if (a.mode == 1) {
-        // merge the slabs' (sum, M2) in rank order: mean, unbiased sigma of the whole row
+        // merge the slabs' (sum, M2) in slab order: mean, unbiased sigma of the whole row
         float tot = 0.0f;
-        for (int r = 0; r < p.cluster; ++r) tot += part[r * BM + row].x;
+        for (int r = 0; r < nslab; ++r) tot += part[r * BM + row].x;
         mean = tot / static_cast<float>(p.N);
         float m2 = 0.0f;
-        for (int r = 0; r < p.cluster; ++r) {
+        for (int r = 0; r < nslab; ++r) {
           const float2 q = part[r * BM + row];
-          const float d = q.x * (1.0f / BN) - mean;
-          m2 += q.y + static_cast<float>(BN) * d * d;
+          const float d = q.x * (1.0f / EC) - mean;
+          m2 += q.y + static_cast<float>(EC) * d * d;
         }
         sigma = sqrtf(m2 / static_cast<float>(p.N - 1));
         inv = 1.0f / (sigma + a.eps);
 #pragma unroll
-        for (int j = 0; j < BN; j += 4) {
-          const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + n0 + j));
-          const float4 bt = __ldg(reinterpret_cast<const float4*>(a.beta + n0 + j));
+        for (int j = 0; j < EC; j += 4) {
+          const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + nc0 + j));
+          const float4 bt = __ldg(reinterpret_cast<const float4*>(a.beta + nc0 + j));
           v[j] = gm.x * (v[j] - mean) * inv + bt.x;
           v[j + 1] = gm.y * (v[j + 1] - mean) * inv + bt.y;
           v[j + 2] = gm.z * (v[j + 2] - mean) * inv + bt.z;
@@ -319,29 +332,26 @@ rowln_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (row_ok) {
           if (a.y) {
 #pragma unroll
-            for (int j = 0; j < BN; j += 4)
-              *reinterpret_cast<float4*>(a.y + grow * a.ld_y + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < EC; j += 4)
+              *reinterpret_cast<float4*>(a.y + grow * a.ld_y + nc0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
           if (a.y_bf16) {
-            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.y_bf16) + grow * a.ld_yb + n0);
+            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.y_bf16) + grow * a.ld_yb + nc0);
 #pragma unroll
-            for (int j = 0; j < BN / 8; ++j)
+            for (int j = 0; j < EC / 8; ++j)
               o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
           }
-          if (a.stats && my_rank == 0) {
+          if (a.stats && slab == 0) {
             a.stats[2 * grow] = mean;
             a.stats[2 * grow + 1] = sigma;
           }
         }
-        if (a.on) {
-          if (exchange) share_pair(part, 1, my_rank, p.cluster, row, ysum, 0.0f);
-          else part[kMaxCluster * BM + row] = make_float2(ysum, 0.0f);
-        }
+        if (a.on) put_pair(part, exchange, 1, slab, p.cluster, row, ysum, 0.0f);
       } else {
-        // mode 2: totals of (sum g, sum g c) over the row, then dx and the column sums of this CTA's 128 rows
+        // mode 2: totals of (sum g, sum g c) over the row, then dx and the column sums of this warp's 32 rows x 32 columns
         float sg = 0.0f, dot = 0.0f;
-        for (int r = 0; r < p.cluster; ++r) {
+        for (int r = 0; r < nslab; ++r) {
           const float2 q = part[r * BM + row];
           sg += q.x;
           dot += q.y;
@@ -350,58 +360,57 @@ rowln_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const float sden = sigma + a.eps;
         const float k2 = (sigma > 0.0f) ? dot / (static_cast<float>(p.N - 1) * sigma * sden * sden) : 0.0f;
         const float rs = (a.rowscale && row_ok) ? __ldg(a.rowscale + grow) : 1.0f;
-#pragma unroll
-        for (int h = 0; h < BN / 32; ++h) {
+        {
           // column sums over this warp's 32 rows, one quantity at a time (one 32-register scratch array)
           float t32[32];
           if (a.dbeta) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) t32[j] = v[32 * h + j];
+            for (int j = 0; j < 32; ++j) t32[j] = v[j];
             const float t = warp_colsum32(t32, lane);
-            atomicAdd(a.dbeta + n0 + 32 * h + lane, t);
+            atomicAdd(a.dbeta + nc0 + lane, t);
           }
           if (a.dgamma) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) t32[j] = v[32 * h + j] * c_[32 * h + j] * inv;
+            for (int j = 0; j < 32; ++j) t32[j] = v[j] * c_[j] * inv;
             const float t = warp_colsum32(t32, lane);
-            atomicAdd(a.dgamma + n0 + 32 * h + lane, t);
+            atomicAdd(a.dgamma + nc0 + lane, t);
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + n0 + 32 * h + j));
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + nc0 + j));
             const float gmv[4] = {gm.x, gm.y, gm.z, gm.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const int jj = 32 * h + j + q;
+              const int jj = j + q;
               v[jj] = row_ok ? (v[jj] * gmv[q] - mg) * inv - c_[jj] * k2 : 0.0f;
             }
           }
           if (a.dxsum) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) t32[j] = v[32 * h + j];
+            for (int j = 0; j < 32; ++j) t32[j] = v[j];
             const float t = warp_colsum32(t32, lane);
-            atomicAdd(a.dxsum + n0 + 32 * h + lane, t);
+            atomicAdd(a.dxsum + nc0 + lane, t);
           }
         }
         if (row_ok) {
           if (a.y) {
 #pragma unroll
-            for (int j = 0; j < BN; j += 4)
-              *reinterpret_cast<float4*>(a.y + grow * a.ld_y + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < EC; j += 4)
+              *reinterpret_cast<float4*>(a.y + grow * a.ld_y + nc0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
           if (a.y_bf16) {
-            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.y_bf16) + grow * a.ld_yb + n0);
+            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.y_bf16) + grow * a.ld_yb + nc0);
 #pragma unroll
-            for (int j = 0; j < BN / 8; ++j)
+            for (int j = 0; j < EC / 8; ++j)
               o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
           }
           if (a.dxg_bf16) {
             // ReLU backward of the layer in front of this LayerNorm, staged as the next GEMM's bf16 operand: (act > 0) ? dx * rowscale : 0
-            const uint4* g4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.gate_bf16) + grow * a.ld_gate + n0);
-            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.dxg_bf16) + grow * a.ld_dxg + n0);
+            const uint4* g4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.gate_bf16) + grow * a.ld_gate + nc0);
+            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.dxg_bf16) + grow * a.ld_dxg + nc0);
 #pragma unroll
-            for (int j = 0; j < BN / 8; ++j) {
+            for (int j = 0; j < EC / 8; ++j) {
               const uint4 g = __ldg(g4 + j);
               const uint32_t w[4] = {g.x, g.y, g.z, g.w};
               float t[8];
@@ -420,9 +429,9 @@ rowln_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (a.mode == 1 && a.on) {
       __syncwarp();
       if (exchange) cluster_sync_all(); else __syncthreads();
-      if (epi && row_ok && my_rank == 0) {
+      if (epi && row_ok && slab == 0) {
         float tot = 0.0f;
-        for (int r = 0; r < p.cluster; ++r) tot += part[(kMaxCluster + r) * BM + row].x;
+        for (int r = 0; r < nslab; ++r) tot += part[(kMaxSlab + r) * BM + row].x;
         a.on[grow] = (tot != 0.0f) ? 1.0f : 0.0f;
       }
     }
