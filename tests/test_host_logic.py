@@ -208,3 +208,33 @@ def test_evaluate_loop_matches_reference_eval(monkeypatch):
         loss, ok, n = infer.evaluate(model, batches, dec_mask=True, with_milnce_loss=True)
         assert n == cnt and abs(loss - tot / cnt) < 5e-3 * abs(tot / cnt), (loss, tot / cnt)
         assert abs(ok - correct) <= 1  # bf16 operands may flip one near-tie argmax
+
+
+def test_fixed_point_row_accumulator_is_order_independent():
+    """The word tables' gradient accumulator (savqa_scatter_add_rows_q48, here its CPU stand-in with the same rounding): the sum of
+    a list of rows with many duplicates does not depend on the order of the additions -- what keeps data-parallel replicas
+    bit-identical (float accumulation does depend on it) -- and equals the float64 sum to 2^-48 per addend."""
+    import fake_ops as F
+    g = torch.Generator().manual_seed(11)
+    n, rows, width = 3000, 13, 24
+    idx = torch.randint(0, rows, (n,), generator=g)
+    idx[::17] = 5  # one very hot row
+    grad_rows = torch.randn(n, width, generator=g) * 1e-3
+    perm = torch.randperm(n, generator=g)
+    a = torch.zeros(rows, width, dtype=torch.int64)
+    b = torch.zeros(rows, width, dtype=torch.int64)
+    F.scatter_add_rows(a, idx, grad_rows, scale=0.125, skip_row=7)
+    F.scatter_add_rows(b, idx[perm], grad_rows[perm], scale=0.125, skip_row=7)
+    assert torch.equal(a, b)
+    assert int(a[7].abs().sum()) == 0  # the padding row takes no gradient
+    ref = torch.zeros(rows, width, dtype=torch.float64)
+    keep = idx != 7
+    ref.index_add_(0, idx[keep], (grad_rows[keep] * 0.125).double())
+    assert float((a.double() / 2.0 ** 48 - ref).abs().max()) <= n * 2.0 ** -48
+    # float accumulation of the same two orders differs in the last bits (the reason for the fixed-point form)
+    fa, fb = torch.zeros(rows, width), torch.zeros(rows, width)
+    for i in range(n):
+        fa[idx[i]] += grad_rows[i] * 0.125
+    for i in perm.tolist():
+        fb[idx[i]] += grad_rows[i] * 0.125
+    assert not torch.equal(fa, fb)
